@@ -1,0 +1,103 @@
+"""ctypes binding of liblhrs_b200.so — the C-ABI declared in include/lhrs_b200.h.
+
+The product path has no CPU fallback: if the shared library is missing or a symbol is absent the import
+of any op fails loudly (``LhrsLibraryError``).  Nothing under ``oracle/`` is ever imported from here.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+
+LIB_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib")
+LIB_PATH = os.path.join(LIB_DIR, "liblhrs_b200.so")
+
+
+class LhrsLibraryError(RuntimeError):
+    pass
+
+
+class LhrsGemm(C.Structure):
+    _fields_ = [
+        ("M", C.c_int32), ("N", C.c_int32), ("K", C.c_int32),
+        ("A", C.c_void_p), ("lda", C.c_int64), ("a_mn_major", C.c_int32),
+        ("B", C.c_void_p * 3), ("num_b", C.c_int32), ("seg_rows", C.c_int32),
+        ("ldb", C.c_int64), ("b_mn_major", C.c_int32),
+        ("epilogue", C.c_int32), ("act", C.c_int32), ("alpha", C.c_float),
+        ("bias", C.c_void_p), ("residual", C.c_void_p), ("ldr", C.c_int64),
+        ("D", C.c_void_p), ("ldd", C.c_int64), ("d_f32", C.c_int32),
+        ("row_map", C.c_void_p),
+        ("rope_cos", C.c_void_p), ("rope_sin", C.c_void_p), ("positions", C.c_void_p),
+        ("rope_seq_len", C.c_int32),
+        ("pre_gate", C.c_void_p), ("pre_up", C.c_void_p),
+    ]
+
+
+class LhrsAttention(C.Structure):
+    _fields_ = [
+        ("q", C.c_void_p), ("k", C.c_void_p), ("v", C.c_void_p), ("o", C.c_void_p),
+        ("lse", C.c_void_p), ("key_mask", C.c_void_p),
+        ("q_bs", C.c_int64), ("q_rs", C.c_int64), ("q_hs", C.c_int64),
+        ("k_bs", C.c_int64), ("k_rs", C.c_int64), ("k_hs", C.c_int64),
+        ("v_bs", C.c_int64), ("v_rs", C.c_int64), ("v_hs", C.c_int64),
+        ("o_bs", C.c_int64), ("o_rs", C.c_int64), ("o_hs", C.c_int64),
+        ("B", C.c_int32), ("H", C.c_int32), ("Sq", C.c_int32), ("Skv", C.c_int32), ("head_dim", C.c_int32),
+        ("causal", C.c_int32), ("scale", C.c_float),
+    ]
+
+
+_P = C.c_void_p
+_I32 = C.c_int32
+_I64 = C.c_int64
+_F = C.c_float
+
+# symbol -> (restype, argtypes).  tests/test_abi.py checks this table against include/lhrs_b200.h.
+SIGNATURES = {
+    "lhrs_last_error": (C.c_char_p, []),
+    "lhrs_version": (C.c_int, []),
+    "lhrs_launch_count": (C.c_uint64, []),
+    "lhrs_gemm_bf16": (C.c_int, [C.POINTER(LhrsGemm), _P]),
+    "lhrs_attention_fwd": (C.c_int, [C.POINTER(LhrsAttention), _P]),
+    "lhrs_rmsnorm_fwd": (C.c_int, [_P, _P, _P, _P, _I64, _I32, _F, _P]),
+    "lhrs_layernorm_fwd": (C.c_int, [_P, _I64, _P, _P, _P, _I64, _P, _P, _I64, _I32, _F, _P]),
+    "lhrs_vit_im2col": (C.c_int, [_P, _P, _I32, _I32, _I32, _I32, _I32, _P]),
+    "lhrs_vit_embed_ln": (C.c_int, [_P, _P, _P, _P, _P, _P, _I32, _I32, _I32, _F, _P]),
+    "lhrs_splice_scan": (C.c_int, [_P, _I32, _I32, _I32, _P, _P]),
+    "lhrs_splice_fill": (C.c_int, [_P, _P, _P, _P, _P, _P, _I32, _I32, _I32, _I32, _I32, _I32, _P, _P, _P, _P, _P]),
+    "lhrs_splice_bwd": (C.c_int, [_P, _P, _P, _I64, _I32, _P]),
+    "lhrs_ce_fwd": (C.c_int, [_P, _I64, _P, _I32, _I32, _I32, _P, _P, _P, _P]),
+    "lhrs_ce_bwd": (C.c_int, [_P, _I64, _P, _I32, _I32, _I32, _P, _P, _F, _P, _P]),
+}
+
+_lock = threading.Lock()
+_lib = None
+
+
+def load() -> C.CDLL:
+    """Load the shared library once; raise (never fall back) if it is missing or incomplete."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(LIB_PATH):
+            raise LhrsLibraryError(
+                f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                f"(or `make -C lhrs_bot_b200/csrc`). There is no CPU fallback for this path.")
+        lib = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            try:
+                fn = getattr(lib, name)
+            except AttributeError as e:
+                raise LhrsLibraryError(f"{LIB_PATH} does not export {name}") from e
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+        return lib
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = load().lhrs_last_error()
+        raise RuntimeError(f"{what} failed (code {rc}): {msg.decode() if msg else '?'}")

@@ -1,0 +1,541 @@
+// Dense bf16 contraction on the 5th-gen tensor cores (sm_100a):
+//   D[M,N] = epilogue(alpha * A[M,K] · B[N,K]^T), fp32 accumulation in TMEM.
+//
+// One persistent CTA per SM, warp-specialised:
+//   warp 0      TMA producer  (cp.async.bulk.tensor -> 128B-swizzled smem ring, mbarrier complete_tx)
+//   warp 1      MMA issuer    (one thread issues tcgen05.mma 128xBNx16, commits free the ring slots)
+//   warp 2      TMEM allocator (2 accumulator stages of BN fp32 columns)
+//   warps 4..7  epilogue      (tcgen05.ld -> registers -> fused epilogue -> global), overlaps the next tile's MMAs
+//
+// Every nn.Linear of the LHRS-Bot hot path goes through here (see include/lhrs_b200.h for the map to
+// the reference call sites); the K-major/MN-major operand switches give the dX and dW backward forms.
+#include <cuda.h>
+
+#include "host_common.h"
+#include "ptx.cuh"
+
+namespace lhrs {
+
+constexpr int BM = 128;
+constexpr int BK = 64;  // 64 bf16 = one 128-byte swizzle atom
+
+struct GemmArgs {
+    int M, N, K;
+    int num_b, seg_rows;
+    int act;
+    float alpha;
+    const __nv_bfloat16* bias;
+    const __nv_bfloat16* residual;
+    long long ldr;
+    void* D;
+    long long ldd;
+    int d_f32;
+    const int* row_map;
+    const float* rope_cos;
+    const float* rope_sin;
+    const int* positions;
+    int rope_seq_len;
+    __nv_bfloat16* pre_gate;
+    __nv_bfloat16* pre_up;
+};
+
+template <int BN>
+struct GemmCfg {
+    static constexpr int STAGES = (BN == 256) ? 4 : 6;
+    static constexpr uint32_t A_BYTES = BM * BK * 2;
+    static constexpr uint32_t B_BYTES = BN * BK * 2;
+    static constexpr uint32_t TMEM_COLS = 2 * BN;
+    static constexpr uint32_t SMEM_BYTES = STAGES * (A_BYTES + B_BYTES) + 256 /*barriers*/ + 1024 /*align slack*/;
+};
+
+__device__ __forceinline__ float act_apply(float v, int act) {
+    if (act == LHRS_ACT_GELU_ERF) return 0.5f * v * (1.0f + erff(v * 0.70710678118654752f));
+    if (act == LHRS_ACT_QUICK_GELU) return v / (1.0f + __expf(-1.702f * v));
+    return v;
+}
+
+__device__ __forceinline__ void load_bf16x32(const __nv_bfloat16* p, float (&out)[32]) {
+    const uint4* q = reinterpret_cast<const uint4*>(p);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        uint4 u = __ldg(q + i);
+        out[i * 8 + 0] = bf16_lo(u.x); out[i * 8 + 1] = bf16_hi(u.x);
+        out[i * 8 + 2] = bf16_lo(u.y); out[i * 8 + 3] = bf16_hi(u.y);
+        out[i * 8 + 4] = bf16_lo(u.z); out[i * 8 + 5] = bf16_hi(u.z);
+        out[i * 8 + 6] = bf16_lo(u.w); out[i * 8 + 7] = bf16_hi(u.w);
+    }
+}
+__device__ __forceinline__ void store_bf16x32(__nv_bfloat16* p, const float (&v)[32]) {
+    uint4* q = reinterpret_cast<uint4*>(p);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        uint4 u;
+        u.x = pack_bf16(v[i * 8 + 0], v[i * 8 + 1]);
+        u.y = pack_bf16(v[i * 8 + 2], v[i * 8 + 3]);
+        u.z = pack_bf16(v[i * 8 + 4], v[i * 8 + 5]);
+        u.w = pack_bf16(v[i * 8 + 6], v[i * 8 + 7]);
+        q[i] = u;
+    }
+}
+__device__ __forceinline__ void store_f32x32(float* p, const float (&v)[32]) {
+    float4* q = reinterpret_cast<float4*>(p);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) q[i] = make_float4(v[i * 4], v[i * 4 + 1], v[i * 4 + 2], v[i * 4 + 3]);
+}
+
+// tile index -> (m_blk, n_blk): groups of GROUP_M row-blocks are walked column by column so that the ~148
+// tiles in flight share a small set of A row-blocks and B column-blocks in L2.
+__device__ __forceinline__ void tile_coords(int tile, int num_m, int num_n, int& m_blk, int& n_blk) {
+    constexpr int GROUP_M = 16;
+    const int group_size = GROUP_M * num_n;
+    const int g = tile / group_size;
+    const int first_m = g * GROUP_M;
+    const int gm = min(GROUP_M, num_m - first_m);
+    const int r = tile - g * group_size;
+    m_blk = first_m + r % gm;
+    n_blk = r / gm;
+}
+
+template <int BN, int KIND, bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(256, 1)
+gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB0,
+                 const __grid_constant__ CUtensorMap tmB1, const __grid_constant__ CUtensorMap tmB2,
+                 const GemmArgs args) {
+    using Cfg = GemmCfg<BN>;
+    constexpr int STAGES = Cfg::STAGES;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* smem_a = smem;
+    uint8_t* smem_b = smem + STAGES * Cfg::A_BYTES;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * (Cfg::A_BYTES + Cfg::B_BYTES));
+    uint64_t* full_bar = bars;
+    uint64_t* empty_bar = bars + STAGES;
+    uint64_t* tmem_full_bar = bars + 2 * STAGES;
+    uint64_t* tmem_empty_bar = bars + 2 * STAGES + 2;
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    const int num_m = (args.M + BM - 1) / BM;
+    const int num_n = (args.N + BN - 1) / BN;
+    const int num_tiles = num_m * num_n;
+    const int num_kb = (args.K + BK - 1) / BK;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmB0);
+        if (args.num_b > 1) tma_prefetch_desc(&tmB1);
+        if (args.num_b > 2) tma_prefetch_desc(&tmB2);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 1);
+        }
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(&tmem_full_bar[s], 1);
+            mbar_init(&tmem_empty_bar[s], 128);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 2) {
+        tmem_alloc(tmem_ptr_smem, Cfg::TMEM_COLS);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_smem;
+
+    if (warp == 0) {
+        // ===================================================================== TMA producer
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                int m_blk, n_blk;
+                tile_coords(tile, num_m, num_n, m_blk, n_blk);
+                const int m0 = m_blk * BM;
+                const int n0 = n_blk * BN;
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    mbar_arrive_expect_tx(&full_bar[stage], Cfg::A_BYTES + Cfg::B_BYTES);
+                    uint8_t* sa = smem_a + stage * Cfg::A_BYTES;
+                    uint8_t* sb = smem_b + stage * Cfg::B_BYTES;
+                    const int k0 = kb * BK;
+                    if constexpr (!A_MN) {
+                        tma_load_2d(sa, &tmA, &full_bar[stage], k0, m0);  // box {64 k, 128 m}
+                    } else {
+#pragma unroll
+                        for (int a = 0; a < BM / 64; ++a)  // box {64 m, 64 k} per 128B atom column
+                            tma_load_2d(sa + a * 8192, &tmA, &full_bar[stage], m0 + a * 64, k0);
+                    }
+                    if constexpr (!B_MN) {
+                        if constexpr (KIND == LHRS_EPI_SWIGLU) {
+                            // tile = [BN/2 gate rows | BN/2 up rows] of the same hidden units
+                            const int h0 = n_blk * (BN / 2);
+                            tma_load_2d(sb, &tmB0, &full_bar[stage], k0, h0);
+                            tma_load_2d(sb + (BN / 2) * BK * 2, &tmB1, &full_bar[stage], k0, h0);
+                        } else {
+                            const int seg = (args.num_b > 1) ? (n0 / args.seg_rows) : 0;
+                            const int r0 = n0 - seg * args.seg_rows;
+                            const CUtensorMap* tm = (seg == 0) ? &tmB0 : (seg == 1 ? &tmB1 : &tmB2);
+                            tma_load_2d(sb, tm, &full_bar[stage], k0, r0);  // box {64 k, BN n}
+                        }
+                    } else {
+#pragma unroll
+                        for (int a = 0; a < BN / 64; ++a)
+                            tma_load_2d(sb + a * 8192, &tmB0, &full_bar[stage], n0 + a * 64, k0);
+                    }
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================================================================== MMA issuer
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc_bf16(BM, BN, A_MN ? 1u : 0u, B_MN ? 1u : 0u);
+            int stage = 0;
+            uint32_t phase = 0;
+            int it = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+                const int as = it & 1;
+                const uint32_t aphase = (it >> 1) & 1;
+                mbar_wait(&tmem_empty_bar[as], aphase ^ 1);
+                tc_fence_after();
+                const uint32_t tmem_d = tmem_base + as * BN;
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    mbar_wait(&full_bar[stage], phase);
+                    tc_fence_after();
+                    const uint32_t a_base = smem_u32(smem_a + stage * Cfg::A_BYTES);
+                    const uint32_t b_base = smem_u32(smem_b + stage * Cfg::B_BYTES);
+#pragma unroll
+                    for (int k = 0; k < BK / 16; ++k) {
+                        // K-major SW128: rows are 128 B apart, 8-row groups 1024 B apart; +32 B per K=16 step.
+                        // MN-major SW128: 64-wide MN atoms 8 KB apart (LBO), 8-row K groups 1 KB apart (SBO); +2 KB per K=16.
+                        const uint64_t da = A_MN ? make_smem_desc(a_base + k * 2048, 8192, 1024, UMMA_LAYOUT_SW128)
+                                                 : make_smem_desc(a_base + k * 32, 0, 1024, UMMA_LAYOUT_SW128);
+                        const uint64_t db = B_MN ? make_smem_desc(b_base + k * 2048, 8192, 1024, UMMA_LAYOUT_SW128)
+                                                 : make_smem_desc(b_base + k * 32, 0, 1024, UMMA_LAYOUT_SW128);
+                        umma_bf16(tmem_d, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+                    }
+                    umma_commit(&empty_bar[stage]);  // slot reusable once these MMAs have read it
+                    if (kb == num_kb - 1) umma_commit(&tmem_full_bar[as]);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp >= 4) {
+        // ===================================================================== epilogue (warps 4..7)
+        const int q = warp - 4;  // == warp % 4: the TMEM lane quarter this warp may read
+        int it = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+            int m_blk, n_blk;
+            tile_coords(tile, num_m, num_n, m_blk, n_blk);
+            const int as = it & 1;
+            const uint32_t aphase = (it >> 1) & 1;
+            mbar_wait(&tmem_full_bar[as], aphase);
+            tc_fence_after();
+
+            const int row = m_blk * BM + q * 32 + lane;
+            const bool row_ok = row < args.M;
+            long long drow = row;
+            if (row_ok && args.row_map != nullptr) drow = args.row_map[row];
+            const bool store_ok = row_ok && drow >= 0;
+            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN;
+            const int n_tile0 = n_blk * BN;
+
+            if constexpr (KIND == LHRS_EPI_LINEAR) {
+#pragma unroll 1
+                for (int c = 0; c < BN / 32; ++c) {
+                    const int n0 = n_tile0 + c * 32;
+                    if (n0 >= args.N) break;
+                    uint32_t r[32];
+                    tmem_ld_32x32(taddr + c * 32, r);
+                    tmem_ld_wait();
+                    float v[32];
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * args.alpha;
+                    const bool full_chunk = (n0 + 32 <= args.N);
+                    if (full_chunk) {
+                        if (args.bias != nullptr) {
+                            float b[32];
+                            load_bf16x32(args.bias + n0, b);
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) v[j] += b[j];
+                        }
+                        if (args.act != LHRS_ACT_NONE) {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) v[j] = act_apply(bf16_round(v[j]), args.act);
+                        }
+                        if (args.residual != nullptr && row_ok) {
+                            float rr[32];
+                            load_bf16x32(args.residual + static_cast<long long>(row) * args.ldr + n0, rr);
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) v[j] = bf16_round(v[j]) + rr[j];
+                        }
+                        if (store_ok) {
+                            if (args.d_f32)
+                                store_f32x32(reinterpret_cast<float*>(args.D) + drow * args.ldd + n0, v);
+                            else
+                                store_bf16x32(reinterpret_cast<__nv_bfloat16*>(args.D) + drow * args.ldd + n0, v);
+                        }
+                    } else {
+                        // ragged N tail (e.g. LoRA rank): scalar, predicated
+                        for (int j = 0; j < 32; ++j) {
+                            const int n = n0 + j;
+                            if (n < args.N && store_ok) {
+                                float x = v[j];
+                                if (args.bias != nullptr) x += __bfloat162float(args.bias[n]);
+                                if (args.act != LHRS_ACT_NONE) x = act_apply(bf16_round(x), args.act);
+                                if (args.residual != nullptr)
+                                    x = bf16_round(x) + __bfloat162float(args.residual[static_cast<long long>(row) * args.ldr + n]);
+                                if (args.d_f32)
+                                    reinterpret_cast<float*>(args.D)[drow * args.ldd + n] = x;
+                                else
+                                    reinterpret_cast<__nv_bfloat16*>(args.D)[drow * args.ldd + n] = __float2bfloat16_rn(x);
+                            }
+                        }
+                    }
+                }
+            } else if constexpr (KIND == LHRS_EPI_SWIGLU) {
+                // accumulator columns [0, BN/2) = gate, [BN/2, BN) = up, same hidden units
+                constexpr int HALF = BN / 2;
+                const int h_tile0 = n_blk * HALF;
+                const int n_hidden = args.N / 2;
+#pragma unroll 1
+                for (int c = 0; c < HALF / 32; ++c) {
+                    const int h0 = h_tile0 + c * 32;
+                    if (h0 >= n_hidden) break;
+                    uint32_t rg[32], ru[32];
+                    tmem_ld_32x32(taddr + c * 32, rg);
+                    tmem_ld_32x32(taddr + HALF + c * 32, ru);
+                    tmem_ld_wait();
+                    float g[32], u[32], o[32];
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        g[j] = bf16_round(__uint_as_float(rg[j]) * args.alpha);
+                        u[j] = bf16_round(__uint_as_float(ru[j]) * args.alpha);
+                        const float s = bf16_round(g[j] / (1.0f + __expf(-g[j])));
+                        o[j] = s * u[j];
+                    }
+                    if (store_ok) {
+                        store_bf16x32(reinterpret_cast<__nv_bfloat16*>(args.D) + drow * args.ldd + h0, o);
+                        if (args.pre_gate != nullptr) {
+                            store_bf16x32(args.pre_gate + static_cast<long long>(row) * n_hidden + h0, g);
+                            store_bf16x32(args.pre_up + static_cast<long long>(row) * n_hidden + h0, u);
+                        }
+                    }
+                }
+            } else {  // LHRS_EPI_ROPE: columns are [q | k | v], each seg_rows wide, heads of 128
+                int pos = 0;
+                if (row_ok) pos = (args.positions != nullptr) ? args.positions[row] : (row % args.rope_seq_len);
+                const float* cs = args.rope_cos + static_cast<long long>(pos) * 64;
+                const float* sn = args.rope_sin + static_cast<long long>(pos) * 64;
+#pragma unroll 1
+                for (int h = 0; h < BN / 128; ++h) {
+                    const int nh0 = n_tile0 + h * 128;
+                    if (nh0 >= args.N) break;
+                    const bool rotate = (nh0 / args.seg_rows) < 2;
+#pragma unroll 1
+                    for (int c = 0; c < 2; ++c) {
+                        uint32_t r1[32], r2[32];
+                        tmem_ld_32x32(taddr + h * 128 + c * 32, r1);
+                        tmem_ld_32x32(taddr + h * 128 + 64 + c * 32, r2);
+                        tmem_ld_wait();
+                        float x1[32], x2[32];
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            x1[j] = bf16_round(__uint_as_float(r1[j]) * args.alpha);
+                            x2[j] = bf16_round(__uint_as_float(r2[j]) * args.alpha);
+                        }
+                        if (rotate && row_ok) {
+#pragma unroll
+                            for (int j4 = 0; j4 < 8; ++j4) {
+                                const float4 c4 = __ldg(reinterpret_cast<const float4*>(cs + c * 32) + j4);
+                                const float4 s4 = __ldg(reinterpret_cast<const float4*>(sn + c * 32) + j4);
+                                const float cc[4] = {c4.x, c4.y, c4.z, c4.w};
+                                const float ss[4] = {s4.x, s4.y, s4.z, s4.w};
+#pragma unroll
+                                for (int e = 0; e < 4; ++e) {
+                                    const int j = j4 * 4 + e;
+                                    const float a = x1[j], b = x2[j];
+                                    // HF rotate_half: out = x*cos + cat(-x2, x1)*sin, each product rounded to bf16
+                                    x1[j] = bf16_round(a * cc[e]) - bf16_round(b * ss[e]);
+                                    x2[j] = bf16_round(b * cc[e]) + bf16_round(a * ss[e]);
+                                }
+                            }
+                        }
+                        if (store_ok) {
+                            __nv_bfloat16* d = reinterpret_cast<__nv_bfloat16*>(args.D) + drow * args.ldd + nh0;
+                            store_bf16x32(d + c * 32, x1);
+                            store_bf16x32(d + 64 + c * 32, x2);
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(&tmem_empty_bar[as]);
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ host
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (fn == nullptr) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+// 2-D bf16 tensor map over a row-major [outer, inner] matrix with `ld` elements between rows, 128B swizzle.
+static int make_tmap(CUtensorMap* out, const void* ptr, uint64_t inner, uint64_t outer, uint64_t ld,
+                     uint32_t box_inner, uint32_t box_outer) {
+    EncodeTiledFn fn = get_encode_fn();
+    if (fn == nullptr) {
+        set_error("cuTensorMapEncodeTiled is not available from the driver");
+        return LHRS_ERR_CUDA;
+    }
+    cuuint64_t dims[2] = {inner, outer};
+    cuuint64_t strides[1] = {ld * 2};
+    cuuint32_t box[2] = {box_inner, box_outer};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled failed (%d): ptr=%p inner=%llu outer=%llu ld=%llu box=%ux%u", (int)r, ptr,
+                  (unsigned long long)inner, (unsigned long long)outer, (unsigned long long)ld, box_inner, box_outer);
+        return LHRS_ERR_CUDA;
+    }
+    return LHRS_OK;
+}
+
+template <int BN, int KIND, bool A_MN, bool B_MN>
+static int launch(const CUtensorMap& tA, const CUtensorMap (&tB)[3], const GemmArgs& a, cudaStream_t stream) {
+    using Cfg = GemmCfg<BN>;
+    auto kern = gemm_bf16_kernel<BN, KIND, A_MN, B_MN>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        LHRS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+        attr_set = true;
+    }
+    const int num_tiles = ((a.M + BM - 1) / BM) * ((a.N + BN - 1) / BN);
+    const int grid = num_tiles < num_sms() ? num_tiles : num_sms();
+    kern<<<grid, 256, Cfg::SMEM_BYTES, stream>>>(tA, tB[0], tB[1], tB[2], a);
+    LHRS_LAUNCH_CHECK("gemm_bf16_kernel");
+    return LHRS_OK;
+}
+
+}  // namespace lhrs
+
+using namespace lhrs;
+
+extern "C" int lhrs_gemm_bf16(const LhrsGemm* g, void* stream_) {
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    LHRS_CHECK_ARG(g != nullptr, "lhrs_gemm_bf16: null descriptor");
+    LHRS_CHECK_ARG(g->M > 0 && g->N > 0 && g->K > 0, "lhrs_gemm_bf16: empty problem M=%d N=%d K=%d", g->M, g->N, g->K);
+    LHRS_CHECK_ARG(g->A != nullptr && g->B[0] != nullptr && g->D != nullptr, "lhrs_gemm_bf16: null operand");
+    LHRS_CHECK_ARG(g->num_b >= 1 && g->num_b <= 3, "lhrs_gemm_bf16: num_b=%d", g->num_b);
+    LHRS_CHECK_ARG((g->lda % 8) == 0 && (g->ldb % 8) == 0, "lhrs_gemm_bf16: lda/ldb must be multiples of 8 elements (TMA 16B stride)");
+    LHRS_CHECK_ARG((reinterpret_cast<uintptr_t>(g->A) & 15) == 0 && (reinterpret_cast<uintptr_t>(g->B[0]) & 15) == 0,
+                   "lhrs_gemm_bf16: operands must be 16-byte aligned");
+    LHRS_CHECK_ARG((g->ldd % 8) == 0 && (reinterpret_cast<uintptr_t>(g->D) & 15) == 0, "lhrs_gemm_bf16: D alignment");
+    if (g->residual) LHRS_CHECK_ARG((g->ldr % 8) == 0 && (reinterpret_cast<uintptr_t>(g->residual) & 15) == 0, "lhrs_gemm_bf16: residual alignment");
+
+    const int kind = g->epilogue;
+    const bool a_mn = g->a_mn_major != 0, b_mn = g->b_mn_major != 0;
+    int bn = 256;
+    if (kind == LHRS_EPI_LINEAR) {
+        if (g->N <= 128 || (g->N % 256) != 0) bn = 128;
+        // small problems: more, smaller tiles fill the 148 SMs better
+        const long long tiles256 = (long long)((g->M + BM - 1) / BM) * ((g->N + 255) / 256);
+        if (tiles256 < num_sms() && g->N > 128) bn = 128;
+        if (g->num_b > 1) {
+            LHRS_CHECK_ARG(!b_mn, "lhrs_gemm_bf16: segmented B must be K-major");
+            LHRS_CHECK_ARG(g->seg_rows > 0 && g->seg_rows * g->num_b == g->N && (g->seg_rows % bn) == 0,
+                           "lhrs_gemm_bf16: seg_rows=%d must tile N=%d by %d", g->seg_rows, g->N, bn);
+        }
+    } else if (kind == LHRS_EPI_SWIGLU) {
+        LHRS_CHECK_ARG(g->num_b == 2 && !a_mn && !b_mn && (g->N % 256) == 0 && g->B[1] != nullptr,
+                       "lhrs_gemm_bf16: SWIGLU needs 2 K-major segments and N %% 256 == 0 (N=%d)", g->N);
+    } else if (kind == LHRS_EPI_ROPE) {
+        LHRS_CHECK_ARG(g->num_b == 3 && !a_mn && !b_mn && g->seg_rows > 0 && (g->seg_rows % 256) == 0 &&
+                           g->seg_rows * 3 == g->N && g->B[1] && g->B[2] && g->rope_cos && g->rope_sin &&
+                           (g->positions != nullptr || g->rope_seq_len > 0),
+                       "lhrs_gemm_bf16: ROPE needs q/k/v segments with seg_rows %% 256 == 0 and cos/sin tables");
+    } else {
+        LHRS_CHECK_ARG(false, "lhrs_gemm_bf16: unknown epilogue %d", kind);
+    }
+
+    CUtensorMap tA, tB[3];
+    int rc;
+    if (!a_mn) rc = make_tmap(&tA, g->A, g->K, g->M, g->lda, BK, BM);
+    else       rc = make_tmap(&tA, g->A, g->M, g->K, g->lda, 64, BK);
+    if (rc) return rc;
+    if (b_mn) {
+        rc = make_tmap(&tB[0], g->B[0], g->N, g->K, g->ldb, 64, BK);
+        if (rc) return rc;
+        tB[1] = tB[0]; tB[2] = tB[0];
+    } else if (kind == LHRS_EPI_SWIGLU) {
+        for (int i = 0; i < 2; ++i) {
+            rc = make_tmap(&tB[i], g->B[i], g->K, g->N / 2, g->ldb, BK, bn / 2);
+            if (rc) return rc;
+        }
+        tB[2] = tB[0];
+    } else {
+        const int rows = (g->num_b > 1) ? g->seg_rows : g->N;
+        for (int i = 0; i < 3; ++i) {
+            if (i < g->num_b) {
+                rc = make_tmap(&tB[i], g->B[i], g->K, rows, g->ldb, BK, bn);
+                if (rc) return rc;
+            } else {
+                tB[i] = tB[0];
+            }
+        }
+    }
+
+    GemmArgs a;
+    a.M = g->M; a.N = g->N; a.K = g->K;
+    a.num_b = g->num_b; a.seg_rows = (g->num_b > 1) ? g->seg_rows : g->N;
+    a.act = g->act; a.alpha = g->alpha;
+    a.bias = reinterpret_cast<const __nv_bfloat16*>(g->bias);
+    a.residual = reinterpret_cast<const __nv_bfloat16*>(g->residual);
+    a.ldr = g->ldr;
+    a.D = g->D; a.ldd = g->ldd; a.d_f32 = g->d_f32;
+    a.row_map = g->row_map;
+    a.rope_cos = g->rope_cos; a.rope_sin = g->rope_sin; a.positions = g->positions; a.rope_seq_len = g->rope_seq_len;
+    a.pre_gate = reinterpret_cast<__nv_bfloat16*>(g->pre_gate);
+    a.pre_up = reinterpret_cast<__nv_bfloat16*>(g->pre_up);
+
+    if (kind == LHRS_EPI_SWIGLU) return launch<256, LHRS_EPI_SWIGLU, false, false>(tA, tB, a, stream);
+    if (kind == LHRS_EPI_ROPE) return launch<256, LHRS_EPI_ROPE, false, false>(tA, tB, a, stream);
+    if (bn == 256) {
+        if (!a_mn && !b_mn) return launch<256, LHRS_EPI_LINEAR, false, false>(tA, tB, a, stream);
+        if (!a_mn && b_mn) return launch<256, LHRS_EPI_LINEAR, false, true>(tA, tB, a, stream);
+        if (a_mn && b_mn) return launch<256, LHRS_EPI_LINEAR, true, true>(tA, tB, a, stream);
+        return launch<256, LHRS_EPI_LINEAR, true, false>(tA, tB, a, stream);
+    } else {
+        if (!a_mn && !b_mn) return launch<128, LHRS_EPI_LINEAR, false, false>(tA, tB, a, stream);
+        if (!a_mn && b_mn) return launch<128, LHRS_EPI_LINEAR, false, true>(tA, tB, a, stream);
+        if (a_mn && b_mn) return launch<128, LHRS_EPI_LINEAR, true, true>(tA, tB, a, stream);
+        return launch<128, LHRS_EPI_LINEAR, true, false>(tA, tB, a, stream);
+    }
+}

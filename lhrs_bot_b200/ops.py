@@ -1,0 +1,274 @@
+"""Torch-tensor front end of the C-ABI ops (device pointers + current stream go straight to liblhrs_b200.so).
+
+Torch is used for device memory and streams only; every arithmetic step below runs in the hand-written
+sm_100a kernels of ``lhrs_bot_b200/csrc``.  There is no eager fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from typing import Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import LhrsAttention, LhrsGemm, check
+
+EPI_LINEAR, EPI_SWIGLU, EPI_ROPE = 0, 1, 2
+ACT_NONE, ACT_GELU_ERF, ACT_QUICK_GELU = 0, 1, 2
+
+IGNORE_INDEX = -100
+IMAGE_TOKEN_INDEX = -200
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _need(t: torch.Tensor, dtype, name: str) -> None:
+    if not t.is_cuda:
+        raise RuntimeError(f"{name}: expected a CUDA tensor (the lhrs_b200 path has no CPU fallback)")
+    if t.dtype != dtype:
+        raise RuntimeError(f"{name}: expected dtype {dtype}, got {t.dtype}")
+
+
+def _rows2d(t: torch.Tensor, name: str) -> Tuple[int, int, int]:
+    """(rows, cols, leading dim) of a 2-D tensor whose rows are contiguous."""
+    if t.dim() != 2 or t.stride(1) != 1:
+        raise RuntimeError(f"{name}: expected a 2-D tensor with unit inner stride, got shape {tuple(t.shape)} strides {t.stride()}")
+    return t.shape[0], t.shape[1], t.stride(0)
+
+
+def gemm(a: torch.Tensor, b, *, out: Optional[torch.Tensor] = None, bias: Optional[torch.Tensor] = None,
+         act: int = ACT_NONE, residual: Optional[torch.Tensor] = None, alpha: float = 1.0,
+         a_mn_major: bool = False, b_mn_major: bool = False, out_f32: bool = False,
+         row_map: Optional[torch.Tensor] = None, epilogue: int = EPI_LINEAR,
+         rope: Optional[Tuple[torch.Tensor, torch.Tensor, Optional[torch.Tensor], int]] = None,
+         pre_gate: Optional[torch.Tensor] = None, pre_up: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """D = epilogue(alpha * A · B^T).  ``b`` is a tensor [N, K] or a list of 2-3 equally shaped segments.
+
+    K-major (default): a is [M, K], b is [N, K] (nn.Linear weight layout).
+    ``a_mn_major``: a is stored [K, M];  ``b_mn_major``: b is stored [K, N].
+    """
+    bs: Sequence[torch.Tensor] = list(b) if isinstance(b, (list, tuple)) else [b]
+    _need(a, torch.bfloat16, "gemm A")
+    for t in bs:
+        _need(t, torch.bfloat16, "gemm B")
+    ar, ac, lda = _rows2d(a, "gemm A")
+    M, K = (ac, ar) if a_mn_major else (ar, ac)
+    br, bc, ldb = _rows2d(bs[0], "gemm B")
+    for t in bs[1:]:
+        if tuple(t.shape) != tuple(bs[0].shape) or t.stride(0) != ldb:
+            raise RuntimeError("gemm: B segments must have identical shape and stride")
+    if b_mn_major:
+        if len(bs) != 1:
+            raise RuntimeError("gemm: MN-major B cannot be segmented")
+        kb, seg = br, bc
+    else:
+        kb, seg = bc, br
+    if kb != K:
+        raise RuntimeError(f"gemm: K mismatch A has {K}, B has {kb}")
+    N = seg * len(bs)
+    n_out = N // 2 if epilogue == EPI_SWIGLU else N
+    if out is None:
+        rows_out = M if row_map is None else None
+        if rows_out is None:
+            raise RuntimeError("gemm: `out` is required with row_map")
+        out = torch.empty((M, n_out), device=a.device, dtype=torch.float32 if out_f32 else torch.bfloat16)
+    _need(out, torch.float32 if out_f32 else torch.bfloat16, "gemm D")
+    _, oc, ldd = _rows2d(out, "gemm D")
+    if oc < n_out:
+        raise RuntimeError(f"gemm: D has {oc} columns, needs {n_out}")
+
+    g = LhrsGemm()
+    g.M, g.N, g.K = M, N, K
+    g.A, g.lda, g.a_mn_major = a.data_ptr(), lda, int(a_mn_major)
+    for i in range(3):
+        g.B[i] = bs[i].data_ptr() if i < len(bs) else None
+    g.num_b, g.seg_rows, g.ldb, g.b_mn_major = len(bs), seg, ldb, int(b_mn_major)
+    g.epilogue, g.act, g.alpha = epilogue, act, alpha
+    if bias is not None:
+        _need(bias, torch.bfloat16, "gemm bias")
+        if bias.numel() != N or not bias.is_contiguous():
+            raise RuntimeError("gemm: bias must be a contiguous [N] tensor")
+    g.bias = _ptr(bias)
+    if residual is not None:
+        _need(residual, torch.bfloat16, "gemm residual")
+        g.ldr = _rows2d(residual, "gemm residual")[2]
+    g.residual = _ptr(residual)
+    g.D, g.ldd, g.d_f32 = out.data_ptr(), ldd, int(out_f32)
+    if row_map is not None:
+        _need(row_map, torch.int32, "gemm row_map")
+    g.row_map = _ptr(row_map)
+    if rope is not None:
+        cos, sin, positions, seq_len = rope
+        _need(cos, torch.float32, "rope cos")
+        _need(sin, torch.float32, "rope sin")
+        g.rope_cos, g.rope_sin = cos.data_ptr(), sin.data_ptr()
+        if positions is not None:
+            _need(positions, torch.int32, "rope positions")
+        g.positions, g.rope_seq_len = _ptr(positions), int(seq_len)
+    g.pre_gate, g.pre_up = _ptr(pre_gate), _ptr(pre_up)
+    check(_lib.load().lhrs_gemm_bf16(C.byref(g), _stream()), "lhrs_gemm_bf16")
+    return out
+
+
+def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, *, causal: bool, scale: Optional[float] = None,
+              key_mask: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None,
+              return_lse: bool = False):
+    """q: (B, Sq, H, hd) view, k/v: (B, Skv, H, hd) views (any batch/row/head strides, unit stride on hd)."""
+    for t, n in ((q, "q"), (k, "k"), (v, "v")):
+        _need(t, torch.bfloat16, f"attention {n}")
+        if t.dim() != 4 or t.stride(3) != 1:
+            raise RuntimeError(f"attention {n}: expected (B, S, H, hd) with unit stride on hd")
+    B, Sq, H, hd = q.shape
+    Skv = k.shape[1]
+    if out is None:
+        out = torch.empty((B, Sq, H, hd), device=q.device, dtype=torch.bfloat16)
+    lse = torch.empty((B, H, Sq), device=q.device, dtype=torch.float32) if return_lse else None
+    a = LhrsAttention()
+    a.q, a.k, a.v, a.o = q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr()
+    a.lse = _ptr(lse)
+    if key_mask is not None:
+        _need(key_mask, torch.uint8, "attention key_mask")
+        if tuple(key_mask.shape) != (B, Skv) or not key_mask.is_contiguous():
+            raise RuntimeError("attention: key_mask must be a contiguous (B, Skv) uint8 tensor")
+    a.key_mask = _ptr(key_mask)
+    a.q_bs, a.q_rs, a.q_hs = q.stride(0), q.stride(1), q.stride(2)
+    a.k_bs, a.k_rs, a.k_hs = k.stride(0), k.stride(1), k.stride(2)
+    a.v_bs, a.v_rs, a.v_hs = v.stride(0), v.stride(1), v.stride(2)
+    a.o_bs, a.o_rs, a.o_hs = out.stride(0), out.stride(1), out.stride(2)
+    a.B, a.H, a.Sq, a.Skv, a.head_dim = B, H, Sq, Skv, hd
+    a.causal = int(causal)
+    a.scale = float(scale if scale is not None else 1.0 / math.sqrt(hd))
+    check(_lib.load().lhrs_attention_fwd(C.byref(a), _stream()), "lhrs_attention_fwd")
+    return (out, lse) if return_lse else out
+
+
+def rmsnorm(x: torch.Tensor, w: torch.Tensor, eps: float, *, return_rstd: bool = False):
+    _need(x, torch.bfloat16, "rmsnorm x")
+    _need(w, torch.bfloat16, "rmsnorm w")
+    x2 = x.reshape(-1, x.shape[-1])
+    if not x2.is_contiguous():
+        x2 = x2.contiguous()
+    y = torch.empty_like(x2)
+    rstd = torch.empty((x2.shape[0],), device=x.device, dtype=torch.float32) if return_rstd else None
+    check(_lib.load().lhrs_rmsnorm_fwd(x2.data_ptr(), w.data_ptr(), y.data_ptr(), _ptr(rstd), x2.shape[0], x2.shape[1],
+                                       float(eps), _stream()), "lhrs_rmsnorm_fwd")
+    y = y.view(x.shape)
+    return (y, rstd) if return_rstd else y
+
+
+def layernorm(x: torch.Tensor, w: torch.Tensor, b: torch.Tensor, eps: float, *, out: Optional[torch.Tensor] = None,
+              return_stats: bool = False):
+    """x: 2-D (rows, dim) possibly row-strided view."""
+    _need(x, torch.bfloat16, "layernorm x")
+    rows, dim, ldx = _rows2d(x, "layernorm x")
+    if out is None:
+        out = torch.empty((rows, dim), device=x.device, dtype=torch.bfloat16)
+    ldy = _rows2d(out, "layernorm y")[2]
+    mean = rstd = None
+    if return_stats:
+        mean = torch.empty((rows,), device=x.device, dtype=torch.float32)
+        rstd = torch.empty((rows,), device=x.device, dtype=torch.float32)
+    check(_lib.load().lhrs_layernorm_fwd(x.data_ptr(), ldx, w.data_ptr(), b.data_ptr(), out.data_ptr(), ldy,
+                                         _ptr(mean), _ptr(rstd), rows, dim, float(eps), _stream()), "lhrs_layernorm_fwd")
+    return (out, mean, rstd) if return_stats else out
+
+
+def vit_im2col(pixels: torch.Tensor, patch: int, kpad: int) -> torch.Tensor:
+    _need(pixels, torch.bfloat16, "vit_im2col pixels")
+    B, Cc, H, W = pixels.shape
+    if Cc != 3 or not pixels.is_contiguous():
+        raise RuntimeError("vit_im2col: expected contiguous (B, 3, H, W)")
+    out = torch.empty((B * (H // patch) * (W // patch), kpad), device=pixels.device, dtype=torch.bfloat16)
+    check(_lib.load().lhrs_vit_im2col(pixels.data_ptr(), out.data_ptr(), B, H, W, patch, kpad, _stream()), "lhrs_vit_im2col")
+    return out
+
+
+def vit_embed_ln(patch_emb: torch.Tensor, cls: torch.Tensor, pos: torch.Tensor, ln_w: torch.Tensor, ln_b: torch.Tensor,
+                 B: int, num_patches: int, eps: float) -> torch.Tensor:
+    dim = patch_emb.shape[-1]
+    out = torch.empty((B * (num_patches + 1), dim), device=patch_emb.device, dtype=torch.bfloat16)
+    check(_lib.load().lhrs_vit_embed_ln(patch_emb.data_ptr(), cls.data_ptr(), pos.data_ptr(), ln_w.data_ptr(),
+                                        ln_b.data_ptr(), out.data_ptr(), B, num_patches, dim, float(eps), _stream()),
+          "lhrs_vit_embed_ln")
+    return out
+
+
+def splice_scan(input_ids: torch.Tensor, num_query: int) -> torch.Tensor:
+    """Device-side scan of IMAGE_TOKEN_INDEX positions.  Returns the int32 info buffer (see lhrs_b200.h)."""
+    _need(input_ids, torch.int64, "splice input_ids")
+    B, T = input_ids.shape
+    ids = input_ids.contiguous()
+    info = torch.empty(((B + 1) * 4 + B * T,), device=input_ids.device, dtype=torch.int32)
+    check(_lib.load().lhrs_splice_scan(ids.data_ptr(), B, T, num_query, info.data_ptr(), _stream()), "lhrs_splice_scan")
+    return info
+
+
+def splice_fill(input_ids, labels, attention_mask, info, embed_table, image_feats, S_out: int, num_query: int,
+                n_slots: int, want_row_map: bool = True):
+    B, T = input_ids.shape
+    dim = embed_table.shape[1]
+    dev = input_ids.device
+    _need(embed_table, torch.bfloat16, "splice embed_table")
+    embeds = torch.empty((B, S_out, dim), device=dev, dtype=torch.bfloat16)
+    labels_out = torch.empty((B, S_out), device=dev, dtype=torch.int64) if labels is not None else None
+    mask_out = torch.empty((B, S_out), device=dev, dtype=torch.uint8) if attention_mask is not None else None
+    row_map = torch.empty((max(n_slots, 1) * num_query,), device=dev, dtype=torch.int32) if want_row_map else None
+    am = None
+    if attention_mask is not None:
+        am = attention_mask.to(torch.uint8).contiguous()
+    if image_feats is not None:
+        _need(image_feats, torch.bfloat16, "splice image_feats")
+        image_feats = image_feats.contiguous()
+    check(_lib.load().lhrs_splice_fill(
+        input_ids.contiguous().data_ptr(), _ptr(labels.contiguous() if labels is not None else None), _ptr(am),
+        info.data_ptr(), embed_table.data_ptr(), _ptr(image_feats), B, T, S_out, num_query, dim, n_slots,
+        embeds.data_ptr(), _ptr(labels_out), _ptr(mask_out), _ptr(row_map), _stream()), "lhrs_splice_fill")
+    return embeds, labels_out, mask_out, row_map
+
+
+def splice_bwd(d_embeds: torch.Tensor, row_map: torch.Tensor, n_slots: int, num_query: int) -> torch.Tensor:
+    dim = d_embeds.shape[-1]
+    d2 = d_embeds.reshape(-1, dim)
+    if not d2.is_contiguous():
+        d2 = d2.contiguous()
+    d_img = torch.empty((n_slots, num_query, dim), device=d_embeds.device, dtype=torch.bfloat16)
+    check(_lib.load().lhrs_splice_bwd(d2.data_ptr(), row_map.data_ptr(), d_img.data_ptr(), n_slots * num_query, dim,
+                                      _stream()), "lhrs_splice_bwd")
+    return d_img
+
+
+def ce_fwd(logits: torch.Tensor, labels: torch.Tensor):
+    """logits (B, S, V) bf16, labels (B, S) int64 -> (loss_sum fp32[1], count int32[1], row_lse fp32[2*B*S])."""
+    _need(logits, torch.bfloat16, "ce logits")
+    _need(labels, torch.int64, "ce labels")
+    B, S, V = logits.shape
+    l2 = logits.view(B * S, V)
+    row = torch.empty((2 * B * S,), device=logits.device, dtype=torch.float32)
+    loss_sum = torch.empty((1,), device=logits.device, dtype=torch.float32)
+    count = torch.empty((1,), device=logits.device, dtype=torch.int32)
+    check(_lib.load().lhrs_ce_fwd(l2.data_ptr(), l2.stride(0), labels.contiguous().data_ptr(), B, S, V, row.data_ptr(),
+                                  loss_sum.data_ptr(), count.data_ptr(), _stream()), "lhrs_ce_fwd")
+    return loss_sum, count, row
+
+
+def ce_bwd(logits: torch.Tensor, labels: torch.Tensor, row_lse: torch.Tensor, count: torch.Tensor, grad_scale: float,
+           out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    B, S, V = logits.shape
+    l2 = logits.view(B * S, V)
+    if out is None:
+        out = torch.empty_like(l2)
+    check(_lib.load().lhrs_ce_bwd(l2.data_ptr(), l2.stride(0), labels.contiguous().data_ptr(), B, S, V,
+                                  row_lse.data_ptr(), count.data_ptr(), float(grad_scale), out.data_ptr(), _stream()),
+          "lhrs_ce_bwd")
+    return out.view(B, S, V)
+
+
+def launch_count() -> int:
+    return int(_lib.load().lhrs_launch_count())
