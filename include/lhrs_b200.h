@@ -60,7 +60,7 @@ typedef struct LhrsGemm {
     int32_t epilogue;     /* LHRS_EPI_*                                                                 */
     int32_t act;          /* LHRS_ACT_* (LINEAR only)                                                   */
     float alpha;          /* accumulator scale, applied first                                           */
-    const void* bias;     /* bf16 [N] or NULL                                                           */
+    const void* bias[3];  /* bf16, one per B segment ([seg_rows] each; bias[0] is [N] when num_b == 1) or NULL  */
     const void* residual; /* bf16 [*, ldr] or NULL; added after activation; indexed by the SOURCE row   */
     int64_t ldr;
     void* D;              /* bf16 (or fp32 if d_f32) [*, ldd]                                           */
@@ -73,8 +73,16 @@ typedef struct LhrsGemm {
     const int32_t* positions; /* [M] or NULL -> position = m % rope_seq_len                            */
     int32_t rope_seq_len;
     /* SwiGLU epilogue: optionally keep the raw gate / up projections for backward (bf16 [M, N/2]) */
-    void* pre_gate;
+    void* pre_gate;       /* LINEAR: optional copy of the pre-activation (alpha*acc + bias), bf16 [M, N] */
     void* pre_up;
+    /* K-extension (LoRA, common_arch-independent; text_modal.py:133-151): after the K loop over A/B the kernel keeps
+     * accumulating A2[:, s*ext_k:(s+1)*ext_k] · B2[s]^T into the same TMEM tile, s = B segment of the tile.
+     * A2 is bf16 [M, lda2] holding num_b blocks of ext_k columns (T = scale * x·lora_A^T); B2[s] is lora_B [seg_rows, ldb2]. */
+    const void* A2;
+    int64_t lda2;
+    const void* B2[3];
+    int64_t ldb2;
+    int32_t ext_k;
 } LhrsGemm;
 
 int lhrs_gemm_bf16(const LhrsGemm* g, void* stream);
@@ -149,6 +157,102 @@ int lhrs_ce_fwd(const void* logits, int64_t ld, const int64_t* labels, int32_t B
                 float* row_lse, float* loss_sum, int32_t* count, void* stream);
 int lhrs_ce_bwd(const void* logits, int64_t ld, const int64_t* labels, int32_t B, int32_t S, int32_t V,
                 const float* row_lse, const int32_t* count, float grad_scale, void* d_logits, void* stream);
+
+
+/* ================================================================================================
+ * Model-level entry points: the layer loops run inside the library (one call per module forward), so
+ * Python adds no per-layer overhead.  Weight tables hold borrowed device pointers (bf16 unless noted),
+ * one entry per layer, in the reference's parameter layout (HF names in comments).
+ * ============================================================================================== */
+
+/* CLIP ViT-L/14 encoder up to the last tap.  VisionModal.encode, lhrs/models/rgb_vision_modal.py:166-184. */
+typedef struct LhrsVitWeights {
+    int32_t num_layers;  /* layers to evaluate = last tap index (22 of 24: layers after the last tap are never read) */
+    int32_t dim, ffn, heads, patch, image, kpad; /* 1024, 4096, 16, 14, 224, 640 (3*14*14=588 zero-padded) */
+    float eps;
+    const void* patch_w;  /* [dim, kpad]  embeddings.patch_embedding.weight.flatten(1), zero-padded columns */
+    const void* cls;      /* [dim]        embeddings.class_embedding */
+    const void* pos;      /* [1+patches, dim] embeddings.position_embedding.weight */
+    const void* pre_ln_w; const void* pre_ln_b;               /* pre_layrnorm */
+    const void* const* ln1_w; const void* const* ln1_b;       /* encoder.layers.N.layer_norm1 */
+    const void* const* q_w; const void* const* q_b;           /* self_attn.q_proj [dim,dim] / [dim] */
+    const void* const* k_w; const void* const* k_b;
+    const void* const* v_w; const void* const* v_b;
+    const void* const* o_w; const void* const* o_b;           /* self_attn.out_proj */
+    const void* const* ln2_w; const void* const* ln2_b;
+    const void* const* fc1_w; const void* const* fc1_b;       /* mlp.fc1 [ffn,dim] */
+    const void* const* fc2_w; const void* const* fc2_b;       /* mlp.fc2 [dim,ffn] */
+} LhrsVitWeights;
+
+size_t lhrs_vit_workspace_bytes(const LhrsVitWeights* w, int32_t B);
+/* pixels (B,3,image,image) bf16 -> out (B, n_taps*patches, dim) bf16 = cat_i hidden_states[taps[i]][:,1:,:].
+ * `taps` is a HOST array, ascending, taps[n_taps-1] == num_layers. */
+int lhrs_vit_fwd(const LhrsVitWeights* w, const void* pixels, int32_t B, const int32_t* taps, int32_t n_taps,
+                 void* out, void* workspace, size_t workspace_bytes, void* stream);
+
+/* AttnPooler (multi-level query perceiver).  lhrs/models/common_arch.py:134-173, 315-333. */
+typedef struct LhrsPoolerWeights {
+    int32_t num_layers, dim, ffn, heads, out_dim; /* 6, 1024, 4096, 16, 4096 */
+    int32_t num_groups;                           /* 3 */
+    int32_t stage_num[4];                         /* queries per group   {64,48,32} */
+    int32_t split_part[4];                        /* image tokens per group {256,256,256} */
+    float eps;
+    const void* query;                                         /* [sum(stage_num), dim] */
+    const void* const* ln1_w; const void* const* ln1_b;        /* layers.N.ln_1 */
+    const void* const* lnkv_w; const void* const* lnkv_b;      /* layers.N.ln_1_kv */
+    const void* const* in_w; const void* const* in_b;          /* layers.N.attn.in_proj_{weight,bias} [3*dim,dim] */
+    const void* const* ao_w; const void* const* ao_b;          /* layers.N.attn.out_proj */
+    const void* const* ln2_w; const void* const* ln2_b;
+    const void* const* fc_w; const void* const* fc_b;          /* layers.N.mlp.c_fc   [ffn,dim] */
+    const void* const* pj_w; const void* const* pj_b;          /* layers.N.mlp.c_proj [dim,ffn] */
+    const void* out_w; const void* out_b;                      /* out_proj [out_dim, dim] */
+} LhrsPoolerWeights;
+
+size_t lhrs_pooler_workspace_bytes(const LhrsPoolerWeights* w, int32_t B);
+/* bytes of the activation stash a later lhrs_pooler_bwd needs (0 is never returned; pass stash=NULL for inference) */
+size_t lhrs_pooler_stash_bytes(const LhrsPoolerWeights* w, int32_t B);
+/* image_embs (B, sum(split_part), dim) bf16 -> out.  Rows are written at out + row_map[b*nq + i]*ldo when row_map is
+ * given (scatter straight into the LLaMA inputs_embeds buffer, fusing the splice), else at (b*nq + i)*ldo. */
+int lhrs_pooler_fwd(const LhrsPoolerWeights* w, const void* image_embs, int32_t B, void* out, int64_t ldo,
+                    const int32_t* row_map, void* stash, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Paged KV cache (HBM): pool is bf16 [layers][2 (k,v)][num_pages][heads][page_size][head_dim]; sequence b owns pages
+ * block_table[b*max_pages + i] (device int32).  K is stored post-RoPE.  Memory is caller-owned (torch). */
+typedef struct LhrsKvCache {
+    void* pool;
+    const int32_t* block_table;
+    int32_t layers, heads, head_dim, page_size, num_pages, max_pages;
+} LhrsKvCache;
+
+/* LLaMA-2 decoder stack.  HF LlamaForCausalLM as called from lhrs/models/text_modal.py:281-290 (train) and
+ * :600-612 (generate).  Optional LoRA on the seven projections (text_modal.py:133-151): A [r,in], B [out,r]. */
+typedef struct LhrsLlamaWeights {
+    int32_t num_layers, dim, ffn, heads, vocab, max_pos; /* 32, 4096, 11008, 32, 32000, 2048 */
+    float eps;
+    const void* const* ln1_w;   /* model.layers.N.input_layernorm.weight [dim] */
+    const void* const* q_w; const void* const* k_w; const void* const* v_w; const void* const* o_w; /* [dim,dim] */
+    const void* const* ln2_w;   /* post_attention_layernorm */
+    const void* const* gate_w; const void* const* up_w;  /* [ffn,dim] */
+    const void* const* down_w;                            /* [dim,ffn] */
+    const void* norm_w;         /* model.norm.weight */
+    const void* lm_head;        /* lm_head.weight [vocab, dim] */
+    const void* embed;          /* model.embed_tokens.weight [vocab, dim] */
+    const float* rope_cos; const float* rope_sin; /* [max_pos, 64] fp32 tables (bf16-rounded values, as HF casts them) */
+    /* LoRA (all NULL when disabled).  Index [layer*7 + p], p in {q,k,v,o,gate,up,down}. */
+    int32_t lora_r; float lora_scale;
+    const void* const* lora_a; const void* const* lora_b;
+} LhrsLlamaWeights;
+
+size_t lhrs_llama_workspace_bytes(const LhrsLlamaWeights* w, int32_t B, int32_t S);
+size_t lhrs_llama_stash_bytes(const LhrsLlamaWeights* w, int32_t B, int32_t S);
+/* inputs_embeds (B,S,dim) bf16 -> hidden_out (B,S,dim) bf16 = model.norm(last layer).  key_mask (B,S) uint8 or NULL.
+ * stash: NULL (inference) or a buffer of lhrs_llama_stash_bytes kept for lhrs_llama_bwd_dx.
+ * kv_cache: NULL, or the paged cache that receives K/V of positions 0..S-1 (prefill before lhrs_llama_decode_step). */
+int lhrs_llama_fwd(const LhrsLlamaWeights* w, const void* inputs_embeds, int32_t B, int32_t S, const uint8_t* key_mask,
+                   void* hidden_out, void* stash, const LhrsKvCache* kv_cache, void* workspace, size_t workspace_bytes,
+                   void* stream);
+/* logits = hidden · lm_head^T (bf16 [rows, vocab]) */
+int lhrs_lm_head(const LhrsLlamaWeights* w, const void* hidden, int64_t rows, void* logits, void* stream);
 
 #ifdef __cplusplus
 }

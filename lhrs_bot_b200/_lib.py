@@ -24,12 +24,13 @@ class LhrsGemm(C.Structure):
         ("B", C.c_void_p * 3), ("num_b", C.c_int32), ("seg_rows", C.c_int32),
         ("ldb", C.c_int64), ("b_mn_major", C.c_int32),
         ("epilogue", C.c_int32), ("act", C.c_int32), ("alpha", C.c_float),
-        ("bias", C.c_void_p), ("residual", C.c_void_p), ("ldr", C.c_int64),
+        ("bias", C.c_void_p * 3), ("residual", C.c_void_p), ("ldr", C.c_int64),
         ("D", C.c_void_p), ("ldd", C.c_int64), ("d_f32", C.c_int32),
         ("row_map", C.c_void_p),
         ("rope_cos", C.c_void_p), ("rope_sin", C.c_void_p), ("positions", C.c_void_p),
         ("rope_seq_len", C.c_int32),
         ("pre_gate", C.c_void_p), ("pre_up", C.c_void_p),
+        ("A2", C.c_void_p), ("lda2", C.c_int64), ("B2", C.c_void_p * 3), ("ldb2", C.c_int64), ("ext_k", C.c_int32),
     ]
 
 
@@ -43,6 +44,50 @@ class LhrsAttention(C.Structure):
         ("o_bs", C.c_int64), ("o_rs", C.c_int64), ("o_hs", C.c_int64),
         ("B", C.c_int32), ("H", C.c_int32), ("Sq", C.c_int32), ("Skv", C.c_int32), ("head_dim", C.c_int32),
         ("causal", C.c_int32), ("scale", C.c_float),
+    ]
+
+
+_PP = C.POINTER(C.c_void_p)
+
+
+class LhrsVitWeights(C.Structure):
+    _fields_ = [
+        ("num_layers", C.c_int32), ("dim", C.c_int32), ("ffn", C.c_int32), ("heads", C.c_int32), ("patch", C.c_int32),
+        ("image", C.c_int32), ("kpad", C.c_int32), ("eps", C.c_float),
+        ("patch_w", C.c_void_p), ("cls", C.c_void_p), ("pos", C.c_void_p), ("pre_ln_w", C.c_void_p), ("pre_ln_b", C.c_void_p),
+        ("ln1_w", _PP), ("ln1_b", _PP), ("q_w", _PP), ("q_b", _PP), ("k_w", _PP), ("k_b", _PP), ("v_w", _PP), ("v_b", _PP),
+        ("o_w", _PP), ("o_b", _PP), ("ln2_w", _PP), ("ln2_b", _PP), ("fc1_w", _PP), ("fc1_b", _PP), ("fc2_w", _PP), ("fc2_b", _PP),
+    ]
+
+
+class LhrsPoolerWeights(C.Structure):
+    _fields_ = [
+        ("num_layers", C.c_int32), ("dim", C.c_int32), ("ffn", C.c_int32), ("heads", C.c_int32), ("out_dim", C.c_int32),
+        ("num_groups", C.c_int32), ("stage_num", C.c_int32 * 4), ("split_part", C.c_int32 * 4), ("eps", C.c_float),
+        ("query", C.c_void_p),
+        ("ln1_w", _PP), ("ln1_b", _PP), ("lnkv_w", _PP), ("lnkv_b", _PP), ("in_w", _PP), ("in_b", _PP),
+        ("ao_w", _PP), ("ao_b", _PP), ("ln2_w", _PP), ("ln2_b", _PP), ("fc_w", _PP), ("fc_b", _PP), ("pj_w", _PP), ("pj_b", _PP),
+        ("out_w", C.c_void_p), ("out_b", C.c_void_p),
+    ]
+
+
+class LhrsKvCache(C.Structure):
+    _fields_ = [
+        ("pool", C.c_void_p), ("block_table", C.c_void_p),
+        ("layers", C.c_int32), ("heads", C.c_int32), ("head_dim", C.c_int32), ("page_size", C.c_int32),
+        ("num_pages", C.c_int32), ("max_pages", C.c_int32),
+    ]
+
+
+class LhrsLlamaWeights(C.Structure):
+    _fields_ = [
+        ("num_layers", C.c_int32), ("dim", C.c_int32), ("ffn", C.c_int32), ("heads", C.c_int32), ("vocab", C.c_int32),
+        ("max_pos", C.c_int32), ("eps", C.c_float),
+        ("ln1_w", _PP), ("q_w", _PP), ("k_w", _PP), ("v_w", _PP), ("o_w", _PP), ("ln2_w", _PP),
+        ("gate_w", _PP), ("up_w", _PP), ("down_w", _PP),
+        ("norm_w", C.c_void_p), ("lm_head", C.c_void_p), ("embed", C.c_void_p),
+        ("rope_cos", C.c_void_p), ("rope_sin", C.c_void_p),
+        ("lora_r", C.c_int32), ("lora_scale", C.c_float), ("lora_a", _PP), ("lora_b", _PP),
     ]
 
 
@@ -67,6 +112,15 @@ SIGNATURES = {
     "lhrs_splice_bwd": (C.c_int, [_P, _P, _P, _I64, _I32, _P]),
     "lhrs_ce_fwd": (C.c_int, [_P, _I64, _P, _I32, _I32, _I32, _P, _P, _P, _P]),
     "lhrs_ce_bwd": (C.c_int, [_P, _I64, _P, _I32, _I32, _I32, _P, _P, _F, _P, _P]),
+    "lhrs_vit_workspace_bytes": (C.c_size_t, [C.POINTER(LhrsVitWeights), _I32]),
+    "lhrs_vit_fwd": (C.c_int, [C.POINTER(LhrsVitWeights), _P, _I32, C.POINTER(C.c_int32), _I32, _P, _P, C.c_size_t, _P]),
+    "lhrs_pooler_workspace_bytes": (C.c_size_t, [C.POINTER(LhrsPoolerWeights), _I32]),
+    "lhrs_pooler_stash_bytes": (C.c_size_t, [C.POINTER(LhrsPoolerWeights), _I32]),
+    "lhrs_pooler_fwd": (C.c_int, [C.POINTER(LhrsPoolerWeights), _P, _I32, _P, _I64, _P, _P, _P, C.c_size_t, _P]),
+    "lhrs_llama_workspace_bytes": (C.c_size_t, [C.POINTER(LhrsLlamaWeights), _I32, _I32]),
+    "lhrs_llama_stash_bytes": (C.c_size_t, [C.POINTER(LhrsLlamaWeights), _I32, _I32]),
+    "lhrs_llama_fwd": (C.c_int, [C.POINTER(LhrsLlamaWeights), _P, _I32, _I32, _P, _P, _P, C.POINTER(LhrsKvCache), _P, C.c_size_t, _P]),
+    "lhrs_lm_head": (C.c_int, [C.POINTER(LhrsLlamaWeights), _P, _I64, _P, _P]),
 }
 
 _lock = threading.Lock()

@@ -24,7 +24,7 @@ struct GemmArgs {
     int num_b, seg_rows;
     int act;
     float alpha;
-    const __nv_bfloat16* bias;
+    const __nv_bfloat16* bias[3];
     const __nv_bfloat16* residual;
     long long ldr;
     void* D;
@@ -37,6 +37,8 @@ struct GemmArgs {
     int rope_seq_len;
     __nv_bfloat16* pre_gate;
     __nv_bfloat16* pre_up;
+    int ext_k;   // LoRA K-extension: columns of A2 per B segment (0 = none)
+    int ext_kb;  // extra 64-wide k-blocks appended after the main K loop
 };
 
 template <int BN>
@@ -100,6 +102,8 @@ template <int BN, int KIND, bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(256, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB0,
                  const __grid_constant__ CUtensorMap tmB1, const __grid_constant__ CUtensorMap tmB2,
+                 const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmE0,
+                 const __grid_constant__ CUtensorMap tmE1, const __grid_constant__ CUtensorMap tmE2,
                  const GemmArgs args) {
     using Cfg = GemmCfg<BN>;
     constexpr int STAGES = Cfg::STAGES;
@@ -120,7 +124,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int num_m = (args.M + BM - 1) / BM;
     const int num_n = (args.N + BN - 1) / BN;
     const int num_tiles = num_m * num_n;
-    const int num_kb = (args.K + BK - 1) / BK;
+    const int num_kb_main = (args.K + BK - 1) / BK;
+    const int num_kb = num_kb_main + args.ext_kb;
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmA);
@@ -163,6 +168,26 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     mbar_arrive_expect_tx(&full_bar[stage], Cfg::A_BYTES + Cfg::B_BYTES);
                     uint8_t* sa = smem_a + stage * Cfg::A_BYTES;
                     uint8_t* sb = smem_b + stage * Cfg::B_BYTES;
+                    if (kb >= num_kb_main) {
+                        // ---- LoRA K-extension: A2 = T (x·A^T, scaled), B2 = lora_B of this tile's segment(s).
+                        // Out-of-range coordinates (negative or >= extent) are zero-filled by TMA, which is what
+                        // confines each segment to its own ext_k columns of T.
+                        const int e0 = (kb - num_kb_main) * BK;
+                        if constexpr (KIND == LHRS_EPI_SWIGLU) {
+                            const int h0 = n_blk * (BN / 2);
+                            tma_load_2d(sa, &tmA2, &full_bar[stage], e0, m0);  // T = [T_gate | T_up]
+                            tma_load_2d(sb, &tmE0, &full_bar[stage], e0, h0);
+                            tma_load_2d(sb + (BN / 2) * BK * 2, &tmE1, &full_bar[stage], e0 - args.ext_k, h0);
+                        } else {
+                            const int seg = (args.num_b > 1) ? (n0 / args.seg_rows) : 0;
+                            const int r0 = n0 - seg * args.seg_rows;
+                            const CUtensorMap* tm = (seg == 0) ? &tmE0 : (seg == 1 ? &tmE1 : &tmE2);
+                            tma_load_2d(sa, &tmA2, &full_bar[stage], seg * args.ext_k + e0, m0);
+                            tma_load_2d(sb, tm, &full_bar[stage], e0, r0);
+                        }
+                        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                        continue;
+                    }
                     const int k0 = kb * BK;
                     if constexpr (!A_MN) {
                         tma_load_2d(sa, &tmA, &full_bar[stage], k0, m0);  // box {64 k, 128 m}
@@ -247,6 +272,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             const int n_tile0 = n_blk * BN;
 
             if constexpr (KIND == LHRS_EPI_LINEAR) {
+                // per-segment bias: a tile never straddles two B segments (seg_rows % BN == 0)
+                const int bseg = (args.num_b > 1) ? (n_tile0 / args.seg_rows) : 0;
+                const __nv_bfloat16* bias_seg = (bseg == 0) ? args.bias[0] : (bseg == 1 ? args.bias[1] : args.bias[2]);
+                const __nv_bfloat16* bias = (bias_seg != nullptr) ? bias_seg - bseg * args.seg_rows : nullptr;  // index by global n
 #pragma unroll 1
                 for (int c = 0; c < BN / 32; ++c) {
                     const int n0 = n_tile0 + c * 32;
@@ -259,12 +288,14 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * args.alpha;
                     const bool full_chunk = (n0 + 32 <= args.N);
                     if (full_chunk) {
-                        if (args.bias != nullptr) {
+                        if (bias != nullptr) {
                             float b[32];
-                            load_bf16x32(args.bias + n0, b);
+                            load_bf16x32(bias + n0, b);
 #pragma unroll
                             for (int j = 0; j < 32; ++j) v[j] += b[j];
                         }
+                        if (args.pre_gate != nullptr && row_ok)  // keep the pre-activation for the backward pass
+                            store_bf16x32(args.pre_gate + static_cast<long long>(row) * args.N + n0, v);
                         if (args.act != LHRS_ACT_NONE) {
 #pragma unroll
                             for (int j = 0; j < 32; ++j) v[j] = act_apply(bf16_round(v[j]), args.act);
@@ -287,7 +318,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                             const int n = n0 + j;
                             if (n < args.N && store_ok) {
                                 float x = v[j];
-                                if (args.bias != nullptr) x += __bfloat162float(args.bias[n]);
+                                if (bias != nullptr) x += __bfloat162float(bias[n]);
                                 if (args.act != LHRS_ACT_NONE) x = act_apply(bf16_round(x), args.act);
                                 if (args.residual != nullptr)
                                     x = bf16_round(x) + __bfloat162float(args.residual[static_cast<long long>(row) * args.ldr + n]);
@@ -429,7 +460,8 @@ static int make_tmap(CUtensorMap* out, const void* ptr, uint64_t inner, uint64_t
 }
 
 template <int BN, int KIND, bool A_MN, bool B_MN>
-static int launch(const CUtensorMap& tA, const CUtensorMap (&tB)[3], const GemmArgs& a, cudaStream_t stream) {
+static int launch(const CUtensorMap& tA, const CUtensorMap (&tB)[3], const CUtensorMap& tA2, const CUtensorMap (&tE)[3],
+                  const GemmArgs& a, cudaStream_t stream) {
     using Cfg = GemmCfg<BN>;
     auto kern = gemm_bf16_kernel<BN, KIND, A_MN, B_MN>;
     static bool attr_set = false;
@@ -439,7 +471,7 @@ static int launch(const CUtensorMap& tA, const CUtensorMap (&tB)[3], const GemmA
     }
     const int num_tiles = ((a.M + BM - 1) / BM) * ((a.N + BN - 1) / BN);
     const int grid = num_tiles < num_sms() ? num_tiles : num_sms();
-    kern<<<grid, 256, Cfg::SMEM_BYTES, stream>>>(tA, tB[0], tB[1], tB[2], a);
+    kern<<<grid, 256, Cfg::SMEM_BYTES, stream>>>(tA, tB[0], tB[1], tB[2], tA2, tE[0], tE[1], tE[2], a);
     LHRS_LAUNCH_CHECK("gemm_bf16_kernel");
     return LHRS_OK;
 }
@@ -512,11 +544,32 @@ extern "C" int lhrs_gemm_bf16(const LhrsGemm* g, void* stream_) {
         }
     }
 
+    CUtensorMap tA2 = tA, tE[3] = {tB[0], tB[0], tB[0]};
+    int ext_k = 0, ext_kb = 0;
+    if (g->A2 != nullptr && g->ext_k > 0) {
+        LHRS_CHECK_ARG(!a_mn && !b_mn, "lhrs_gemm_bf16: the K-extension needs K-major operands");
+        LHRS_CHECK_ARG((g->ext_k % 8) == 0 && (g->lda2 % 8) == 0 && (g->ldb2 % 8) == 0 &&
+                           (reinterpret_cast<uintptr_t>(g->A2) & 15) == 0,
+                       "lhrs_gemm_bf16: K-extension alignment (ext_k=%d lda2=%lld ldb2=%lld)", g->ext_k, (long long)g->lda2, (long long)g->ldb2);
+        ext_k = g->ext_k;
+        const int span = (kind == LHRS_EPI_SWIGLU) ? 2 * ext_k : ext_k;
+        ext_kb = (span + BK - 1) / BK;
+        rc = make_tmap(&tA2, g->A2, (uint64_t)g->num_b * ext_k, g->M, g->lda2, BK, BM);
+        if (rc) return rc;
+        const int rows = (g->num_b > 1) ? g->seg_rows : g->N;
+        for (int i = 0; i < g->num_b; ++i) {
+            LHRS_CHECK_ARG(g->B2[i] != nullptr && (reinterpret_cast<uintptr_t>(g->B2[i]) & 15) == 0, "lhrs_gemm_bf16: B2[%d] null/unaligned", i);
+            rc = make_tmap(&tE[i], g->B2[i], ext_k, rows, g->ldb2, BK, (kind == LHRS_EPI_SWIGLU) ? bn / 2 : bn);
+            if (rc) return rc;
+        }
+    }
+
     GemmArgs a;
+    a.ext_k = ext_k; a.ext_kb = ext_kb;
     a.M = g->M; a.N = g->N; a.K = g->K;
     a.num_b = g->num_b; a.seg_rows = (g->num_b > 1) ? g->seg_rows : g->N;
     a.act = g->act; a.alpha = g->alpha;
-    a.bias = reinterpret_cast<const __nv_bfloat16*>(g->bias);
+    for (int i = 0; i < 3; ++i) a.bias[i] = reinterpret_cast<const __nv_bfloat16*>(g->bias[i]);
     a.residual = reinterpret_cast<const __nv_bfloat16*>(g->residual);
     a.ldr = g->ldr;
     a.D = g->D; a.ldd = g->ldd; a.d_f32 = g->d_f32;
@@ -525,17 +578,17 @@ extern "C" int lhrs_gemm_bf16(const LhrsGemm* g, void* stream_) {
     a.pre_gate = reinterpret_cast<__nv_bfloat16*>(g->pre_gate);
     a.pre_up = reinterpret_cast<__nv_bfloat16*>(g->pre_up);
 
-    if (kind == LHRS_EPI_SWIGLU) return launch<256, LHRS_EPI_SWIGLU, false, false>(tA, tB, a, stream);
-    if (kind == LHRS_EPI_ROPE) return launch<256, LHRS_EPI_ROPE, false, false>(tA, tB, a, stream);
+    if (kind == LHRS_EPI_SWIGLU) return launch<256, LHRS_EPI_SWIGLU, false, false>(tA, tB, tA2, tE, a, stream);
+    if (kind == LHRS_EPI_ROPE) return launch<256, LHRS_EPI_ROPE, false, false>(tA, tB, tA2, tE, a, stream);
     if (bn == 256) {
-        if (!a_mn && !b_mn) return launch<256, LHRS_EPI_LINEAR, false, false>(tA, tB, a, stream);
-        if (!a_mn && b_mn) return launch<256, LHRS_EPI_LINEAR, false, true>(tA, tB, a, stream);
-        if (a_mn && b_mn) return launch<256, LHRS_EPI_LINEAR, true, true>(tA, tB, a, stream);
-        return launch<256, LHRS_EPI_LINEAR, true, false>(tA, tB, a, stream);
+        if (!a_mn && !b_mn) return launch<256, LHRS_EPI_LINEAR, false, false>(tA, tB, tA2, tE, a, stream);
+        if (!a_mn && b_mn) return launch<256, LHRS_EPI_LINEAR, false, true>(tA, tB, tA2, tE, a, stream);
+        if (a_mn && b_mn) return launch<256, LHRS_EPI_LINEAR, true, true>(tA, tB, tA2, tE, a, stream);
+        return launch<256, LHRS_EPI_LINEAR, true, false>(tA, tB, tA2, tE, a, stream);
     } else {
-        if (!a_mn && !b_mn) return launch<128, LHRS_EPI_LINEAR, false, false>(tA, tB, a, stream);
-        if (!a_mn && b_mn) return launch<128, LHRS_EPI_LINEAR, false, true>(tA, tB, a, stream);
-        if (a_mn && b_mn) return launch<128, LHRS_EPI_LINEAR, true, true>(tA, tB, a, stream);
-        return launch<128, LHRS_EPI_LINEAR, true, false>(tA, tB, a, stream);
+        if (!a_mn && !b_mn) return launch<128, LHRS_EPI_LINEAR, false, false>(tA, tB, tA2, tE, a, stream);
+        if (!a_mn && b_mn) return launch<128, LHRS_EPI_LINEAR, false, true>(tA, tB, tA2, tE, a, stream);
+        if (a_mn && b_mn) return launch<128, LHRS_EPI_LINEAR, true, true>(tA, tB, tA2, tE, a, stream);
+        return launch<128, LHRS_EPI_LINEAR, true, false>(tA, tB, tA2, tE, a, stream);
     }
 }

@@ -91,11 +91,20 @@ def gemm(a: torch.Tensor, b, *, out: Optional[torch.Tensor] = None, bias: Option
         g.B[i] = bs[i].data_ptr() if i < len(bs) else None
     g.num_b, g.seg_rows, g.ldb, g.b_mn_major = len(bs), seg, ldb, int(b_mn_major)
     g.epilogue, g.act, g.alpha = epilogue, act, alpha
-    if bias is not None:
-        _need(bias, torch.bfloat16, "gemm bias")
-        if bias.numel() != N or not bias.is_contiguous():
-            raise RuntimeError("gemm: bias must be a contiguous [N] tensor")
-    g.bias = _ptr(bias)
+    biases = list(bias) if isinstance(bias, (list, tuple)) else ([bias] if bias is not None else [])
+    for i in range(3):
+        g.bias[i] = None
+    for i, bt in enumerate(biases):
+        _need(bt, torch.bfloat16, "gemm bias")
+        want = seg if len(biases) > 1 else N
+        if bt.numel() != want or not bt.is_contiguous():
+            raise RuntimeError(f"gemm: bias {i} must be a contiguous [{want}] tensor")
+        g.bias[i] = bt.data_ptr()
+    if len(biases) not in (0, 1, len(bs)):
+        raise RuntimeError("gemm: give one bias or one per B segment")
+    if len(biases) == 1 and len(bs) > 1:
+        for i in range(1, len(bs)):  # one [N] bias shared across segments
+            g.bias[i] = biases[0].data_ptr() + i * seg * 2
     if residual is not None:
         _need(residual, torch.bfloat16, "gemm residual")
         g.ldr = _rows2d(residual, "gemm residual")[2]

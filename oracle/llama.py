@@ -34,7 +34,7 @@ def rms_norm(x: torch.Tensor, w: torch.Tensor, eps: float) -> torch.Tensor:
 
 
 def rope_cos_sin(positions: torch.Tensor, head_dim: int, theta: float = 10000.0) -> Tuple[torch.Tensor, torch.Tensor]:
-    inv = 1.0 / (theta ** (torch.arange(0, head_dim, 2, dtype=torch.int64).float() / head_dim))
+    inv = 1.0 / (theta ** (torch.arange(0, head_dim, 2, dtype=torch.int64, device=positions.device).float() / head_dim))
     freqs = positions.float()[:, None] * inv[None, :]
     emb = torch.cat([freqs, freqs], dim=-1)
     return emb.cos(), emb.sin()
@@ -83,14 +83,14 @@ def decoder_layer(x, sd, i: int, n_head: int, eps: float, cos, sin, add_mask, lo
     return x, (k, v)
 
 
-def _additive_mask(B: int, Sq: int, Skv: int, key_mask: Optional[torch.Tensor], dtype) -> torch.Tensor:
+def _additive_mask(B: int, Sq: int, Skv: int, key_mask: Optional[torch.Tensor], dtype, device="cpu") -> torch.Tensor:
     """causal (query i sees keys <= i + Skv - Sq) AND key-padding mask, as an additive (B,1,Sq,Skv) tensor."""
-    i = torch.arange(Sq)[:, None]
-    j = torch.arange(Skv)[None, :]
+    i = torch.arange(Sq, device=device)[:, None]
+    j = torch.arange(Skv, device=device)[None, :]
     allowed = (j <= i + (Skv - Sq))[None, None].expand(B, 1, Sq, Skv)
     if key_mask is not None:
         allowed = allowed & key_mask.bool()[:, None, None, :]
-    m = torch.zeros(B, 1, Sq, Skv, dtype=dtype)
+    m = torch.zeros(B, 1, Sq, Skv, dtype=dtype, device=device)
     return m.masked_fill(~allowed, torch.finfo(dtype).min)
 
 
@@ -98,8 +98,9 @@ def llama_hidden(inputs_embeds: torch.Tensor, sd: Dict[str, torch.Tensor], num_l
                  attention_mask: Optional[torch.Tensor] = None, lora_scale: float = 0.0, theta: float = 10000.0,
                  return_kv: bool = False):
     B, S, D = inputs_embeds.shape
-    cos, sin = rope_cos_sin(torch.arange(S), D // n_head, theta)
-    add_mask = _additive_mask(B, S, S, attention_mask, inputs_embeds.dtype)
+    dev = inputs_embeds.device
+    cos, sin = rope_cos_sin(torch.arange(S, device=dev), D // n_head, theta)
+    add_mask = _additive_mask(B, S, S, attention_mask, inputs_embeds.dtype, dev)
     x = inputs_embeds
     kvs = []
     for i in range(num_layers):
@@ -139,8 +140,9 @@ def greedy_decode(inputs_embeds: torch.Tensor, sd, num_layers: int, n_head: int,
             break
         if len(tokens) == max_new_tokens:
             break
-        h = sd["model.embed_tokens.weight"][torch.tensor([[tok]])].to(inputs_embeds.dtype)
-        cos, sin = rope_cos_sin(torch.tensor([pos]), hd, theta)
+        dev = inputs_embeds.device
+        h = sd["model.embed_tokens.weight"][torch.tensor([[tok]], device=dev)].to(inputs_embeds.dtype)
+        cos, sin = rope_cos_sin(torch.tensor([pos], device=dev), hd, theta)
         new_kvs = []
         for i in range(num_layers):
             h, kv = decoder_layer(h, sd, i, n_head, eps, cos, sin, None, lora_scale, past=kvs[i])

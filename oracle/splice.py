@@ -61,7 +61,7 @@ def prepare_inputs_for_multimodal(
             pieces.append(image_embedding[cur_image_idx].to(embed_table.dtype))
             if labels is not None:
                 lab_pieces.append(labels[b, start:p])
-                lab_pieces.append(torch.full((nq,), IGNORE_INDEX, dtype=labels.dtype))
+                lab_pieces.append(torch.full((nq,), IGNORE_INDEX, dtype=labels.dtype, device=labels.device))
             cur_image_idx += 1
             start = p + 1
         if start < T:                                             # :409-423
@@ -75,18 +75,18 @@ def prepare_inputs_for_multimodal(
     lens = [e.shape[0] for e in new_embeds]
     max_len = max(lens)
     if any(l != lens[0] for l in lens):                           # ragged branch :440-505
-        embeds = torch.zeros(B, max_len, dim, dtype=embed_table.dtype)
+        embeds = torch.zeros(B, max_len, dim, dtype=embed_table.dtype, device=embed_table.device)
         for b, e in enumerate(new_embeds):
             embeds[b, : e.shape[0]] = e
         out_labels = None
         if labels is not None:
-            out_labels = torch.full((B, max_len), IGNORE_INDEX, dtype=labels.dtype)
+            out_labels = torch.full((B, max_len), IGNORE_INDEX, dtype=labels.dtype, device=labels.device)
             for b, l in enumerate(new_labels):
                 out_labels[b, : l.shape[0]] = l
         out_mask = None
         if attention_mask is not None:
             # :474-497 — note: requires labels in the reference (it sizes the left pad from the new labels)
-            out_mask = torch.zeros(B, max_len, dtype=attention_mask.dtype)
+            out_mask = torch.zeros(B, max_len, dtype=attention_mask.dtype, device=attention_mask.device)
             for b in range(B):
                 grown = lens[b] - T
                 out_mask[b, :grown] = True
@@ -96,6 +96,6 @@ def prepare_inputs_for_multimodal(
         out_labels = torch.stack(new_labels, 0) if labels is not None else None
         out_mask = None
         if attention_mask is not None:
-            left = torch.full((B, max_len - T), True, dtype=attention_mask.dtype)
+            left = torch.full((B, max_len - T), True, dtype=attention_mask.dtype, device=attention_mask.device)
             out_mask = torch.cat((left, attention_mask), dim=1)
     return out_mask, embeds, out_labels
