@@ -30,6 +30,11 @@ const char* lhrs_last_error(void);
 int lhrs_version(void);
 /* Number of kernels this library has launched in this process (bench.py's `gpu_launches`). */
 uint64_t lhrs_launch_count(void);
+/* Optional per-kernel timing for the roofline report: when enabled, CUDA events bracket every launch of the
+ * GEMM (kind 0) and attention (kind 1) kernels on their stream.  lhrs_prof_summary synchronises the device and
+ * returns the summed durations and the summed ALGORITHMIC flops / bytes of the launches recorded since enable. */
+int lhrs_prof_enable(int on);
+int lhrs_prof_summary(int kind, double* ms, double* flops, double* bytes, int64_t* launches);
 
 /* ------------------------------------------------------------------------------------------------
  * Dense contraction (tcgen05 + TMEM accumulators + TMA operand staging).
@@ -110,6 +115,17 @@ typedef struct LhrsAttention {
 } LhrsAttention;
 
 int lhrs_attention_fwd(const LhrsAttention* a, void* stream);
+
+/* Backward of lhrs_attention_fwd (recompute-based; needs the forward's O and lse).  dQ/dK/dV are bf16 with their own
+ * (batch,row,head) strides so they can land in a packed [rows, 3*H*hd] buffer.  delta: fp32 scratch [B,H,Sq]. */
+typedef struct LhrsAttentionBwd {
+    LhrsAttention fwd;   /* the forward problem: q,k,v,o,lse,key_mask,strides,sizes */
+    const void* d_o;     /* same layout as fwd.o */
+    void* dq; void* dk; void* dv;
+    float* delta;
+    int64_t dq_bs, dq_rs, dq_hs, dk_bs, dk_rs, dk_hs, dv_bs, dv_rs, dv_hs;
+} LhrsAttentionBwd;
+int lhrs_attention_bwd(const LhrsAttentionBwd* a, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Row-wise normalisations and small fused elementwise steps (HBM-bound, one pass each).

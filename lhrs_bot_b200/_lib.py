@@ -101,6 +101,8 @@ SIGNATURES = {
     "lhrs_last_error": (C.c_char_p, []),
     "lhrs_version": (C.c_int, []),
     "lhrs_launch_count": (C.c_uint64, []),
+    "lhrs_prof_enable": (C.c_int, [C.c_int]),
+    "lhrs_prof_summary": (C.c_int, [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
     "lhrs_gemm_bf16": (C.c_int, [C.POINTER(LhrsGemm), _P]),
     "lhrs_attention_fwd": (C.c_int, [C.POINTER(LhrsAttention), _P]),
     "lhrs_rmsnorm_fwd": (C.c_int, [_P, _P, _P, _P, _I64, _I32, _F, _P]),

@@ -256,7 +256,13 @@ static int launch_attn(const AttnArgs& a, cudaStream_t stream) {
         attr_set = true;
     }
     dim3 grid((a.Sq + 63) / 64, a.H, a.B);
+    const bool prof = prof_on();
+    if (prof) {
+        const double pairs = CAUSAL ? 0.5 * a.Sq * (double)a.Skv : (double)a.Sq * a.Skv;  // causal counted at half
+        prof_begin(PROF_ATTN, 4.0 * a.B * a.H * pairs * HD, 2.0 * a.B * a.H * HD * (2.0 * a.Sq + 2.0 * a.Skv), stream);
+    }
     kern<<<grid, 128, SMEM, stream>>>(a);
+    if (prof) prof_end(stream);
     LHRS_LAUNCH_CHECK("attn_fwd_kernel");
     return LHRS_OK;
 }

@@ -471,7 +471,13 @@ static int launch(const CUtensorMap& tA, const CUtensorMap (&tB)[3], const CUten
     }
     const int num_tiles = ((a.M + BM - 1) / BM) * ((a.N + BN - 1) / BN);
     const int grid = num_tiles < num_sms() ? num_tiles : num_sms();
+    const bool prof = prof_on();
+    if (prof) {
+        const double kk = (double)a.K + (double)a.ext_k;  // algorithmic reduction length (LoRA rank, not its 64-padding)
+        prof_begin(PROF_GEMM, 2.0 * a.M * (double)a.N * kk, 2.0 * ((double)a.M * a.K + (double)a.N * a.K + (double)a.M * a.N), stream);
+    }
     kern<<<grid, 256, Cfg::SMEM_BYTES, stream>>>(tA, tB[0], tB[1], tB[2], tA2, tE[0], tE[1], tE[2], a);
+    if (prof) prof_end(stream);
     LHRS_LAUNCH_CHECK("gemm_bf16_kernel");
     return LHRS_OK;
 }
