@@ -172,7 +172,8 @@ int lhrs_splice_bwd(const void* d_embeds, const int32_t* row_of_slot, void* d_im
 int lhrs_ce_fwd(const void* logits, int64_t ld, const int64_t* labels, int32_t B, int32_t S, int32_t V,
                 float* row_lse, float* loss_sum, int32_t* count, void* stream);
 int lhrs_ce_bwd(const void* logits, int64_t ld, const int64_t* labels, int32_t B, int32_t S, int32_t V,
-                const float* row_lse, const int32_t* count, float grad_scale, void* d_logits, void* stream);
+                const float* row_lse, const int32_t* count, float grad_scale, const float* grad_scale_dev /*nullable, x[0]*/,
+                void* d_logits, void* stream);
 
 
 /* ================================================================================================
@@ -269,6 +270,49 @@ int lhrs_llama_fwd(const LhrsLlamaWeights* w, const void* inputs_embeds, int32_t
                    void* stream);
 /* logits = hidden · lm_head^T (bf16 [rows, vocab]) */
 int lhrs_lm_head(const LhrsLlamaWeights* w, const void* hidden, int64_t rows, void* logits, void* stream);
+
+/* ================================================================================================
+ * Backward and the flat-buffer optimizer step (§8f-2).
+ * ============================================================================================== */
+int lhrs_rmsnorm_bwd(const void* x, const void* w, const float* rstd, const void* dy, const void* dres /*nullable: added*/,
+                     void* dx, int64_t rows, int32_t dim, void* stream);
+size_t lhrs_layernorm_bwd_scratch_bytes(int32_t dim);
+/* dx = dres + LN'(dy); dw/db (bf16 [dim], nullable) = column reductions; scratch: lhrs_layernorm_bwd_scratch_bytes */
+int lhrs_layernorm_bwd(const void* x, int64_t ldx, const void* w, const float* mean, const float* rstd, const void* dy,
+                       const void* dres, void* dx, void* dw, void* db, int32_t accumulate, float* scratch, int64_t rows,
+                       int32_t dim, void* stream);
+size_t lhrs_colsum_scratch_bytes(int32_t n);
+int lhrs_colsum(const void* a, int64_t ld, int64_t rows, int32_t n, void* out, int32_t accumulate, float* scratch, void* stream);
+/* d_gu[rows, 2f] = [d_gate | d_up] from d_act and the stashed pre-activations (HF LlamaMLP backward) */
+int lhrs_swiglu_bwd(const void* d_act, const void* pre_gate, const void* pre_up, void* d_gu, int64_t rows, int32_t f, void* stream);
+int lhrs_gelu_bwd(void* d /*in place*/, const void* pre, int64_t n, void* stream);
+/* inverse rotation, in place on the q and k blocks of a packed [rows, 3*dim] gradient (head_dim 128) */
+int lhrs_rope_bwd(void* dqkv, int64_t ld, int64_t rows, int32_t dim, const float* cos, const float* sin,
+                  const int32_t* positions, int32_t seq_len, void* stream);
+
+/* dX-only backward of the LLaMA stack (weights frozen) + LoRA factor gradients.
+ * lora_a_grads / lora_b_grads: arrays [layers*7] of bf16 destinations (entries or the arrays themselves may be NULL).
+ * d_hidden: grad w.r.t. the output of lhrs_llama_fwd (post final norm).  Writes d_inputs_embeds (B,S,dim) bf16. */
+size_t lhrs_llama_bwd_workspace_bytes(const LhrsLlamaWeights* w, int32_t B, int32_t S);
+int lhrs_llama_bwd(const LhrsLlamaWeights* w, void* const* lora_a_grads, void* const* lora_b_grads, const void* d_hidden,
+                   int32_t B, int32_t S, const uint8_t* key_mask, const void* stash, void* d_inputs_embeds, void* workspace,
+                   size_t workspace_bytes, void* stream);
+int lhrs_lm_head_bwd(const LhrsLlamaWeights* w, const void* d_logits, int64_t rows, void* d_hidden, void* stream);
+
+/* Full backward of the AttnPooler.  `grads` has the layout of the weight table; each pointer is the bf16 DESTINATION of
+ * that parameter's gradient (overwritten), NULL to skip.  d_out: (B, nq, out_dim) rows ldo apart.  d_image: nullable. */
+size_t lhrs_pooler_bwd_workspace_bytes(const LhrsPoolerWeights* w, int32_t B);
+int lhrs_pooler_bwd(const LhrsPoolerWeights* w, const LhrsPoolerWeights* grads, const void* d_out, int64_t ldo, int32_t B,
+                    const void* stash, void* d_image, void* workspace, size_t workspace_bytes, void* stream);
+
+/* sum of squares of a bf16 flat gradient buffer -> out[0] (fp32); scratch >= 1024 floats */
+int lhrs_grad_sumsq(const void* g, int64_t n, float* out, float* scratch, void* stream);
+/* AdamW (decoupled decay, bias-corrected) on flat buffers: fp32 master/m/v, bf16 grad in, bf16 params out.
+ * grad_scale multiplies the gradient first (1/world for a summed allreduce); if max_norm > 0 the gradient is clipped to
+ * max_norm using gnorm_sq[0] (sum of squares of the UNSCALED gradient).  decay_mask: per-element 0/1 or NULL (= all 1). */
+int lhrs_adamw_step(float* master, float* m, float* v, const void* grad, void* param_bf16, const float* decay_mask, int64_t n,
+                    float lr, float beta1, float beta2, float eps, float weight_decay, int32_t step, const float* gnorm_sq,
+                    float max_norm, float grad_scale, void* stream);
 
 #ifdef __cplusplus
 }

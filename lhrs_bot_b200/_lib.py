@@ -71,6 +71,16 @@ class LhrsPoolerWeights(C.Structure):
     ]
 
 
+class LhrsAttentionBwd(C.Structure):
+    _fields_ = [
+        ("fwd", LhrsAttention), ("d_o", C.c_void_p), ("dq", C.c_void_p), ("dk", C.c_void_p), ("dv", C.c_void_p),
+        ("delta", C.c_void_p),
+        ("dq_bs", C.c_int64), ("dq_rs", C.c_int64), ("dq_hs", C.c_int64),
+        ("dk_bs", C.c_int64), ("dk_rs", C.c_int64), ("dk_hs", C.c_int64),
+        ("dv_bs", C.c_int64), ("dv_rs", C.c_int64), ("dv_hs", C.c_int64),
+    ]
+
+
 class LhrsKvCache(C.Structure):
     _fields_ = [
         ("pool", C.c_void_p), ("block_table", C.c_void_p),
@@ -113,7 +123,7 @@ SIGNATURES = {
     "lhrs_splice_fill": (C.c_int, [_P, _P, _P, _P, _P, _P, _I32, _I32, _I32, _I32, _I32, _I32, _P, _P, _P, _P, _P]),
     "lhrs_splice_bwd": (C.c_int, [_P, _P, _P, _I64, _I32, _P]),
     "lhrs_ce_fwd": (C.c_int, [_P, _I64, _P, _I32, _I32, _I32, _P, _P, _P, _P]),
-    "lhrs_ce_bwd": (C.c_int, [_P, _I64, _P, _I32, _I32, _I32, _P, _P, _F, _P, _P]),
+    "lhrs_ce_bwd": (C.c_int, [_P, _I64, _P, _I32, _I32, _I32, _P, _P, _F, _P, _P, _P]),
     "lhrs_vit_workspace_bytes": (C.c_size_t, [C.POINTER(LhrsVitWeights), _I32]),
     "lhrs_vit_fwd": (C.c_int, [C.POINTER(LhrsVitWeights), _P, _I32, C.POINTER(C.c_int32), _I32, _P, _P, C.c_size_t, _P]),
     "lhrs_pooler_workspace_bytes": (C.c_size_t, [C.POINTER(LhrsPoolerWeights), _I32]),
@@ -123,6 +133,22 @@ SIGNATURES = {
     "lhrs_llama_stash_bytes": (C.c_size_t, [C.POINTER(LhrsLlamaWeights), _I32, _I32]),
     "lhrs_llama_fwd": (C.c_int, [C.POINTER(LhrsLlamaWeights), _P, _I32, _I32, _P, _P, _P, C.POINTER(LhrsKvCache), _P, C.c_size_t, _P]),
     "lhrs_lm_head": (C.c_int, [C.POINTER(LhrsLlamaWeights), _P, _I64, _P, _P]),
+    "lhrs_attention_bwd": (C.c_int, [C.POINTER(LhrsAttentionBwd), _P]),
+    "lhrs_rmsnorm_bwd": (C.c_int, [_P, _P, _P, _P, _P, _P, _I64, _I32, _P]),
+    "lhrs_layernorm_bwd_scratch_bytes": (C.c_size_t, [_I32]),
+    "lhrs_layernorm_bwd": (C.c_int, [_P, _I64, _P, _P, _P, _P, _P, _P, _P, _P, _I32, _P, _I64, _I32, _P]),
+    "lhrs_colsum_scratch_bytes": (C.c_size_t, [_I32]),
+    "lhrs_colsum": (C.c_int, [_P, _I64, _I64, _I32, _P, _I32, _P, _P]),
+    "lhrs_swiglu_bwd": (C.c_int, [_P, _P, _P, _P, _I64, _I32, _P]),
+    "lhrs_gelu_bwd": (C.c_int, [_P, _P, _I64, _P]),
+    "lhrs_rope_bwd": (C.c_int, [_P, _I64, _I64, _I32, _P, _P, _P, _I32, _P]),
+    "lhrs_llama_bwd_workspace_bytes": (C.c_size_t, [C.POINTER(LhrsLlamaWeights), _I32, _I32]),
+    "lhrs_llama_bwd": (C.c_int, [C.POINTER(LhrsLlamaWeights), _PP, _PP, _P, _I32, _I32, _P, _P, _P, _P, C.c_size_t, _P]),
+    "lhrs_lm_head_bwd": (C.c_int, [C.POINTER(LhrsLlamaWeights), _P, _I64, _P, _P]),
+    "lhrs_pooler_bwd_workspace_bytes": (C.c_size_t, [C.POINTER(LhrsPoolerWeights), _I32]),
+    "lhrs_pooler_bwd": (C.c_int, [C.POINTER(LhrsPoolerWeights), C.POINTER(LhrsPoolerWeights), _P, _I64, _I32, _P, _P, _P, C.c_size_t, _P]),
+    "lhrs_grad_sumsq": (C.c_int, [_P, _I64, _P, _P, _P]),
+    "lhrs_adamw_step": (C.c_int, [_P, _P, _P, _P, _P, _P, _I64, _F, _F, _F, _F, _F, _I32, _P, _F, _F, _P]),
 }
 
 _lock = threading.Lock()

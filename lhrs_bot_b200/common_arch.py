@@ -92,21 +92,32 @@ class AttnPooler(nn.Module):
         for p in params:
             runtime.require_bf16_cuda(p, "AttnPooler parameter")
         runtime.contiguous_params(self)
+        table = self.build_table(lambda p: p)
+        self._table, self._table_sig = table, sig
+        return table[0]
+
+    def build_table(self, pick):
+        """LhrsPoolerWeights whose pointers are ``pick(param)`` (the parameter itself, or its gradient destination;
+        ``pick`` may return None to skip a gradient).  Returns (struct, keep-alive list)."""
         L = self.layers
         groups = self._groups()
         if len(groups) != len(self.split_part) or len(groups) > 4:
             raise RuntimeError("AttnPooler: stage_num and split_part must have the same length (<= 4)")
         w = LhrsPoolerWeights()
+
+        def ptr(p):
+            t = pick(p)
+            return None if t is None else t.data_ptr()
         w.num_layers, w.dim, w.ffn = len(L), self.hidden_size, L[0].mlp.c_fc.out_features
         w.heads, w.out_dim, w.num_groups = self.num_heads, self.output_size, len(groups)
         for i, (s, p) in enumerate(zip(groups, self.split_part)):
             w.stage_num[i], w.split_part[i] = s, p
         w.eps = L[0].ln_1.eps
-        w.query = self.query.data_ptr()
+        w.query = ptr(self.query)
         keep = []
 
         def arr(fn):
-            a = runtime.PtrArray([fn(l) for l in L])
+            a = runtime.PtrArray([pick(fn(l)) for l in L])
             keep.append(a)
             return a.ptr()
 
@@ -117,9 +128,8 @@ class AttnPooler(nn.Module):
         w.ln2_w, w.ln2_b = arr(lambda l: l.ln_2.weight), arr(lambda l: l.ln_2.bias)
         w.fc_w, w.fc_b = arr(lambda l: l.mlp.c_fc.weight), arr(lambda l: l.mlp.c_fc.bias)
         w.pj_w, w.pj_b = arr(lambda l: l.mlp.c_proj.weight), arr(lambda l: l.mlp.c_proj.bias)
-        w.out_w, w.out_b = self.out_proj.weight.data_ptr(), self.out_proj.bias.data_ptr()
-        self._table, self._table_sig = (w, keep), sig
-        return w
+        w.out_w, w.out_b = ptr(self.out_proj.weight), ptr(self.out_proj.bias)
+        return w, keep
 
     # ------------------------------------------------------------------ forward
     def forward(self, image_embs: torch.Tensor, scatter_into: Optional[torch.Tensor] = None,

@@ -415,6 +415,7 @@ ce_reduce_kernel(const float* __restrict__ row_loss, const long long* __restrict
 __global__ void __launch_bounds__(NORM_THREADS)
 ce_bwd_kernel(const __nv_bfloat16* __restrict__ logits, long long ld, const long long* __restrict__ labels, int S,
               int V, const float* __restrict__ row_lse, const int* __restrict__ count, float grad_scale,
+              const float* __restrict__ grad_scale_dev,
               __nv_bfloat16* __restrict__ d_logits) {
     const long long r = blockIdx.x;
     const int s = r % S;
@@ -429,7 +430,7 @@ ce_bwd_kernel(const __nv_bfloat16* __restrict__ logits, long long ld, const long
     const uint4* lr = reinterpret_cast<const uint4*>(logits + r * ld);
     const float lse = row_lse[r];
     const int n = count[0];
-    const float g = grad_scale / static_cast<float>(n > 0 ? n : 1);
+    const float g = grad_scale * (grad_scale_dev ? grad_scale_dev[0] : 1.f) / static_cast<float>(n > 0 ? n : 1);
     for (int c = threadIdx.x; c < nchunks; c += NORM_THREADS) {
         float f[8];
         unpack8(__ldg(lr + c), f);
@@ -542,12 +543,13 @@ extern "C" int lhrs_ce_fwd(const void* logits, int64_t ld, const int64_t* labels
 }
 
 extern "C" int lhrs_ce_bwd(const void* logits, int64_t ld, const int64_t* labels, int32_t B, int32_t S, int32_t V,
-                           const float* row_lse, const int32_t* count, float grad_scale, void* d_logits, void* stream) {
+                           const float* row_lse, const int32_t* count, float grad_scale, const float* grad_scale_dev,
+                           void* d_logits, void* stream) {
     LHRS_CHECK_ARG(logits && labels && row_lse && count && d_logits, "lhrs_ce_bwd: null operand");
     LHRS_CHECK_ARG(ld % 8 == 0 && V % 8 == 0, "lhrs_ce_bwd: ld and V must be multiples of 8");
     const long long rows = (long long)B * S;
     ce_bwd_kernel<<<static_cast<unsigned>(rows), NORM_THREADS, 0, (cudaStream_t)stream>>>(
-        (const bf16*)logits, ld, (const long long*)labels, S, V, row_lse, count, grad_scale, (bf16*)d_logits);
+        (const bf16*)logits, ld, (const long long*)labels, S, V, row_lse, count, grad_scale, grad_scale_dev, (bf16*)d_logits);
     LHRS_LAUNCH_CHECK("ce_bwd_kernel");
     return LHRS_OK;
 }

@@ -37,6 +37,7 @@ struct GemmArgs {
     int rope_seq_len;
     __nv_bfloat16* pre_gate;
     __nv_bfloat16* pre_up;
+    int kseg;    // MN-major B stacked along K: reduction length per segment (0 = single B)
     int ext_k;   // LoRA K-extension: columns of A2 per B segment (0 = none)
     int ext_kb;  // extra 64-wide k-blocks appended after the main K loop
 };
@@ -209,9 +210,14 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                             tma_load_2d(sb, tm, &full_bar[stage], k0, r0);  // box {64 k, BN n}
                         }
                     } else {
+                        // MN-major B.  With kseg > 0 the B segments are stacked along K: the dX of a concatenated output,
+                        // e.g. [dq|dk|dv] · [Wq;Wk;Wv], runs as ONE contraction with fp32 accumulation across the segments.
+                        const int seg = (args.kseg > 0) ? (k0 / args.kseg) : 0;
+                        const int kk = k0 - seg * args.kseg;
+                        const CUtensorMap* tm = (seg == 0) ? &tmB0 : (seg == 1 ? &tmB1 : &tmB2);
 #pragma unroll
                         for (int a = 0; a < BN / 64; ++a)
-                            tma_load_2d(sb + a * 8192, &tmB0, &full_bar[stage], n0 + a * 64, k0);
+                            tma_load_2d(sb + a * 8192, tm, &full_bar[stage], n0 + a * 64, kk);
                     }
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
@@ -506,8 +512,11 @@ extern "C" int lhrs_gemm_bf16(const LhrsGemm* g, void* stream_) {
         // small problems: more, smaller tiles fill the 148 SMs better
         const long long tiles256 = (long long)((g->M + BM - 1) / BM) * ((g->N + 255) / 256);
         if (tiles256 < num_sms() && g->N > 128) bn = 128;
-        if (g->num_b > 1) {
-            LHRS_CHECK_ARG(!b_mn, "lhrs_gemm_bf16: segmented B must be K-major");
+        if (g->num_b > 1 && b_mn) {
+            // segments stacked along K (each [K/num_b, ldb>=N]); seg_rows is ignored
+            LHRS_CHECK_ARG((g->K % g->num_b) == 0 && ((g->K / g->num_b) % BK) == 0 && g->B[1] != nullptr && (g->num_b < 3 || g->B[2] != nullptr),
+                           "lhrs_gemm_bf16: K=%d must split into %d segments of a multiple of %d", g->K, g->num_b, BK);
+        } else if (g->num_b > 1) {
             LHRS_CHECK_ARG(g->seg_rows > 0 && g->seg_rows * g->num_b == g->N && (g->seg_rows % bn) == 0,
                            "lhrs_gemm_bf16: seg_rows=%d must tile N=%d by %d", g->seg_rows, g->N, bn);
         }
@@ -528,10 +537,18 @@ extern "C" int lhrs_gemm_bf16(const LhrsGemm* g, void* stream_) {
     if (!a_mn) rc = make_tmap(&tA, g->A, g->K, g->M, g->lda, BK, BM);
     else       rc = make_tmap(&tA, g->A, g->M, g->K, g->lda, 64, BK);
     if (rc) return rc;
+    int kseg = 0;
     if (b_mn) {
-        rc = make_tmap(&tB[0], g->B[0], g->N, g->K, g->ldb, 64, BK);
-        if (rc) return rc;
-        tB[1] = tB[0]; tB[2] = tB[0];
+        const int nseg = g->num_b;
+        if (nseg > 1) kseg = g->K / nseg;
+        for (int i = 0; i < 3; ++i) {
+            if (i < nseg) {
+                rc = make_tmap(&tB[i], g->B[i], g->N, nseg > 1 ? kseg : g->K, g->ldb, 64, BK);
+                if (rc) return rc;
+            } else {
+                tB[i] = tB[0];
+            }
+        }
     } else if (kind == LHRS_EPI_SWIGLU) {
         for (int i = 0; i < 2; ++i) {
             rc = make_tmap(&tB[i], g->B[i], g->K, g->N / 2, g->ldb, BK, bn / 2);
@@ -573,7 +590,9 @@ extern "C" int lhrs_gemm_bf16(const LhrsGemm* g, void* stream_) {
     GemmArgs a;
     a.ext_k = ext_k; a.ext_kb = ext_kb;
     a.M = g->M; a.N = g->N; a.K = g->K;
-    a.num_b = g->num_b; a.seg_rows = (g->num_b > 1) ? g->seg_rows : g->N;
+    a.kseg = kseg;
+    a.num_b = (kseg > 0) ? 1 : g->num_b;   // K-stacked segments look like a single B to the epilogue
+    a.seg_rows = (a.num_b > 1) ? g->seg_rows : g->N;
     a.act = g->act; a.alpha = g->alpha;
     for (int i = 0; i < 3; ++i) a.bias[i] = reinterpret_cast<const __nv_bfloat16*>(g->bias[i]);
     a.residual = reinterpret_cast<const __nv_bfloat16*>(g->residual);

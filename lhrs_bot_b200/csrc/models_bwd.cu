@@ -1,0 +1,325 @@
+// Backward layer loops, one C call per module:
+//   lhrs_llama_bwd   dX-only backward of the frozen LLaMA stack (+ LoRA dA/dB), from the activation stash of lhrs_llama_fwd
+//   lhrs_pooler_bwd  full backward of the AttnPooler (dX and every parameter gradient)
+// Frozen weights need no dW, so the LLaMA backward is ~1x the forward FLOPs: each Linear's dX is one tcgen05 GEMM with the
+// weight read MN-major in place (no transposed copies); concatenated outputs ([dq|dk|dv], [dgate|dup]) contract in ONE GEMM
+// with the weight segments stacked along K.  dW of the pooler / LoRA factors are the TN form of the same kernel.
+#include "host_common.h"
+#include "ptx.cuh"
+#include "models_common.h"
+
+namespace lhrs {
+
+__device__ __forceinline__ void up8b(const uint4& u, float (&f)[8]) {
+    f[0] = bf16_lo(u.x); f[1] = bf16_hi(u.x); f[2] = bf16_lo(u.y); f[3] = bf16_hi(u.y);
+    f[4] = bf16_lo(u.z); f[5] = bf16_hi(u.z); f[6] = bf16_lo(u.w); f[7] = bf16_hi(u.w);
+}
+
+// gradient of the learned queries = sum over the batch of (grad of the initial query state + grad of the query rows of kv)
+__global__ void __launch_bounds__(128)
+pooler_dquery_kernel(const __nv_bfloat16* __restrict__ dxq, const __nv_bfloat16* __restrict__ dkv, PoolerGeom geo, int B, int dim,
+                     __nv_bfloat16* __restrict__ dquery) {
+    const int qi = blockIdx.x;
+    int g = 0;
+    while (g + 1 < geo.G && qi >= geo.q_off[g + 1]) ++g;
+    const int j = qi - geo.q_off[g];
+    const int lkv = geo.stage[g] + geo.split[g];
+    for (int c = threadIdx.x; c < dim / 8; c += blockDim.x) {
+        float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        for (int b = 0; b < B; ++b) {
+            float a[8], k[8];
+            up8b(reinterpret_cast<const uint4*>(dxq + (static_cast<long long>(B) * geo.q_off[g] + static_cast<long long>(b) * geo.stage[g] + j) * dim)[c], a);
+            up8b(reinterpret_cast<const uint4*>(dkv + (static_cast<long long>(B) * geo.kv_off[g] + static_cast<long long>(b) * lkv + j) * dim)[c], k);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) acc[e] += a[e] + k[e];
+        }
+        uint4 u;
+        u.x = pack_bf16(acc[0], acc[1]); u.y = pack_bf16(acc[2], acc[3]); u.z = pack_bf16(acc[4], acc[5]); u.w = pack_bf16(acc[6], acc[7]);
+        reinterpret_cast<uint4*>(dquery + static_cast<long long>(qi) * dim)[c] = u;
+    }
+}
+
+// image-token rows of the kv gradient back to the batch-major (B, img_total, dim) layout of image_embs
+__global__ void __launch_bounds__(128)
+pooler_dimage_kernel(const __nv_bfloat16* __restrict__ dkv, PoolerGeom geo, int B, int dim, __nv_bfloat16* __restrict__ dimg) {
+    const long long r = blockIdx.x;
+    const int b = r / geo.img_total, t = r % geo.img_total;
+    int g = 0;
+    while (g + 1 < geo.G && t >= geo.img_off[g + 1]) ++g;
+    const int lkv = geo.stage[g] + geo.split[g];
+    const long long src = static_cast<long long>(B) * geo.kv_off[g] + static_cast<long long>(b) * lkv + geo.stage[g] + (t - geo.img_off[g]);
+    for (int c = threadIdx.x; c < dim / 8; c += blockDim.x)
+        reinterpret_cast<uint4*>(dimg + r * dim)[c] = reinterpret_cast<const uint4*>(dkv + src * dim)[c];
+}
+
+// batch-major d_out rows -> group-major order (inverse of the forward's scatter epilogue)
+__global__ void __launch_bounds__(128)
+pooler_dout_gather_kernel(const __nv_bfloat16* __restrict__ dout, long long ldo, PoolerGeom geo, int B, int dim,
+                          __nv_bfloat16* __restrict__ dst) {
+    const int r = blockIdx.x;
+    int g = 0;
+    while (g + 1 < geo.G && r >= B * geo.q_off[g + 1]) ++g;
+    const int rl = r - B * geo.q_off[g];
+    const int b = rl / geo.stage[g], i = rl % geo.stage[g];
+    const long long src = static_cast<long long>(b) * geo.nq + geo.q_off[g] + i;
+    for (int c = threadIdx.x; c < dim / 8; c += blockDim.x)
+        reinterpret_cast<uint4*>(dst + static_cast<long long>(r) * dim)[c] = reinterpret_cast<const uint4*>(dout + src * ldo)[c];
+}
+
+// ---- GEMM helpers for the three backward forms
+// dX[M,N] = dY[M,K] · W[K,N]   (W is the nn.Linear weight [out=K, in=N], read MN-major in place)
+static int gemm_dx(cudaStream_t st, long long M, int N, int K, const void* dY, long long ldy, const void* W, long long ldw, void* dX,
+                   long long ldx, const void* residual = nullptr, float alpha = 1.f) {
+    LhrsGemm g = gemm_desc(M, N, K, dY, ldy, W, ldw, dX, ldx);
+    g.b_mn_major = 1; g.alpha = alpha;
+    if (residual) { g.residual = residual; g.ldr = ldx; }
+    return lhrs_gemm_bf16(&g, st);
+}
+// dW[out,in] = dY[rows,out]^T · X[rows,in]   (both operands read MN-major, reduction over rows)
+static int gemm_dw(cudaStream_t st, int out, int in, long long rows, const void* dY, long long ldy, const void* X, long long ldx,
+                   void* dW, long long ldw, float alpha = 1.f) {
+    LhrsGemm g = gemm_desc(out, in, static_cast<int>(rows), dY, ldy, X, ldx, dW, ldw);
+    g.a_mn_major = 1; g.b_mn_major = 1; g.alpha = alpha;
+    return lhrs_gemm_bf16(&g, st);
+}
+
+// LoRA backward for `nproj` projections that share the input x:  y_p += s * (x A_p^T) B_p^T
+//   dB_p = dy_p^T T_p,  dT_p = dy_p B_p,  dA_p = s * dT_p^T x,  dx += s * dT_p A_p        (T_p = s * x A_p^T recomputed)
+static int lora_bwd(cudaStream_t st, const LhrsLlamaWeights* w, void* const* ga, void* const* gb, int layer, int first, int nproj,
+                    const void* x, long long ldx, int in_dim, const void* const* dy, long long ldy, int out_dim, long long M,
+                    void* dx, long long lddx, __nv_bfloat16* t_buf, __nv_bfloat16* dt_buf) {
+    if (w->lora_r <= 0 || w->lora_a == nullptr) return LHRS_OK;
+    const int r = w->lora_r;
+    const long long ldt = (long long)nproj * r;
+    int rc;
+    for (int p = 0; p < nproj; ++p) {
+        const int idx = layer * 7 + first + p;
+        const void* A = w->lora_a[idx];
+        const void* Bm = w->lora_b[idx];
+        {   // T_p = s * x A_p^T
+            LhrsGemm g = gemm_desc(M, r, in_dim, x, ldx, A, in_dim, t_buf + p * r, ldt);
+            g.alpha = w->lora_scale;
+            if ((rc = lhrs_gemm_bf16(&g, st))) return rc;
+        }
+        if (gb && gb[idx]) if ((rc = gemm_dw(st, out_dim, r, M, dy[p], ldy, t_buf + p * r, ldt, gb[idx], r))) return rc;
+        if ((rc = gemm_dx(st, M, r, out_dim, dy[p], ldy, Bm, r, dt_buf + p * r, ldt))) return rc;
+        if (ga && ga[idx]) if ((rc = gemm_dw(st, r, in_dim, M, dt_buf + p * r, ldt, x, ldx, ga[idx], in_dim, w->lora_scale))) return rc;
+        if (dx) if ((rc = gemm_dx(st, M, in_dim, r, dt_buf + p * r, ldt, A, in_dim, dx, lddx, dx, w->lora_scale))) return rc;
+    }
+    return LHRS_OK;
+}
+
+}  // namespace lhrs
+
+using namespace lhrs;
+typedef __nv_bfloat16 bf16;
+
+// ================================================================================================ LLaMA backward
+namespace {
+struct LlamaBwdBufs { bf16 *dxa, *dxb, *dh, *d_act, *d_gu, *dqkv, *d_o, *h, *t, *dt; float* delta; };
+LlamaBwdBufs llama_bwd_plan(Arena& a, const LhrsLlamaWeights* w, long long M) {
+    LlamaBwdBufs b;
+    const int D = w->dim, F = w->ffn;
+    b.dxa = a.take<bf16>(M * D); b.dxb = a.take<bf16>(M * D); b.dh = a.take<bf16>(M * D);
+    b.d_act = a.take<bf16>(M * F); b.d_gu = a.take<bf16>(M * 2 * F);
+    b.dqkv = a.take<bf16>(M * 3 * D); b.d_o = a.take<bf16>(M * D);
+    b.delta = a.take<float>(M * w->heads);
+    const bool lora = w->lora_r > 0;
+    b.h = lora ? a.take<bf16>(M * D) : nullptr;
+    b.t = lora ? a.take<bf16>(M * 3 * w->lora_r) : nullptr;
+    b.dt = lora ? a.take<bf16>(M * 3 * w->lora_r) : nullptr;
+    return b;
+}
+}  // namespace
+
+extern "C" size_t lhrs_llama_bwd_workspace_bytes(const LhrsLlamaWeights* w, int32_t B, int32_t S) {
+    Arena a(nullptr, 0);
+    llama_bwd_plan(a, w, (long long)B * S);
+    return a.used();
+}
+
+extern "C" int lhrs_lm_head_bwd(const LhrsLlamaWeights* w, const void* d_logits, int64_t rows, void* d_hidden, void* stream) {
+    LHRS_CHECK_ARG(w && d_logits && d_hidden && rows > 0, "lhrs_lm_head_bwd: null/empty");
+    return gemm_dx((cudaStream_t)stream, rows, w->dim, w->vocab, d_logits, w->vocab, w->lm_head, w->dim, d_hidden, w->dim);
+}
+
+extern "C" int lhrs_llama_bwd(const LhrsLlamaWeights* w, void* const* lora_a_grads, void* const* lora_b_grads, const void* d_hidden,
+                              int32_t B, int32_t S, const uint8_t* key_mask, const void* stash, void* d_inputs_embeds,
+                              void* workspace, size_t workspace_bytes, void* stream_) {
+    cudaStream_t st = (cudaStream_t)stream_;
+    LHRS_CHECK_ARG(w && d_hidden && stash && d_inputs_embeds && B > 0 && S > 0, "lhrs_llama_bwd: null/empty");
+    const long long M = (long long)B * S;
+    const int D = w->dim, F = w->ffn;
+    Arena a(workspace, workspace_bytes);
+    LlamaBwdBufs b = llama_bwd_plan(a, w, M);
+    LHRS_CHECK_ARG(a.fits(), "lhrs_llama_bwd: workspace too small (%zu < %zu)", workspace_bytes, a.used());
+    Arena sa(const_cast<void*>(stash), (size_t)-1);
+    LlamaStash s = llama_stash_plan(sa, w, B, S);
+    int rc;
+    bf16* dx = b.dxa;
+    bf16* dx_other = b.dxb;
+    if ((rc = lhrs_rmsnorm_bwd(s.x_final, w->norm_w, s.rstd_final, d_hidden, nullptr, dx, M, D, st))) return rc;
+    for (int l = w->num_layers - 1; l >= 0; --l) {
+        const LlamaLayerStash& t = s.layer[l];
+        // ---- MLP: x_out = x_mid + down(silu(gate(h2)) * up(h2)),  h2 = rmsnorm(x_mid)
+        if ((rc = gemm_dx(st, M, F, D, dx, D, w->down_w[l], F, b.d_act, F))) return rc;
+        {
+            const void* dy[1] = {dx};
+            if ((rc = lora_bwd(st, w, lora_a_grads, lora_b_grads, l, 6, 1, t.act, F, F, dy, D, D, M, b.d_act, F, b.t, b.dt))) return rc;
+        }
+        if ((rc = lhrs_swiglu_bwd(b.d_act, t.pre_gate, t.pre_up, b.d_gu, M, F, st))) return rc;
+        {
+            LhrsGemm g = gemm_desc(M, D, 2 * F, b.d_gu, 2 * F, w->gate_w[l], D, b.dh, D);
+            g.b_mn_major = 1; g.B[1] = w->up_w[l]; g.num_b = 2;
+            if ((rc = lhrs_gemm_bf16(&g, st))) return rc;
+        }
+        if (w->lora_r > 0) {
+            if ((rc = lhrs_rmsnorm_fwd(t.x_mid, w->ln2_w[l], b.h, nullptr, M, D, w->eps, st))) return rc;
+            const void* dy[2] = {b.d_gu, b.d_gu + F};
+            if ((rc = lora_bwd(st, w, lora_a_grads, lora_b_grads, l, 4, 2, b.h, D, D, dy, 2 * F, F, M, b.dh, D, b.t, b.dt))) return rc;
+        }
+        if ((rc = lhrs_rmsnorm_bwd(t.x_mid, w->ln2_w[l], t.rstd2, b.dh, dx, dx_other, M, D, st))) return rc;
+        { bf16* tmp = dx; dx = dx_other; dx_other = tmp; }   // dx = grad wrt x_mid
+        // ---- attention: x_mid = x_in + o_proj(attn(rope(q), rope(k), v)),  q,k,v = proj(h1), h1 = rmsnorm(x_in)
+        if ((rc = gemm_dx(st, M, D, D, dx, D, w->o_w[l], D, b.d_o, D))) return rc;
+        {
+            const void* dy[1] = {dx};
+            if ((rc = lora_bwd(st, w, lora_a_grads, lora_b_grads, l, 3, 1, t.o, D, D, dy, D, D, M, b.d_o, D, b.t, b.dt))) return rc;
+        }
+        {
+            LhrsAttentionBwd ab;
+            memset(&ab, 0, sizeof(ab));
+            ab.fwd = attn_desc(t.qkv, t.qkv + D, t.qkv + 2 * D, 3 * D, (long long)S * 3 * D, t.o, D, (long long)S * D, B, w->heads, S, S, 128, 1);
+            ab.fwd.lse = t.lse; ab.fwd.key_mask = key_mask;
+            ab.d_o = b.d_o; ab.delta = b.delta;
+            ab.dq = b.dqkv; ab.dk = b.dqkv + D; ab.dv = b.dqkv + 2 * D;
+            ab.dq_rs = ab.dk_rs = ab.dv_rs = 3 * D; ab.dq_bs = ab.dk_bs = ab.dv_bs = (long long)S * 3 * D;
+            ab.dq_hs = ab.dk_hs = ab.dv_hs = 128;
+            if ((rc = lhrs_attention_bwd(&ab, st))) return rc;
+        }
+        if ((rc = lhrs_rope_bwd(b.dqkv, 3 * D, M, D, w->rope_cos, w->rope_sin, nullptr, S, st))) return rc;
+        {
+            LhrsGemm g = gemm_desc(M, D, 3 * D, b.dqkv, 3 * D, w->q_w[l], D, b.dh, D);
+            g.b_mn_major = 1; g.B[1] = w->k_w[l]; g.B[2] = w->v_w[l]; g.num_b = 3;
+            if ((rc = lhrs_gemm_bf16(&g, st))) return rc;
+        }
+        if (w->lora_r > 0) {
+            if ((rc = lhrs_rmsnorm_fwd(t.x_in, w->ln1_w[l], b.h, nullptr, M, D, w->eps, st))) return rc;
+            const void* dy[3] = {b.dqkv, b.dqkv + D, b.dqkv + 2 * D};
+            if ((rc = lora_bwd(st, w, lora_a_grads, lora_b_grads, l, 0, 3, b.h, D, D, dy, 3 * D, D, M, b.dh, D, b.t, b.dt))) return rc;
+        }
+        bf16* dst = (l == 0) ? reinterpret_cast<bf16*>(d_inputs_embeds) : dx_other;
+        if ((rc = lhrs_rmsnorm_bwd(t.x_in, w->ln1_w[l], t.rstd1, b.dh, dx, dst, M, D, st))) return rc;
+        { bf16* tmp = dx; dx = dx_other; dx_other = tmp; }
+    }
+    return LHRS_OK;
+}
+
+// ================================================================================================ AttnPooler backward
+namespace {
+struct PoolBwdBufs { bf16 *dout_gm, *dx, *dx2, *d_f, *dh, *d_ao, *dqp, *dkvp, *dkvn, *dkv_raw; float *delta, *scratch; };
+PoolBwdBufs pool_bwd_plan(Arena& a, const LhrsPoolerWeights* w, int B, const PoolerGeom& geo) {
+    PoolBwdBufs p;
+    const long long RQ = (long long)B * geo.nq, RKV = (long long)B * geo.kv_total;
+    const int D = w->dim, F = w->ffn;
+    p.dout_gm = a.take<bf16>(RQ * w->out_dim);
+    p.dx = a.take<bf16>(RQ * D); p.dx2 = a.take<bf16>(RQ * D);
+    p.d_f = a.take<bf16>(RQ * F); p.dh = a.take<bf16>(RQ * D); p.d_ao = a.take<bf16>(RQ * D); p.dqp = a.take<bf16>(RQ * D);
+    p.dkvp = a.take<bf16>(RKV * 2 * D); p.dkvn = a.take<bf16>(RKV * D); p.dkv_raw = a.take<bf16>(RKV * D);
+    p.delta = a.take<float>(RQ * w->heads);
+    const int widest = F > w->out_dim ? F : w->out_dim;
+    p.scratch = a.take<float>((long long)2 * 296 * (widest > 2 * D ? widest : 2 * D));
+    return p;
+}
+}  // namespace
+
+extern "C" size_t lhrs_pooler_bwd_workspace_bytes(const LhrsPoolerWeights* w, int32_t B) {
+    Arena a(nullptr, 0);
+    pool_bwd_plan(a, w, B, pooler_geom(w));
+    return a.used();
+}
+
+extern "C" int lhrs_pooler_bwd(const LhrsPoolerWeights* w, const LhrsPoolerWeights* gr, const void* d_out, int64_t ldo, int32_t B,
+                               const void* stash, void* d_image, void* workspace, size_t workspace_bytes, void* stream_) {
+    cudaStream_t st = (cudaStream_t)stream_;
+    LHRS_CHECK_ARG(w && gr && d_out && stash && B > 0, "lhrs_pooler_bwd: null/empty");
+    const PoolerGeom geo = pooler_geom(w);
+    Arena a(workspace, workspace_bytes);
+    PoolBwdBufs p = pool_bwd_plan(a, w, B, geo);
+    LHRS_CHECK_ARG(a.fits(), "lhrs_pooler_bwd: workspace too small (%zu < %zu)", workspace_bytes, a.used());
+    Arena sa(const_cast<void*>(stash), (size_t)-1);
+    PoolerStash s = pooler_stash_plan(sa, w, B, geo);
+    const int D = w->dim, F = w->ffn, O = w->out_dim;
+    const long long RQ = (long long)B * geo.nq, RKV = (long long)B * geo.kv_total;
+    int rc;
+    auto G = [](const void* p) { return const_cast<void*>(p); };
+
+    // ---- out_proj: out = x_final W_out^T + b
+    pooler_dout_gather_kernel<<<(unsigned)RQ, 128, 0, st>>>((const bf16*)d_out, ldo, geo, B, O, p.dout_gm);
+    LHRS_LAUNCH_CHECK("pooler_dout_gather_kernel");
+    if (gr->out_w) if ((rc = gemm_dw(st, O, D, RQ, p.dout_gm, O, s.x_final, D, G(gr->out_w), D))) return rc;
+    if (gr->out_b) if ((rc = lhrs_colsum(p.dout_gm, O, RQ, O, G(gr->out_b), 0, p.scratch, st))) return rc;
+    bf16* dx = p.dx;
+    bf16* dx_other = p.dx2;
+    if ((rc = gemm_dx(st, RQ, D, O, p.dout_gm, O, w->out_w, D, dx, D))) return rc;
+    LHRS_CUDA(cudaMemsetAsync(p.dkv_raw, 0, RKV * D * 2, st));
+
+    for (int l = w->num_layers - 1; l >= 0; --l) {
+        const PoolerLayerStash& t = s.layer[l];
+        const bf16* in_w = (const bf16*)w->in_w[l];
+        bf16* g_in_w = (bf16*)G(gr->in_w ? gr->in_w[l] : nullptr);
+        bf16* g_in_b = (bf16*)G(gr->in_b ? gr->in_b[l] : nullptr);
+        // ---- MLP: x_out = x_mid + c_proj(gelu(c_fc(ln_2(x_mid))))
+        if (gr->pj_w && gr->pj_w[l]) if ((rc = gemm_dw(st, D, F, RQ, dx, D, t.f_act, F, G(gr->pj_w[l]), F))) return rc;
+        if (gr->pj_b && gr->pj_b[l]) if ((rc = lhrs_colsum(dx, D, RQ, D, G(gr->pj_b[l]), 0, p.scratch, st))) return rc;
+        if ((rc = gemm_dx(st, RQ, F, D, dx, D, w->pj_w[l], F, p.d_f, F))) return rc;
+        if ((rc = lhrs_gelu_bwd(p.d_f, t.f_pre, RQ * F, st))) return rc;
+        if (gr->fc_w && gr->fc_w[l]) if ((rc = gemm_dw(st, F, D, RQ, p.d_f, F, t.h2, D, G(gr->fc_w[l]), D))) return rc;
+        if (gr->fc_b && gr->fc_b[l]) if ((rc = lhrs_colsum(p.d_f, F, RQ, F, G(gr->fc_b[l]), 0, p.scratch, st))) return rc;
+        if ((rc = gemm_dx(st, RQ, D, F, p.d_f, F, w->fc_w[l], D, p.dh, D))) return rc;
+        if ((rc = lhrs_layernorm_bwd(t.x_mid, D, w->ln2_w[l], t.m_mean, t.m_rstd, p.dh, dx, dx_other, G(gr->ln2_w ? gr->ln2_w[l] : nullptr),
+                                     G(gr->ln2_b ? gr->ln2_b[l] : nullptr), 0, p.scratch, RQ, D, st))) return rc;
+        { bf16* tmp = dx; dx = dx_other; dx_other = tmp; }   // dx = grad wrt x_mid
+        // ---- attention: x_mid = x_in + out_proj(MHA(q = ln_1(x_in) Wq, k/v = ln_1_kv(kv) Wk/Wv))
+        if (gr->ao_w && gr->ao_w[l]) if ((rc = gemm_dw(st, D, D, RQ, dx, D, t.ao, D, G(gr->ao_w[l]), D))) return rc;
+        if (gr->ao_b && gr->ao_b[l]) if ((rc = lhrs_colsum(dx, D, RQ, D, G(gr->ao_b[l]), 0, p.scratch, st))) return rc;
+        if ((rc = gemm_dx(st, RQ, D, D, dx, D, w->ao_w[l], D, p.d_ao, D))) return rc;
+        for (int g = 0; g < geo.G; ++g) {
+            const int Lq = geo.stage[g], Lkv = geo.stage[g] + geo.split[g];
+            const long long qo = (long long)B * geo.q_off[g], ko = (long long)B * geo.kv_off[g];
+            LhrsAttentionBwd ab;
+            memset(&ab, 0, sizeof(ab));
+            ab.fwd = attn_desc(t.qp + qo * D, t.kvp + ko * 2 * D, t.kvp + ko * 2 * D + D, D, (long long)Lq * D, t.ao + qo * D, D,
+                               (long long)Lq * D, B, w->heads, Lq, Lkv, 64, 0);
+            ab.fwd.k_rs = ab.fwd.v_rs = 2 * D; ab.fwd.k_bs = ab.fwd.v_bs = (long long)Lkv * 2 * D;
+            ab.fwd.lse = t.lse + qo * w->heads;
+            ab.d_o = p.d_ao + qo * D; ab.delta = p.delta + qo * w->heads;
+            ab.dq = p.dqp + qo * D; ab.dq_rs = D; ab.dq_bs = (long long)Lq * D; ab.dq_hs = 64;
+            ab.dk = p.dkvp + ko * 2 * D; ab.dv = p.dkvp + ko * 2 * D + D;
+            ab.dk_rs = ab.dv_rs = 2 * D; ab.dk_bs = ab.dv_bs = (long long)Lkv * 2 * D; ab.dk_hs = ab.dv_hs = 64;
+            if ((rc = lhrs_attention_bwd(&ab, st))) return rc;
+        }
+        // q projection (in_proj rows [0, D)) and k/v projection (rows [D, 3D))
+        if (g_in_w) if ((rc = gemm_dw(st, D, D, RQ, p.dqp, D, t.hq, D, g_in_w, D))) return rc;
+        if (g_in_b) if ((rc = lhrs_colsum(p.dqp, D, RQ, D, g_in_b, 0, p.scratch, st))) return rc;
+        if ((rc = gemm_dx(st, RQ, D, D, p.dqp, D, in_w, D, p.dh, D))) return rc;
+        if (g_in_w) if ((rc = gemm_dw(st, 2 * D, D, RKV, p.dkvp, 2 * D, t.kvn, D, g_in_w + (long long)D * D, D))) return rc;
+        if (g_in_b) if ((rc = lhrs_colsum(p.dkvp, 2 * D, RKV, 2 * D, g_in_b + D, 0, p.scratch, st))) return rc;
+        if ((rc = gemm_dx(st, RKV, D, 2 * D, p.dkvp, 2 * D, in_w + (long long)D * D, D, p.dkvn, D))) return rc;
+        if ((rc = lhrs_layernorm_bwd(t.x_in, D, w->ln1_w[l], t.q_mean, t.q_rstd, p.dh, dx, dx_other, G(gr->ln1_w ? gr->ln1_w[l] : nullptr),
+                                     G(gr->ln1_b ? gr->ln1_b[l] : nullptr), 0, p.scratch, RQ, D, st))) return rc;
+        { bf16* tmp = dx; dx = dx_other; dx_other = tmp; }   // dx = grad wrt x_in (the previous layer's output)
+        // the kv input is the same tensor for every layer: accumulate its gradient in place
+        if ((rc = lhrs_layernorm_bwd(s.kv_raw, D, w->lnkv_w[l], t.kv_mean, t.kv_rstd, p.dkvn, p.dkv_raw, p.dkv_raw,
+                                     G(gr->lnkv_w ? gr->lnkv_w[l] : nullptr), G(gr->lnkv_b ? gr->lnkv_b[l] : nullptr), 0, p.scratch, RKV, D, st))) return rc;
+    }
+    if (gr->query) {
+        pooler_dquery_kernel<<<geo.nq, 128, 0, st>>>(dx, p.dkv_raw, geo, B, D, (bf16*)G(gr->query));
+        LHRS_LAUNCH_CHECK("pooler_dquery_kernel");
+    }
+    if (d_image != nullptr) {
+        pooler_dimage_kernel<<<(unsigned)((long long)B * geo.img_total), 128, 0, st>>>(p.dkv_raw, geo, B, D, (bf16*)d_image);
+        LHRS_LAUNCH_CHECK("pooler_dimage_kernel");
+    }
+    return LHRS_OK;
+}

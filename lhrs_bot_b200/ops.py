@@ -65,14 +65,13 @@ def gemm(a: torch.Tensor, b, *, out: Optional[torch.Tensor] = None, bias: Option
         if tuple(t.shape) != tuple(bs[0].shape) or t.stride(0) != ldb:
             raise RuntimeError("gemm: B segments must have identical shape and stride")
     if b_mn_major:
-        if len(bs) != 1:
-            raise RuntimeError("gemm: MN-major B cannot be segmented")
-        kb, seg = br, bc
+        # MN-major segments are stacked along K (dX of a concatenated output): each is [K/len(bs), N]
+        kb, seg = br * len(bs), bc
     else:
         kb, seg = bc, br
     if kb != K:
         raise RuntimeError(f"gemm: K mismatch A has {K}, B has {kb}")
-    N = seg * len(bs)
+    N = seg if b_mn_major else seg * len(bs)
     n_out = N // 2 if epilogue == EPI_SWIGLU else N
     if out is None:
         rows_out = M if row_map is None else None
@@ -268,16 +267,96 @@ def ce_fwd(logits: torch.Tensor, labels: torch.Tensor):
 
 
 def ce_bwd(logits: torch.Tensor, labels: torch.Tensor, row_lse: torch.Tensor, count: torch.Tensor, grad_scale: float,
-           out: Optional[torch.Tensor] = None) -> torch.Tensor:
+           out: Optional[torch.Tensor] = None, grad_scale_dev: Optional[torch.Tensor] = None) -> torch.Tensor:
     B, S, V = logits.shape
     l2 = logits.view(B * S, V)
     if out is None:
         out = torch.empty_like(l2)
+    out = out.view(B * S, V)
     check(_lib.load().lhrs_ce_bwd(l2.data_ptr(), l2.stride(0), labels.contiguous().data_ptr(), B, S, V,
-                                  row_lse.data_ptr(), count.data_ptr(), float(grad_scale), out.data_ptr(), _stream()),
+                                  row_lse.data_ptr(), count.data_ptr(), float(grad_scale), _ptr(grad_scale_dev), out.data_ptr(), _stream()),
           "lhrs_ce_bwd")
     return out.view(B, S, V)
 
 
 def launch_count() -> int:
     return int(_lib.load().lhrs_launch_count())
+
+
+# ---------------------------------------------------------------------------------------------- backward ops
+def attention_bwd(q, k, v, o, lse, d_o, *, causal: bool, scale: Optional[float] = None, key_mask=None):
+    """(B,S,H,hd) views as in ``attention``; returns (dq, dk, dv) contiguous bf16."""
+    from ._lib import LhrsAttentionBwd
+    B, Sq, H, hd = q.shape
+    Skv = k.shape[1]
+    dq, dk, dv = torch.empty_like(q, memory_format=torch.contiguous_format), torch.empty(k.shape, device=k.device, dtype=k.dtype), \
+        torch.empty(v.shape, device=v.device, dtype=v.dtype)
+    delta = torch.empty((B, H, Sq), device=q.device, dtype=torch.float32)
+    d_o = d_o.contiguous()
+    if not o.is_contiguous():
+        o = o.contiguous()
+    a = LhrsAttentionBwd()
+    f = a.fwd
+    f.q, f.k, f.v, f.o = q.data_ptr(), k.data_ptr(), v.data_ptr(), o.data_ptr()
+    f.lse, f.key_mask = lse.data_ptr(), _ptr(key_mask)
+    f.q_bs, f.q_rs, f.q_hs = q.stride(0), q.stride(1), q.stride(2)
+    f.k_bs, f.k_rs, f.k_hs = k.stride(0), k.stride(1), k.stride(2)
+    f.v_bs, f.v_rs, f.v_hs = v.stride(0), v.stride(1), v.stride(2)
+    f.o_bs, f.o_rs, f.o_hs = o.stride(0), o.stride(1), o.stride(2)
+    f.B, f.H, f.Sq, f.Skv, f.head_dim, f.causal = B, H, Sq, Skv, hd, int(causal)
+    f.scale = float(scale if scale is not None else 1.0 / math.sqrt(hd))
+    a.d_o, a.dq, a.dk, a.dv, a.delta = d_o.data_ptr(), dq.data_ptr(), dk.data_ptr(), dv.data_ptr(), delta.data_ptr()
+    a.dq_bs, a.dq_rs, a.dq_hs = dq.stride(0), dq.stride(1), dq.stride(2)
+    a.dk_bs, a.dk_rs, a.dk_hs = dk.stride(0), dk.stride(1), dk.stride(2)
+    a.dv_bs, a.dv_rs, a.dv_hs = dv.stride(0), dv.stride(1), dv.stride(2)
+    check(_lib.load().lhrs_attention_bwd(C.byref(a), _stream()), "lhrs_attention_bwd")
+    return dq, dk, dv
+
+
+def rmsnorm_bwd(x, w, rstd, dy, dres=None):
+    x2, dy2 = x.reshape(-1, x.shape[-1]).contiguous(), dy.reshape(-1, x.shape[-1]).contiguous()
+    dx = torch.empty_like(x2)
+    dr = None if dres is None else dres.reshape(-1, x.shape[-1]).contiguous()
+    check(_lib.load().lhrs_rmsnorm_bwd(x2.data_ptr(), w.data_ptr(), rstd.data_ptr(), dy2.data_ptr(), _ptr(dr), dx.data_ptr(),
+                                       x2.shape[0], x2.shape[1], _stream()), "lhrs_rmsnorm_bwd")
+    return dx.view(x.shape)
+
+
+def layernorm_bwd(x, w, mean, rstd, dy, dres=None):
+    lib = _lib.load()
+    rows, dim = x.shape
+    dx, dw, db = torch.empty_like(x), torch.empty_like(w), torch.empty_like(w)
+    scratch = torch.empty((lib.lhrs_layernorm_bwd_scratch_bytes(dim) // 4,), device=x.device, dtype=torch.float32)
+    check(lib.lhrs_layernorm_bwd(x.data_ptr(), x.stride(0), w.data_ptr(), mean.data_ptr(), rstd.data_ptr(), dy.contiguous().data_ptr(),
+                                 _ptr(dres), dx.data_ptr(), dw.data_ptr(), db.data_ptr(), 0, scratch.data_ptr(), rows, dim, _stream()),
+          "lhrs_layernorm_bwd")
+    return dx, dw, db
+
+
+def colsum(a):
+    lib = _lib.load()
+    rows, n = a.shape
+    out = torch.empty((n,), device=a.device, dtype=torch.bfloat16)
+    scratch = torch.empty((lib.lhrs_colsum_scratch_bytes(n) // 4,), device=a.device, dtype=torch.float32)
+    check(lib.lhrs_colsum(a.data_ptr(), a.stride(0), rows, n, out.data_ptr(), 0, scratch.data_ptr(), _stream()), "lhrs_colsum")
+    return out
+
+
+def swiglu_bwd(d_act, pre_gate, pre_up):
+    rows, f = d_act.shape
+    out = torch.empty((rows, 2 * f), device=d_act.device, dtype=torch.bfloat16)
+    check(_lib.load().lhrs_swiglu_bwd(d_act.contiguous().data_ptr(), pre_gate.data_ptr(), pre_up.data_ptr(), out.data_ptr(), rows, f,
+                                      _stream()), "lhrs_swiglu_bwd")
+    return out
+
+
+def gelu_bwd_(d, pre):
+    check(_lib.load().lhrs_gelu_bwd(d.data_ptr(), pre.data_ptr(), d.numel(), _stream()), "lhrs_gelu_bwd")
+    return d
+
+
+def rope_bwd_(dqkv, dim, cos, sin, seq_len):
+    rows = dqkv.shape[0]
+    check(_lib.load().lhrs_rope_bwd(dqkv.data_ptr(), dqkv.stride(0), rows, dim, cos.data_ptr(), sin.data_ptr(), None, seq_len,
+                                    _stream()), "lhrs_rope_bwd")
+    return dqkv

@@ -341,6 +341,19 @@ class TextModal(BaseModal):
         self._table, self._table_sig = (w, keep), sig
         return w
 
+    def lora_pairs(self):
+        """[(lora_A.weight, lora_B.weight)] in weight-table order [layer*7 + proj]; empty without LoRA."""
+        te = self.text_encoder
+        if not te.has_lora():
+            return []
+        pairs = []
+        for l in te.model.layers:
+            for holder, names in ((l.self_attn, PROJ_NAMES[:4]), (l.mlp, PROJ_NAMES[4:])):
+                for n in names:
+                    m = getattr(holder, n)
+                    pairs.append((m.lora_A["default"].weight, m.lora_B["default"].weight))
+        return pairs
+
     # ------------------------------------------------------------------ splice
     def prepare_inputs_for_multimodal(self, input_ids: torch.Tensor, attention_mask: Optional[torch.Tensor],
                                       labels: Optional[torch.Tensor], past_key_values=None,

@@ -1,10 +1,124 @@
-"""Training step of the hot path (stage-1/2/3): forward + backward over pooler / LoRA, flat-gradient allreduce, AdamW.
+"""Training step of the hot path (stages 1-3): forward + backward over pooler / LoRA, ONE flat-gradient allreduce, fused AdamW.
 
-Filled in once the backward kernels are in place; bench.py reads ``AVAILABLE``.
+Replaces, for this path, what the reference gets from DeepSpeed ZeRO-2 (main_pretrain_stage1.py:28-85, 215-220;
+hook/deepspeed_hook.py:5-9): the trainable set (pooler 79.9 M, + LoRA) lives in one flat bf16 parameter buffer and one flat
+bf16 gradient buffer; the backward kernels write gradients straight into the flat buffer (``_grad_sink``), a single NCCL
+allreduce (sum) over NVLink follows, and one kernel applies global-norm clipping + AdamW on fp32 master weights.  The frozen
+ViT / LLaMA weights are replicated and never communicated.  LR schedule: linear warm-up + cosine (lr_scheduler_hook.py:243-272).
 """
-AVAILABLE = False
+from __future__ import annotations
+
+import math
+from typing import Dict, List, Optional
+
+import torch
+
+from . import _lib, runtime
+from ._lib import check
+
+AVAILABLE = True
+
+
+def trainable_parameters(model) -> List[torch.nn.Parameter]:
+    return [p for p in model.parameters() if p.requires_grad]
+
+
+class FlatAdamW:
+    """Flat-buffer AdamW with global-norm clipping (torch.optim.AdamW semantics, betas (0.9, 0.95) as the reference's
+    DeepSpeed config, main_pretrain_stage1.py:30-41).  1-D parameters and biases get no weight decay (build_optimizer.py:20-46)."""
+
+    def __init__(self, params: List[torch.nn.Parameter], lr=2e-4, betas=(0.9, 0.95), eps=1e-8, weight_decay=0.0, max_grad_norm=1.0):
+        assert params, "no trainable parameters"
+        dev = params[0].device
+        self.params = params
+        self.numel = sum(p.numel() for p in params)
+        self.flat_param = torch.empty((self.numel,), device=dev, dtype=torch.bfloat16)
+        self.flat_grad = torch.zeros((self.numel,), device=dev, dtype=torch.bfloat16)
+        self.master = torch.empty((self.numel,), device=dev, dtype=torch.float32)
+        self.m = torch.zeros((self.numel,), device=dev, dtype=torch.float32)
+        self.v = torch.zeros((self.numel,), device=dev, dtype=torch.float32)
+        self.decay_mask = torch.empty((self.numel,), device=dev, dtype=torch.float32) if weight_decay > 0 else None
+        self.grad_views: Dict[torch.nn.Parameter, torch.Tensor] = {}
+        off = 0
+        for p in params:
+            runtime.require_bf16_cuda(p, "trainable parameter")
+            n = p.numel()
+            # 16-byte alignment of every view keeps the TMA / vector paths of the kernels valid
+            assert off % 8 == 0, "parameter sizes must be multiples of 8 elements"
+            self.flat_param[off: off + n].copy_(p.data.reshape(-1))
+            p.data = self.flat_param[off: off + n].view(p.shape)          # re-point storage into the flat buffer
+            self.grad_views[p] = self.flat_grad[off: off + n].view(p.shape)
+            if self.decay_mask is not None:
+                self.decay_mask[off: off + n] = 0.0 if p.dim() <= 1 else 1.0
+            off += n
+        self.master.copy_(self.flat_param)
+        self.lr, self.betas, self.eps, self.weight_decay, self.max_grad_norm = lr, betas, eps, weight_decay, max_grad_norm
+        self.step_count = 0
+        self._sumsq = torch.zeros((1,), device=dev, dtype=torch.float32)
+        self._scratch = torch.empty((1024,), device=dev, dtype=torch.float32)
+
+    def step(self, lr: Optional[float] = None, grad_scale: float = 1.0) -> None:
+        lib = _lib.load()
+        self.step_count += 1
+        st = runtime.stream()
+        gn = None
+        if self.max_grad_norm and self.max_grad_norm > 0:
+            check(lib.lhrs_grad_sumsq(self.flat_grad.data_ptr(), self.numel, self._sumsq.data_ptr(), self._scratch.data_ptr(), st),
+                  "lhrs_grad_sumsq")
+            gn = self._sumsq.data_ptr()
+        check(lib.lhrs_adamw_step(self.master.data_ptr(), self.m.data_ptr(), self.v.data_ptr(), self.flat_grad.data_ptr(),
+                                  self.flat_param.data_ptr(), None if self.decay_mask is None else self.decay_mask.data_ptr(),
+                                  self.numel, float(self.lr if lr is None else lr), self.betas[0], self.betas[1], self.eps,
+                                  self.weight_decay, self.step_count, gn, float(self.max_grad_norm or 0.0), float(grad_scale), st),
+              "lhrs_adamw_step")
+
+    def grad_norm(self) -> float:
+        return float(self._sumsq.sqrt().item())
+
+
+def cosine_lr(step: int, base_lr: float, warmup: int, total: int, min_lr: float = 0.0) -> float:
+    if step < warmup:
+        return base_lr * (step + 1) / max(1, warmup)
+    t = min(1.0, (step - warmup) / max(1, total - warmup))
+    return min_lr + 0.5 * (base_lr - min_lr) * (1.0 + math.cos(math.pi * t))
 
 
 class SftStepper:
-    def __init__(self, model, world_size=1):
-        raise NotImplementedError("the backward path is not built yet")
+    """One data-parallel training step: ``loss = stepper.step(batch)``.
+
+    ``model`` is a ``UniBind`` after ``prepare_for_training`` (or with LoRA enabled by config); the trainable set is
+    whatever has ``requires_grad`` (pooler and/or LoRA factors).  With ``world_size > 1`` the default process group must
+    be initialised (NCCL); ranks see different batches and the flat gradient is summed then scaled by 1/world.
+    """
+
+    def __init__(self, model, world_size: int = 1, lr: float = 2e-4, weight_decay: float = 0.0, max_grad_norm: float = 1.0,
+                 warmup_steps: int = 0, total_steps: int = 0, prepare: bool = True):
+        self.model = model
+        self.world = world_size
+        if prepare:
+            has_lora = model.text.text_encoder.has_lora()
+            model.prepare_for_training(freeze_vision=True, freeze_text=True, tune_rgb_pooler=True, model_path=None,
+                                       tune_im_start=False, compute_dtype=torch.bfloat16)
+            if has_lora:
+                for a, b in model.text.lora_pairs():
+                    a.requires_grad_(True)
+                    b.requires_grad_(True)
+        params = trainable_parameters(model)
+        self.opt = FlatAdamW(params, lr=lr, weight_decay=weight_decay, max_grad_norm=max_grad_norm)
+        # the backward kernels write into the flat gradient buffer directly
+        model.rgb_pooler._grad_sink = {p: g for p, g in self.opt.grad_views.items()}
+        model.text._grad_sink = model.rgb_pooler._grad_sink
+        self.base_lr, self.warmup, self.total = lr, warmup_steps, total_steps
+        self.it = 0
+
+    def step(self, batch) -> torch.Tensor:
+        out = self.model(batch)
+        loss = out["total_loss"]
+        loss.backward()
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(self.opt.flat_grad, op=dist.ReduceOp.SUM)     # the one collective of the step (NCCL over NVLink)
+        lr = cosine_lr(self.it, self.base_lr, self.warmup, self.total) if self.total > 0 else self.base_lr
+        self.opt.step(lr=lr, grad_scale=1.0 / self.world)
+        self.it += 1
+        return loss.detach()

@@ -1,0 +1,232 @@
+"""Backward parity: the CUDA backward kernels / layer loops against torch.autograd through the fp32 oracle
+on the same weights and inputs.  Gradients are produced in bf16: we require cosine similarity >= 0.999 and relative L2 error
+<= 3e-2 per tensor (<= 5e-2 for the tiny bias / norm-weight gradients that are sums of many rounded terms)."""
+import math
+
+import pytest
+import torch
+
+from helpers import build_small_model, rel_l2, small_config, synthetic_batch, to_device
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _cmp(name, got, ref, tol=3e-2):
+    got, ref = got.float().flatten(), ref.float().flatten()
+    assert torch.isfinite(got).all(), f"{name}: non-finite gradient"
+    cos = torch.nn.functional.cosine_similarity(got, ref, dim=0).item()
+    e = rel_l2(got, ref)
+    print(f"{name}: cos {cos:.5f} rel-L2 {e:.3e}")
+    assert cos >= 0.999 and e <= tol, f"{name}: cos {cos:.5f} rel-L2 {e:.3e}"
+
+
+def _randn(*shape, scale=1.0, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    return (torch.randn(*shape, generator=g) * scale).bfloat16().to(DEV)
+
+
+@pytest.mark.parametrize("B,H,Sq,Skv,hd,causal", [
+    (2, 2, 128, 128, 128, True), (1, 4, 200, 200, 128, True), (2, 4, 257, 257, 64, False), (2, 2, 64, 320, 64, False),
+    (2, 2, 48, 304, 64, False), (1, 2, 32, 288, 64, False), (1, 2, 100, 100, 64, True),
+])
+def test_attention_bwd(B, H, Sq, Skv, hd, causal):
+    from lhrs_bot_b200 import ops
+    q, k, v = _randn(B, Sq, H, hd, seed=1), _randn(B, Skv, H, hd, seed=2), _randn(B, Skv, H, hd, seed=3)
+    d_o = _randn(B, Sq, H, hd, seed=4)
+    mask = None
+    if causal and B > 1:
+        mask = torch.ones(B, Skv, dtype=torch.uint8, device=DEV)
+        mask[1, Skv - 20:] = 0
+    o, lse = ops.attention(q, k, v, causal=causal, key_mask=mask, return_lse=True)
+    dq, dk, dv = ops.attention_bwd(q, k, v, o, lse, d_o, causal=causal, key_mask=mask)
+    qf, kf, vf = (t.float().detach().requires_grad_(True) for t in (q, k, v))
+    sc = (qf.permute(0, 2, 1, 3) @ kf.permute(0, 2, 3, 1)) / math.sqrt(hd)
+    if causal:
+        i = torch.arange(Sq, device=DEV)[:, None]
+        j = torch.arange(Skv, device=DEV)[None, :]
+        sc = sc.masked_fill(j > i + (Skv - Sq), float("-inf"))
+    if mask is not None:
+        sc = sc.masked_fill(mask[:, None, None, :] == 0, float("-inf"))
+    ref = (torch.softmax(sc, -1) @ vf.permute(0, 2, 1, 3)).permute(0, 2, 1, 3)
+    go = d_o.float().clone()
+    if mask is not None:
+        go[1, Skv - 20:] = 0       # padded query rows carry no gradient in the model (labels -100, never attended)
+        d_o2 = go.bfloat16()
+        dq, dk, dv = ops.attention_bwd(q, k, v, o, lse, d_o2, causal=causal, key_mask=mask)
+    ref.backward(go)
+    _cmp("dq", dq, qf.grad)
+    _cmp("dk", dk, kf.grad)
+    _cmp("dv", dv, vf.grad)
+
+
+def test_norm_and_elementwise_bwd():
+    from lhrs_bot_b200 import ops
+    x, dy, dres = _randn(300, 1024, seed=5), _randn(300, 1024, seed=6), _randn(300, 1024, seed=7)
+    w = (1 + 0.1 * torch.randn(1024)).bfloat16().to(DEV)
+    b = (0.1 * torch.randn(1024)).bfloat16().to(DEV)
+    # RMSNorm
+    _, rstd = ops.rmsnorm(x, w, 1e-5, return_rstd=True)
+    dx = ops.rmsnorm_bwd(x, w, rstd, dy, dres)
+    xf = x.float().requires_grad_(True)
+    y = w.float() * (xf * torch.rsqrt(xf.pow(2).mean(-1, keepdim=True) + 1e-5))
+    y.backward(dy.float())
+    _cmp("rmsnorm dx(+res)", dx, xf.grad + dres.float())
+    # LayerNorm
+    _, mean, rs = ops.layernorm(x, w, b, 1e-5, return_stats=True)
+    dx, dw, db = ops.layernorm_bwd(x, w, mean, rs, dy)
+    xf = x.float().requires_grad_(True)
+    wf, bf = w.float().requires_grad_(True), b.float().requires_grad_(True)
+    torch.nn.functional.layer_norm(xf, (1024,), wf, bf, 1e-5).backward(dy.float())
+    _cmp("layernorm dx", dx, xf.grad)
+    _cmp("layernorm dw", dw, wf.grad, 5e-2)
+    _cmp("layernorm db", db, bf.grad, 5e-2)
+    _cmp("colsum", ops.colsum(dy), dy.float().sum(0), 5e-2)
+    # SwiGLU
+    g, u, da = _randn(64, 512, seed=8), _randn(64, 512, seed=9), _randn(64, 512, seed=10)
+    dgu = ops.swiglu_bwd(da, g, u)
+    gf, uf = g.float().requires_grad_(True), u.float().requires_grad_(True)
+    (torch.nn.functional.silu(gf) * uf).backward(da.float())
+    _cmp("swiglu dg", dgu[:, :512], gf.grad)
+    _cmp("swiglu du", dgu[:, 512:], uf.grad)
+    # GELU
+    pre, d = _randn(64, 512, seed=11), _randn(64, 512, seed=12)
+    pf = pre.float().requires_grad_(True)
+    torch.nn.functional.gelu(pf).backward(d.float())
+    _cmp("gelu", ops.gelu_bwd_(d.clone(), pre), pf.grad)
+
+
+def test_rope_bwd_and_kseg_gemm():
+    from lhrs_bot_b200 import ops
+    from oracle.llama import rope_cos_sin, rotate_half
+    M, S, D = 96, 48, 256
+    dqkv = _randn(M, 3 * D, seed=13)
+    cos, sin = rope_cos_sin(torch.arange(2048), 128)
+    cos_t, sin_t = cos[:, :64].contiguous().to(DEV), sin[:, :64].contiguous().to(DEV)
+    got = ops.rope_bwd_(dqkv.clone(), D, cos_t, sin_t, S)
+    x = torch.zeros(M, 3 * D, device=DEV, requires_grad=True)
+    pos = torch.arange(M, device=DEV) % S
+    c = cos.to(DEV)[pos][:, None, :]
+    s = sin.to(DEV)[pos][:, None, :]
+    xq = x[:, :2 * D].view(M, 2 * D // 128, 128)
+    y = torch.cat([(xq * c + rotate_half(xq) * s).reshape(M, 2 * D), x[:, 2 * D:]], 1)
+    y.backward(dqkv.float())
+    _cmp("rope bwd", got, x.grad)
+    # dX of a concatenated output in one contraction: [dq|dk|dv] · [Wq;Wk;Wv]
+    ws = [_randn(D, D, scale=1 / 16, seed=14 + i) for i in range(3)]
+    out = ops.gemm(dqkv, ws, b_mn_major=True, out_f32=True)
+    ref = sum(dqkv[:, i * D:(i + 1) * D].float() @ ws[i].float() for i in range(3))
+    assert rel_l2(out, ref) < 2e-3
+
+
+@pytest.fixture(scope="module")
+def small():
+    from oracle import unibind
+    cfg = small_config()
+    model = build_small_model(cfg, DEV, seed=0)
+    st = to_device(unibind.export_state(model), DEV)
+    return cfg, model, st
+
+
+def test_pooler_backward(small):
+    cfg, model, st = small
+    from oracle import pooler
+    ap = cfg.rgb_vision.attn_pooler
+    x = _randn(3, 768, cfg.rgb_vision.hidden_size, seed=20)
+    dout = _randn(3, 144, cfg.text.hidden_size, seed=21)
+    for p in model.rgb_pooler.parameters():
+        p.requires_grad_(True)
+        p.grad = None
+    xin = x.clone().requires_grad_(True)
+    out = model.rgb_pooler(xin)
+    out.backward(dout)
+    sd = {k: v.clone().requires_grad_(True) for k, v in st["pooler"].items()}
+    xr = x.float().requires_grad_(True)
+    pooler.attn_pooler_forward(xr, sd, ap.num_layers, ap.num_attn_heads).backward(dout.float())
+    _cmp("pooler d_image", xin.grad, xr.grad)
+    for name, p in model.rgb_pooler.named_parameters():
+        tol = 5e-2 if (p.dim() == 1 or "bias" in name) else 3e-2
+        _cmp(f"pooler {name}", p.grad, sd[name].grad, tol)
+
+
+def _oracle_loss_grads(cfg, st, batch, lora=False):
+    from oracle import unibind
+    sd = {k: {kk: vv.clone().requires_grad_(vv.is_floating_point()) for kk, vv in v.items()} for k, v in st.items()}
+    b32 = dict(batch)
+    b32["rgb"] = batch["rgb"].float()
+    loss = unibind.forward_loss(b32, sd, cfg)
+    loss.backward()
+    return loss, sd
+
+
+def test_unibind_backward_stage1(small):
+    """Stage-1 flags: pooler trainable, ViT + LLaMA frozen (BASELINE.json config 1/3)."""
+    cfg, model, st = small
+    model.prepare_for_training(freeze_vision=True, freeze_text=True, tune_rgb_pooler=True, model_path=None,
+                               tune_im_start=False, compute_dtype=torch.bfloat16)
+    assert all(not p.requires_grad for p in model.text.parameters()) and all(not p.requires_grad for p in model.rgb.parameters())
+    batch = synthetic_batch(4, 24, cfg.text.vocab_size, DEV, seed=22, text_only=(2,), ragged_mask=True)
+    for p in model.rgb_pooler.parameters():
+        p.grad = None
+    out = model(batch)
+    out["total_loss"].backward()
+    ref_loss, sd = _oracle_loss_grads(cfg, st, batch)
+    assert abs(out["total_loss"].item() - ref_loss.item()) <= 2e-2
+    for name, p in model.rgb_pooler.named_parameters():
+        tol = 6e-2 if (p.dim() == 1 or "bias" in name) else 4e-2
+        _cmp(f"stage1 pooler {name}", p.grad, sd["pooler"][name].grad, tol)
+    model.eval()
+
+
+def test_unibind_backward_lora():
+    """Stage-2 flags: pooler + LoRA (r=16) trainable."""
+    from oracle import unibind
+    cfg = small_config(lora=dict(enable=True, lora_r=16, lora_alpha=32, lora_dropout=0.0, lora_bias="none"), stage=2)
+    model = build_small_model(cfg, DEV, seed=5)
+    st = to_device(unibind.export_state(model), DEV)
+    model.prepare_for_training(freeze_vision=True, freeze_text=True, tune_rgb_pooler=True, model_path=None,
+                               tune_im_start=False, compute_dtype=torch.bfloat16)
+    for a, b in model.text.lora_pairs():
+        a.requires_grad_(True)
+        b.requires_grad_(True)
+    batch = synthetic_batch(3, 20, cfg.text.vocab_size, DEV, seed=23, text_only=(), ragged_mask=True)
+    out = model(batch)
+    out["total_loss"].backward()
+    ref_loss, sd = _oracle_loss_grads(cfg, st, batch)
+    assert abs(out["total_loss"].item() - ref_loss.item()) <= 2e-2
+    worst = 0.0
+    for name, p in model.text.text_encoder.named_parameters():
+        if "lora_" not in name:
+            assert p.grad is None
+            continue
+        key = name.replace(".default.", ".")
+        _cmp(f"lora {name}", p.grad, sd["llama"][key].grad, 5e-2)
+    _cmp("lora-run pooler query", model.rgb_pooler.query.grad, sd["pooler"]["query"].grad, 5e-2)
+
+
+def test_adamw_and_stepper(small):
+    from lhrs_bot_b200.training import FlatAdamW, SftStepper
+    torch.manual_seed(0)
+    ps = [torch.nn.Parameter(torch.randn(64, 32, device=DEV).bfloat16()), torch.nn.Parameter(torch.randn(128, device=DEV).bfloat16())]
+    ref = [p.detach().float().clone().requires_grad_(True) for p in ps]
+    opt = FlatAdamW(ps, lr=1e-2, betas=(0.9, 0.95), eps=1e-8, weight_decay=0.1, max_grad_norm=0.0)
+    ropt = torch.optim.AdamW([{"params": [ref[0]], "weight_decay": 0.1}, {"params": [ref[1]], "weight_decay": 0.0}], lr=1e-2,
+                             betas=(0.9, 0.95), eps=1e-8)
+    for it in range(5):
+        for p, r in zip(ps, ref):
+            g = torch.randn(p.shape, device=DEV).bfloat16()
+            opt.grad_views[p].copy_(g)
+            r.grad = g.float()
+        opt.step()
+        ropt.step()
+    for p, r, m in zip(ps, ref, (opt.master[:2048], opt.master[2048:])):
+        assert torch.allclose(m.view(r.shape), r.detach(), atol=1e-5, rtol=1e-5)
+        assert torch.equal(p.detach(), m.view(r.shape).bfloat16())
+    # a few optimisation steps on a fixed batch must reduce the loss
+    cfg = small_config()
+    model = build_small_model(cfg, DEV, seed=7)
+    stepper = SftStepper(model, world_size=1, lr=2e-3, max_grad_norm=1.0)
+    batch = synthetic_batch(4, 24, cfg.text.vocab_size, DEV, seed=24, text_only=(), ragged_mask=False)
+    losses = [stepper.step(batch).item() for _ in range(8)]
+    print("stepper losses", [round(l, 4) for l in losses])
+    assert losses[-1] < losses[0] - 0.05 and all(math.isfinite(l) for l in losses)
