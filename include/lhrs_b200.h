@@ -314,6 +314,28 @@ int lhrs_adamw_step(float* master, float* m, float* v, const void* grad, void* p
                     float lr, float beta1, float beta2, float eps, float weight_decay, int32_t step, const float* gnorm_sq,
                     float max_norm, float grad_scale, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Single-sequence decode (HF generate loop reached from TextModal.generate, lhrs/models/text_modal.py:600-612, with the
+ * generation-input rule of :36-60).  All buffers are caller-owned device memory (bf16 unless noted):
+ *   xbuf [dim] residual stream of the token being fed, qkv [3*dim], obuf [dim], act [ffn], logits fp32 [vocab],
+ *   part_val fp32 / part_idx int32 [>= 8*SMs] argmax partials, state int32[4] = {next token, ctx_len, tokens emitted, -},
+ *   tokens_out int32 [max_tokens].
+ * first_token: logits/argmax of the prefill's last (post-norm) hidden row; sets ctx_len and feeds the token's embedding.
+ * decode_step: one token through every layer (5 launches per layer), K/V appended to the paged cache at ctx_len.
+ * greedy=1 commits argmax on the device (no host sync per token); greedy=0 leaves the fp32 logits for a host-side sampler,
+ * which then calls lhrs_decode_commit_token(token, set_ctx): set_ctx = prompt length after first_token, -2 after a step.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct LhrsDecodeBuffers {
+    void* xbuf; void* qkv; void* obuf; void* act;
+    float* logits; float* part_val; int32_t* part_idx;
+    int32_t* state; int32_t* tokens_out; int32_t max_tokens;
+} LhrsDecodeBuffers;
+int lhrs_llama_first_token(const LhrsLlamaWeights* w, const void* hidden_last, int32_t ctx_len, const LhrsDecodeBuffers* b,
+                           int32_t greedy, void* stream);
+int lhrs_llama_decode_step(const LhrsLlamaWeights* w, const LhrsKvCache* kv, const LhrsDecodeBuffers* b, int32_t greedy,
+                           int32_t max_ctx, void* stream);
+int lhrs_decode_commit_token(const LhrsLlamaWeights* w, const LhrsDecodeBuffers* b, int32_t token, int32_t set_ctx, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

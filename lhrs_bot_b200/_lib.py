@@ -89,6 +89,14 @@ class LhrsKvCache(C.Structure):
     ]
 
 
+class LhrsDecodeBuffers(C.Structure):
+    _fields_ = [
+        ("xbuf", C.c_void_p), ("qkv", C.c_void_p), ("obuf", C.c_void_p), ("act", C.c_void_p),
+        ("logits", C.c_void_p), ("part_val", C.c_void_p), ("part_idx", C.c_void_p),
+        ("state", C.c_void_p), ("tokens_out", C.c_void_p), ("max_tokens", C.c_int32),
+    ]
+
+
 class LhrsLlamaWeights(C.Structure):
     _fields_ = [
         ("num_layers", C.c_int32), ("dim", C.c_int32), ("ffn", C.c_int32), ("heads", C.c_int32), ("vocab", C.c_int32),
@@ -133,6 +141,9 @@ SIGNATURES = {
     "lhrs_llama_stash_bytes": (C.c_size_t, [C.POINTER(LhrsLlamaWeights), _I32, _I32]),
     "lhrs_llama_fwd": (C.c_int, [C.POINTER(LhrsLlamaWeights), _P, _I32, _I32, _P, _P, _P, C.POINTER(LhrsKvCache), _P, C.c_size_t, _P]),
     "lhrs_lm_head": (C.c_int, [C.POINTER(LhrsLlamaWeights), _P, _I64, _P, _P]),
+    "lhrs_llama_first_token": (C.c_int, [C.POINTER(LhrsLlamaWeights), _P, _I32, C.POINTER(LhrsDecodeBuffers), _I32, _P]),
+    "lhrs_llama_decode_step": (C.c_int, [C.POINTER(LhrsLlamaWeights), C.POINTER(LhrsKvCache), C.POINTER(LhrsDecodeBuffers), _I32, _I32, _P]),
+    "lhrs_decode_commit_token": (C.c_int, [C.POINTER(LhrsLlamaWeights), C.POINTER(LhrsDecodeBuffers), _I32, _I32, _P]),
     "lhrs_attention_bwd": (C.c_int, [C.POINTER(LhrsAttentionBwd), _P]),
     "lhrs_rmsnorm_bwd": (C.c_int, [_P, _P, _P, _P, _P, _P, _I64, _I32, _P]),
     "lhrs_layernorm_bwd_scratch_bytes": (C.c_size_t, [_I32]),
