@@ -76,6 +76,15 @@ class FlatAdamW:
         return float(self._sumsq.sqrt().item())
 
 
+def allreduce_flat_gradients(flat_grad: torch.Tensor, world: int) -> float:
+    """The one collective of a training step: SUM the flat gradient buffer over the data-parallel ranks (NCCL over NVLink
+    on GPUs; gloo in the CPU tests) and return the 1/world factor the optimizer kernel folds into its update."""
+    if world > 1:
+        import torch.distributed as dist
+        dist.all_reduce(flat_grad, op=dist.ReduceOp.SUM)
+    return 1.0 / world
+
+
 def cosine_lr(step: int, base_lr: float, warmup: int, total: int, min_lr: float = 0.0) -> float:
     if step < warmup:
         return base_lr * (step + 1) / max(1, warmup)
@@ -115,10 +124,8 @@ class SftStepper:
         out = self.model(batch)
         loss = out["total_loss"]
         loss.backward()
-        if self.world > 1:
-            import torch.distributed as dist
-            dist.all_reduce(self.opt.flat_grad, op=dist.ReduceOp.SUM)     # the one collective of the step (NCCL over NVLink)
+        scale = allreduce_flat_gradients(self.opt.flat_grad, self.world)
         lr = cosine_lr(self.it, self.base_lr, self.warmup, self.total) if self.total > 0 else self.base_lr
-        self.opt.step(lr=lr, grad_scale=1.0 / self.world)
+        self.opt.step(lr=lr, grad_scale=scale)
         self.it += 1
         return loss.detach()

@@ -1,0 +1,137 @@
+"""Host-side logic that runs without a GPU: config surface, module construction / state-dict keys (drop-in with the reference's
+checkpoints), freezing rules, tokenizer_image_token, LR schedule, and the data-parallel flat-gradient exchange on gloo (world 2)."""
+import os
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from helpers import build_small_model, small_config
+
+
+def test_config_yaml_surface(tmp_path):
+    from lhrs_bot_b200.config import default_config, load_yaml
+    cfg = default_config()
+    assert cfg.rgb_vision.attn_pooler.num_query == 144 and cfg.text.hidden_size == 4096 and cfg.lora.lora_r == 128
+    p = tmp_path / "c.yaml"
+    p.write_text("stage: 2\nlora:\n  enable: True\n  lora_r: 16\ntext:\n  hidden_size: 4096\n")
+    y = load_yaml(str(p), stage=3)        # CLI-style override wins (config_parser.py:47-49)
+    assert y.stage == 3 and y.lora.enable is True and y["lora"]["lora_r"] == 16
+
+
+def test_state_dict_keys_match_reference_layout():
+    """Keys the reference's FINAL.pt / TextLoRA loaders expect."""
+    cfg = small_config()
+    m = build_small_model(cfg, "cpu")
+    keys = set(m.state_dict().keys())
+    for k in ["rgb.encoder.vision_model.embeddings.class_embedding", "rgb.encoder.vision_model.embeddings.patch_embedding.weight",
+              "rgb.encoder.vision_model.pre_layrnorm.weight", "rgb.encoder.vision_model.encoder.layers.0.self_attn.q_proj.bias",
+              "rgb.encoder.vision_model.encoder.layers.5.mlp.fc2.weight", "rgb.encoder.vision_model.post_layernorm.bias",
+              "rgb_pooler.query", "rgb_pooler.layers.0.ln_1_kv.weight", "rgb_pooler.layers.1.attn.in_proj_weight",
+              "rgb_pooler.layers.1.attn.out_proj.bias", "rgb_pooler.layers.0.mlp.c_fc.weight", "rgb_pooler.out_proj.weight",
+              "text.text_encoder.model.embed_tokens.weight", "text.text_encoder.model.layers.1.self_attn.o_proj.weight",
+              "text.text_encoder.model.layers.0.mlp.gate_proj.weight", "text.text_encoder.model.norm.weight",
+              "text.text_encoder.lm_head.weight"]:
+        assert k in keys, k
+    assert m.rgb_pooler.query.shape == (1, 144, cfg.rgb_vision.hidden_size)
+    assert m.rgb.extract_stage == [1, 3, 4]          # {L/3-1, 2L/3-1, L-2} for L=6 (rgb_vision_modal.py:159-164)
+    cfg2 = small_config(lora=dict(enable=True, lora_r=16, lora_alpha=32, lora_dropout=0.05, lora_bias="none"))
+    m2 = build_small_model(cfg2, "cpu")
+    k2 = set(m2.state_dict().keys())
+    assert "text.text_encoder.model.layers.0.self_attn.q_proj.base_layer.weight" in k2
+    assert "text.text_encoder.model.layers.0.mlp.down_proj.lora_A.default.weight" in k2
+    assert "text.text_encoder.lm_head.weight" in k2 and not any("lm_head.lora" in k for k in k2)
+    assert len(m2.text.lora_pairs()) == 7 * cfg2.text.num_hidden_layers
+
+
+def test_prepare_for_training_trainable_sets():
+    cfg = small_config()
+    m = build_small_model(cfg, "cpu")
+    m.prepare_for_training(freeze_vision=True, freeze_text=True, tune_rgb_pooler=True, model_path=None, tune_im_start=False,
+                           compute_dtype=torch.bfloat16)
+    assert all(p.requires_grad for p in m.rgb_pooler.parameters())
+    assert not any(p.requires_grad for p in m.rgb.parameters())
+    assert not any(p.requires_grad for p in m.text.parameters())      # the LLaMA body really is frozen (BASELINE.json stage 1)
+    m.prepare_for_training(freeze_vision=True, freeze_text=False, tune_rgb_pooler=False, model_path=None, tune_im_start=False,
+                           compute_dtype=torch.bfloat16)
+    assert not any(p.requires_grad for p in m.rgb_pooler.parameters())
+    te = m.text.get_text_encoder()
+    assert not te.get_input_embeddings().weight.requires_grad and not te.get_output_embeddings().weight.requires_grad
+    with pytest.raises(NotImplementedError):
+        m.prepare_for_training(compute_dtype=torch.float16)
+
+
+def test_checkpoint_roundtrip(tmp_path):
+    cfg = small_config(stage=2, lora=dict(enable=True, lora_r=16, lora_alpha=32, lora_dropout=0.0, lora_bias="none"))
+    m = build_small_model(cfg, "cpu", seed=1)
+    ck = m.custom_save_checkpoint(str(tmp_path / "FINAL.pt"))
+    assert set(ck) == {"rgb_ckpt", "other_ckpt"} and "rgb_pooler" in ck["other_ckpt"]
+    torch.save(ck, tmp_path / "FINAL.pt")
+    assert (tmp_path / "TextLoRA" / "adapter_model.bin").exists()
+    cfg3 = small_config(stage=3)
+    m3 = build_small_model(cfg3, "cpu", seed=2)
+    m3.custom_load_state_dict(str(tmp_path / "FINAL.pt"))
+    assert torch.equal(m3.rgb_pooler.query.float(), m.rgb_pooler.query.float())
+    a0, b0 = m.text.lora_pairs()[3]
+    a1, b1 = m3.text.lora_pairs()[3]
+    assert torch.equal(a0.float(), a1.float()) and torch.equal(b0.float(), b1.float())
+    assert a1.requires_grad                                           # stage > 2 loads the adapters trainable (UniBind.py:110)
+
+
+def test_tokenizer_image_token():
+    from lhrs_bot_b200.text_modal import tokenizer_image_token
+
+    class Tok:
+        bos_token_id = 1
+
+        def __call__(self, s):
+            class R:
+                pass
+            r = R()
+            r.input_ids = [1] + [10 + len(w) for w in s.split()]
+            return r
+    ids = tokenizer_image_token("a bb <image> ccc <image> d", Tok())
+    assert ids == [1, 11, 12, -200, 13, -200, 11]
+    t = tokenizer_image_token("<image> x", Tok(), return_tensors="pt")
+    assert t.tolist() == [1, -200, 11] and t.dtype == torch.long
+
+
+def test_cosine_lr():
+    from lhrs_bot_b200.training import cosine_lr
+    assert cosine_lr(0, 1.0, 10, 100) == pytest.approx(0.1)
+    assert cosine_lr(9, 1.0, 10, 100) == pytest.approx(1.0)
+    assert cosine_lr(55, 1.0, 10, 100) == pytest.approx(0.5, abs=1e-6)
+    assert cosine_lr(100, 1.0, 10, 100) == pytest.approx(0.0, abs=1e-9)
+
+
+def _dp_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from lhrs_bot_b200.training import allreduce_flat_gradients
+    torch.manual_seed(rank)
+    g = torch.randn(1000, dtype=torch.float32)
+    local = g.clone()
+    scale = allreduce_flat_gradients(g, world)
+    gathered = [torch.zeros_like(local) for _ in range(world)]
+    dist.all_gather(gathered, local)
+    expect = sum(gathered) * scale
+    ok = torch.allclose(g * scale, expect, atol=1e-6) and scale == pytest.approx(1.0 / world)
+    if rank == 0:
+        out.put(bool(ok))
+    dist.destroy_process_group()
+
+
+def test_flat_gradient_allreduce_world2_gloo():
+    """N>1 path: each rank contributes its local flat gradient; after the sum + 1/world scale every rank holds the mean,
+    i.e. the gradient of the concatenated batch."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_dp_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    assert q.get(timeout=10) is True
