@@ -43,7 +43,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=8)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="auto", choices=["auto", "sft_step", "prefill"])
+    ap.add_argument("--workload", default="auto", choices=["auto", "sft_step", "prefill", "decode"])
     ap.add_argument("--batch", type=int, default=PER_GPU_BATCH)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
@@ -216,6 +216,75 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+# ------------------------------------------------------------------------------------------------ decode workload
+def run_decode(args, dev, rank, world, local):
+    """BASELINE config 2: 1 image + 32-token prompt -> 128 greedy tokens (cli_qa.py path), one sequence per GPU (replicas)."""
+    from lhrs_bot_b200.build import build_model
+    from lhrs_bot_b200.config import default_config
+    from lhrs_bot_b200 import ops
+    import torch.distributed as dist
+    cfg = default_config(stage=0, local_rank=local, is_distribute=world > 1)
+    torch.manual_seed(322 + rank)
+    model = build_model(cfg).to(device=dev, dtype=torch.bfloat16).eval()
+    n_new, T = 128, 32
+    g = torch.Generator().manual_seed(rank)
+    ids = torch.randint(3, 32000, (1, T), generator=g)
+    ids[0, 0], ids[0, 5] = 1, -200
+    px_host = torch.randn(1, 3, 224, 224, generator=g).to(torch.bfloat16).pin_memory()
+    ids_host = ids.pin_memory()
+
+    def run(n):
+        px, idd = px_host.to(dev, non_blocking=True), ids_host.to(dev, non_blocking=True)
+        return model.generate(idd, images=px, do_sample=False, max_new_tokens=n, eos_token_id=None)
+
+    def timed(n, reps):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            out = run(n)
+            out.cpu()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / reps
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    for _ in range(max(args.warmup, 3)):
+        run(8)
+    l0 = ops.launch_count()
+    with ClockSampler(local) as clocks:
+        ms_full = timed(n_new, args.steps)
+    launches = ops.launch_count() - l0
+    ms_prefill = timed(1, args.steps)
+    ms_tok = (ms_full - ms_prefill) / (n_new - 1)
+    S = T + 143
+    bytes_tok = 2.0 * (32 * (4 * 4096 * 4096 + 3 * 4096 * 11008) + 32000 * 4096) + 2 * 32 * 4096 * 2 * (S + n_new / 2)
+    pk = peaks()
+    achieved = bytes_tok / (ms_tok * 1e-3) / 1e9
+    if rank == 0:
+        line = dict(metric="decode tokens/sec (LLaMA-7B, 224px, 1 image + 32-token prompt -> 128 greedy tokens), aggregate",
+                    value=world * 1e3 / ms_tok, unit="tokens/s", n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3),
+                    ms_per_step=ms_full, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="bf16", data="synthetic",
+                    config=dict(workload="greedy_decode_b1_prompt175_new128 (cli_qa.py path)", prefill_ms=ms_prefill, ms_per_token=ms_tok,
+                                parallelism=f"replicas{world}", inputs_vs_l2="13.5 GB of weights streamed per token >> 126 MB L2"),
+                    clocks=clocks.summary(),
+                    e2e=dict(value=world * n_new / (ms_full * 1e-3), unit="tokens/s (incl. image encode + prefill)",
+                             h2d_bytes_per_step=int(px_host.numel() * 2 + ids_host.numel() * 8), d2h_bytes_per_step=n_new * 8),
+                    gpu_launches=int(launches),
+                    roofline=dict(bound="hbm", achieved=achieved, peak=pk["hbm"], unit="GB/s", frac=achieved / pk["hbm"], traffic=None,
+                                  kernel="gemv_kernel chain (decode step)", peak_source=pk["which"]),
+                    cpu_baseline=None)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 # ------------------------------------------------------------------------------------------------ GPU arm
 def main():
     args = parse()
@@ -238,6 +307,8 @@ def main():
 
     lib = _lib.load()
     workload = args.workload
+    if workload == "decode":
+        return run_decode(args, dev, rank, world, local)
     if workload == "auto":
         workload = "sft_step" if training.AVAILABLE else "prefill"
     B = args.batch

@@ -88,6 +88,9 @@ typedef struct LhrsGemm {
     const void* B2[3];
     int64_t ldb2;
     int32_t ext_k;
+    /* MN-major B with num_b > 1 = segments stacked along K.  b_seg_nshift > 0 makes them block-diagonal: segment s is
+     * [K/num_b, b_seg_nshift] and contributes only to output columns [s*b_seg_nshift, (s+1)*b_seg_nshift). */
+    int32_t b_seg_nshift;
 } LhrsGemm;
 
 int lhrs_gemm_bf16(const LhrsGemm* g, void* stream);

@@ -152,6 +152,7 @@ class UniBind(nn.Module):
             return image_embedding.mean(dim=1)
         return image_embedding
 
+    @torch.no_grad()   # HF generate never tracks gradients; callers need not wrap (cli_qa.py:176 uses inference_mode anyway)
     def generate(self, input_ids: torch.Tensor, images: torch.Tensor = None, do_sample: bool = True,
                  temperature: float = 0.2, max_new_tokens: int = 1024, streamer=None, use_cache: bool = True,
                  stopping_criteria=None, **kwargs):

@@ -31,6 +31,7 @@ class LhrsGemm(C.Structure):
         ("rope_seq_len", C.c_int32),
         ("pre_gate", C.c_void_p), ("pre_up", C.c_void_p),
         ("A2", C.c_void_p), ("lda2", C.c_int64), ("B2", C.c_void_p * 3), ("ldb2", C.c_int64), ("ext_k", C.c_int32),
+        ("b_seg_nshift", C.c_int32),
     ]
 
 

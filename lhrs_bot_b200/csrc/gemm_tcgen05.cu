@@ -38,6 +38,7 @@ struct GemmArgs {
     __nv_bfloat16* pre_gate;
     __nv_bfloat16* pre_up;
     int kseg;    // MN-major B stacked along K: reduction length per segment (0 = single B)
+    int kseg_nshift;  // segment s lands in output columns [s*nshift, s*nshift + its width): block-diagonal B (LoRA dT)
     int ext_k;   // LoRA K-extension: columns of A2 per B segment (0 = none)
     int ext_kb;  // extra 64-wide k-blocks appended after the main K loop
 };
@@ -217,7 +218,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                         const CUtensorMap* tm = (seg == 0) ? &tmB0 : (seg == 1 ? &tmB1 : &tmB2);
 #pragma unroll
                         for (int a = 0; a < BN / 64; ++a)
-                            tma_load_2d(sb + a * 8192, tm, &full_bar[stage], n0 + a * 64, kk);
+                            tma_load_2d(sb + a * 8192, tm, &full_bar[stage], n0 + a * 64 - seg * args.kseg_nshift, kk);
                     }
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
@@ -543,7 +544,9 @@ extern "C" int lhrs_gemm_bf16(const LhrsGemm* g, void* stream_) {
         if (nseg > 1) kseg = g->K / nseg;
         for (int i = 0; i < 3; ++i) {
             if (i < nseg) {
-                rc = make_tmap(&tB[i], g->B[i], g->N, nseg > 1 ? kseg : g->K, g->ldb, 64, BK);
+                // block-diagonal mode: each segment is only b_seg_nshift columns wide (zero-filled elsewhere by TMA)
+                const uint64_t seg_n = (nseg > 1 && g->b_seg_nshift > 0) ? (uint64_t)g->b_seg_nshift : (uint64_t)g->N;
+                rc = make_tmap(&tB[i], g->B[i], seg_n, nseg > 1 ? kseg : g->K, g->ldb, 64, BK);
                 if (rc) return rc;
             } else {
                 tB[i] = tB[0];
@@ -591,6 +594,7 @@ extern "C" int lhrs_gemm_bf16(const LhrsGemm* g, void* stream_) {
     a.ext_k = ext_k; a.ext_kb = ext_kb;
     a.M = g->M; a.N = g->N; a.K = g->K;
     a.kseg = kseg;
+    a.kseg_nshift = (kseg > 0) ? g->b_seg_nshift : 0;
     a.num_b = (kseg > 0) ? 1 : g->num_b;   // K-stacked segments look like a single B to the epilogue
     a.seg_rows = (a.num_b > 1) ? g->seg_rows : g->N;
     a.act = g->act; a.alpha = g->alpha;

@@ -83,17 +83,66 @@ static int gemm_dw(cudaStream_t st, int out, int in, long long rows, const void*
     return lhrs_gemm_bf16(&g, st);
 }
 
+// diagonal blocks of a [n*out, n*r] product -> the n separate [out, r] gradient tensors
+__global__ void lora_extract_diag_kernel(const __nv_bfloat16* __restrict__ full, int n, int out_dim, int r,
+                                         __nv_bfloat16* g0, __nv_bfloat16* g1, __nv_bfloat16* g2) {
+    const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+    const long long per = static_cast<long long>(out_dim) * r;
+    if (i >= per * n) return;
+    const int p = i / per;
+    const long long e = i % per;
+    const int row = e / r, col = e % r;
+    __nv_bfloat16* dst = (p == 0) ? g0 : (p == 1 ? g1 : g2);
+    if (dst != nullptr) dst[e] = full[(static_cast<long long>(p) * out_dim + row) * (n * r) + p * r + col];
+}
+
 // LoRA backward for `nproj` projections that share the input x:  y_p += s * (x A_p^T) B_p^T
 //   dB_p = dy_p^T T_p,  dT_p = dy_p B_p,  dA_p = s * dT_p^T x,  dx += s * dT_p A_p        (T_p = s * x A_p^T recomputed)
+// When the A factors (and their gradient destinations) are contiguous and the dy_p are column blocks of one matrix,
+// every step is ONE GEMM over all projections (5 launches instead of 5*nproj, each big operand read once).
 static int lora_bwd(cudaStream_t st, const LhrsLlamaWeights* w, void* const* ga, void* const* gb, int layer, int first, int nproj,
                     const void* x, long long ldx, int in_dim, const void* const* dy, long long ldy, int out_dim, long long M,
-                    void* dx, long long lddx, __nv_bfloat16* t_buf, __nv_bfloat16* dt_buf) {
+                    void* dx, long long lddx, __nv_bfloat16* t_buf, __nv_bfloat16* dt_buf, __nv_bfloat16* diag_buf) {
     if (w->lora_r <= 0 || w->lora_a == nullptr) return LHRS_OK;
     const int r = w->lora_r;
     const long long ldt = (long long)nproj * r;
+    const int idx0 = layer * 7 + first;
     int rc;
+    bool grouped = lora_a_adjacent(w->lora_a, idx0, nproj, (long long)r * in_dim) &&
+                   (ga == nullptr || lora_a_adjacent(ga, idx0, nproj, (long long)r * in_dim));
+    for (int p = 1; p < nproj && grouped; ++p)
+        grouped = reinterpret_cast<const __nv_bfloat16*>(dy[p]) == reinterpret_cast<const __nv_bfloat16*>(dy[0]) + (long long)p * out_dim;
+    if (grouped && nproj * out_dim == ldy) {
+        {   // T = s * x [A_0;A_1;..]^T
+            LhrsGemm g = gemm_desc(M, nproj * r, in_dim, x, ldx, w->lora_a[idx0], in_dim, t_buf, ldt);
+            g.alpha = w->lora_scale;
+            if ((rc = lhrs_gemm_bf16(&g, st))) return rc;
+        }
+        if (gb != nullptr) {   // [dy_0|dy_1|..]^T T -> diagonal blocks are the dB_p
+            if (nproj == 1) {
+                if (gb[idx0]) if ((rc = gemm_dw(st, out_dim, r, M, dy[0], ldy, t_buf, ldt, gb[idx0], r))) return rc;
+            } else {
+                if ((rc = gemm_dw(st, nproj * out_dim, nproj * r, M, dy[0], ldy, t_buf, ldt, diag_buf, ldt))) return rc;
+                const long long total = (long long)nproj * out_dim * r;
+                lora_extract_diag_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(
+                    diag_buf, nproj, out_dim, r, (__nv_bfloat16*)gb[idx0], (__nv_bfloat16*)gb[idx0 + 1],
+                    nproj > 2 ? (__nv_bfloat16*)gb[idx0 + 2] : nullptr);
+                LHRS_LAUNCH_CHECK("lora_extract_diag_kernel");
+            }
+        }
+        {   // dT = [dy_0|dy_1|..] · blockdiag(B_0, B_1, ..): K-stacked block-diagonal segments
+            LhrsGemm g = gemm_desc(M, nproj * r, nproj * out_dim, dy[0], ldy, w->lora_b[idx0], r, dt_buf, ldt);
+            g.b_mn_major = 1; g.num_b = nproj;
+            for (int p = 1; p < nproj; ++p) g.B[p] = w->lora_b[idx0 + p];
+            if (nproj > 1) g.b_seg_nshift = r;
+            if ((rc = lhrs_gemm_bf16(&g, st))) return rc;
+        }
+        if (ga != nullptr && ga[idx0]) if ((rc = gemm_dw(st, nproj * r, in_dim, M, dt_buf, ldt, x, ldx, ga[idx0], in_dim, w->lora_scale))) return rc;
+        if (dx) if ((rc = gemm_dx(st, M, in_dim, nproj * r, dt_buf, ldt, w->lora_a[idx0], in_dim, dx, lddx, dx, w->lora_scale))) return rc;
+        return LHRS_OK;
+    }
     for (int p = 0; p < nproj; ++p) {
-        const int idx = layer * 7 + first + p;
+        const int idx = idx0 + p;
         const void* A = w->lora_a[idx];
         const void* Bm = w->lora_b[idx];
         {   // T_p = s * x A_p^T
@@ -116,7 +165,7 @@ typedef __nv_bfloat16 bf16;
 
 // ================================================================================================ LLaMA backward
 namespace {
-struct LlamaBwdBufs { bf16 *dxa, *dxb, *dh, *d_act, *d_gu, *dqkv, *d_o, *h, *t, *dt; float* delta; };
+struct LlamaBwdBufs { bf16 *dxa, *dxb, *dh, *d_act, *d_gu, *dqkv, *d_o, *h, *t, *dt, *diag; float* delta; };
 LlamaBwdBufs llama_bwd_plan(Arena& a, const LhrsLlamaWeights* w, long long M) {
     LlamaBwdBufs b;
     const int D = w->dim, F = w->ffn;
@@ -128,6 +177,8 @@ LlamaBwdBufs llama_bwd_plan(Arena& a, const LhrsLlamaWeights* w, long long M) {
     b.h = lora ? a.take<bf16>(M * D) : nullptr;
     b.t = lora ? a.take<bf16>(M * 3 * w->lora_r) : nullptr;
     b.dt = lora ? a.take<bf16>(M * 3 * w->lora_r) : nullptr;
+    const long long widest = (3LL * w->dim > 2LL * w->ffn) ? 3LL * w->dim : 2LL * w->ffn;
+    b.diag = lora ? a.take<bf16>(widest * 3 * w->lora_r) : nullptr;
     return b;
 }
 }  // namespace
@@ -165,7 +216,7 @@ extern "C" int lhrs_llama_bwd(const LhrsLlamaWeights* w, void* const* lora_a_gra
         if ((rc = gemm_dx(st, M, F, D, dx, D, w->down_w[l], F, b.d_act, F))) return rc;
         {
             const void* dy[1] = {dx};
-            if ((rc = lora_bwd(st, w, lora_a_grads, lora_b_grads, l, 6, 1, t.act, F, F, dy, D, D, M, b.d_act, F, b.t, b.dt))) return rc;
+            if ((rc = lora_bwd(st, w, lora_a_grads, lora_b_grads, l, 6, 1, t.act, F, F, dy, D, D, M, b.d_act, F, b.t, b.dt, b.diag))) return rc;
         }
         if ((rc = lhrs_swiglu_bwd(b.d_act, t.pre_gate, t.pre_up, b.d_gu, M, F, st))) return rc;
         {
@@ -176,7 +227,7 @@ extern "C" int lhrs_llama_bwd(const LhrsLlamaWeights* w, void* const* lora_a_gra
         if (w->lora_r > 0) {
             if ((rc = lhrs_rmsnorm_fwd(t.x_mid, w->ln2_w[l], b.h, nullptr, M, D, w->eps, st))) return rc;
             const void* dy[2] = {b.d_gu, b.d_gu + F};
-            if ((rc = lora_bwd(st, w, lora_a_grads, lora_b_grads, l, 4, 2, b.h, D, D, dy, 2 * F, F, M, b.dh, D, b.t, b.dt))) return rc;
+            if ((rc = lora_bwd(st, w, lora_a_grads, lora_b_grads, l, 4, 2, b.h, D, D, dy, 2 * F, F, M, b.dh, D, b.t, b.dt, b.diag))) return rc;
         }
         if ((rc = lhrs_rmsnorm_bwd(t.x_mid, w->ln2_w[l], t.rstd2, b.dh, dx, dx_other, M, D, st))) return rc;
         { bf16* tmp = dx; dx = dx_other; dx_other = tmp; }   // dx = grad wrt x_mid
@@ -184,7 +235,7 @@ extern "C" int lhrs_llama_bwd(const LhrsLlamaWeights* w, void* const* lora_a_gra
         if ((rc = gemm_dx(st, M, D, D, dx, D, w->o_w[l], D, b.d_o, D))) return rc;
         {
             const void* dy[1] = {dx};
-            if ((rc = lora_bwd(st, w, lora_a_grads, lora_b_grads, l, 3, 1, t.o, D, D, dy, D, D, M, b.d_o, D, b.t, b.dt))) return rc;
+            if ((rc = lora_bwd(st, w, lora_a_grads, lora_b_grads, l, 3, 1, t.o, D, D, dy, D, D, M, b.d_o, D, b.t, b.dt, b.diag))) return rc;
         }
         {
             LhrsAttentionBwd ab;
@@ -206,7 +257,7 @@ extern "C" int lhrs_llama_bwd(const LhrsLlamaWeights* w, void* const* lora_a_gra
         if (w->lora_r > 0) {
             if ((rc = lhrs_rmsnorm_fwd(t.x_in, w->ln1_w[l], b.h, nullptr, M, D, w->eps, st))) return rc;
             const void* dy[3] = {b.dqkv, b.dqkv + D, b.dqkv + 2 * D};
-            if ((rc = lora_bwd(st, w, lora_a_grads, lora_b_grads, l, 0, 3, b.h, D, D, dy, 3 * D, D, M, b.dh, D, b.t, b.dt))) return rc;
+            if ((rc = lora_bwd(st, w, lora_a_grads, lora_b_grads, l, 0, 3, b.h, D, D, dy, 3 * D, D, M, b.dh, D, b.t, b.dt, b.diag))) return rc;
         }
         bf16* dst = (l == 0) ? reinterpret_cast<bf16*>(d_inputs_embeds) : dx_other;
         if ((rc = lhrs_rmsnorm_bwd(t.x_in, w->ln1_w[l], t.rstd1, b.dh, dx, dst, M, D, st))) return rc;

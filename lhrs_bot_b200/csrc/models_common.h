@@ -156,4 +156,6 @@ __host__ __device__ inline __nv_bfloat16* kv_ptr(const KvGeom& kv, int layer, in
 int lora_attach(LhrsGemm& g, const LhrsLlamaWeights* w, int layer, int first_proj, int nproj, const void* x, long long ldx,
                 long long M, __nv_bfloat16* t_buf, void* stream);
 
+bool lora_a_adjacent(const void* const* arr, int idx, int nproj, long long elems_each);
+
 }  // namespace lhrs

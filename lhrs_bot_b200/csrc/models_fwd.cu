@@ -70,18 +70,36 @@ kv_write_kernel(const __nv_bfloat16* __restrict__ qkv, long long ldq, int dim, i
     }
 }
 
+// true when the nproj LoRA-A factors starting at idx are laid out back to back ([nproj*r, in] contiguous) — the flat
+// parameter buffer of training.SftStepper orders them that way so that the side GEMMs batch over projections
+bool lora_a_adjacent(const void* const* arr, int idx, int nproj, long long elems_each) {
+    if (arr == nullptr) return false;
+    for (int p = 0; p < nproj; ++p) {
+        if (arr[idx + p] == nullptr) return false;
+        if (reinterpret_cast<const __nv_bfloat16*>(arr[idx + p]) != reinterpret_cast<const __nv_bfloat16*>(arr[idx]) + p * elems_each) return false;
+    }
+    return true;
+}
+
 int lora_attach(LhrsGemm& g, const LhrsLlamaWeights* w, int layer, int first_proj, int nproj, const void* x, long long ldx,
                 long long M, __nv_bfloat16* t_buf, void* stream) {
     if (w->lora_r <= 0 || w->lora_a == nullptr || w->lora_b == nullptr) return LHRS_OK;
     const int r = w->lora_r;
-    for (int p = 0; p < nproj; ++p) {
-        // T_p = (alpha/r) * x · A_p^T   (skinny, HBM-bound: one pass over x)
-        LhrsGemm t = gemm_desc(M, r, g.K, x, ldx, w->lora_a[layer * 7 + first_proj + p], g.K, t_buf + p * r, (long long)nproj * r);
+    const int idx = layer * 7 + first_proj;
+    int rc;
+    if (lora_a_adjacent(w->lora_a, idx, nproj, (long long)r * g.K)) {
+        // T = (alpha/r) * x · [A_0; A_1; ..]^T in ONE skinny GEMM (one pass over x)
+        LhrsGemm t = gemm_desc(M, nproj * r, g.K, x, ldx, w->lora_a[idx], g.K, t_buf, (long long)nproj * r);
         t.alpha = w->lora_scale;
-        int rc = lhrs_gemm_bf16(&t, stream);
-        if (rc) return rc;
-        g.B2[p] = w->lora_b[layer * 7 + first_proj + p];
+        if ((rc = lhrs_gemm_bf16(&t, stream))) return rc;
+    } else {
+        for (int p = 0; p < nproj; ++p) {
+            LhrsGemm t = gemm_desc(M, r, g.K, x, ldx, w->lora_a[idx + p], g.K, t_buf + p * r, (long long)nproj * r);
+            t.alpha = w->lora_scale;
+            if ((rc = lhrs_gemm_bf16(&t, stream))) return rc;
+        }
     }
+    for (int p = 0; p < nproj; ++p) g.B2[p] = w->lora_b[idx + p];
     g.A2 = t_buf; g.lda2 = (long long)nproj * r; g.ldb2 = r; g.ext_k = r;
     return LHRS_OK;
 }

@@ -112,7 +112,13 @@ class SftStepper:
                 for a, b in model.text.lora_pairs():
                     a.requires_grad_(True)
                     b.requires_grad_(True)
-        params = trainable_parameters(model)
+        # Flat layout: pooler, then every LoRA A factor in [layer][q,k,v,o,gate,up,down] order, then the B factors.  Keeping
+        # A_q/A_k/A_v (and A_gate/A_up) back to back makes [A_q;A_k;A_v] one contiguous [3r, in] matrix, which lets the
+        # library batch the LoRA side GEMMs of projections that share an input (lora_a_adjacent in csrc/models_fwd.cu).
+        pairs = model.text.lora_pairs()
+        ordered = [a for a, _ in pairs if a.requires_grad] + [b for _, b in pairs if b.requires_grad]
+        seen = {id(p) for p in ordered}
+        params = [p for p in trainable_parameters(model) if id(p) not in seen] + ordered
         self.opt = FlatAdamW(params, lr=lr, weight_decay=weight_decay, max_grad_norm=max_grad_norm)
         # the backward kernels write into the flat gradient buffer directly
         model.rgb_pooler._grad_sink = {p: g for p, g in self.opt.grad_views.items()}

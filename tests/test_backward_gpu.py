@@ -230,3 +230,26 @@ def test_adamw_and_stepper(small):
     losses = [stepper.step(batch).item() for _ in range(8)]
     print("stepper losses", [round(l, 4) for l in losses])
     assert losses[-1] < losses[0] - 0.05 and all(math.isfinite(l) for l in losses)
+
+
+def test_unibind_backward_lora_grouped_flat_layout():
+    """Same as above but with the SftStepper's flat parameter layout, which makes A_q/A_k/A_v (and A_gate/A_up) contiguous
+    and switches the library to the batched LoRA side-GEMM path (one GEMM per step over all projections of a group)."""
+    from oracle import unibind
+    from lhrs_bot_b200.training import SftStepper
+    cfg = small_config(lora=dict(enable=True, lora_r=16, lora_alpha=32, lora_dropout=0.0, lora_bias="none"), stage=2)
+    model = build_small_model(cfg, DEV, seed=5)
+    stepper = SftStepper(model, world_size=1, lr=1e-3)
+    a_q, _ = model.text.lora_pairs()[0]
+    a_k, _ = model.text.lora_pairs()[1]
+    assert a_k.data_ptr() == a_q.data_ptr() + a_q.numel() * 2, "flat layout must keep A_q and A_k back to back"
+    st = to_device(unibind.export_state(model), DEV)
+    batch = synthetic_batch(3, 20, cfg.text.vocab_size, DEV, seed=23, text_only=(), ragged_mask=True)
+    out = model(batch)
+    out["total_loss"].backward()
+    ref_loss, sd = _oracle_loss_grads(cfg, st, batch)
+    assert abs(out["total_loss"].item() - ref_loss.item()) <= 2e-2
+    for name, p in model.text.text_encoder.named_parameters():
+        if "lora_" in name and ("layers.0." in name or "layers.1.mlp" in name):
+            _cmp(f"grouped {name}", stepper.opt.grad_views[p], sd["llama"][name.replace(".default.", ".")].grad, 5e-2)
+    _cmp("grouped pooler out_proj.weight", stepper.opt.grad_views[model.rgb_pooler.out_proj.weight], sd["pooler"]["out_proj.weight"].grad, 5e-2)
