@@ -10,6 +10,8 @@
 // Every nn.Linear of the LHRS-Bot hot path goes through here (see include/lhrs_b200.h for the map to
 // the reference call sites); the K-major/MN-major operand switches give the dX and dW backward forms.
 #include <cuda.h>
+#include <stdlib.h>
+#include <string.h>
 
 #include "host_common.h"
 #include "ptx.cuh"
@@ -43,11 +45,15 @@ struct GemmArgs {
     int ext_kb;  // extra 64-wide k-blocks appended after the main K loop
 };
 
-template <int BN>
+// CG = 1: one CTA per 128 x BN tile.  CG = 2: a CTA pair (cluster of 2, tcgen05 cta_group::2) owns a 256 x BN tile; each CTA
+// stages its own 128 rows of A and HALF of B (BN/2 rows), the pair's single MMA reads both halves, which cuts the operand
+// traffic per flop (L2 -> SM and smem writes) by a third.
+template <int BN, int CG = 1>
 struct GemmCfg {
-    static constexpr int STAGES = (BN == 256) ? 4 : 6;
+    static constexpr int BN_CTA = BN / CG;   // B rows staged by one CTA
+    static constexpr int STAGES = (BN_CTA == 256) ? 4 : 6;
     static constexpr uint32_t A_BYTES = BM * BK * 2;
-    static constexpr uint32_t B_BYTES = BN * BK * 2;
+    static constexpr uint32_t B_BYTES = BN_CTA * BK * 2;
     static constexpr uint32_t TMEM_COLS = 2 * BN;
     static constexpr uint32_t SMEM_BYTES = STAGES * (A_BYTES + B_BYTES) + 256 /*barriers*/ + 1024 /*align slack*/;
 };
@@ -100,15 +106,17 @@ __device__ __forceinline__ void tile_coords(int tile, int num_m, int num_n, int&
     n_blk = r / gm;
 }
 
-template <int BN, int KIND, bool A_MN, bool B_MN>
+template <int BN, int KIND, bool A_MN, bool B_MN, int CG>
 __global__ void __launch_bounds__(256, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB0,
                  const __grid_constant__ CUtensorMap tmB1, const __grid_constant__ CUtensorMap tmB2,
                  const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmE0,
                  const __grid_constant__ CUtensorMap tmE1, const __grid_constant__ CUtensorMap tmE2,
                  const GemmArgs args) {
-    using Cfg = GemmCfg<BN>;
+    using Cfg = GemmCfg<BN, CG>;
     constexpr int STAGES = Cfg::STAGES;
+    constexpr int BN_CTA = Cfg::BN_CTA;
+    const uint32_t rank = (CG == 2) ? cluster_ctarank() : 0u;   // 0 = leader of the pair (issues the MMAs)
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* smem_a = smem;
@@ -123,7 +131,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
 
-    const int num_m = (args.M + BM - 1) / BM;
+    const int num_m = (args.M + BM * CG - 1) / (BM * CG);   // row-blocks of 128*CG (one per CTA or per CTA pair)
     const int num_n = (args.N + BN - 1) / BN;
     const int num_tiles = num_m * num_n;
     const int num_kb_main = (args.K + BK - 1) / BK;
@@ -137,21 +145,22 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < STAGES; ++s) {
-            mbar_init(&full_bar[s], 1);
+            mbar_init(&full_bar[s], CG);      // pair: both CTAs' producers arrive on the leader's barrier
             mbar_init(&empty_bar[s], 1);
         }
         for (int s = 0; s < 2; ++s) {
             mbar_init(&tmem_full_bar[s], 1);
-            mbar_init(&tmem_empty_bar[s], 128);
+            mbar_init(&tmem_empty_bar[s], 128 * CG);   // pair: both CTAs' epilogue threads arrive on the leader's barrier
         }
         fence_barrier_init();
     }
+    if constexpr (CG == 2) cluster_sync_all();   // peer barriers must exist before anything targets them
     if (warp == 2) {
-        tmem_alloc(tmem_ptr_smem, Cfg::TMEM_COLS);
-        tmem_relinquish();
+        if constexpr (CG == 2) { tmem_alloc_2sm(tmem_ptr_smem, Cfg::TMEM_COLS); tmem_relinquish_2sm(); }
+        else { tmem_alloc(tmem_ptr_smem, Cfg::TMEM_COLS); tmem_relinquish(); }
     }
     tc_fence_before();
-    __syncthreads();
+    if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr_smem;
 
@@ -160,14 +169,25 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            for (int tile = blockIdx.x / CG; tile < num_tiles; tile += gridDim.x / CG) {
                 int m_blk, n_blk;
                 tile_coords(tile, num_m, num_n, m_blk, n_blk);
-                const int m0 = m_blk * BM;
+                const int m0 = (m_blk * CG + static_cast<int>(rank)) * BM;
                 const int n0 = n_blk * BN;
+                const int nb0 = n0 + static_cast<int>(rank) * BN_CTA;   // first B row staged by this CTA
+                // TMA issue: plain for CG=1; for a pair the completion is signalled on the leader's full barrier
+                auto LD = [&](void* dst, const CUtensorMap* tm, int c0, int c1) {
+                    if constexpr (CG == 2) tma_load_2d_2sm(dst, tm, &full_bar[stage], c0, c1);
+                    else tma_load_2d(dst, tm, &full_bar[stage], c0, c1);
+                };
                 for (int kb = 0; kb < num_kb; ++kb) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
-                    mbar_arrive_expect_tx(&full_bar[stage], Cfg::A_BYTES + Cfg::B_BYTES);
+                    if constexpr (CG == 2) {
+                        if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * (Cfg::A_BYTES + Cfg::B_BYTES));
+                        else mbar_arrive_cluster(&full_bar[stage], 0);
+                    } else {
+                        mbar_arrive_expect_tx(&full_bar[stage], Cfg::A_BYTES + Cfg::B_BYTES);
+                    }
                     uint8_t* sa = smem_a + stage * Cfg::A_BYTES;
                     uint8_t* sb = smem_b + stage * Cfg::B_BYTES;
                     if (kb >= num_kb_main) {
@@ -177,38 +197,46 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                         const int e0 = (kb - num_kb_main) * BK;
                         if constexpr (KIND == LHRS_EPI_SWIGLU) {
                             const int h0 = n_blk * (BN / 2);
-                            tma_load_2d(sa, &tmA2, &full_bar[stage], e0, m0);  // T = [T_gate | T_up]
-                            tma_load_2d(sb, &tmE0, &full_bar[stage], e0, h0);
-                            tma_load_2d(sb + (BN / 2) * BK * 2, &tmE1, &full_bar[stage], e0 - args.ext_k, h0);
+                            LD(sa, &tmA2, e0, m0);  // T = [T_gate | T_up]
+                            if constexpr (CG == 2) {   // rank 0 stages the gate half, rank 1 the up half
+                                if (rank == 0) LD(sb, &tmE0, e0, h0); else LD(sb, &tmE1, e0 - args.ext_k, h0);
+                            } else {
+                                LD(sb, &tmE0, e0, h0);
+                                LD(sb + (BN / 2) * BK * 2, &tmE1, e0 - args.ext_k, h0);
+                            }
                         } else {
                             const int seg = (args.num_b > 1) ? (n0 / args.seg_rows) : 0;
-                            const int r0 = n0 - seg * args.seg_rows;
+                            const int r0 = nb0 - seg * args.seg_rows;
                             const CUtensorMap* tm = (seg == 0) ? &tmE0 : (seg == 1 ? &tmE1 : &tmE2);
-                            tma_load_2d(sa, &tmA2, &full_bar[stage], seg * args.ext_k + e0, m0);
-                            tma_load_2d(sb, tm, &full_bar[stage], e0, r0);
+                            LD(sa, &tmA2, seg * args.ext_k + e0, m0);
+                            LD(sb, tm, e0, r0);
                         }
                         if (++stage == STAGES) { stage = 0; phase ^= 1; }
                         continue;
                     }
                     const int k0 = kb * BK;
                     if constexpr (!A_MN) {
-                        tma_load_2d(sa, &tmA, &full_bar[stage], k0, m0);  // box {64 k, 128 m}
+                        LD(sa, &tmA, k0, m0);  // box {64 k, 128 m}
                     } else {
 #pragma unroll
                         for (int a = 0; a < BM / 64; ++a)  // box {64 m, 64 k} per 128B atom column
-                            tma_load_2d(sa + a * 8192, &tmA, &full_bar[stage], m0 + a * 64, k0);
+                            LD(sa + a * 8192, &tmA, m0 + a * 64, k0);
                     }
                     if constexpr (!B_MN) {
                         if constexpr (KIND == LHRS_EPI_SWIGLU) {
                             // tile = [BN/2 gate rows | BN/2 up rows] of the same hidden units
                             const int h0 = n_blk * (BN / 2);
-                            tma_load_2d(sb, &tmB0, &full_bar[stage], k0, h0);
-                            tma_load_2d(sb + (BN / 2) * BK * 2, &tmB1, &full_bar[stage], k0, h0);
+                            if constexpr (CG == 2) {   // rank 0 stages the gate rows, rank 1 the up rows
+                                LD(sb, rank == 0 ? &tmB0 : &tmB1, k0, h0);
+                            } else {
+                                LD(sb, &tmB0, k0, h0);
+                                LD(sb + (BN / 2) * BK * 2, &tmB1, k0, h0);
+                            }
                         } else {
                             const int seg = (args.num_b > 1) ? (n0 / args.seg_rows) : 0;
-                            const int r0 = n0 - seg * args.seg_rows;
+                            const int r0 = nb0 - seg * args.seg_rows;
                             const CUtensorMap* tm = (seg == 0) ? &tmB0 : (seg == 1 ? &tmB1 : &tmB2);
-                            tma_load_2d(sb, tm, &full_bar[stage], k0, r0);  // box {64 k, BN n}
+                            LD(sb, tm, k0, r0);  // box {64 k, BN_CTA n}
                         }
                     } else {
                         // MN-major B.  With kseg > 0 the B segments are stacked along K: the dX of a concatenated output,
@@ -217,21 +245,21 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                         const int kk = k0 - seg * args.kseg;
                         const CUtensorMap* tm = (seg == 0) ? &tmB0 : (seg == 1 ? &tmB1 : &tmB2);
 #pragma unroll
-                        for (int a = 0; a < BN / 64; ++a)
-                            tma_load_2d(sb + a * 8192, tm, &full_bar[stage], n0 + a * 64 - seg * args.kseg_nshift, kk);
+                        for (int a = 0; a < BN_CTA / 64; ++a)
+                            LD(sb + a * 8192, tm, nb0 + a * 64 - seg * args.kseg_nshift, kk);
                     }
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
             }
         }
     } else if (warp == 1) {
-        // ===================================================================== MMA issuer
-        if (lane == 0) {
-            constexpr uint32_t idesc = make_idesc_bf16(BM, BN, A_MN ? 1u : 0u, B_MN ? 1u : 0u);
+        // ===================================================================== MMA issuer (pair: the leader CTA only)
+        if (lane == 0 && rank == 0) {
+            constexpr uint32_t idesc = make_idesc_bf16(BM * CG, BN, A_MN ? 1u : 0u, B_MN ? 1u : 0u);
             int stage = 0;
             uint32_t phase = 0;
             int it = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+            for (int tile = blockIdx.x / CG; tile < num_tiles; tile += gridDim.x / CG, ++it) {
                 const int as = it & 1;
                 const uint32_t aphase = (it >> 1) & 1;
                 mbar_wait(&tmem_empty_bar[as], aphase ^ 1);
@@ -250,10 +278,14 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                                                  : make_smem_desc(a_base + k * 32, 0, 1024, UMMA_LAYOUT_SW128);
                         const uint64_t db = B_MN ? make_smem_desc(b_base + k * 2048, 8192, 1024, UMMA_LAYOUT_SW128)
                                                  : make_smem_desc(b_base + k * 32, 0, 1024, UMMA_LAYOUT_SW128);
-                        umma_bf16(tmem_d, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+                        if constexpr (CG == 2) umma_bf16_2sm(tmem_d, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+                        else umma_bf16(tmem_d, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
                     }
-                    umma_commit(&empty_bar[stage]);  // slot reusable once these MMAs have read it
-                    if (kb == num_kb - 1) umma_commit(&tmem_full_bar[as]);
+                    // slot reusable once these MMAs have read it (pair: released in both CTAs)
+                    if constexpr (CG == 2) umma_commit_2sm(&empty_bar[stage]); else umma_commit(&empty_bar[stage]);
+                    if (kb == num_kb - 1) {
+                        if constexpr (CG == 2) umma_commit_2sm(&tmem_full_bar[as]); else umma_commit(&tmem_full_bar[as]);
+                    }
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
             }
@@ -262,7 +294,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         // ===================================================================== epilogue (warps 4..7)
         const int q = warp - 4;  // == warp % 4: the TMEM lane quarter this warp may read
         int it = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+        for (int tile = blockIdx.x / CG; tile < num_tiles; tile += gridDim.x / CG, ++it) {
             int m_blk, n_blk;
             tile_coords(tile, num_m, num_n, m_blk, n_blk);
             const int as = it & 1;
@@ -270,7 +302,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             mbar_wait(&tmem_full_bar[as], aphase);
             tc_fence_after();
 
-            const int row = m_blk * BM + q * 32 + lane;
+            const int row = (m_blk * CG + static_cast<int>(rank)) * BM + q * 32 + lane;
             const bool row_ok = row < args.M;
             long long drow = row;
             if (row_ok && args.row_map != nullptr) drow = args.row_map[row];
@@ -414,15 +446,15 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 }
             }
             tc_fence_before();
-            mbar_arrive(&tmem_empty_bar[as]);
+            if constexpr (CG == 2) mbar_arrive_cluster(&tmem_empty_bar[as], 0); else mbar_arrive(&tmem_empty_bar[as]);
         }
     }
 
     tc_fence_before();
-    __syncthreads();
+    if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();
     if (warp == 2) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+        if constexpr (CG == 2) tmem_dealloc_2sm(tmem_base, Cfg::TMEM_COLS); else tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
     }
 }
 
@@ -466,24 +498,36 @@ static int make_tmap(CUtensorMap* out, const void* ptr, uint64_t inner, uint64_t
     return LHRS_OK;
 }
 
-template <int BN, int KIND, bool A_MN, bool B_MN>
+template <int BN, int KIND, bool A_MN, bool B_MN, int CG = 1>
 static int launch(const CUtensorMap& tA, const CUtensorMap (&tB)[3], const CUtensorMap& tA2, const CUtensorMap (&tE)[3],
                   const GemmArgs& a, cudaStream_t stream) {
-    using Cfg = GemmCfg<BN>;
-    auto kern = gemm_bf16_kernel<BN, KIND, A_MN, B_MN>;
+    using Cfg = GemmCfg<BN, CG>;
+    auto kern = gemm_bf16_kernel<BN, KIND, A_MN, B_MN, CG>;
     static bool attr_set = false;
     if (!attr_set) {
         LHRS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
         attr_set = true;
     }
-    const int num_tiles = ((a.M + BM - 1) / BM) * ((a.N + BN - 1) / BN);
-    const int grid = num_tiles < num_sms() ? num_tiles : num_sms();
+    const int num_tiles = ((a.M + BM * CG - 1) / (BM * CG)) * ((a.N + BN - 1) / BN);   // tiles per CTA (CG=1) or per CTA pair
+    const int max_units = num_sms() / CG;
+    const int grid = (num_tiles < max_units ? num_tiles : max_units) * CG;
     const bool prof = prof_on();
     if (prof) {
         const double kk = (double)a.K + (double)a.ext_k;  // algorithmic reduction length (LoRA rank, not its 64-padding)
         prof_begin(PROF_GEMM, 2.0 * a.M * (double)a.N * kk, 2.0 * ((double)a.M * a.K + (double)a.N * a.K + (double)a.M * a.N), stream);
     }
-    kern<<<grid, 256, Cfg::SMEM_BYTES, stream>>>(tA, tB[0], tB[1], tB[2], tA2, tE[0], tE[1], tE[2], a);
+    if constexpr (CG == 2) {
+        cudaLaunchConfig_t cfg;
+        memset(&cfg, 0, sizeof(cfg));
+        cfg.gridDim = dim3(grid); cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = Cfg::SMEM_BYTES; cfg.stream = stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        LHRS_CUDA(cudaLaunchKernelEx(&cfg, kern, tA, tB[0], tB[1], tB[2], tA2, tE[0], tE[1], tE[2], a));
+    } else {
+        kern<<<grid, 256, Cfg::SMEM_BYTES, stream>>>(tA, tB[0], tB[1], tB[2], tA2, tE[0], tE[1], tE[2], a);
+    }
     if (prof) prof_end(stream);
     LHRS_LAUNCH_CHECK("gemm_bf16_kernel");
     return LHRS_OK;
@@ -533,6 +577,16 @@ extern "C" int lhrs_gemm_bf16(const LhrsGemm* g, void* stream_) {
         LHRS_CHECK_ARG(false, "lhrs_gemm_bf16: unknown epilogue %d", kind);
     }
 
+    // CTA pairs (cta_group::2, 256 x 256 tiles) when the problem has at least one pair-tile per SM pair; LHRS_GEMM_CG=1/2 forces
+    int cg = 1;
+    {
+        static int forced = -1;
+        if (forced < 0) { const char* e = getenv("LHRS_GEMM_CG"); forced = e ? atoi(e) : 0; }
+        const long long pair_tiles = (long long)((g->M + 2 * BM - 1) / (2 * BM)) * ((g->N + 255) / 256);
+        if (bn == 256 && (g->N % 256) == 0 && pair_tiles >= num_sms() / 2) cg = 2;
+        if (forced == 1) cg = 1;
+        if (forced == 2 && bn == 256 && (g->N % 256) == 0) cg = 2;
+    }
     CUtensorMap tA, tB[3];
     int rc;
     if (!a_mn) rc = make_tmap(&tA, g->A, g->K, g->M, g->lda, BK, BM);
@@ -562,7 +616,7 @@ extern "C" int lhrs_gemm_bf16(const LhrsGemm* g, void* stream_) {
         const int rows = (g->num_b > 1) ? g->seg_rows : g->N;
         for (int i = 0; i < 3; ++i) {
             if (i < g->num_b) {
-                rc = make_tmap(&tB[i], g->B[i], g->K, rows, g->ldb, BK, bn);
+                rc = make_tmap(&tB[i], g->B[i], g->K, rows, g->ldb, BK, bn / cg);
                 if (rc) return rc;
             } else {
                 tB[i] = tB[0];
@@ -585,7 +639,7 @@ extern "C" int lhrs_gemm_bf16(const LhrsGemm* g, void* stream_) {
         const int rows = (g->num_b > 1) ? g->seg_rows : g->N;
         for (int i = 0; i < g->num_b; ++i) {
             LHRS_CHECK_ARG(g->B2[i] != nullptr && (reinterpret_cast<uintptr_t>(g->B2[i]) & 15) == 0, "lhrs_gemm_bf16: B2[%d] null/unaligned", i);
-            rc = make_tmap(&tE[i], g->B2[i], ext_k, rows, g->ldb2, BK, (kind == LHRS_EPI_SWIGLU) ? bn / 2 : bn);
+            rc = make_tmap(&tE[i], g->B2[i], ext_k, rows, g->ldb2, BK, (kind == LHRS_EPI_SWIGLU) ? bn / 2 : bn / cg);
             if (rc) return rc;
         }
     }
@@ -607,6 +661,14 @@ extern "C" int lhrs_gemm_bf16(const LhrsGemm* g, void* stream_) {
     a.pre_gate = reinterpret_cast<__nv_bfloat16*>(g->pre_gate);
     a.pre_up = reinterpret_cast<__nv_bfloat16*>(g->pre_up);
 
+    if (cg == 2) {
+        if (kind == LHRS_EPI_SWIGLU) return launch<256, LHRS_EPI_SWIGLU, false, false, 2>(tA, tB, tA2, tE, a, stream);
+        if (kind == LHRS_EPI_ROPE) return launch<256, LHRS_EPI_ROPE, false, false, 2>(tA, tB, tA2, tE, a, stream);
+        if (!a_mn && !b_mn) return launch<256, LHRS_EPI_LINEAR, false, false, 2>(tA, tB, tA2, tE, a, stream);
+        if (!a_mn && b_mn) return launch<256, LHRS_EPI_LINEAR, false, true, 2>(tA, tB, tA2, tE, a, stream);
+        if (a_mn && b_mn) return launch<256, LHRS_EPI_LINEAR, true, true, 2>(tA, tB, tA2, tE, a, stream);
+        return launch<256, LHRS_EPI_LINEAR, true, false, 2>(tA, tB, tA2, tE, a, stream);
+    }
     if (kind == LHRS_EPI_SWIGLU) return launch<256, LHRS_EPI_SWIGLU, false, false>(tA, tB, tA2, tE, a, stream);
     if (kind == LHRS_EPI_ROPE) return launch<256, LHRS_EPI_ROPE, false, false>(tA, tB, tA2, tE, a, stream);
     if (bn == 256) {

@@ -1,0 +1,53 @@
+"""Time the tcgen05 GEMM on the LLaMA-7B shapes of the hot path (CUDA events, inputs >> L2 rotated between calls)."""
+import math
+import os
+import sys
+import torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from lhrs_bot_b200 import ops
+
+M = int(os.environ.get("M", "8192"))
+dev = "cuda"
+D, F, V = 4096, 11008, 32000
+rope = None
+
+
+def bench(name, fn, flops, iters=20):
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / iters
+    print(f"{name:34s} {ms*1e3:9.1f} us  {flops/ms/1e9:8.1f} TFLOP/s", flush=True)
+
+
+x = torch.randn(M, D, device=dev).bfloat16()
+xf = torch.randn(M, F, device=dev).bfloat16()
+w = lambda n, k: (torch.randn(n, k, device=dev) / math.sqrt(k)).bfloat16()
+wq, wk, wv, wo = w(D, D), w(D, D), w(D, D), w(D, D)
+wg, wu, wd = w(F, D), w(F, D), w(D, F)
+res = torch.randn(M, D, device=dev).bfloat16()
+inv = 1.0 / (10000 ** (torch.arange(0, 128, 2).float() / 128))
+fr = torch.outer(torch.arange(2048).float(), inv)
+cos, sin = fr.cos().to(dev).contiguous(), fr.sin().to(dev).contiguous()
+out_qkv = torch.empty(M, 3 * D, device=dev, dtype=torch.bfloat16)
+out_d = torch.empty(M, D, device=dev, dtype=torch.bfloat16)
+out_f = torch.empty(M, F, device=dev, dtype=torch.bfloat16)
+dgu = torch.randn(M, 2 * F, device=dev).bfloat16()
+print(f"M={M} LHRS_GEMM_CG={os.environ.get('LHRS_GEMM_CG', 'auto')}")
+bench("qkv+rope  [M,4096]x[12288,4096]", lambda: ops.gemm(x, [wq, wk, wv], out=out_qkv, epilogue=ops.EPI_ROPE, rope=(cos, sin, None, 512)), 2 * M * 3 * D * D)
+bench("o_proj+res [M,4096]x[4096,4096]", lambda: ops.gemm(x, wo, out=out_d, residual=res), 2 * M * D * D)
+bench("gate/up swiglu [M,4096]x[22016,4096]", lambda: ops.gemm(x, [wg, wu], out=out_f, epilogue=ops.EPI_SWIGLU), 2 * M * 2 * F * D)
+bench("down+res [M,11008]x[4096,11008]", lambda: ops.gemm(xf, wd, out=out_d, residual=res), 2 * M * D * F)
+bench("dX down (MN-major B) N=11008 K=4096", lambda: ops.gemm(x, wd, out=out_f, b_mn_major=True), 2 * M * D * F)
+bench("dX gate/up K-seg N=4096 K=22016", lambda: ops.gemm(dgu, [wg, wu], out=out_d, b_mn_major=True), 2 * M * 2 * F * D)
+a8 = torch.randn(8192, 8192, device=dev).bfloat16()
+b8 = torch.randn(8192, 8192, device=dev).bfloat16()
+o8 = torch.empty(8192, 8192, device=dev, dtype=torch.bfloat16)
+bench("square 8192^3", lambda: ops.gemm(a8, b8, out=o8), 2 * 8192 ** 3)
+bench("torch.matmul 8192^3 (cuBLAS)", lambda: torch.matmul(a8, b8.t(), out=o8), 2 * 8192 ** 3)
