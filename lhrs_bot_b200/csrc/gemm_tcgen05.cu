@@ -204,6 +204,12 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                                 LD(sb, &tmE0, e0, h0);
                                 LD(sb + (BN / 2) * BK * 2, &tmE1, e0 - args.ext_k, h0);
                             }
+                        } else if constexpr (B_MN) {
+                            // dX form: A2 = dT [M, ext_k] (K-major), B2 = [ext_k, N] read MN-major in place (LoRA A stack);
+                            // rows of B2 beyond ext_k are zero-filled by TMA
+                            LD(sa, &tmA2, e0, m0);
+#pragma unroll
+                            for (int a = 0; a < BN_CTA / 64; ++a) LD(sb + a * 8192, &tmE0, nb0 + a * 64, e0);
                         } else {
                             const int seg = (args.num_b > 1) ? (n0 / args.seg_rows) : 0;
                             const int r0 = nb0 - seg * args.seg_rows;
@@ -517,8 +523,7 @@ static int launch(const CUtensorMap& tA, const CUtensorMap (&tB)[3], const CUten
         prof_begin(PROF_GEMM, 2.0 * a.M * (double)a.N * kk, 2.0 * ((double)a.M * a.K + (double)a.N * a.K + (double)a.M * a.N), stream);
     }
     if constexpr (CG == 2) {
-        cudaLaunchConfig_t cfg;
-        memset(&cfg, 0, sizeof(cfg));
+        cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3(grid); cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = Cfg::SMEM_BYTES; cfg.stream = stream;
         cudaLaunchAttribute attr[1];
         attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -627,13 +632,22 @@ extern "C" int lhrs_gemm_bf16(const LhrsGemm* g, void* stream_) {
     CUtensorMap tA2 = tA, tE[3] = {tB[0], tB[0], tB[0]};
     int ext_k = 0, ext_kb = 0;
     if (g->A2 != nullptr && g->ext_k > 0) {
-        LHRS_CHECK_ARG(!a_mn && !b_mn, "lhrs_gemm_bf16: the K-extension needs K-major operands");
+        LHRS_CHECK_ARG(!a_mn, "lhrs_gemm_bf16: the K-extension needs a K-major A operand");
         LHRS_CHECK_ARG((g->ext_k % 8) == 0 && (g->lda2 % 8) == 0 && (g->ldb2 % 8) == 0 &&
                            (reinterpret_cast<uintptr_t>(g->A2) & 15) == 0,
                        "lhrs_gemm_bf16: K-extension alignment (ext_k=%d lda2=%lld ldb2=%lld)", g->ext_k, (long long)g->lda2, (long long)g->ldb2);
         ext_k = g->ext_k;
         const int span = (kind == LHRS_EPI_SWIGLU) ? 2 * ext_k : ext_k;
         ext_kb = (span + BK - 1) / BK;
+        if (b_mn) {
+            // A2 [M, ext_k] K-major; B2[0] = [ext_k, ldb2 >= N] MN-major (one matrix, whatever the K-segmentation of B)
+            rc = make_tmap(&tA2, g->A2, (uint64_t)ext_k, g->M, g->lda2, BK, BM);
+            if (rc) return rc;
+            LHRS_CHECK_ARG(g->B2[0] != nullptr && (reinterpret_cast<uintptr_t>(g->B2[0]) & 15) == 0, "lhrs_gemm_bf16: B2[0] null/unaligned");
+            rc = make_tmap(&tE[0], g->B2[0], g->N, ext_k, g->ldb2, 64, BK);
+            if (rc) return rc;
+            tE[1] = tE[0]; tE[2] = tE[0];
+        } else {
         rc = make_tmap(&tA2, g->A2, (uint64_t)g->num_b * ext_k, g->M, g->lda2, BK, BM);
         if (rc) return rc;
         const int rows = (g->num_b > 1) ? g->seg_rows : g->N;
@@ -641,6 +655,7 @@ extern "C" int lhrs_gemm_bf16(const LhrsGemm* g, void* stream_) {
             LHRS_CHECK_ARG(g->B2[i] != nullptr && (reinterpret_cast<uintptr_t>(g->B2[i]) & 15) == 0, "lhrs_gemm_bf16: B2[%d] null/unaligned", i);
             rc = make_tmap(&tE[i], g->B2[i], ext_k, rows, g->ldb2, BK, (kind == LHRS_EPI_SWIGLU) ? bn / 2 : bn / cg);
             if (rc) return rc;
+        }
         }
     }
 

@@ -96,66 +96,83 @@ __global__ void lora_extract_diag_kernel(const __nv_bfloat16* __restrict__ full,
     if (dst != nullptr) dst[e] = full[(static_cast<long long>(p) * out_dim + row) * (n * r) + p * r + col];
 }
 
-// LoRA backward for `nproj` projections that share the input x:  y_p += s * (x A_p^T) B_p^T
-//   dB_p = dy_p^T T_p,  dT_p = dy_p B_p,  dA_p = s * dT_p^T x,  dx += s * dT_p A_p        (T_p = s * x A_p^T recomputed)
-// When the A factors (and their gradient destinations) are contiguous and the dy_p are column blocks of one matrix,
-// every step is ONE GEMM over all projections (5 launches instead of 5*nproj, each big operand read once).
-static int lora_bwd(cudaStream_t st, const LhrsLlamaWeights* w, void* const* ga, void* const* gb, int layer, int first, int nproj,
-                    const void* x, long long ldx, int in_dim, const void* const* dy, long long ldy, int out_dim, long long M,
-                    void* dx, long long lddx, __nv_bfloat16* t_buf, __nv_bfloat16* dt_buf, __nv_bfloat16* diag_buf) {
-    if (w->lora_r <= 0 || w->lora_a == nullptr) return LHRS_OK;
-    const int r = w->lora_r;
-    const long long ldt = (long long)nproj * r;
-    const int idx0 = layer * 7 + first;
+// LoRA backward for `nproj` projections that share the input x:  y_p += (s * x A_p^T) B_p^T = T_p B_p^T
+//   dT_p = s * dy_p B_p,   dx += dT_p A_p,   dA_p = dT_p^T x,   dB_p = dy_p^T T_p        (T kept from the forward pass)
+// Grouped path (A factors and their gradients contiguous, dy_p column blocks of one matrix): dT for all projections is ONE
+// block-diagonal K-segmented GEMM, `dx += dT A` rides on the main dX GEMM as a K-extension (no extra pass over dx), and
+// dA / dB are one TN GEMM each.  lora_bwd_pre runs before the main dX GEMM `g`, lora_bwd_post after it.
+struct LoraBwd {
+    bool active = false, grouped = false;
+    int idx0 = 0, nproj = 0, in_dim = 0, out_dim = 0;
+    const void* x = nullptr; long long ldx = 0;
+    const void* dy[3] = {nullptr, nullptr, nullptr}; long long ldy = 0;
+    const __nv_bfloat16* T = nullptr;   // [M, nproj*r] from the forward stash
+    __nv_bfloat16* dt = nullptr;        // [M, nproj*r]
+    long long M = 0;
+};
+
+static int lora_bwd_pre(cudaStream_t st, const LhrsLlamaWeights* w, void* const* ga, LoraBwd& L, LhrsGemm& g) {
+    if (!L.active) return LHRS_OK;
+    const int r = w->lora_r, n = L.nproj;
+    const long long ldt = (long long)n * r;
     int rc;
-    bool grouped = lora_a_adjacent(w->lora_a, idx0, nproj, (long long)r * in_dim) &&
-                   (ga == nullptr || lora_a_adjacent(ga, idx0, nproj, (long long)r * in_dim));
-    for (int p = 1; p < nproj && grouped; ++p)
-        grouped = reinterpret_cast<const __nv_bfloat16*>(dy[p]) == reinterpret_cast<const __nv_bfloat16*>(dy[0]) + (long long)p * out_dim;
-    if (grouped && nproj * out_dim == ldy) {
-        {   // T = s * x [A_0;A_1;..]^T
-            LhrsGemm g = gemm_desc(M, nproj * r, in_dim, x, ldx, w->lora_a[idx0], in_dim, t_buf, ldt);
-            g.alpha = w->lora_scale;
-            if ((rc = lhrs_gemm_bf16(&g, st))) return rc;
-        }
+    L.grouped = lora_a_adjacent(w->lora_a, L.idx0, n, (long long)r * L.in_dim) &&
+                (ga == nullptr || lora_a_adjacent(ga, L.idx0, n, (long long)r * L.in_dim)) && (long long)n * L.out_dim == L.ldy;
+    for (int p = 1; p < n && L.grouped; ++p)
+        L.grouped = reinterpret_cast<const __nv_bfloat16*>(L.dy[p]) == reinterpret_cast<const __nv_bfloat16*>(L.dy[0]) + (long long)p * L.out_dim;
+    if (!L.grouped) return LHRS_OK;
+    {   // dT = s * [dy_0|dy_1|..] · blockdiag(B_0, B_1, ..)
+        LhrsGemm d = gemm_desc(L.M, n * r, n * L.out_dim, L.dy[0], L.ldy, w->lora_b[L.idx0], r, L.dt, ldt);
+        d.b_mn_major = 1; d.num_b = n; d.alpha = w->lora_scale;
+        for (int p = 1; p < n; ++p) d.B[p] = w->lora_b[L.idx0 + p];
+        if (n > 1) d.b_seg_nshift = r;
+        if ((rc = lhrs_gemm_bf16(&d, st))) return rc;
+    }
+    // dx += dT · [A_0;A_1;..] accumulates in the main GEMM's TMEM tile
+    g.A2 = L.dt; g.lda2 = ldt; g.B2[0] = w->lora_a[L.idx0]; g.ldb2 = L.in_dim; g.ext_k = n * r;
+    return LHRS_OK;
+}
+
+static int lora_bwd_post(cudaStream_t st, const LhrsLlamaWeights* w, void* const* ga, void* const* gb, LoraBwd& L, void* dx,
+                         long long lddx, __nv_bfloat16* diag_buf) {
+    if (!L.active) return LHRS_OK;
+    const int r = w->lora_r, n = L.nproj;
+    const long long ldt = (long long)n * r;
+    int rc;
+    if (L.grouped) {
         if (gb != nullptr) {   // [dy_0|dy_1|..]^T T -> diagonal blocks are the dB_p
-            if (nproj == 1) {
-                if (gb[idx0]) if ((rc = gemm_dw(st, out_dim, r, M, dy[0], ldy, t_buf, ldt, gb[idx0], r))) return rc;
+            if (n == 1) {
+                if (gb[L.idx0]) if ((rc = gemm_dw(st, L.out_dim, r, L.M, L.dy[0], L.ldy, L.T, ldt, gb[L.idx0], r))) return rc;
             } else {
-                if ((rc = gemm_dw(st, nproj * out_dim, nproj * r, M, dy[0], ldy, t_buf, ldt, diag_buf, ldt))) return rc;
-                const long long total = (long long)nproj * out_dim * r;
+                if ((rc = gemm_dw(st, n * L.out_dim, n * r, L.M, L.dy[0], L.ldy, L.T, ldt, diag_buf, ldt))) return rc;
+                const long long total = (long long)n * L.out_dim * r;
                 lora_extract_diag_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(
-                    diag_buf, nproj, out_dim, r, (__nv_bfloat16*)gb[idx0], (__nv_bfloat16*)gb[idx0 + 1],
-                    nproj > 2 ? (__nv_bfloat16*)gb[idx0 + 2] : nullptr);
+                    diag_buf, n, L.out_dim, r, (__nv_bfloat16*)gb[L.idx0], (__nv_bfloat16*)gb[L.idx0 + 1],
+                    n > 2 ? (__nv_bfloat16*)gb[L.idx0 + 2] : nullptr);
                 LHRS_LAUNCH_CHECK("lora_extract_diag_kernel");
             }
         }
-        {   // dT = [dy_0|dy_1|..] · blockdiag(B_0, B_1, ..): K-stacked block-diagonal segments
-            LhrsGemm g = gemm_desc(M, nproj * r, nproj * out_dim, dy[0], ldy, w->lora_b[idx0], r, dt_buf, ldt);
-            g.b_mn_major = 1; g.num_b = nproj;
-            for (int p = 1; p < nproj; ++p) g.B[p] = w->lora_b[idx0 + p];
-            if (nproj > 1) g.b_seg_nshift = r;
-            if ((rc = lhrs_gemm_bf16(&g, st))) return rc;
-        }
-        if (ga != nullptr && ga[idx0]) if ((rc = gemm_dw(st, nproj * r, in_dim, M, dt_buf, ldt, x, ldx, ga[idx0], in_dim, w->lora_scale))) return rc;
-        if (dx) if ((rc = gemm_dx(st, M, in_dim, nproj * r, dt_buf, ldt, w->lora_a[idx0], in_dim, dx, lddx, dx, w->lora_scale))) return rc;
+        if (ga != nullptr && ga[L.idx0]) if ((rc = gemm_dw(st, n * r, L.in_dim, L.M, L.dt, ldt, L.x, L.ldx, ga[L.idx0], L.in_dim))) return rc;
         return LHRS_OK;
     }
-    for (int p = 0; p < nproj; ++p) {
-        const int idx = idx0 + p;
-        const void* A = w->lora_a[idx];
-        const void* Bm = w->lora_b[idx];
-        {   // T_p = s * x A_p^T
-            LhrsGemm g = gemm_desc(M, r, in_dim, x, ldx, A, in_dim, t_buf + p * r, ldt);
-            g.alpha = w->lora_scale;
-            if ((rc = lhrs_gemm_bf16(&g, st))) return rc;
-        }
-        if (gb && gb[idx]) if ((rc = gemm_dw(st, out_dim, r, M, dy[p], ldy, t_buf + p * r, ldt, gb[idx], r))) return rc;
-        if ((rc = gemm_dx(st, M, r, out_dim, dy[p], ldy, Bm, r, dt_buf + p * r, ldt))) return rc;
-        if (ga && ga[idx]) if ((rc = gemm_dw(st, r, in_dim, M, dt_buf + p * r, ldt, x, ldx, ga[idx], in_dim, w->lora_scale))) return rc;
-        if (dx) if ((rc = gemm_dx(st, M, in_dim, r, dt_buf + p * r, ldt, A, in_dim, dx, lddx, dx, w->lora_scale))) return rc;
+    for (int p = 0; p < n; ++p) {   // separate tensors: one projection at a time, dx accumulated in a read-modify-write pass
+        const int idx = L.idx0 + p;
+        if (gb && gb[idx]) if ((rc = gemm_dw(st, L.out_dim, r, L.M, L.dy[p], L.ldy, L.T + p * r, ldt, gb[idx], r))) return rc;
+        if ((rc = gemm_dx(st, L.M, r, L.out_dim, L.dy[p], L.ldy, w->lora_b[idx], r, L.dt + p * r, ldt, nullptr, w->lora_scale))) return rc;
+        if (ga && ga[idx]) if ((rc = gemm_dw(st, r, L.in_dim, L.M, L.dt + p * r, ldt, L.x, L.ldx, ga[idx], L.in_dim))) return rc;
+        if (dx) if ((rc = gemm_dx(st, L.M, L.in_dim, r, L.dt + p * r, ldt, w->lora_a[idx], L.in_dim, dx, lddx, dx))) return rc;
     }
     return LHRS_OK;
+}
+
+static LoraBwd lora_ctx(const LhrsLlamaWeights* w, int layer, int first, int nproj, const void* x, long long ldx, int in_dim,
+                        const void* dy0, long long ldy, int out_dim, long long M, const __nv_bfloat16* T, __nv_bfloat16* dt) {
+    LoraBwd L;
+    L.active = w->lora_r > 0 && w->lora_a != nullptr && w->lora_b != nullptr;
+    L.idx0 = layer * 7 + first; L.nproj = nproj; L.in_dim = in_dim; L.out_dim = out_dim;
+    L.x = x; L.ldx = ldx; L.ldy = ldy; L.M = M; L.T = T; L.dt = dt;
+    for (int p = 0; p < nproj; ++p) L.dy[p] = reinterpret_cast<const __nv_bfloat16*>(dy0) + (long long)p * out_dim;
+    return L;
 }
 
 }  // namespace lhrs
@@ -213,29 +230,34 @@ extern "C" int lhrs_llama_bwd(const LhrsLlamaWeights* w, void* const* lora_a_gra
     for (int l = w->num_layers - 1; l >= 0; --l) {
         const LlamaLayerStash& t = s.layer[l];
         // ---- MLP: x_out = x_mid + down(silu(gate(h2)) * up(h2)),  h2 = rmsnorm(x_mid)
-        if ((rc = gemm_dx(st, M, F, D, dx, D, w->down_w[l], F, b.d_act, F))) return rc;
         {
-            const void* dy[1] = {dx};
-            if ((rc = lora_bwd(st, w, lora_a_grads, lora_b_grads, l, 6, 1, t.act, F, F, dy, D, D, M, b.d_act, F, b.t, b.dt, b.diag))) return rc;
+            LoraBwd L = lora_ctx(w, l, 6, 1, t.act, F, F, dx, D, D, M, t.lora_t[3], b.dt);
+            LhrsGemm g = gemm_desc(M, F, D, dx, D, w->down_w[l], F, b.d_act, F);
+            g.b_mn_major = 1;
+            if ((rc = lora_bwd_pre(st, w, lora_a_grads, L, g))) return rc;
+            if ((rc = lhrs_gemm_bf16(&g, st))) return rc;
+            if ((rc = lora_bwd_post(st, w, lora_a_grads, lora_b_grads, L, b.d_act, F, b.diag))) return rc;
         }
         if ((rc = lhrs_swiglu_bwd(b.d_act, t.pre_gate, t.pre_up, b.d_gu, M, F, st))) return rc;
         {
+            if (w->lora_r > 0) if ((rc = lhrs_rmsnorm_fwd(t.x_mid, w->ln2_w[l], b.h, nullptr, M, D, w->eps, st))) return rc;
+            LoraBwd L = lora_ctx(w, l, 4, 2, b.h, D, D, b.d_gu, 2 * F, F, M, t.lora_t[2], b.dt);
             LhrsGemm g = gemm_desc(M, D, 2 * F, b.d_gu, 2 * F, w->gate_w[l], D, b.dh, D);
             g.b_mn_major = 1; g.B[1] = w->up_w[l]; g.num_b = 2;
+            if ((rc = lora_bwd_pre(st, w, lora_a_grads, L, g))) return rc;
             if ((rc = lhrs_gemm_bf16(&g, st))) return rc;
-        }
-        if (w->lora_r > 0) {
-            if ((rc = lhrs_rmsnorm_fwd(t.x_mid, w->ln2_w[l], b.h, nullptr, M, D, w->eps, st))) return rc;
-            const void* dy[2] = {b.d_gu, b.d_gu + F};
-            if ((rc = lora_bwd(st, w, lora_a_grads, lora_b_grads, l, 4, 2, b.h, D, D, dy, 2 * F, F, M, b.dh, D, b.t, b.dt, b.diag))) return rc;
+            if ((rc = lora_bwd_post(st, w, lora_a_grads, lora_b_grads, L, b.dh, D, b.diag))) return rc;
         }
         if ((rc = lhrs_rmsnorm_bwd(t.x_mid, w->ln2_w[l], t.rstd2, b.dh, dx, dx_other, M, D, st))) return rc;
         { bf16* tmp = dx; dx = dx_other; dx_other = tmp; }   // dx = grad wrt x_mid
         // ---- attention: x_mid = x_in + o_proj(attn(rope(q), rope(k), v)),  q,k,v = proj(h1), h1 = rmsnorm(x_in)
-        if ((rc = gemm_dx(st, M, D, D, dx, D, w->o_w[l], D, b.d_o, D))) return rc;
         {
-            const void* dy[1] = {dx};
-            if ((rc = lora_bwd(st, w, lora_a_grads, lora_b_grads, l, 3, 1, t.o, D, D, dy, D, D, M, b.d_o, D, b.t, b.dt, b.diag))) return rc;
+            LoraBwd L = lora_ctx(w, l, 3, 1, t.o, D, D, dx, D, D, M, t.lora_t[1], b.dt);
+            LhrsGemm g = gemm_desc(M, D, D, dx, D, w->o_w[l], D, b.d_o, D);
+            g.b_mn_major = 1;
+            if ((rc = lora_bwd_pre(st, w, lora_a_grads, L, g))) return rc;
+            if ((rc = lhrs_gemm_bf16(&g, st))) return rc;
+            if ((rc = lora_bwd_post(st, w, lora_a_grads, lora_b_grads, L, b.d_o, D, b.diag))) return rc;
         }
         {
             LhrsAttentionBwd ab;
@@ -250,14 +272,13 @@ extern "C" int lhrs_llama_bwd(const LhrsLlamaWeights* w, void* const* lora_a_gra
         }
         if ((rc = lhrs_rope_bwd(b.dqkv, 3 * D, M, D, w->rope_cos, w->rope_sin, nullptr, S, st))) return rc;
         {
+            if (w->lora_r > 0) if ((rc = lhrs_rmsnorm_fwd(t.x_in, w->ln1_w[l], b.h, nullptr, M, D, w->eps, st))) return rc;
+            LoraBwd L = lora_ctx(w, l, 0, 3, b.h, D, D, b.dqkv, 3 * D, D, M, t.lora_t[0], b.dt);
             LhrsGemm g = gemm_desc(M, D, 3 * D, b.dqkv, 3 * D, w->q_w[l], D, b.dh, D);
             g.b_mn_major = 1; g.B[1] = w->k_w[l]; g.B[2] = w->v_w[l]; g.num_b = 3;
+            if ((rc = lora_bwd_pre(st, w, lora_a_grads, L, g))) return rc;
             if ((rc = lhrs_gemm_bf16(&g, st))) return rc;
-        }
-        if (w->lora_r > 0) {
-            if ((rc = lhrs_rmsnorm_fwd(t.x_in, w->ln1_w[l], b.h, nullptr, M, D, w->eps, st))) return rc;
-            const void* dy[3] = {b.dqkv, b.dqkv + D, b.dqkv + 2 * D};
-            if ((rc = lora_bwd(st, w, lora_a_grads, lora_b_grads, l, 0, 3, b.h, D, D, dy, 3 * D, D, M, b.dh, D, b.t, b.dt, b.diag))) return rc;
+            if ((rc = lora_bwd_post(st, w, lora_a_grads, lora_b_grads, L, b.dh, D, b.diag))) return rc;
         }
         bf16* dst = (l == 0) ? reinterpret_cast<bf16*>(d_inputs_embeds) : dx_other;
         if ((rc = lhrs_rmsnorm_bwd(t.x_in, w->ln1_w[l], t.rstd1, b.dh, dx, dst, M, D, st))) return rc;

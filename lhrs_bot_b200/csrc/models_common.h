@@ -113,6 +113,7 @@ inline PoolerStash pooler_stash_plan(Arena& a, const LhrsPoolerWeights* w, int B
 struct LlamaLayerStash {
     __nv_bfloat16 *x_in, *x_mid, *qkv, *o, *pre_gate, *pre_up, *act;
     float *rstd1, *rstd2, *lse;
+    __nv_bfloat16* lora_t[4];   // T = s*x*A^T of the four projection groups {qkv, o, gate/up, down} (LoRA only)
 };
 struct LlamaStash {
     LlamaLayerStash layer[80];
@@ -135,6 +136,8 @@ inline LlamaStash llama_stash_plan(Arena& a, const LhrsLlamaWeights* w, int B, i
         t.rstd1 = a.take<float>(M);
         t.rstd2 = a.take<float>(M);
         t.lse = a.take<float>(M * w->heads);
+        const int np[4] = {3, 1, 2, 1};
+        for (int g = 0; g < 4; ++g) t.lora_t[g] = (w->lora_r > 0) ? a.take<__nv_bfloat16>(M * np[g] * w->lora_r) : nullptr;
     }
     s.x_final = a.take<__nv_bfloat16>(M * D);
     s.rstd_final = a.take<float>(M);

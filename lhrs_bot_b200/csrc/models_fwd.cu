@@ -369,7 +369,7 @@ extern "C" int lhrs_llama_fwd(const LhrsLlamaWeights* w, const void* inputs_embe
             LhrsGemm g = gemm_desc(M, 3 * D, D, b.h, D, w->q_w[l], D, qkv, 3 * D);
             g.B[1] = w->k_w[l]; g.B[2] = w->v_w[l]; g.num_b = 3; g.seg_rows = D;
             g.epilogue = LHRS_EPI_ROPE; g.rope_cos = w->rope_cos; g.rope_sin = w->rope_sin; g.rope_seq_len = S;
-            if ((rc = lora_attach(g, w, l, 0, 3, b.h, D, M, b.lora_t, stream))) return rc;
+            if ((rc = lora_attach(g, w, l, 0, 3, b.h, D, M, ls ? ls->lora_t[0] : b.lora_t, stream))) return rc;
             if ((rc = lhrs_gemm_bf16(&g, stream))) return rc;
         }
         if (kv != nullptr) {
@@ -386,7 +386,7 @@ extern "C" int lhrs_llama_fwd(const LhrsLlamaWeights* w, const void* inputs_embe
         {
             LhrsGemm g = gemm_desc(M, D, D, o, D, w->o_w[l], D, b.x, D);
             g.residual = b.x; g.ldr = D;
-            if ((rc = lora_attach(g, w, l, 3, 1, o, D, M, b.lora_t, stream))) return rc;
+            if ((rc = lora_attach(g, w, l, 3, 1, o, D, M, ls ? ls->lora_t[1] : b.lora_t, stream))) return rc;
             if ((rc = lhrs_gemm_bf16(&g, stream))) return rc;
         }
         if (ls) LHRS_CUDA(cudaMemcpyAsync(ls->x_mid, b.x, M * D * 2, cudaMemcpyDeviceToDevice, stream));
@@ -396,13 +396,13 @@ extern "C" int lhrs_llama_fwd(const LhrsLlamaWeights* w, const void* inputs_embe
             LhrsGemm g = gemm_desc(M, 2 * F, D, b.h, D, w->gate_w[l], D, act, F);
             g.B[1] = w->up_w[l]; g.num_b = 2; g.seg_rows = F; g.epilogue = LHRS_EPI_SWIGLU;
             if (ls) { g.pre_gate = ls->pre_gate; g.pre_up = ls->pre_up; }
-            if ((rc = lora_attach(g, w, l, 4, 2, b.h, D, M, b.lora_t, stream))) return rc;
+            if ((rc = lora_attach(g, w, l, 4, 2, b.h, D, M, ls ? ls->lora_t[2] : b.lora_t, stream))) return rc;
             if ((rc = lhrs_gemm_bf16(&g, stream))) return rc;
         }
         {
             LhrsGemm g = gemm_desc(M, D, F, act, F, w->down_w[l], F, b.x, D);
             g.residual = b.x; g.ldr = D;
-            if ((rc = lora_attach(g, w, l, 6, 1, act, F, M, b.lora_t, stream))) return rc;
+            if ((rc = lora_attach(g, w, l, 6, 1, act, F, M, ls ? ls->lora_t[3] : b.lora_t, stream))) return rc;
             if ((rc = lhrs_gemm_bf16(&g, stream))) return rc;
         }
     }
