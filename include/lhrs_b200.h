@@ -91,9 +91,14 @@ typedef struct LhrsGemm {
     /* MN-major B with num_b > 1 = segments stacked along K.  b_seg_nshift > 0 makes them block-diagonal: segment s is
      * [K/num_b, b_seg_nshift] and contributes only to output columns [s*b_seg_nshift, (s+1)*b_seg_nshift). */
     int32_t b_seg_nshift;
+    /* split_k > 1: split the K loop over that many CTAs per output tile (skinny problems that would otherwise occupy few
+     * SMs).  Partial sums are added with fp32 atomics: D must be fp32 (d_f32) and zero-initialised; plain LINEAR epilogue. */
+    int32_t split_k;
 } LhrsGemm;
 
 int lhrs_gemm_bf16(const LhrsGemm* g, void* stream);
+/* fp32 -> bf16 (round to nearest even), n elements, n % 4 == 0 (finishes a split-K accumulation) */
+int lhrs_cast_f32_bf16(const float* src, void* dst, int64_t n, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Fused attention forward: O = softmax(scale * Q K^T + causal/key-padding mask) V, online softmax.

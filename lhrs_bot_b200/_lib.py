@@ -31,7 +31,7 @@ class LhrsGemm(C.Structure):
         ("rope_seq_len", C.c_int32),
         ("pre_gate", C.c_void_p), ("pre_up", C.c_void_p),
         ("A2", C.c_void_p), ("lda2", C.c_int64), ("B2", C.c_void_p * 3), ("ldb2", C.c_int64), ("ext_k", C.c_int32),
-        ("b_seg_nshift", C.c_int32),
+        ("b_seg_nshift", C.c_int32), ("split_k", C.c_int32),
     ]
 
 
@@ -123,6 +123,7 @@ SIGNATURES = {
     "lhrs_prof_enable": (C.c_int, [C.c_int]),
     "lhrs_prof_summary": (C.c_int, [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
     "lhrs_gemm_bf16": (C.c_int, [C.POINTER(LhrsGemm), _P]),
+    "lhrs_cast_f32_bf16": (C.c_int, [_P, _P, _I64, _P]),
     "lhrs_attention_fwd": (C.c_int, [C.POINTER(LhrsAttention), _P]),
     "lhrs_rmsnorm_fwd": (C.c_int, [_P, _P, _P, _P, _I64, _I32, _F, _P]),
     "lhrs_layernorm_fwd": (C.c_int, [_P, _I64, _P, _P, _P, _I64, _P, _P, _I64, _I32, _F, _P]),

@@ -81,6 +81,7 @@ attn_fwd_kernel(const AttnArgs p) {
     const uint32_t sQ = smem_u32(smem);
     const uint32_t sK = sQ + BQ * HD * 2;
     const uint32_t sV = sK + 2 * BKV * HD * 2;
+    __shared__ uint8_t sMask[2][BKV];   // key-padding mask of the current / next key tile
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int qb = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
@@ -100,6 +101,7 @@ attn_fwd_kernel(const AttnArgs p) {
     load_tile<HD, BKV, THREADS>(sK, kg, p.k_rs, 0, p.Skv, tid);
     load_tile<HD, BKV, THREADS>(sV, vg, p.v_rs, 0, p.Skv, tid);
     cp_async_commit();
+    if (km != nullptr && tid < BKV) sMask[0][tid] = (tid < p.Skv) ? km[tid] : 0;
 
     uint32_t qf[KSTEPS][4];
     float o[DTILES][4];
@@ -117,6 +119,10 @@ attn_fwd_kernel(const AttnArgs p) {
             load_tile<HD, BKV, THREADS>(sK + (buf ^ 1) * BKV * HD * 2, kg, p.k_rs, (j + 1) * BKV, p.Skv, tid);
             load_tile<HD, BKV, THREADS>(sV + (buf ^ 1) * BKV * HD * 2, vg, p.v_rs, (j + 1) * BKV, p.Skv, tid);
             cp_async_commit();
+            if (km != nullptr && tid < BKV) {
+                const int key = (j + 1) * BKV + tid;
+                sMask[buf ^ 1][tid] = (key < p.Skv) ? km[key] : 0;
+            }
             cp_async_wait<1>();
         } else {
             cp_async_wait<0>();
@@ -156,19 +162,27 @@ attn_fwd_kernel(const AttnArgs p) {
         // ---- mask + online softmax (rows g and g+8 of this warp's 16)
         const int kbase = j * BKV;
         float mx[2] = {-INFINITY, -INFINITY};
+        // masking is only evaluated on tiles that need it: the diagonal tile (causal), the ragged last tile, a padding mask
+        const bool tile_masked = (km != nullptr) || (kbase + BKV > p.Skv) || (CAUSAL && kbase + BKV - 1 > q0 + warp * 16 + causal_shift);
+        if (tile_masked) {
+#pragma unroll
+            for (int i = 0; i < BKV / 8; ++i) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const int kl = i * 8 + t4 * 2 + (e & 1);
+                    const int key = kbase + kl;
+                    const int qr = qrow0 + (e >> 1) * 8;
+                    bool ok = key < p.Skv;
+                    if (CAUSAL) ok = ok && (key <= qr + causal_shift);
+                    if (km != nullptr) ok = ok && (sMask[buf][kl] != 0);
+                    if (!ok) s[i][e] = -INFINITY;
+                }
+            }
+        }
 #pragma unroll
         for (int i = 0; i < BKV / 8; ++i) {
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                const int key = kbase + i * 8 + t4 * 2 + (e & 1);
-                const int qr = qrow0 + (e >> 1) * 8;
-                bool ok = key < p.Skv;
-                if (CAUSAL) ok = ok && (key <= qr + causal_shift);
-                if (km != nullptr && ok) ok = km[key] != 0;
-                const float val = ok ? s[i][e] : -INFINITY;
-                s[i][e] = val;
-                mx[e >> 1] = fmaxf(mx[e >> 1], val);
-            }
+            mx[0] = fmaxf(mx[0], fmaxf(s[i][0], s[i][1]));
+            mx[1] = fmaxf(mx[1], fmaxf(s[i][2], s[i][3]));
         }
         float scale_o[2];
 #pragma unroll

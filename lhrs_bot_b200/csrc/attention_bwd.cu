@@ -91,6 +91,7 @@ __global__ void __launch_bounds__(128) attn_bwd_dq_kernel(const AttnBwdArgs p) {
     const uint32_t sdO = sQ + BQ * HD * 2;
     const uint32_t sK = sdO + BQ * HD * 2;
     const uint32_t sV = sK + 2 * BKV * HD * 2;
+    __shared__ uint8_t sMask[2][BKV];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t4 = lane & 3;
     const int qb = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
     const int q0 = qb * BQ;
@@ -109,6 +110,7 @@ __global__ void __launch_bounds__(128) attn_bwd_dq_kernel(const AttnBwdArgs p) {
     load_rows<HD, BKV, THREADS>(sK, kg, p.k_rs, 0, p.Skv, tid);
     load_rows<HD, BKV, THREADS>(sV, vg, p.v_rs, 0, p.Skv, tid);
     cp_commit();
+    if (km != nullptr && tid < BKV) sMask[0][tid] = (tid < p.Skv) ? km[tid] : 0;
 
     const int qrow0 = q0 + warp * 16 + g;
     float lse2[2], dl[2];
@@ -132,6 +134,10 @@ __global__ void __launch_bounds__(128) attn_bwd_dq_kernel(const AttnBwdArgs p) {
             load_rows<HD, BKV, THREADS>(sK + (buf ^ 1) * BKV * HD * 2, kg, p.k_rs, (j + 1) * BKV, p.Skv, tid);
             load_rows<HD, BKV, THREADS>(sV + (buf ^ 1) * BKV * HD * 2, vg, p.v_rs, (j + 1) * BKV, p.Skv, tid);
             cp_commit();
+            if (km != nullptr && tid < BKV) {
+                const int key = (j + 1) * BKV + tid;
+                sMask[buf ^ 1][tid] = (key < p.Skv) ? km[key] : 0;
+            }
             cp_wait<1>();
         } else {
             cp_wait<0>();
@@ -169,12 +175,13 @@ __global__ void __launch_bounds__(128) attn_bwd_dq_kernel(const AttnBwdArgs p) {
             float dsv[4];
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-                const int key = kbase + i * 8 + t4 * 2 + (e & 1);
+                const int kl = i * 8 + t4 * 2 + (e & 1);
+                const int key = kbase + kl;
                 const int r = e >> 1;
                 const int qr = qrow0 + r * 8;
                 bool ok = key < p.Skv;
                 if (CAUSAL) ok = ok && (key <= qr + shift);
-                if (km != nullptr && ok) ok = km[key] != 0;
+                if (km != nullptr) ok = ok && (sMask[buf][kl] != 0);
                 const float pv = ok ? exp2f(s[i][e] * p.scale_log2 - lse2[r]) : 0.f;
                 dsv[e] = pv * (dp[i][e] - dl[r]) * p.scale;
             }

@@ -42,26 +42,53 @@ __device__ __forceinline__ float warp_red(float v) {
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     return v;
 }
+// Programmatic dependent launch: every decode kernel is launched with the stream-serialization attribute, lets its
+// successor start early (launch_dependents) and waits for its predecessor's results only where it first needs them.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
-// two weight rows against the smem-resident input, 4 x 16-byte loads in flight per row
-__device__ __forceinline__ void dot_rows2(const __nv_bfloat16* r0, const __nv_bfloat16* r1, const uint4* xs, int nchunks, int lane,
-                                          float& a0, float& a1) {
-    const uint4* p0 = reinterpret_cast<const uint4*>(r0);
-    const uint4* p1 = reinterpret_cast<const uint4*>(r1);
-    a0 = 0.f; a1 = 0.f;
+constexpr int GV_INFLIGHT = 8;   // 16-byte loads in flight per lane
+
+__device__ __forceinline__ void prefetch_row(const __nv_bfloat16* row, int nchunks, int lane, uint4 (&pre)[GV_INFLIGHT]) {
+    const uint4* p = reinterpret_cast<const uint4*>(row);
+#pragma unroll
+    for (int i = 0; i < GV_INFLIGHT; ++i) {
+        const int c = lane + i * 32;
+        pre[i] = (c < nchunks) ? ldg_stream(p + c) : make_uint4(0, 0, 0, 0);
+    }
+}
+// one weight row against the smem-resident input; `pre` optionally holds the first GV_INFLIGHT chunks (already loaded)
+__device__ __forceinline__ float dot_row(const __nv_bfloat16* row, const uint4* xs, int nchunks, int lane, bool have_pre,
+                                         const uint4 (&pre)[GV_INFLIGHT]) {
+    const uint4* p = reinterpret_cast<const uint4*>(row);
+    float acc = 0.f;
     int c = lane;
-    for (; c + 96 < nchunks; c += 128) {
-        uint4 w00 = ldg_stream(p0 + c), w01 = ldg_stream(p0 + c + 32), w02 = ldg_stream(p0 + c + 64), w03 = ldg_stream(p0 + c + 96);
-        uint4 w10 = ldg_stream(p1 + c), w11 = ldg_stream(p1 + c + 32), w12 = ldg_stream(p1 + c + 64), w13 = ldg_stream(p1 + c + 96);
-        a0 += dot8(w00, xs[c]) + dot8(w01, xs[c + 32]) + dot8(w02, xs[c + 64]) + dot8(w03, xs[c + 96]);
-        a1 += dot8(w10, xs[c]) + dot8(w11, xs[c + 32]) + dot8(w12, xs[c + 64]) + dot8(w13, xs[c + 96]);
+    if (have_pre) {
+#pragma unroll
+        for (int i = 0; i < GV_INFLIGHT; ++i)
+            if (c + i * 32 < nchunks) acc += dot8(pre[i], xs[c + i * 32]);
+        c += GV_INFLIGHT * 32;
     }
-    for (; c < nchunks; c += 32) {
-        a0 += dot8(ldg_stream(p0 + c), xs[c]);
-        a1 += dot8(ldg_stream(p1 + c), xs[c]);
+    for (; c + (GV_INFLIGHT - 1) * 32 < nchunks; c += GV_INFLIGHT * 32) {
+        uint4 w[GV_INFLIGHT];
+#pragma unroll
+        for (int i = 0; i < GV_INFLIGHT; ++i) w[i] = ldg_stream(p + c + i * 32);
+#pragma unroll
+        for (int i = 0; i < GV_INFLIGHT; ++i) acc += dot8(w[i], xs[c + i * 32]);
     }
-    a0 = warp_red(a0);
-    a1 = warp_red(a1);
+    for (; c < nchunks; c += 32) acc += dot8(ldg_stream(p + c), xs[c]);
+    return warp_red(acc);
+}
+
+template <int MODE>
+__device__ __forceinline__ const __nv_bfloat16* gemv_row(const GemvArgs& a, int n) {
+    if constexpr (MODE == GV_QKV) {
+        const int s = n / a.rows;
+        const __nv_bfloat16* m = s == 0 ? a.w0 : (s == 1 ? a.w1 : a.w2);
+        return m + static_cast<long long>(n - s * a.rows) * a.K;
+    } else {
+        return a.w0 + static_cast<long long>(n) * a.K;
+    }
 }
 
 template <int MODE>
@@ -74,6 +101,13 @@ gemv_kernel(const GemvArgs a) {
     __shared__ int bidx[8];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int nchunks = a.K / 8;
+    const int total = (MODE == GV_QKV) ? 3 * a.rows : a.rows;
+    const int gw = blockIdx.x * 8 + warp, nw = gridDim.x * 8;
+    pdl_launch_dependents();
+    // weights do not depend on the previous kernel: start streaming the first row before waiting for the input vector
+    uint4 pre[GV_INFLIGHT];
+    if (gw < total) prefetch_row(gemv_row<MODE>(a, gw), nchunks, lane, pre);
+    pdl_wait();
     // ---- stage the input vector (with the HF RMSNorm fused: w * bf16(x * rstd))
     if (a.norm_w != nullptr) {
         float ss = 0.f;
@@ -95,60 +129,35 @@ gemv_kernel(const GemvArgs a) {
 
     float best = -INFINITY;
     int best_i = 0x7fffffff;
-    if constexpr (MODE == GV_GATEUP) {
-        for (int n = blockIdx.x * 8 + warp; n < a.rows; n += gridDim.x * 8) {
-            float g, u;
-            dot_rows2(a.w0 + static_cast<long long>(n) * a.K, a.w1 + static_cast<long long>(n) * a.K, xv, nchunks, lane, g, u);
+    bool first = true;
+    for (int n = gw; n < total; n += nw, first = false) {
+        const float v0 = dot_row(gemv_row<MODE>(a, n), xv, nchunks, lane, first, pre);
+        if constexpr (MODE == GV_GATEUP) {
+            const float u0 = dot_row(a.w1 + static_cast<long long>(n) * a.K, xv, nchunks, lane, false, pre);
             if (lane == 0) {
-                g = bf16_round(g); u = bf16_round(u);
+                const float g = bf16_round(v0), u = bf16_round(u0);
                 a.out[n] = __float2bfloat16_rn(bf16_round(g / (1.f + __expf(-g))) * u);
             }
-        }
-    } else {
-        const int total = (MODE == GV_QKV) ? 3 * a.rows : a.rows;
-        // each warp takes two rows per trip (independent load streams)
-        for (int n = (blockIdx.x * 8 + warp) * 2; n < total; n += gridDim.x * 16) {
-            const int n1 = min(n + 1, total - 1);
-            const __nv_bfloat16 *r0, *r1;
+        } else if (lane == 0) {
             if constexpr (MODE == GV_QKV) {
-                const int s0 = n / a.rows, s1 = n1 / a.rows;
-                const __nv_bfloat16* m0 = s0 == 0 ? a.w0 : (s0 == 1 ? a.w1 : a.w2);
-                const __nv_bfloat16* m1 = s1 == 0 ? a.w0 : (s1 == 1 ? a.w1 : a.w2);
-                r0 = m0 + static_cast<long long>(n - s0 * a.rows) * a.K;
-                r1 = m1 + static_cast<long long>(n1 - s1 * a.rows) * a.K;
-            } else {
-                r0 = a.w0 + static_cast<long long>(n) * a.K;
-                r1 = a.w0 + static_cast<long long>(n1) * a.K;
-            }
-            float v0, v1;
-            dot_rows2(r0, r1, xv, nchunks, lane, v0, v1);
-            if (lane == 0) {
-                if constexpr (MODE == GV_QKV) {
-                    a.out[n] = __float2bfloat16_rn(v0);
-                    if (n1 != n) a.out[n1] = __float2bfloat16_rn(v1);
-                } else if constexpr (MODE == GV_O || MODE == GV_DOWN) {
-                    a.out[n] = __float2bfloat16_rn(bf16_round(v0) + __bfloat162float(a.out[n]));
-                    if (n1 != n) a.out[n1] = __float2bfloat16_rn(bf16_round(v1) + __bfloat162float(a.out[n1]));
-                } else {  // LMHEAD: HF casts the bf16 logits to fp32
-                    v0 = bf16_round(v0); v1 = bf16_round(v1);
-                    a.logits[n] = v0;
-                    if (v0 > best || (v0 == best && n < best_i)) { best = v0; best_i = n; }
-                    if (n1 != n) {
-                        a.logits[n1] = v1;
-                        if (v1 > best || (v1 == best && n1 < best_i)) { best = v1; best_i = n1; }
-                    }
-                }
+                a.out[n] = __float2bfloat16_rn(v0);
+            } else if constexpr (MODE == GV_O || MODE == GV_DOWN) {
+                a.out[n] = __float2bfloat16_rn(bf16_round(v0) + __bfloat162float(a.out[n]));
+            } else {  // LMHEAD: HF casts the bf16 logits to fp32
+                const float v = bf16_round(v0);
+                a.logits[n] = v;
+                if (v > best || (v == best && n < best_i)) { best = v; best_i = n; }
             }
         }
-        if constexpr (MODE == GV_LMHEAD) {
-            if (lane == 0) { bval[warp] = best; bidx[warp] = best_i; }
-            __syncthreads();
-            if (tid == 0) {
-                for (int i = 1; i < 8; ++i)
-                    if (bval[i] > bval[0] || (bval[i] == bval[0] && bidx[i] < bidx[0])) { bval[0] = bval[i]; bidx[0] = bidx[i]; }
-                a.part_val[blockIdx.x] = bval[0];
-                a.part_idx[blockIdx.x] = bidx[0];
-            }
+    }
+    if constexpr (MODE == GV_LMHEAD) {
+        if (lane == 0) { bval[warp] = best; bidx[warp] = best_i; }
+        __syncthreads();
+        if (tid == 0) {
+            for (int i = 1; i < 8; ++i)
+                if (bval[i] > bval[0] || (bval[i] == bval[0] && bidx[i] < bidx[0])) { bval[0] = bval[i]; bidx[0] = bidx[i]; }
+            a.part_val[blockIdx.x] = bval[0];
+            a.part_idx[blockIdx.x] = bidx[0];
         }
     }
 }
@@ -159,6 +168,8 @@ commit_token_kernel(const float* __restrict__ part_val, const int* __restrict__ 
                     int* __restrict__ state, int* __restrict__ tokens_out, int max_tokens, int set_ctx,
                     const __nv_bfloat16* __restrict__ embed, int dim, __nv_bfloat16* __restrict__ xbuf) {
     __shared__ int s_tok;
+    pdl_launch_dependents();
+    pdl_wait();
     if (threadIdx.x == 0) {
         int tok = forced_token;
         if (tok < 0) {
@@ -185,19 +196,26 @@ commit_token_kernel(const float* __restrict__ part_val, const int* __restrict__ 
 }
 
 // one block per head: RoPE + KV append + attention over the paged cache for the single new query
-__global__ void __launch_bounds__(128)
+// dynamic smem: scores [max_ctx] fp32 | page ids [max_pages] int32
+__global__ void __launch_bounds__(256)
 attn_decode_kernel(const __nv_bfloat16* __restrict__ qkv, int dim, KvGeom kv, int layer, int* __restrict__ state,
-                   const float* __restrict__ cosT, const float* __restrict__ sinT, __nv_bfloat16* __restrict__ obuf) {
-    extern __shared__ float sc[];            // scores [ctx+1]
+                   const float* __restrict__ cosT, const float* __restrict__ sinT, __nv_bfloat16* __restrict__ obuf, int max_ctx) {
+    extern __shared__ float sc[];            // scores [max_ctx]
+    int* spg = reinterpret_cast<int*>(sc + max_ctx);
     __shared__ float qs[128];
-    __shared__ float red[4];
+    __shared__ float red[8];
+    __shared__ float part[8][128];
     const int h = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    pdl_launch_dependents();
+    pdl_wait();
     const int pos = state[1];
     const int n = pos + 1;
+    const int npages = (n + kv.page_size - 1) / kv.page_size;
     const float scale = rsqrtf(128.f);
     const __nv_bfloat16* q = qkv + h * 128;
     const __nv_bfloat16* k = qkv + dim + h * 128;
     const __nv_bfloat16* v = qkv + 2 * dim + h * 128;
+    for (int i = tid; i < npages; i += 256) spg[i] = kv.block_table[i];
     const int page_new = kv.block_table[pos / kv.page_size];
     const int slot_new = pos % kv.page_size;
     if (tid < 64) {
@@ -210,24 +228,26 @@ attn_decode_kernel(const __nv_bfloat16* __restrict__ qkv, int dim, KvGeom kv, in
         __nv_bfloat16* kd = kv_ptr(kv, layer, 0, page_new, h, slot_new);
         kd[tid] = __float2bfloat16_rn(bf16_round(k1 * c) - bf16_round(k2 * s));
         kd[tid + 64] = __float2bfloat16_rn(bf16_round(k2 * c) + bf16_round(k1 * s));
-    } else {
+    } else if (tid < 128) {
         __nv_bfloat16* vd = kv_ptr(kv, layer, 1, page_new, h, slot_new);
         const int d = tid - 64;
         vd[d] = v[d];
         vd[d + 64] = v[d + 64];
     }
     __syncthreads();
-    // scores
+    // ---- scores: one position per thread, 16 x 16-byte loads of its K row in flight
     float mx = -INFINITY;
-    for (int p = tid; p < n; p += 128) {
-        const __nv_bfloat16* kp = kv_ptr(kv, layer, 0, kv.block_table[p / kv.page_size], h, p % kv.page_size);
+    for (int p = tid; p < n; p += 256) {
+        const uint4* kp = reinterpret_cast<const uint4*>(kv_ptr(kv, layer, 0, spg[p / kv.page_size], h, p % kv.page_size));
+        uint4 w[16];
+#pragma unroll
+        for (int c = 0; c < 16; ++c) w[c] = kp[c];
         float acc = 0.f;
 #pragma unroll
         for (int c = 0; c < 16; ++c) {
-            const uint4 w = reinterpret_cast<const uint4*>(kp)[c];
             const float* qq = qs + c * 8;
-            acc += bf16_lo(w.x) * qq[0] + bf16_hi(w.x) * qq[1] + bf16_lo(w.y) * qq[2] + bf16_hi(w.y) * qq[3] +
-                   bf16_lo(w.z) * qq[4] + bf16_hi(w.z) * qq[5] + bf16_lo(w.w) * qq[6] + bf16_hi(w.w) * qq[7];
+            acc += bf16_lo(w[c].x) * qq[0] + bf16_hi(w[c].x) * qq[1] + bf16_lo(w[c].y) * qq[2] + bf16_hi(w[c].y) * qq[3] +
+                   bf16_lo(w[c].z) * qq[4] + bf16_hi(w[c].z) * qq[5] + bf16_lo(w[c].w) * qq[6] + bf16_hi(w[c].w) * qq[7];
         }
         acc *= scale;                    // scores stay fp32 (as in the prefill flash kernel)
         sc[p] = acc;
@@ -237,10 +257,12 @@ attn_decode_kernel(const __nv_bfloat16* __restrict__ qkv, int dim, KvGeom kv, in
     for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
     if (lane == 0) red[warp] = mx;
     __syncthreads();
-    mx = fmaxf(fmaxf(red[0], red[1]), fmaxf(red[2], red[3]));
+    mx = red[0];
+#pragma unroll
+    for (int i = 1; i < 8; ++i) mx = fmaxf(mx, red[i]);
     __syncthreads();
     float sum = 0.f;
-    for (int p = tid; p < n; p += 128) {
+    for (int p = tid; p < n; p += 256) {
         const float e = __expf(sc[p] - mx);
         sc[p] = e;
         sum += e;
@@ -248,22 +270,53 @@ attn_decode_kernel(const __nv_bfloat16* __restrict__ qkv, int dim, KvGeom kv, in
     sum = warp_red(sum);
     if (lane == 0) red[warp] = sum;
     __syncthreads();
-    const float inv = 1.f / (red[0] + red[1] + red[2] + red[3]);
-    // out[d] = sum_p P[p] V[p][d]; thread d owns one output dim (coalesced 256-byte rows)
-    float acc0 = 0.f, acc1 = 0.f;
-    const int npages = (n + kv.page_size - 1) / kv.page_size;
-    for (int pg = 0; pg < npages; ++pg) {
-        const __nv_bfloat16* vbase = kv_ptr(kv, layer, 1, kv.block_table[pg], h, 0) + tid;
-        const int p0 = pg * kv.page_size;
-        const int cnt = min(kv.page_size, n - p0);
-        int s = 0;
-        for (; s + 1 < cnt; s += 2) {   // independent loads / accumulators hide the L2 latency
-            acc0 += sc[p0 + s] * __bfloat162float(vbase[s * 128]);
-            acc1 += sc[p0 + s + 1] * __bfloat162float(vbase[(s + 1) * 128]);
+    float tot = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) tot += red[i];
+    const float inv = 1.f / tot;
+    // ---- out = P V: warp w takes positions w, w+8, ...; lane l owns dims 4l..4l+3 (one coalesced 256-byte row per load)
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    int p = warp;
+    for (; p + 24 < n; p += 32) {        // 4 independent row loads in flight
+        uint2 r[4];
+        float pr[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int pp = p + i * 8;
+            r[i] = reinterpret_cast<const uint2*>(kv_ptr(kv, layer, 1, spg[pp / kv.page_size], h, pp % kv.page_size))[lane];
+            pr[i] = sc[pp];
         }
-        if (s < cnt) acc0 += sc[p0 + s] * __bfloat162float(vbase[s * 128]);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            a0 += pr[i] * bf16_lo(r[i].x); a1 += pr[i] * bf16_hi(r[i].x);
+            a2 += pr[i] * bf16_lo(r[i].y); a3 += pr[i] * bf16_hi(r[i].y);
+        }
     }
-    obuf[h * 128 + tid] = __float2bfloat16_rn((acc0 + acc1) * inv);
+    for (; p < n; p += 8) {
+        const uint2 r = reinterpret_cast<const uint2*>(kv_ptr(kv, layer, 1, spg[p / kv.page_size], h, p % kv.page_size))[lane];
+        const float pr = sc[p];
+        a0 += pr * bf16_lo(r.x); a1 += pr * bf16_hi(r.x); a2 += pr * bf16_lo(r.y); a3 += pr * bf16_hi(r.y);
+    }
+    part[warp][lane * 4 + 0] = a0; part[warp][lane * 4 + 1] = a1; part[warp][lane * 4 + 2] = a2; part[warp][lane * 4 + 3] = a3;
+    __syncthreads();
+    if (tid < 128) {
+        float o = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o += part[i][tid];
+        obuf[h * 128 + tid] = __float2bfloat16_rn(o * inv);
+    }
+}
+
+// launch with programmatic stream serialization (PDL): the kernel may start while its predecessor drains
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
 }
 
 }  // namespace lhrs
@@ -273,7 +326,7 @@ typedef __nv_bfloat16 bf16;
 
 template <int MODE>
 static int launch_gemv(const GemvArgs& a, cudaStream_t st) {
-    const int units = (MODE == GV_GATEUP) ? a.rows : ((MODE == GV_QKV ? 3 * a.rows : a.rows) + 1) / 2;
+    const int units = (MODE == GV_QKV) ? 3 * a.rows : a.rows;   // one weight row (GATEUP: one gate+up row pair) per warp trip
     int grid = (units + 7) / 8;
     const int cap = num_sms() * 8;
     if (grid > cap) grid = cap;
@@ -287,7 +340,7 @@ static int launch_gemv(const GemvArgs& a, cudaStream_t st) {
     LHRS_CHECK_ARG(smem <= 64 * 1024 && a.K % 8 == 0, "gemv: K=%d unsupported", a.K);
     const bool prof = prof_on();
     if (prof) prof_begin(PROF_OTHER, 0.0, 2.0 * (double)a.K * (MODE == GV_QKV ? 3.0 * a.rows : (MODE == GV_GATEUP ? 2.0 * a.rows : (double)a.rows)), st);
-    kern<<<grid, 256, smem, st>>>(a);
+    LHRS_CUDA(launch_pdl(kern, dim3(grid), dim3(256), smem, st, a));
     if (prof) prof_end(st);
     LHRS_LAUNCH_CHECK("gemv_kernel");
     return grid;
@@ -302,8 +355,8 @@ static int lm_head_and_commit(const LhrsLlamaWeights* w, const LhrsDecodeBuffers
     const int grid = launch_gemv<GV_LMHEAD>(a, st);
     if (grid <= 0) return LHRS_ERR_CUDA;
     if (greedy) {
-        commit_token_kernel<<<1, 256, 0, st>>>(b->part_val, b->part_idx, grid, -1, b->state, b->tokens_out, b->max_tokens, set_ctx,
-                                               (const bf16*)w->embed, w->dim, (bf16*)b->xbuf);
+        LHRS_CUDA(launch_pdl(commit_token_kernel, dim3(1), dim3(256), 0, st, (const float*)b->part_val, (const int*)b->part_idx, grid, -1,
+                             (int*)b->state, (int*)b->tokens_out, (int)b->max_tokens, set_ctx, (const bf16*)w->embed, (int)w->dim, (bf16*)b->xbuf));
         LHRS_LAUNCH_CHECK("commit_token_kernel");
     }
     return LHRS_OK;
@@ -311,8 +364,9 @@ static int lm_head_and_commit(const LhrsLlamaWeights* w, const LhrsDecodeBuffers
 
 extern "C" int lhrs_decode_commit_token(const LhrsLlamaWeights* w, const LhrsDecodeBuffers* b, int32_t token, int32_t set_ctx, void* stream) {
     LHRS_CHECK_ARG(w && b && token >= 0 && token < w->vocab, "lhrs_decode_commit_token: bad token %d", token);
-    commit_token_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(b->part_val, b->part_idx, 0, token, b->state, b->tokens_out, b->max_tokens,
-                                                            set_ctx, (const bf16*)w->embed, w->dim, (bf16*)b->xbuf);
+    LHRS_CUDA(launch_pdl(commit_token_kernel, dim3(1), dim3(256), 0, (cudaStream_t)stream, (const float*)b->part_val, (const int*)b->part_idx, 0,
+                         (int)token, (int*)b->state, (int*)b->tokens_out, (int)b->max_tokens, (int)set_ctx, (const bf16*)w->embed, (int)w->dim,
+                         (bf16*)b->xbuf));
     LHRS_LAUNCH_CHECK("commit_token_kernel");
     return LHRS_OK;
 }
@@ -339,8 +393,9 @@ extern "C" int lhrs_llama_decode_step(const LhrsLlamaWeights* w, const LhrsKvCac
         a.w0 = (const bf16*)w->q_w[l]; a.w1 = (const bf16*)w->k_w[l]; a.w2 = (const bf16*)w->v_w[l];
         a.rows = D; a.K = D; a.x = x; a.norm_w = (const bf16*)w->ln1_w[l]; a.eps = w->eps; a.out = (bf16*)b->qkv;
         if (launch_gemv<GV_QKV>(a, st) <= 0) return LHRS_ERR_CUDA;
-        attn_decode_kernel<<<w->heads, 128, (size_t)max_ctx * sizeof(float), st>>>((const bf16*)b->qkv, D, *kv, l, b->state, w->rope_cos,
-                                                                                 w->rope_sin, (bf16*)b->obuf);
+        LHRS_CUDA(launch_pdl(attn_decode_kernel, dim3(w->heads), dim3(256), (size_t)max_ctx * sizeof(float) + (size_t)kv->max_pages * sizeof(int), st,
+                             (const bf16*)b->qkv, D, *kv, l, (int*)b->state, (const float*)w->rope_cos, (const float*)w->rope_sin, (bf16*)b->obuf,
+                             (int)max_ctx));
         LHRS_LAUNCH_CHECK("attn_decode_kernel");
         memset(&a, 0, sizeof(a));
         a.w0 = (const bf16*)w->o_w[l]; a.rows = D; a.K = D; a.x = (const bf16*)b->obuf; a.out = x;

@@ -444,10 +444,26 @@ ce_bwd_kernel(const __nv_bfloat16* __restrict__ logits, long long ld, const long
     }
 }
 
+__global__ void cast_f32_bf16_kernel(const float4* __restrict__ src, uint2* __restrict__ dst, long long n4) {
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n4; i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const float4 v = src[i];
+        dst[i] = make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
+    }
+}
+
 }  // namespace lhrs
 
 using namespace lhrs;
 typedef __nv_bfloat16 bf16;
+
+extern "C" int lhrs_cast_f32_bf16(const float* src, void* dst, int64_t n, void* stream) {
+    LHRS_CHECK_ARG(src && dst && n > 0 && n % 4 == 0, "lhrs_cast_f32_bf16: bad args");
+    long long blocks = (n / 4 + 255) / 256;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    cast_f32_bf16_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((const float4*)src, (uint2*)dst, n / 4);
+    LHRS_LAUNCH_CHECK("cast_f32_bf16_kernel");
+    return LHRS_OK;
+}
 
 extern "C" int lhrs_rmsnorm_fwd(const void* x, const void* w, void* y, float* rstd_out, int64_t rows, int32_t dim,
                                 float eps, void* stream) {

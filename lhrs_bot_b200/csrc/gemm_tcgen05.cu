@@ -41,6 +41,7 @@ struct GemmArgs {
     __nv_bfloat16* pre_up;
     int kseg;    // MN-major B stacked along K: reduction length per segment (0 = single B)
     int kseg_nshift;  // segment s lands in output columns [s*nshift, s*nshift + its width): block-diagonal B (LoRA dT)
+    int splitk;  // >1: the K loop is split over `splitk` CTAs per tile; partial sums are added with fp32 atomics into D
     int ext_k;   // LoRA K-extension: columns of A2 per B segment (0 = none)
     int ext_kb;  // extra 64-wide k-blocks appended after the main K loop
 };
@@ -133,9 +134,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
     const int num_m = (args.M + BM * CG - 1) / (BM * CG);   // row-blocks of 128*CG (one per CTA or per CTA pair)
     const int num_n = (args.N + BN - 1) / BN;
-    const int num_tiles = num_m * num_n;
+    const int splitk = args.splitk;                         // 1 unless the host asked for a K split (skinny problems)
+    const int num_tiles = num_m * num_n * splitk;
     const int num_kb_main = (args.K + BK - 1) / BK;
     const int num_kb = num_kb_main + args.ext_kb;
+    const int kb_per = (num_kb + splitk - 1) / splitk;     // k-blocks per split (ext_kb == 0 when splitk > 1)
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmA);
@@ -171,7 +174,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             uint32_t phase = 0;
             for (int tile = blockIdx.x / CG; tile < num_tiles; tile += gridDim.x / CG) {
                 int m_blk, n_blk;
-                tile_coords(tile, num_m, num_n, m_blk, n_blk);
+                tile_coords(tile / splitk, num_m, num_n, m_blk, n_blk);
+                const int kb_begin = (tile % splitk) * kb_per, kb_end = min(kb_begin + kb_per, num_kb);
                 const int m0 = (m_blk * CG + static_cast<int>(rank)) * BM;
                 const int n0 = n_blk * BN;
                 const int nb0 = n0 + static_cast<int>(rank) * BN_CTA;   // first B row staged by this CTA
@@ -180,7 +184,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     if constexpr (CG == 2) tma_load_2d_2sm(dst, tm, &full_bar[stage], c0, c1);
                     else tma_load_2d(dst, tm, &full_bar[stage], c0, c1);
                 };
-                for (int kb = 0; kb < num_kb; ++kb) {
+                for (int kb = kb_begin; kb < kb_end; ++kb) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
                     if constexpr (CG == 2) {
                         if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * (Cfg::A_BYTES + Cfg::B_BYTES));
@@ -271,7 +275,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 mbar_wait(&tmem_empty_bar[as], aphase ^ 1);
                 tc_fence_after();
                 const uint32_t tmem_d = tmem_base + as * BN;
-                for (int kb = 0; kb < num_kb; ++kb) {
+                const int kb_begin = (tile % splitk) * kb_per, kb_end = min(kb_begin + kb_per, num_kb);
+                for (int kb = kb_begin; kb < kb_end; ++kb) {
                     mbar_wait(&full_bar[stage], phase);
                     tc_fence_after();
                     const uint32_t a_base = smem_u32(smem_a + stage * Cfg::A_BYTES);
@@ -284,12 +289,13 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                                                  : make_smem_desc(a_base + k * 32, 0, 1024, UMMA_LAYOUT_SW128);
                         const uint64_t db = B_MN ? make_smem_desc(b_base + k * 2048, 8192, 1024, UMMA_LAYOUT_SW128)
                                                  : make_smem_desc(b_base + k * 32, 0, 1024, UMMA_LAYOUT_SW128);
-                        if constexpr (CG == 2) umma_bf16_2sm(tmem_d, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
-                        else umma_bf16(tmem_d, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+                        const uint32_t acc = (kb != kb_begin || k != 0) ? 1u : 0u;
+                        if constexpr (CG == 2) umma_bf16_2sm(tmem_d, da, db, idesc, acc);
+                        else umma_bf16(tmem_d, da, db, idesc, acc);
                     }
                     // slot reusable once these MMAs have read it (pair: released in both CTAs)
                     if constexpr (CG == 2) umma_commit_2sm(&empty_bar[stage]); else umma_commit(&empty_bar[stage]);
-                    if (kb == num_kb - 1) {
+                    if (kb == kb_end - 1) {
                         if constexpr (CG == 2) umma_commit_2sm(&tmem_full_bar[as]); else umma_commit(&tmem_full_bar[as]);
                     }
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -302,7 +308,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         int it = 0;
         for (int tile = blockIdx.x / CG; tile < num_tiles; tile += gridDim.x / CG, ++it) {
             int m_blk, n_blk;
-            tile_coords(tile, num_m, num_n, m_blk, n_blk);
+            tile_coords(tile / splitk, num_m, num_n, m_blk, n_blk);
             const int as = it & 1;
             const uint32_t aphase = (it >> 1) & 1;
             mbar_wait(&tmem_full_bar[as], aphase);
@@ -331,6 +337,15 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     float v[32];
 #pragma unroll
                     for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * args.alpha;
+                    if (splitk > 1) {   // partial sum of a K split: fp32 atomics into the (zero-initialised) fp32 output
+                        if (store_ok) {
+                            float* d = reinterpret_cast<float*>(args.D) + drow * args.ldd + n0;
+#pragma unroll
+                            for (int j = 0; j < 32; ++j)
+                                if (n0 + j < args.N) atomicAdd(d + j, v[j]);
+                        }
+                        continue;
+                    }
                     const bool full_chunk = (n0 + 32 <= args.N);
                     if (full_chunk) {
                         if (bias != nullptr) {
@@ -514,7 +529,7 @@ static int launch(const CUtensorMap& tA, const CUtensorMap (&tB)[3], const CUten
         LHRS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
         attr_set = true;
     }
-    const int num_tiles = ((a.M + BM * CG - 1) / (BM * CG)) * ((a.N + BN - 1) / BN);   // tiles per CTA (CG=1) or per CTA pair
+    const int num_tiles = ((a.M + BM * CG - 1) / (BM * CG)) * ((a.N + BN - 1) / BN) * a.splitk;   // per CTA (CG=1) or CTA pair
     const int max_units = num_sms() / CG;
     const int grid = (num_tiles < max_units ? num_tiles : max_units) * CG;
     const bool prof = prof_on();
@@ -661,6 +676,15 @@ extern "C" int lhrs_gemm_bf16(const LhrsGemm* g, void* stream_) {
 
     GemmArgs a;
     a.ext_k = ext_k; a.ext_kb = ext_kb;
+    a.splitk = 1;
+    if (g->split_k > 1) {
+        LHRS_CHECK_ARG(kind == LHRS_EPI_LINEAR && g->d_f32 && ext_kb == 0 && !g->bias[0] && !g->residual && g->act == LHRS_ACT_NONE && !g->pre_gate,
+                       "lhrs_gemm_bf16: split_k needs a plain LINEAR epilogue with an fp32 (zero-initialised) output");
+        const int nkb = (g->K + BK - 1) / BK;
+        int sk = g->split_k < nkb ? g->split_k : nkb;
+        while (sk > 1 && ((nkb + sk - 1) / sk) * (sk - 1) >= nkb) --sk;   // every split must own at least one k-block
+        a.splitk = sk;
+    }
     a.M = g->M; a.N = g->N; a.K = g->K;
     a.kseg = kseg;
     a.kseg_nshift = (kseg > 0) ? g->b_seg_nshift : 0;

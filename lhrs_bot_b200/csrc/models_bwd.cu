@@ -77,10 +77,10 @@ static int gemm_dx(cudaStream_t st, long long M, int N, int K, const void* dY, l
 }
 // dW[out,in] = dY[rows,out]^T · X[rows,in]   (both operands read MN-major, reduction over rows)
 static int gemm_dw(cudaStream_t st, int out, int in, long long rows, const void* dY, long long ldy, const void* X, long long ldx,
-                   void* dW, long long ldw, float alpha = 1.f) {
+                   void* dW, long long ldw, float alpha = 1.f, float* skinny_scratch = nullptr) {
     LhrsGemm g = gemm_desc(out, in, static_cast<int>(rows), dY, ldy, X, ldx, dW, ldw);
     g.a_mn_major = 1; g.b_mn_major = 1; g.alpha = alpha;
-    return lhrs_gemm_bf16(&g, st);
+    return skinny_gemm(g, skinny_scratch, st);   // plain launch unless the problem is skinny and scratch is given
 }
 
 // diagonal blocks of a [n*out, n*r] product -> the n separate [out, r] gradient tensors
@@ -108,6 +108,7 @@ struct LoraBwd {
     const void* dy[3] = {nullptr, nullptr, nullptr}; long long ldy = 0;
     const __nv_bfloat16* T = nullptr;   // [M, nproj*r] from the forward stash
     __nv_bfloat16* dt = nullptr;        // [M, nproj*r]
+    float* scratch = nullptr;           // fp32 split-K accumulator for the skinny side GEMMs
     long long M = 0;
 };
 
@@ -126,7 +127,7 @@ static int lora_bwd_pre(cudaStream_t st, const LhrsLlamaWeights* w, void* const*
         d.b_mn_major = 1; d.num_b = n; d.alpha = w->lora_scale;
         for (int p = 1; p < n; ++p) d.B[p] = w->lora_b[L.idx0 + p];
         if (n > 1) d.b_seg_nshift = r;
-        if ((rc = lhrs_gemm_bf16(&d, st))) return rc;
+        if ((rc = skinny_gemm(d, L.scratch, st))) return rc;
     }
     // dx += dT · [A_0;A_1;..] accumulates in the main GEMM's TMEM tile
     g.A2 = L.dt; g.lda2 = ldt; g.B2[0] = w->lora_a[L.idx0]; g.ldb2 = L.in_dim; g.ext_k = n * r;
@@ -142,9 +143,9 @@ static int lora_bwd_post(cudaStream_t st, const LhrsLlamaWeights* w, void* const
     if (L.grouped) {
         if (gb != nullptr) {   // [dy_0|dy_1|..]^T T -> diagonal blocks are the dB_p
             if (n == 1) {
-                if (gb[L.idx0]) if ((rc = gemm_dw(st, L.out_dim, r, L.M, L.dy[0], L.ldy, L.T, ldt, gb[L.idx0], r))) return rc;
+                if (gb[L.idx0]) if ((rc = gemm_dw(st, L.out_dim, r, L.M, L.dy[0], L.ldy, L.T, ldt, gb[L.idx0], r, 1.f, L.scratch))) return rc;
             } else {
-                if ((rc = gemm_dw(st, n * L.out_dim, n * r, L.M, L.dy[0], L.ldy, L.T, ldt, diag_buf, ldt))) return rc;
+                if ((rc = gemm_dw(st, n * L.out_dim, n * r, L.M, L.dy[0], L.ldy, L.T, ldt, diag_buf, ldt, 1.f, L.scratch))) return rc;
                 const long long total = (long long)n * L.out_dim * r;
                 lora_extract_diag_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(
                     diag_buf, n, L.out_dim, r, (__nv_bfloat16*)gb[L.idx0], (__nv_bfloat16*)gb[L.idx0 + 1],
@@ -152,7 +153,7 @@ static int lora_bwd_post(cudaStream_t st, const LhrsLlamaWeights* w, void* const
                 LHRS_LAUNCH_CHECK("lora_extract_diag_kernel");
             }
         }
-        if (ga != nullptr && ga[L.idx0]) if ((rc = gemm_dw(st, n * r, L.in_dim, L.M, L.dt, ldt, L.x, L.ldx, ga[L.idx0], L.in_dim))) return rc;
+        if (ga != nullptr && ga[L.idx0]) if ((rc = gemm_dw(st, n * r, L.in_dim, L.M, L.dt, ldt, L.x, L.ldx, ga[L.idx0], L.in_dim, 1.f, L.scratch))) return rc;
         return LHRS_OK;
     }
     for (int p = 0; p < n; ++p) {   // separate tensors: one projection at a time, dx accumulated in a read-modify-write pass
@@ -166,8 +167,10 @@ static int lora_bwd_post(cudaStream_t st, const LhrsLlamaWeights* w, void* const
 }
 
 static LoraBwd lora_ctx(const LhrsLlamaWeights* w, int layer, int first, int nproj, const void* x, long long ldx, int in_dim,
-                        const void* dy0, long long ldy, int out_dim, long long M, const __nv_bfloat16* T, __nv_bfloat16* dt) {
+                        const void* dy0, long long ldy, int out_dim, long long M, const __nv_bfloat16* T, __nv_bfloat16* dt,
+                        float* scratch) {
     LoraBwd L;
+    L.scratch = scratch;
     L.active = w->lora_r > 0 && w->lora_a != nullptr && w->lora_b != nullptr;
     L.idx0 = layer * 7 + first; L.nproj = nproj; L.in_dim = in_dim; L.out_dim = out_dim;
     L.x = x; L.ldx = ldx; L.ldy = ldy; L.M = M; L.T = T; L.dt = dt;
@@ -182,7 +185,7 @@ typedef __nv_bfloat16 bf16;
 
 // ================================================================================================ LLaMA backward
 namespace {
-struct LlamaBwdBufs { bf16 *dxa, *dxb, *dh, *d_act, *d_gu, *dqkv, *d_o, *h, *t, *dt, *diag; float* delta; };
+struct LlamaBwdBufs { bf16 *dxa, *dxb, *dh, *d_act, *d_gu, *dqkv, *d_o, *h, *t, *dt, *diag; float *delta, *skinny; };
 LlamaBwdBufs llama_bwd_plan(Arena& a, const LhrsLlamaWeights* w, long long M) {
     LlamaBwdBufs b;
     const int D = w->dim, F = w->ffn;
@@ -196,6 +199,7 @@ LlamaBwdBufs llama_bwd_plan(Arena& a, const LhrsLlamaWeights* w, long long M) {
     b.dt = lora ? a.take<bf16>(M * 3 * w->lora_r) : nullptr;
     const long long widest = (3LL * w->dim > 2LL * w->ffn) ? 3LL * w->dim : 2LL * w->ffn;
     b.diag = lora ? a.take<bf16>(widest * 3 * w->lora_r) : nullptr;
+    b.skinny = lora ? a.take<float>(skinny_scratch_elems(w, M)) : nullptr;
     return b;
 }
 }  // namespace
@@ -231,7 +235,7 @@ extern "C" int lhrs_llama_bwd(const LhrsLlamaWeights* w, void* const* lora_a_gra
         const LlamaLayerStash& t = s.layer[l];
         // ---- MLP: x_out = x_mid + down(silu(gate(h2)) * up(h2)),  h2 = rmsnorm(x_mid)
         {
-            LoraBwd L = lora_ctx(w, l, 6, 1, t.act, F, F, dx, D, D, M, t.lora_t[3], b.dt);
+            LoraBwd L = lora_ctx(w, l, 6, 1, t.act, F, F, dx, D, D, M, t.lora_t[3], b.dt, b.skinny);
             LhrsGemm g = gemm_desc(M, F, D, dx, D, w->down_w[l], F, b.d_act, F);
             g.b_mn_major = 1;
             if ((rc = lora_bwd_pre(st, w, lora_a_grads, L, g))) return rc;
@@ -241,7 +245,7 @@ extern "C" int lhrs_llama_bwd(const LhrsLlamaWeights* w, void* const* lora_a_gra
         if ((rc = lhrs_swiglu_bwd(b.d_act, t.pre_gate, t.pre_up, b.d_gu, M, F, st))) return rc;
         {
             if (w->lora_r > 0) if ((rc = lhrs_rmsnorm_fwd(t.x_mid, w->ln2_w[l], b.h, nullptr, M, D, w->eps, st))) return rc;
-            LoraBwd L = lora_ctx(w, l, 4, 2, b.h, D, D, b.d_gu, 2 * F, F, M, t.lora_t[2], b.dt);
+            LoraBwd L = lora_ctx(w, l, 4, 2, b.h, D, D, b.d_gu, 2 * F, F, M, t.lora_t[2], b.dt, b.skinny);
             LhrsGemm g = gemm_desc(M, D, 2 * F, b.d_gu, 2 * F, w->gate_w[l], D, b.dh, D);
             g.b_mn_major = 1; g.B[1] = w->up_w[l]; g.num_b = 2;
             if ((rc = lora_bwd_pre(st, w, lora_a_grads, L, g))) return rc;
@@ -252,7 +256,7 @@ extern "C" int lhrs_llama_bwd(const LhrsLlamaWeights* w, void* const* lora_a_gra
         { bf16* tmp = dx; dx = dx_other; dx_other = tmp; }   // dx = grad wrt x_mid
         // ---- attention: x_mid = x_in + o_proj(attn(rope(q), rope(k), v)),  q,k,v = proj(h1), h1 = rmsnorm(x_in)
         {
-            LoraBwd L = lora_ctx(w, l, 3, 1, t.o, D, D, dx, D, D, M, t.lora_t[1], b.dt);
+            LoraBwd L = lora_ctx(w, l, 3, 1, t.o, D, D, dx, D, D, M, t.lora_t[1], b.dt, b.skinny);
             LhrsGemm g = gemm_desc(M, D, D, dx, D, w->o_w[l], D, b.d_o, D);
             g.b_mn_major = 1;
             if ((rc = lora_bwd_pre(st, w, lora_a_grads, L, g))) return rc;
@@ -273,7 +277,7 @@ extern "C" int lhrs_llama_bwd(const LhrsLlamaWeights* w, void* const* lora_a_gra
         if ((rc = lhrs_rope_bwd(b.dqkv, 3 * D, M, D, w->rope_cos, w->rope_sin, nullptr, S, st))) return rc;
         {
             if (w->lora_r > 0) if ((rc = lhrs_rmsnorm_fwd(t.x_in, w->ln1_w[l], b.h, nullptr, M, D, w->eps, st))) return rc;
-            LoraBwd L = lora_ctx(w, l, 0, 3, b.h, D, D, b.dqkv, 3 * D, D, M, t.lora_t[0], b.dt);
+            LoraBwd L = lora_ctx(w, l, 0, 3, b.h, D, D, b.dqkv, 3 * D, D, M, t.lora_t[0], b.dt, b.skinny);
             LhrsGemm g = gemm_desc(M, D, 3 * D, b.dqkv, 3 * D, w->q_w[l], D, b.dh, D);
             g.b_mn_major = 1; g.B[1] = w->k_w[l]; g.B[2] = w->v_w[l]; g.num_b = 3;
             if ((rc = lora_bwd_pre(st, w, lora_a_grads, L, g))) return rc;

@@ -157,8 +157,20 @@ __host__ __device__ inline __nv_bfloat16* kv_ptr(const KvGeom& kv, int layer, in
 // LoRA: compute T = scale * x · A^T for `nproj` projections sharing the input x and attach the K-extension
 // (A2 = T, B2 = lora_B) to the parent GEMM so that B·T accumulates into the same TMEM tile.  No-op when LoRA is off.
 int lora_attach(LhrsGemm& g, const LhrsLlamaWeights* w, int layer, int first_proj, int nproj, const void* x, long long ldx,
-                long long M, __nv_bfloat16* t_buf, void* stream);
+                long long M, __nv_bfloat16* t_buf, float* scratch, void* stream);
 
 bool lora_a_adjacent(const void* const* arr, int idx, int nproj, long long elems_each);
+
+// Run a skinny GEMM (few output tiles, long K) with a K split sized to fill the SMs: fp32 atomics into `scratch`
+// (>= M*N floats), then one cast into the bf16 destination (which must be contiguous, ldd == N).  Falls back to the
+// plain launch when the problem already has enough tiles or no scratch is given.
+int skinny_gemm(LhrsGemm& g, float* scratch, void* stream);
+inline long long skinny_scratch_elems(const LhrsLlamaWeights* w, long long M) {
+    long long rows = M;
+    if (2LL * w->ffn > rows) rows = 2LL * w->ffn;
+    if (3LL * w->dim > rows) rows = 3LL * w->dim;
+    long long a = rows * 3 * w->lora_r, b = 3LL * w->lora_r * (w->ffn > w->dim ? w->ffn : w->dim);
+    return a > b ? a : b;
+}
 
 }  // namespace lhrs

@@ -81,8 +81,28 @@ bool lora_a_adjacent(const void* const* arr, int idx, int nproj, long long elems
     return true;
 }
 
+int skinny_gemm(LhrsGemm& g, float* scratch, void* stream) {
+    const long long tiles = ((g.M + 127) / 128) * (long long)((g.N + 127) / 128);
+    const int nkb = (g.K + 63) / 64;
+    // measured on B200: the split pays only when a launch would otherwise occupy < 1/3 of the SMs (its fixed cost is a
+    // memset + a cast); 4 splits of >= 8 k-blocks each is the sweet spot for the token-reduction (TN) forms
+    int sk = (tiles * 3 <= num_sms()) ? 4 : 1;
+    if (sk > nkb / 8) sk = nkb / 8;
+    if (scratch == nullptr || sk < 2 || g.ldd != g.N || g.d_f32 || g.bias[0] || g.residual || g.act != LHRS_ACT_NONE || g.A2 ||
+        (static_cast<long long>(g.M) * g.N) % 4 != 0)
+        return lhrs_gemm_bf16(&g, stream);
+    void* dst = g.D;
+    const long long n = static_cast<long long>(g.M) * g.N;
+    LHRS_CUDA(cudaMemsetAsync(scratch, 0, n * sizeof(float), (cudaStream_t)stream));
+    g.D = scratch; g.d_f32 = 1; g.split_k = sk;
+    int rc = lhrs_gemm_bf16(&g, stream);
+    g.D = dst; g.d_f32 = 0; g.split_k = 0;
+    if (rc) return rc;
+    return lhrs_cast_f32_bf16(scratch, dst, n, stream);
+}
+
 int lora_attach(LhrsGemm& g, const LhrsLlamaWeights* w, int layer, int first_proj, int nproj, const void* x, long long ldx,
-                long long M, __nv_bfloat16* t_buf, void* stream) {
+                long long M, __nv_bfloat16* t_buf, float* scratch, void* stream) {
     if (w->lora_r <= 0 || w->lora_a == nullptr || w->lora_b == nullptr) return LHRS_OK;
     const int r = w->lora_r;
     const int idx = layer * 7 + first_proj;
@@ -91,7 +111,7 @@ int lora_attach(LhrsGemm& g, const LhrsLlamaWeights* w, int layer, int first_pro
         // T = (alpha/r) * x · [A_0; A_1; ..]^T in ONE skinny GEMM (one pass over x)
         LhrsGemm t = gemm_desc(M, nproj * r, g.K, x, ldx, w->lora_a[idx], g.K, t_buf, (long long)nproj * r);
         t.alpha = w->lora_scale;
-        if ((rc = lhrs_gemm_bf16(&t, stream))) return rc;
+        if ((rc = skinny_gemm(t, scratch, stream))) return rc;
     } else {
         for (int p = 0; p < nproj; ++p) {
             LhrsGemm t = gemm_desc(M, r, g.K, x, ldx, w->lora_a[idx + p], g.K, t_buf + p * r, (long long)nproj * r);
@@ -315,7 +335,7 @@ extern "C" int lhrs_pooler_fwd(const LhrsPoolerWeights* w, const void* image_emb
 
 // ================================================================================================ LLaMA
 namespace {
-struct LlamaBufs { bf16 *x, *h, *qkv, *o, *act, *lora_t; };
+struct LlamaBufs { bf16 *x, *h, *qkv, *o, *act, *lora_t; float* skinny; };
 LlamaBufs llama_plan(Arena& a, const LhrsLlamaWeights* w, long long M, bool have_stash) {
     LlamaBufs b;
     b.x = a.take<bf16>(M * w->dim);
@@ -324,6 +344,7 @@ LlamaBufs llama_plan(Arena& a, const LhrsLlamaWeights* w, long long M, bool have
     b.o = have_stash ? nullptr : a.take<bf16>(M * w->dim);
     b.act = have_stash ? nullptr : a.take<bf16>(M * w->ffn);
     b.lora_t = (w->lora_r > 0) ? a.take<bf16>(M * 3 * w->lora_r) : nullptr;
+    b.skinny = (w->lora_r > 0) ? a.take<float>(skinny_scratch_elems(w, M)) : nullptr;
     return b;
 }
 }  // namespace
@@ -369,7 +390,7 @@ extern "C" int lhrs_llama_fwd(const LhrsLlamaWeights* w, const void* inputs_embe
             LhrsGemm g = gemm_desc(M, 3 * D, D, b.h, D, w->q_w[l], D, qkv, 3 * D);
             g.B[1] = w->k_w[l]; g.B[2] = w->v_w[l]; g.num_b = 3; g.seg_rows = D;
             g.epilogue = LHRS_EPI_ROPE; g.rope_cos = w->rope_cos; g.rope_sin = w->rope_sin; g.rope_seq_len = S;
-            if ((rc = lora_attach(g, w, l, 0, 3, b.h, D, M, ls ? ls->lora_t[0] : b.lora_t, stream))) return rc;
+            if ((rc = lora_attach(g, w, l, 0, 3, b.h, D, M, ls ? ls->lora_t[0] : b.lora_t, b.skinny, stream))) return rc;
             if ((rc = lhrs_gemm_bf16(&g, stream))) return rc;
         }
         if (kv != nullptr) {
@@ -386,7 +407,7 @@ extern "C" int lhrs_llama_fwd(const LhrsLlamaWeights* w, const void* inputs_embe
         {
             LhrsGemm g = gemm_desc(M, D, D, o, D, w->o_w[l], D, b.x, D);
             g.residual = b.x; g.ldr = D;
-            if ((rc = lora_attach(g, w, l, 3, 1, o, D, M, ls ? ls->lora_t[1] : b.lora_t, stream))) return rc;
+            if ((rc = lora_attach(g, w, l, 3, 1, o, D, M, ls ? ls->lora_t[1] : b.lora_t, b.skinny, stream))) return rc;
             if ((rc = lhrs_gemm_bf16(&g, stream))) return rc;
         }
         if (ls) LHRS_CUDA(cudaMemcpyAsync(ls->x_mid, b.x, M * D * 2, cudaMemcpyDeviceToDevice, stream));
@@ -396,13 +417,13 @@ extern "C" int lhrs_llama_fwd(const LhrsLlamaWeights* w, const void* inputs_embe
             LhrsGemm g = gemm_desc(M, 2 * F, D, b.h, D, w->gate_w[l], D, act, F);
             g.B[1] = w->up_w[l]; g.num_b = 2; g.seg_rows = F; g.epilogue = LHRS_EPI_SWIGLU;
             if (ls) { g.pre_gate = ls->pre_gate; g.pre_up = ls->pre_up; }
-            if ((rc = lora_attach(g, w, l, 4, 2, b.h, D, M, ls ? ls->lora_t[2] : b.lora_t, stream))) return rc;
+            if ((rc = lora_attach(g, w, l, 4, 2, b.h, D, M, ls ? ls->lora_t[2] : b.lora_t, b.skinny, stream))) return rc;
             if ((rc = lhrs_gemm_bf16(&g, stream))) return rc;
         }
         {
             LhrsGemm g = gemm_desc(M, D, F, act, F, w->down_w[l], F, b.x, D);
             g.residual = b.x; g.ldr = D;
-            if ((rc = lora_attach(g, w, l, 6, 1, act, F, M, ls ? ls->lora_t[3] : b.lora_t, stream))) return rc;
+            if ((rc = lora_attach(g, w, l, 6, 1, act, F, M, ls ? ls->lora_t[3] : b.lora_t, b.skinny, stream))) return rc;
             if ((rc = lhrs_gemm_bf16(&g, stream))) return rc;
         }
     }

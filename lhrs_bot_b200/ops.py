@@ -48,7 +48,7 @@ def gemm(a: torch.Tensor, b, *, out: Optional[torch.Tensor] = None, bias: Option
          a_mn_major: bool = False, b_mn_major: bool = False, out_f32: bool = False,
          row_map: Optional[torch.Tensor] = None, epilogue: int = EPI_LINEAR,
          rope: Optional[Tuple[torch.Tensor, torch.Tensor, Optional[torch.Tensor], int]] = None,
-         pre_gate: Optional[torch.Tensor] = None, pre_up: Optional[torch.Tensor] = None) -> torch.Tensor:
+         pre_gate: Optional[torch.Tensor] = None, pre_up: Optional[torch.Tensor] = None, split_k: int = 0) -> torch.Tensor:
     """D = epilogue(alpha * A · B^T).  ``b`` is a tensor [N, K] or a list of 2-3 equally shaped segments.
 
     K-major (default): a is [M, K], b is [N, K] (nn.Linear weight layout).
@@ -121,6 +121,7 @@ def gemm(a: torch.Tensor, b, *, out: Optional[torch.Tensor] = None, bias: Option
             _need(positions, torch.int32, "rope positions")
         g.positions, g.rope_seq_len = _ptr(positions), int(seq_len)
     g.pre_gate, g.pre_up = _ptr(pre_gate), _ptr(pre_up)
+    g.split_k = int(split_k)     # > 1: fp32 atomics into a zero-initialised fp32 `out`
     check(_lib.load().lhrs_gemm_bf16(C.byref(g), _stream()), "lhrs_gemm_bf16")
     return out
 

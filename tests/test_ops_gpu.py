@@ -91,6 +91,20 @@ def test_gemm_epilogue_linear(M, N, K):
     _report("row_map", dst, exp, 2e-2)
 
 
+@pytest.mark.parametrize("M,N,K,sk,a_mn,b_mn", [(8192, 48, 4096, 4, False, False), (48, 4096, 8192, 4, True, True),
+                                                 (4096, 16, 8192, 8, True, True), (1000, 48, 1024, 3, False, True)])
+def test_gemm_split_k(M, N, K, sk, a_mn, b_mn):
+    """K split over several CTAs per tile with fp32 atomics (skinny LoRA side GEMMs)."""
+    ops = _ops()
+    a = _randn(*((K, M) if a_mn else (M, K)), seed=41)
+    b = _randn(*((K, N) if b_mn else (N, K)), scale=1.0 / math.sqrt(K), seed=42)
+    out = torch.zeros(M, N, device=DEV, dtype=torch.float32)
+    ops.gemm(a, b, out=out, out_f32=True, a_mn_major=a_mn, b_mn_major=b_mn, split_k=sk, alpha=0.5)
+    af = a.float().T if a_mn else a.float()
+    bf = b.float() if b_mn else b.float().T
+    _report(f"split_k {M}x{N}x{K}/{sk}", out, 0.5 * (af @ bf), 2e-3)
+
+
 def test_gemm_segments():
     ops = _ops()
     M, K, seg = 384, 512, 256

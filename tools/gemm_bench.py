@@ -51,3 +51,46 @@ b8 = torch.randn(8192, 8192, device=dev).bfloat16()
 o8 = torch.empty(8192, 8192, device=dev, dtype=torch.bfloat16)
 bench("square 8192^3", lambda: ops.gemm(a8, b8, out=o8), 2 * 8192 ** 3)
 bench("torch.matmul 8192^3 (cuBLAS)", lambda: torch.matmul(a8, b8.t(), out=o8), 2 * 8192 ** 3)
+
+# ---- skinny LoRA side GEMMs (memory-bound): report GB/s of the big operand
+def bench_bw(name, fn, nbytes, iters=30):
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / iters
+    print(f"{name:44s} {ms*1e3:9.1f} us  {nbytes/ms/1e6:8.1f} GB/s", flush=True)
+
+r = 16
+A3 = w(3 * r, D)
+T3 = torch.empty(M, 3 * r, device=dev, dtype=torch.bfloat16)
+dqkv = torch.randn(M, 3 * D, device=dev).bfloat16()
+Bs = [w(D, r) for _ in range(3)]
+dT3 = torch.empty(M, 3 * r, device=dev, dtype=torch.bfloat16)
+dB_full = torch.empty(3 * D, 3 * r, device=dev, dtype=torch.bfloat16)
+dA3 = torch.empty(3 * r, D, device=dev, dtype=torch.bfloat16)
+bench_bw("T = x A^T        [8192,4096]x[48,4096]", lambda: ops.gemm(x, A3, out=T3), M * D * 2)
+bench_bw("  torch            same", lambda: torch.matmul(x, A3.t(), out=T3), M * D * 2)
+bench_bw("dT = dy blockdiag(B) [8192,12288]->48", lambda: ops.gemm(dqkv, Bs, out=dT3, b_mn_major=True), M * 3 * D * 2)
+bench_bw("dB = dy^T T  TN  [12288,48] K=8192", lambda: ops.gemm(dqkv, T3, out=dB_full, a_mn_major=True, b_mn_major=True), M * 3 * D * 2)
+bench_bw("  torch            same", lambda: torch.matmul(dqkv.t(), T3, out=dB_full), M * 3 * D * 2)
+bench_bw("dA = dT^T x  TN  [48,4096] K=8192", lambda: ops.gemm(dT3, x, out=dA3, a_mn_major=True, b_mn_major=True), M * D * 2)
+bench_bw("  torch            same", lambda: torch.matmul(dT3.t(), x, out=dA3), M * D * 2)
+xo = torch.randn(M, D, device=dev).bfloat16()
+A1 = w(r, D)
+T1 = torch.empty(M, r, device=dev, dtype=torch.bfloat16)
+dB1 = torch.empty(D, r, device=dev, dtype=torch.bfloat16)
+bench_bw("T(o) [8192,4096]x[16,4096]", lambda: ops.gemm(xo, A1, out=T1), M * D * 2)
+bench_bw("dB(o) TN [4096,16] K=8192", lambda: ops.gemm(xo, T1, out=dB1, a_mn_major=True, b_mn_major=True), M * D * 2)
+
+T3f = torch.zeros(M, 3 * r, device=dev, dtype=torch.float32)
+dA3f = torch.zeros(3 * r, D, device=dev, dtype=torch.float32)
+for sk in (2, 3, 4, 6, 8):
+    bench_bw(f"T split_k={sk}", lambda: ops.gemm(x, A3, out=T3f, out_f32=True, split_k=sk), M * D * 2)
+for sk in (2, 4, 6, 8):
+    bench_bw(f"dA split_k={sk}", lambda: ops.gemm(dT3, x, out=dA3f, out_f32=True, a_mn_major=True, b_mn_major=True, split_k=sk), M * D * 2)
