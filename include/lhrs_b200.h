@@ -79,7 +79,8 @@ typedef struct LhrsGemm {
     int32_t rope_seq_len;
     /* SwiGLU epilogue: optionally keep the raw gate / up projections for backward (bf16 [M, N/2]) */
     void* pre_gate;       /* LINEAR: optional copy of the pre-activation (alpha*acc + bias), bf16 [M, N] */
-    void* pre_up;
+    void* pre_up;         /* LINEAR with BOTH set (N % 32 == 0): fused SwiGLU backward — the accumulator is d_act, pre_gate /
+                             pre_up are the stashed forward pre-activations (inputs), D [M, 2N] receives [d_gate | d_up] */
     /* K-extension (LoRA, common_arch-independent; text_modal.py:133-151): after the K loop over A/B the kernel keeps
      * accumulating A2[:, s*ext_k:(s+1)*ext_k] · B2[s]^T into the same TMEM tile, s = B segment of the tile.
      * A2 is bf16 [M, lda2] holding num_b blocks of ext_k columns (T = scale * x·lora_A^T); B2[s] is lora_B [seg_rows, ldb2]. */
@@ -132,6 +133,10 @@ typedef struct LhrsAttentionBwd {
     void* dq; void* dk; void* dv;
     float* delta;
     int64_t dq_bs, dq_rs, dq_hs, dk_bs, dk_rs, dk_hs, dv_bs, dv_rs, dv_hs;
+    /* optional (head_dim 128): undo the RoPE rotation on dQ and dK before they are stored (position = row index), so the
+     * gradients come out w.r.t. the un-rotated projections; tables [max_pos, 64] fp32 as in LhrsGemm */
+    const float* rope_cos;
+    const float* rope_sin;
 } LhrsAttentionBwd;
 int lhrs_attention_bwd(const LhrsAttentionBwd* a, void* stream);
 

@@ -79,6 +79,7 @@ class LhrsAttentionBwd(C.Structure):
         ("dq_bs", C.c_int64), ("dq_rs", C.c_int64), ("dq_hs", C.c_int64),
         ("dk_bs", C.c_int64), ("dk_rs", C.c_int64), ("dk_hs", C.c_int64),
         ("dv_bs", C.c_int64), ("dv_rs", C.c_int64), ("dv_hs", C.c_int64),
+        ("rope_cos", C.c_void_p), ("rope_sin", C.c_void_p),
     ]
 
 

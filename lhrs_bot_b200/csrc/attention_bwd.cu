@@ -21,7 +21,33 @@ struct AttnBwdArgs {
     long long dq_bs, dq_rs, dq_hs, dk_bs, dk_rs, dk_hs, dv_bs, dv_rs, dv_hs;
     int B, H, Sq, Skv;
     float scale, scale_log2;
+    const float* rope_cos;   // non-null (HD 128 only): inverse RoPE on dQ / dK at store time
+    const float* rope_sin;
 };
+
+// inverse rotate-half on one thread's fragment: tiles i (dims 8i+2t, +1) and i+8 (dims +64) of the same row pair up
+template <int DTILES>
+__device__ __forceinline__ void unrope_frag(float (&g)[DTILES][4], const float* cosT, const float* sinT, int row_a, int row_b, int t4,
+                                            int nrows) {
+    if constexpr (DTILES == 16) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int j = i * 8 + t4 * 2;
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+                const int row = r == 0 ? row_a : row_b;
+                if (row >= nrows) continue;
+                const float2 c = *reinterpret_cast<const float2*>(cosT + static_cast<long long>(row) * 64 + j);
+                const float2 s = *reinterpret_cast<const float2*>(sinT + static_cast<long long>(row) * 64 + j);
+                const float y1a = g[i][r * 2], y1b = g[i][r * 2 + 1], y2a = g[i + 8][r * 2], y2b = g[i + 8][r * 2 + 1];
+                g[i][r * 2] = y1a * c.x + y2a * s.x;          // dx1 = dy1 c + dy2 s
+                g[i][r * 2 + 1] = y1b * c.y + y2b * s.y;
+                g[i + 8][r * 2] = y2a * c.x - y1a * s.x;      // dx2 = dy2 c - dy1 s
+                g[i + 8][r * 2 + 1] = y2b * c.y - y1b * s.y;
+            }
+        }
+    }
+}
 
 __device__ __forceinline__ void cp_async16b(uint32_t dst, const void* src, bool valid) {
     const int sz = valid ? 16 : 0;
@@ -204,6 +230,7 @@ __global__ void __launch_bounds__(128) attn_bwd_dq_kernel(const AttnBwdArgs p) {
         }
         __syncthreads();
     }
+    if (p.rope_cos != nullptr) unrope_frag<DTILES>(dq, p.rope_cos, p.rope_sin, qrow0, qrow0 + 8, t4, p.Sq);
     __nv_bfloat16* dqg = p.dq + b * p.dq_bs + h * p.dq_hs;
 #pragma unroll
     for (int i = 0; i < DTILES; ++i) {
@@ -342,6 +369,7 @@ __global__ void __launch_bounds__(128) attn_bwd_dkv_kernel(const AttnBwdArgs p) 
         }
         __syncthreads();
     }
+    if (p.rope_cos != nullptr) unrope_frag<DTILES>(dk, p.rope_cos, p.rope_sin, krow0, krow0 + 8, t4, p.Skv);
     __nv_bfloat16* dkg = p.dk + b * p.dk_bs + h * p.dk_hs;
     __nv_bfloat16* dvg = p.dv + b * p.dv_bs + h * p.dv_hs;
 #pragma unroll
@@ -412,6 +440,9 @@ extern "C" int lhrs_attention_bwd(const LhrsAttentionBwd* d, void* stream_) {
     a.dv_bs = d->dv_bs; a.dv_rs = d->dv_rs; a.dv_hs = d->dv_hs;
     a.B = f->B; a.H = f->H; a.Sq = f->Sq; a.Skv = f->Skv;
     a.scale = f->scale; a.scale_log2 = f->scale * 1.4426950408889634f;
+    a.rope_cos = d->rope_cos; a.rope_sin = d->rope_sin;
+    LHRS_CHECK_ARG(a.rope_cos == nullptr || (f->head_dim == 128 && a.rope_sin != nullptr && f->Sq == f->Skv),
+                   "lhrs_attention_bwd: fused un-RoPE needs head_dim 128, both tables and Sq == Skv");
     if (f->head_dim == 128) return f->causal ? launch_bwd<128, true>(a, stream) : launch_bwd<128, false>(a, stream);
     return f->causal ? launch_bwd<64, true>(a, stream) : launch_bwd<64, false>(a, stream);
 }

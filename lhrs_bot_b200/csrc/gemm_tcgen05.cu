@@ -41,6 +41,9 @@ struct GemmArgs {
     __nv_bfloat16* pre_up;
     int kseg;    // MN-major B stacked along K: reduction length per segment (0 = single B)
     int kseg_nshift;  // segment s lands in output columns [s*nshift, s*nshift + its width): block-diagonal B (LoRA dT)
+    int coalesce; // epilogue I/O through the per-warp smem transpose (1) or direct per-lane rows (0)
+    int group_m; // row-blocks per rasterisation group (L2 reuse)
+    int pf_dist; // k-blocks of L2 prefetch distance ahead of the TMA loads (0 = off)
     int splitk;  // >1: the K loop is split over `splitk` CTAs per tile; partial sums are added with fp32 atomics into D
     int ext_k;   // LoRA K-extension: columns of A2 per B segment (0 = none)
     int ext_kb;  // extra 64-wide k-blocks appended after the main K loop
@@ -56,7 +59,8 @@ struct GemmCfg {
     static constexpr uint32_t A_BYTES = BM * BK * 2;
     static constexpr uint32_t B_BYTES = BN_CTA * BK * 2;
     static constexpr uint32_t TMEM_COLS = 2 * BN;
-    static constexpr uint32_t SMEM_BYTES = STAGES * (A_BYTES + B_BYTES) + 256 /*barriers*/ + 1024 /*align slack*/;
+    static constexpr uint32_t EPI_STAGE_BYTES = 32 * 80;   // per epilogue warp: 32 rows x 32 bf16, rows padded to 80 B
+    static constexpr uint32_t SMEM_BYTES = STAGES * (A_BYTES + B_BYTES) + 256 /*barriers*/ + 4 * EPI_STAGE_BYTES + 1024 /*align slack*/;
 };
 
 __device__ __forceinline__ float act_apply(float v, int act) {
@@ -94,10 +98,50 @@ __device__ __forceinline__ void store_f32x32(float* p, const float (&v)[32]) {
     for (int i = 0; i < 8; ++i) q[i] = make_float4(v[i * 4], v[i * 4 + 1], v[i * 4 + 2], v[i * 4 + 3]);
 }
 
+// ---- coalesced epilogue I/O.  A warp owns 32 rows x 32 columns with lane = row (the TMEM read layout).  Storing that
+// directly makes every instruction touch 32 different rows (half-used 32-byte sectors).  Instead the tile is transposed
+// through a small per-warp smem slab so that each instruction moves 8 rows x 64 contiguous bytes.
+__device__ __forceinline__ void tile_store(uint8_t* slab, const float (&v)[32], __nv_bfloat16* g_row0, long long ld, int nvalid, int lane) {
+    uint4* mine = reinterpret_cast<uint4*>(slab + lane * 80);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        uint4 u;
+        u.x = pack_bf16(v[i * 8 + 0], v[i * 8 + 1]); u.y = pack_bf16(v[i * 8 + 2], v[i * 8 + 3]);
+        u.z = pack_bf16(v[i * 8 + 4], v[i * 8 + 5]); u.w = pack_bf16(v[i * 8 + 6], v[i * 8 + 7]);
+        mine[i] = u;
+    }
+    __syncwarp();
+    const int cc = lane & 3;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int rr = (lane >> 2) + 8 * i;
+        if (rr < nvalid) *reinterpret_cast<uint4*>(g_row0 + rr * ld + cc * 8) = *reinterpret_cast<const uint4*>(slab + rr * 80 + cc * 16);
+    }
+    __syncwarp();
+}
+__device__ __forceinline__ void tile_load(uint8_t* slab, float (&out)[32], const __nv_bfloat16* g_row0, long long ld, int nvalid, int lane) {
+    const int cc = lane & 3;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int rr = (lane >> 2) + 8 * i;
+        uint4 u = make_uint4(0, 0, 0, 0);
+        if (rr < nvalid) u = __ldg(reinterpret_cast<const uint4*>(g_row0 + rr * ld + cc * 8));
+        *reinterpret_cast<uint4*>(slab + rr * 80 + cc * 16) = u;
+    }
+    __syncwarp();
+    const uint4* mine = reinterpret_cast<const uint4*>(slab + lane * 80);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const uint4 u = mine[i];
+        out[i * 8 + 0] = bf16_lo(u.x); out[i * 8 + 1] = bf16_hi(u.x); out[i * 8 + 2] = bf16_lo(u.y); out[i * 8 + 3] = bf16_hi(u.y);
+        out[i * 8 + 4] = bf16_lo(u.z); out[i * 8 + 5] = bf16_hi(u.z); out[i * 8 + 6] = bf16_lo(u.w); out[i * 8 + 7] = bf16_hi(u.w);
+    }
+    __syncwarp();
+}
+
 // tile index -> (m_blk, n_blk): groups of GROUP_M row-blocks are walked column by column so that the ~148
 // tiles in flight share a small set of A row-blocks and B column-blocks in L2.
-__device__ __forceinline__ void tile_coords(int tile, int num_m, int num_n, int& m_blk, int& n_blk) {
-    constexpr int GROUP_M = 16;
+__device__ __forceinline__ void tile_coords(int tile, int num_m, int num_n, int& m_blk, int& n_blk, int GROUP_M) {
     const int group_size = GROUP_M * num_n;
     const int g = tile / group_size;
     const int first_m = g * GROUP_M;
@@ -128,6 +172,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     uint64_t* tmem_full_bar = bars + 2 * STAGES;
     uint64_t* tmem_empty_bar = bars + 2 * STAGES + 2;
     uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+    uint8_t* epi_stage_base = reinterpret_cast<uint8_t*>(bars) + 256;   // 4 x EPI_STAGE_BYTES, one slab per epilogue warp
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -174,24 +219,20 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             uint32_t phase = 0;
             for (int tile = blockIdx.x / CG; tile < num_tiles; tile += gridDim.x / CG) {
                 int m_blk, n_blk;
-                tile_coords(tile / splitk, num_m, num_n, m_blk, n_blk);
+                tile_coords(tile / splitk, num_m, num_n, m_blk, n_blk, args.group_m);
                 const int kb_begin = (tile % splitk) * kb_per, kb_end = min(kb_begin + kb_per, num_kb);
                 const int m0 = (m_blk * CG + static_cast<int>(rank)) * BM;
                 const int n0 = n_blk * BN;
                 const int nb0 = n0 + static_cast<int>(rank) * BN_CTA;   // first B row staged by this CTA
-                // TMA issue: plain for CG=1; for a pair the completion is signalled on the leader's full barrier
+                // TMA issue: plain for CG=1; for a pair the completion is signalled on the leader's full barrier.
+                // In prefetch mode the same coordinates are only pulled into L2 (no smem destination, no barrier).
+                bool pf_mode = false;
                 auto LD = [&](void* dst, const CUtensorMap* tm, int c0, int c1) {
+                    if (pf_mode) { tma_prefetch_2d(tm, c0, c1); return; }
                     if constexpr (CG == 2) tma_load_2d_2sm(dst, tm, &full_bar[stage], c0, c1);
                     else tma_load_2d(dst, tm, &full_bar[stage], c0, c1);
                 };
-                for (int kb = kb_begin; kb < kb_end; ++kb) {
-                    mbar_wait(&empty_bar[stage], phase ^ 1);
-                    if constexpr (CG == 2) {
-                        if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * (Cfg::A_BYTES + Cfg::B_BYTES));
-                        else mbar_arrive_cluster(&full_bar[stage], 0);
-                    } else {
-                        mbar_arrive_expect_tx(&full_bar[stage], Cfg::A_BYTES + Cfg::B_BYTES);
-                    }
+                auto issue = [&](int kb) {
                     uint8_t* sa = smem_a + stage * Cfg::A_BYTES;
                     uint8_t* sb = smem_b + stage * Cfg::B_BYTES;
                     if (kb >= num_kb_main) {
@@ -221,8 +262,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                             LD(sa, &tmA2, seg * args.ext_k + e0, m0);
                             LD(sb, tm, e0, r0);
                         }
-                        if (++stage == STAGES) { stage = 0; phase ^= 1; }
-                        continue;
+                        return;
                     }
                     const int k0 = kb * BK;
                     if constexpr (!A_MN) {
@@ -258,6 +298,21 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                         for (int a = 0; a < BN_CTA / 64; ++a)
                             LD(sb + a * 8192, tm, nb0 + a * 64 - seg * args.kseg_nshift, kk);
                     }
+                };
+                for (int kb = kb_begin; kb < kb_end; ++kb) {
+                    if (args.pf_dist > 0 && kb + args.pf_dist < kb_end) {   // warm L2 a few k-blocks ahead of the smem ring
+                        pf_mode = true;
+                        issue(kb + args.pf_dist);
+                        pf_mode = false;
+                    }
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    if constexpr (CG == 2) {
+                        if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * (Cfg::A_BYTES + Cfg::B_BYTES));
+                        else mbar_arrive_cluster(&full_bar[stage], 0);
+                    } else {
+                        mbar_arrive_expect_tx(&full_bar[stage], Cfg::A_BYTES + Cfg::B_BYTES);
+                    }
+                    issue(kb);
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
             }
@@ -308,7 +363,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         int it = 0;
         for (int tile = blockIdx.x / CG; tile < num_tiles; tile += gridDim.x / CG, ++it) {
             int m_blk, n_blk;
-            tile_coords(tile / splitk, num_m, num_n, m_blk, n_blk);
+            tile_coords(tile / splitk, num_m, num_n, m_blk, n_blk, args.group_m);
             const int as = it & 1;
             const uint32_t aphase = (it >> 1) & 1;
             mbar_wait(&tmem_full_bar[as], aphase);
@@ -319,6 +374,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             long long drow = row;
             if (row_ok && args.row_map != nullptr) drow = args.row_map[row];
             const bool store_ok = row_ok && drow >= 0;
+            // coalesced path (all epilogues unless rows are scattered or the output is fp32)
+            const bool coal = (args.row_map == nullptr) && !args.d_f32 && args.coalesce;
+            const long long row_w0 = static_cast<long long>(m_blk * CG + static_cast<int>(rank)) * BM + q * 32;   // first row of this warp
+            const int nvalid = static_cast<int>(min(32LL, max(0LL, static_cast<long long>(args.M) - row_w0)));
+            uint8_t* slab = epi_stage_base + q * Cfg::EPI_STAGE_BYTES;
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN;
             const int n_tile0 = n_blk * BN;
 
@@ -337,6 +397,37 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     float v[32];
 #pragma unroll
                     for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * args.alpha;
+                    if (args.pre_up != nullptr) {
+                        // SwiGLU backward fused into the dX GEMM of down_proj: acc = d_act; with the stashed pre-activations
+                        // (pre_gate = g, pre_up = u) write [d_gate | d_up] into D = d_gu [M, 2N] and never store d_act
+                        if (n0 + 32 <= args.N) {
+                            float g[32], u[32], dg[32], du[32];
+                            if (coal) {
+                                tile_load(slab, g, args.pre_gate + row_w0 * args.N + n0, args.N, nvalid, lane);
+                                tile_load(slab, u, args.pre_up + row_w0 * args.N + n0, args.N, nvalid, lane);
+                            } else if (row_ok) {
+                                load_bf16x32(args.pre_gate + static_cast<long long>(row) * args.N + n0, g);
+                                load_bf16x32(args.pre_up + static_cast<long long>(row) * args.N + n0, u);
+                            }
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) {
+                                const float da = bf16_round(v[j]);
+                                const float sg = 1.f / (1.f + __expf(-g[j]));
+                                dg[j] = da * u[j] * sg * (1.f + g[j] * (1.f - sg));
+                                du[j] = da * g[j] * sg;
+                            }
+                            if (coal) {
+                                __nv_bfloat16* d = reinterpret_cast<__nv_bfloat16*>(args.D) + row_w0 * args.ldd + n0;
+                                tile_store(slab, dg, d, args.ldd, nvalid, lane);
+                                tile_store(slab, du, d + args.N, args.ldd, nvalid, lane);
+                            } else if (store_ok) {
+                                __nv_bfloat16* d = reinterpret_cast<__nv_bfloat16*>(args.D) + drow * args.ldd + n0;
+                                store_bf16x32(d, dg);
+                                store_bf16x32(d + args.N, du);
+                            }
+                        }
+                        continue;
+                    }
                     if (splitk > 1) {   // partial sum of a K split: fp32 atomics into the (zero-initialised) fp32 output
                         if (store_ok) {
                             float* d = reinterpret_cast<float*>(args.D) + drow * args.ldd + n0;
@@ -354,19 +445,26 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
                             for (int j = 0; j < 32; ++j) v[j] += b[j];
                         }
-                        if (args.pre_gate != nullptr && row_ok)  // keep the pre-activation for the backward pass
-                            store_bf16x32(args.pre_gate + static_cast<long long>(row) * args.N + n0, v);
+                        if (args.pre_gate != nullptr && args.pre_up == nullptr) {   // keep the pre-activation for the backward pass
+                            if (args.coalesce) tile_store(slab, v, args.pre_gate + row_w0 * args.N + n0, args.N, nvalid, lane);
+                            else if (row_ok) store_bf16x32(args.pre_gate + static_cast<long long>(row) * args.N + n0, v);
+                        }
                         if (args.act != LHRS_ACT_NONE) {
 #pragma unroll
                             for (int j = 0; j < 32; ++j) v[j] = act_apply(bf16_round(v[j]), args.act);
                         }
-                        if (args.residual != nullptr && row_ok) {
+                        if (args.residual != nullptr) {
                             float rr[32];
-                            load_bf16x32(args.residual + static_cast<long long>(row) * args.ldr + n0, rr);
+                            if (args.coalesce) tile_load(slab, rr, args.residual + row_w0 * args.ldr + n0, args.ldr, nvalid, lane);
+                            else if (row_ok) load_bf16x32(args.residual + static_cast<long long>(row) * args.ldr + n0, rr);
+                            if (args.coalesce || row_ok) {
 #pragma unroll
-                            for (int j = 0; j < 32; ++j) v[j] = bf16_round(v[j]) + rr[j];
+                                for (int j = 0; j < 32; ++j) v[j] = bf16_round(v[j]) + rr[j];
+                            }
                         }
-                        if (store_ok) {
+                        if (coal) {
+                            tile_store(slab, v, reinterpret_cast<__nv_bfloat16*>(args.D) + row_w0 * args.ldd + n0, args.ldd, nvalid, lane);
+                        } else if (store_ok) {
                             if (args.d_f32)
                                 store_f32x32(reinterpret_cast<float*>(args.D) + drow * args.ldd + n0, v);
                             else
@@ -411,7 +509,13 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                         const float s = bf16_round(g[j] / (1.0f + __expf(-g[j])));
                         o[j] = s * u[j];
                     }
-                    if (store_ok) {
+                    if (coal) {
+                        tile_store(slab, o, reinterpret_cast<__nv_bfloat16*>(args.D) + row_w0 * args.ldd + h0, args.ldd, nvalid, lane);
+                        if (args.pre_gate != nullptr) {
+                            tile_store(slab, g, args.pre_gate + row_w0 * n_hidden + h0, n_hidden, nvalid, lane);
+                            tile_store(slab, u, args.pre_up + row_w0 * n_hidden + h0, n_hidden, nvalid, lane);
+                        }
+                    } else if (store_ok) {
                         store_bf16x32(reinterpret_cast<__nv_bfloat16*>(args.D) + drow * args.ldd + h0, o);
                         if (args.pre_gate != nullptr) {
                             store_bf16x32(args.pre_gate + static_cast<long long>(row) * n_hidden + h0, g);
@@ -458,7 +562,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                                 }
                             }
                         }
-                        if (store_ok) {
+                        if (coal) {
+                            __nv_bfloat16* d = reinterpret_cast<__nv_bfloat16*>(args.D) + row_w0 * args.ldd + nh0;
+                            tile_store(slab, x1, d + c * 32, args.ldd, nvalid, lane);
+                            tile_store(slab, x2, d + 64 + c * 32, args.ldd, nvalid, lane);
+                        } else if (store_ok) {
                             __nv_bfloat16* d = reinterpret_cast<__nv_bfloat16*>(args.D) + drow * args.ldd + nh0;
                             store_bf16x32(d + c * 32, x1);
                             store_bf16x32(d + 64 + c * 32, x2);
@@ -644,6 +752,9 @@ extern "C" int lhrs_gemm_bf16(const LhrsGemm* g, void* stream_) {
         }
     }
 
+    if (kind == LHRS_EPI_LINEAR && g->pre_up != nullptr)
+        LHRS_CHECK_ARG(g->pre_gate != nullptr && (g->N % 32) == 0 && !g->d_f32 && !g->bias[0] && !g->residual && g->act == LHRS_ACT_NONE && g->split_k <= 1,
+                       "lhrs_gemm_bf16: fused SwiGLU backward needs pre_gate+pre_up, N %% 32 == 0 and a plain bf16 epilogue");
     CUtensorMap tA2 = tA, tE[3] = {tB[0], tB[0], tB[0]};
     int ext_k = 0, ext_kb = 0;
     if (g->A2 != nullptr && g->ext_k > 0) {
@@ -676,6 +787,16 @@ extern "C" int lhrs_gemm_bf16(const LhrsGemm* g, void* stream_) {
 
     GemmArgs a;
     a.ext_k = ext_k; a.ext_kb = ext_kb;
+    {
+        static int env_gm = -1, env_pf = -1;
+        if (env_gm < 0) { const char* e = getenv("LHRS_GEMM_GROUP_M"); env_gm = e ? atoi(e) : 0; }
+        if (env_pf < 0) { const char* e = getenv("LHRS_GEMM_PF"); env_pf = e ? atoi(e) : -2; }
+        static int env_coal = -1;
+        if (env_coal < 0) { const char* e = getenv("LHRS_EPI_COAL"); env_coal = e ? atoi(e) : 1; }
+        a.coalesce = env_coal;
+        a.group_m = env_gm > 0 ? env_gm : 16;
+        a.pf_dist = env_pf >= 0 ? env_pf : 0;
+    }
     a.splitk = 1;
     if (g->split_k > 1) {
         LHRS_CHECK_ARG(kind == LHRS_EPI_LINEAR && g->d_f32 && ext_kb == 0 && !g->bias[0] && !g->residual && g->act == LHRS_ACT_NONE && !g->pre_gate,

@@ -4,6 +4,7 @@
 // Frozen weights need no dW, so the LLaMA backward is ~1x the forward FLOPs: each Linear's dX is one tcgen05 GEMM with the
 // weight read MN-major in place (no transposed copies); concatenated outputs ([dq|dk|dv], [dgate|dup]) contract in ONE GEMM
 // with the weight segments stacked along K.  dW of the pooler / LoRA factors are the TN form of the same kernel.
+#include <stdlib.h>
 #include "host_common.h"
 #include "ptx.cuh"
 #include "models_common.h"
@@ -236,13 +237,23 @@ extern "C" int lhrs_llama_bwd(const LhrsLlamaWeights* w, void* const* lora_a_gra
         // ---- MLP: x_out = x_mid + down(silu(gate(h2)) * up(h2)),  h2 = rmsnorm(x_mid)
         {
             LoraBwd L = lora_ctx(w, l, 6, 1, t.act, F, F, dx, D, D, M, t.lora_t[3], b.dt, b.skinny);
-            LhrsGemm g = gemm_desc(M, F, D, dx, D, w->down_w[l], F, b.d_act, F);
+            // d_act = dx · W_down (+ LoRA) with the SwiGLU backward applied in the epilogue: writes d_gu = [d_gate | d_up]
+            LhrsGemm g = gemm_desc(M, F, D, dx, D, w->down_w[l], F, b.d_gu, 2 * F);
             g.b_mn_major = 1;
+            static int fuse = -1;
+            if (fuse < 0) { const char* e = getenv("LHRS_FUSE_SWIGLU_BWD"); fuse = e ? atoi(e) : 0; }
+            g.pre_gate = t.pre_gate; g.pre_up = t.pre_up;
             if ((rc = lora_bwd_pre(st, w, lora_a_grads, L, g))) return rc;
-            if ((rc = lhrs_gemm_bf16(&g, st))) return rc;
-            if ((rc = lora_bwd_post(st, w, lora_a_grads, lora_b_grads, L, b.d_act, F, b.diag))) return rc;
+            if ((L.active && !L.grouped) || !fuse) {   // un-batched LoRA fallback needs d_act materialised for its read-modify-write pass
+                g.D = b.d_act; g.ldd = F; g.pre_gate = nullptr; g.pre_up = nullptr;
+                if ((rc = lhrs_gemm_bf16(&g, st))) return rc;
+                if ((rc = lora_bwd_post(st, w, lora_a_grads, lora_b_grads, L, b.d_act, F, b.diag))) return rc;
+                if ((rc = lhrs_swiglu_bwd(b.d_act, t.pre_gate, t.pre_up, b.d_gu, M, F, st))) return rc;
+            } else {
+                if ((rc = lhrs_gemm_bf16(&g, st))) return rc;
+                if ((rc = lora_bwd_post(st, w, lora_a_grads, lora_b_grads, L, nullptr, F, b.diag))) return rc;
+            }
         }
-        if ((rc = lhrs_swiglu_bwd(b.d_act, t.pre_gate, t.pre_up, b.d_gu, M, F, st))) return rc;
         {
             if (w->lora_r > 0) if ((rc = lhrs_rmsnorm_fwd(t.x_mid, w->ln2_w[l], b.h, nullptr, M, D, w->eps, st))) return rc;
             LoraBwd L = lora_ctx(w, l, 4, 2, b.h, D, D, b.d_gu, 2 * F, F, M, t.lora_t[2], b.dt, b.skinny);
@@ -272,9 +283,9 @@ extern "C" int lhrs_llama_bwd(const LhrsLlamaWeights* w, void* const* lora_a_gra
             ab.dq = b.dqkv; ab.dk = b.dqkv + D; ab.dv = b.dqkv + 2 * D;
             ab.dq_rs = ab.dk_rs = ab.dv_rs = 3 * D; ab.dq_bs = ab.dk_bs = ab.dv_bs = (long long)S * 3 * D;
             ab.dq_hs = ab.dk_hs = ab.dv_hs = 128;
+            ab.rope_cos = w->rope_cos; ab.rope_sin = w->rope_sin;   // dq / dk leave the kernel already un-rotated
             if ((rc = lhrs_attention_bwd(&ab, st))) return rc;
         }
-        if ((rc = lhrs_rope_bwd(b.dqkv, 3 * D, M, D, w->rope_cos, w->rope_sin, nullptr, S, st))) return rc;
         {
             if (w->lora_r > 0) if ((rc = lhrs_rmsnorm_fwd(t.x_in, w->ln1_w[l], b.h, nullptr, M, D, w->eps, st))) return rc;
             LoraBwd L = lora_ctx(w, l, 0, 3, b.h, D, D, b.dqkv, 3 * D, D, M, t.lora_t[0], b.dt, b.skinny);

@@ -379,13 +379,17 @@ extern "C" int lhrs_llama_fwd(const LhrsLlamaWeights* w, const void* inputs_embe
         st = llama_stash_plan(sa, w, B, S);
     }
     int rc;
-    LHRS_CUDA(cudaMemcpyAsync(b.x, inputs_embeds, M * D * 2, cudaMemcpyDeviceToDevice, stream));
+    // Residual stream: in inference it is updated in place in b.x; with a stash every GEMM that produces the next state of
+    // the stream writes it straight into its stash slot (x_in[l] -> x_mid[l] -> x_in[l+1] ... -> x_final), no copies.
+    const bf16* x_cur = stash ? st.layer[0].x_in : b.x;
+    LHRS_CUDA(cudaMemcpyAsync(const_cast<bf16*>(x_cur), inputs_embeds, M * D * 2, cudaMemcpyDeviceToDevice, stream));
     for (int l = 0; l < w->num_layers; ++l) {
         LlamaLayerStash* ls = stash ? &st.layer[l] : nullptr;
         bf16* qkv = ls ? ls->qkv : b.qkv;
         bf16* o = ls ? ls->o : b.o;
-        if (ls) LHRS_CUDA(cudaMemcpyAsync(ls->x_in, b.x, M * D * 2, cudaMemcpyDeviceToDevice, stream));
-        if ((rc = lhrs_rmsnorm_fwd(b.x, w->ln1_w[l], b.h, ls ? ls->rstd1 : nullptr, M, D, w->eps, stream))) return rc;
+        bf16* x_mid = ls ? ls->x_mid : b.x;
+        bf16* x_next = !stash ? b.x : (l + 1 < w->num_layers ? st.layer[l + 1].x_in : st.x_final);
+        if ((rc = lhrs_rmsnorm_fwd(x_cur, w->ln1_w[l], b.h, ls ? ls->rstd1 : nullptr, M, D, w->eps, stream))) return rc;
         {
             LhrsGemm g = gemm_desc(M, 3 * D, D, b.h, D, w->q_w[l], D, qkv, 3 * D);
             g.B[1] = w->k_w[l]; g.B[2] = w->v_w[l]; g.num_b = 3; g.seg_rows = D;
@@ -405,13 +409,12 @@ extern "C" int lhrs_llama_fwd(const LhrsLlamaWeights* w, const void* inputs_embe
             if ((rc = lhrs_attention_fwd(&at, stream))) return rc;
         }
         {
-            LhrsGemm g = gemm_desc(M, D, D, o, D, w->o_w[l], D, b.x, D);
-            g.residual = b.x; g.ldr = D;
+            LhrsGemm g = gemm_desc(M, D, D, o, D, w->o_w[l], D, x_mid, D);
+            g.residual = x_cur; g.ldr = D;
             if ((rc = lora_attach(g, w, l, 3, 1, o, D, M, ls ? ls->lora_t[1] : b.lora_t, b.skinny, stream))) return rc;
             if ((rc = lhrs_gemm_bf16(&g, stream))) return rc;
         }
-        if (ls) LHRS_CUDA(cudaMemcpyAsync(ls->x_mid, b.x, M * D * 2, cudaMemcpyDeviceToDevice, stream));
-        if ((rc = lhrs_rmsnorm_fwd(b.x, w->ln2_w[l], b.h, ls ? ls->rstd2 : nullptr, M, D, w->eps, stream))) return rc;
+        if ((rc = lhrs_rmsnorm_fwd(x_mid, w->ln2_w[l], b.h, ls ? ls->rstd2 : nullptr, M, D, w->eps, stream))) return rc;
         bf16* act = ls ? ls->act : b.act;
         {
             LhrsGemm g = gemm_desc(M, 2 * F, D, b.h, D, w->gate_w[l], D, act, F);
@@ -421,14 +424,14 @@ extern "C" int lhrs_llama_fwd(const LhrsLlamaWeights* w, const void* inputs_embe
             if ((rc = lhrs_gemm_bf16(&g, stream))) return rc;
         }
         {
-            LhrsGemm g = gemm_desc(M, D, F, act, F, w->down_w[l], F, b.x, D);
-            g.residual = b.x; g.ldr = D;
+            LhrsGemm g = gemm_desc(M, D, F, act, F, w->down_w[l], F, x_next, D);
+            g.residual = x_mid; g.ldr = D;
             if ((rc = lora_attach(g, w, l, 6, 1, act, F, M, ls ? ls->lora_t[3] : b.lora_t, b.skinny, stream))) return rc;
             if ((rc = lhrs_gemm_bf16(&g, stream))) return rc;
         }
+        x_cur = x_next;
     }
-    if (stash) LHRS_CUDA(cudaMemcpyAsync(st.x_final, b.x, M * D * 2, cudaMemcpyDeviceToDevice, stream));
-    if ((rc = lhrs_rmsnorm_fwd(b.x, w->norm_w, hidden_out, stash ? st.rstd_final : nullptr, M, D, w->eps, stream))) return rc;
+    if ((rc = lhrs_rmsnorm_fwd(x_cur, w->norm_w, hidden_out, stash ? st.rstd_final : nullptr, M, D, w->eps, stream))) return rc;
     return LHRS_OK;
 }
 
