@@ -281,6 +281,14 @@ static int launch_attn(const AttnArgs& a, cudaStream_t stream) {
     return LHRS_OK;
 }
 
+int attention_fwd_tc(const LhrsAttention* d, cudaStream_t stream);   // attention_tc.cu
+
+static bool use_tc_attention() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("LHRS_ATTN_TC"); v = e ? atoi(e) : 1; }
+    return v != 0;
+}
+
 }  // namespace lhrs
 
 using namespace lhrs;
@@ -292,6 +300,8 @@ extern "C" int lhrs_attention_fwd(const LhrsAttention* d, void* stream_) {
     LHRS_CHECK_ARG(d->B > 0 && d->H > 0 && d->Sq > 0 && d->Skv > 0, "lhrs_attention_fwd: empty problem");
     const long long strides[] = {d->q_bs, d->q_rs, d->q_hs, d->k_bs, d->k_rs, d->k_hs, d->v_bs, d->v_rs, d->v_hs, d->o_rs, d->o_hs, d->o_bs};
     for (long long s : strides) LHRS_CHECK_ARG((s % 8) == 0, "lhrs_attention_fwd: strides must be multiples of 8 elements");
+    // head_dim 128 with at least one full 128-row query tile runs on the tcgen05 kernel (attention_tc.cu)
+    if (d->head_dim == 128 && d->Sq >= 128 && use_tc_attention()) return attention_fwd_tc(d, stream);
     AttnArgs a;
     a.q = reinterpret_cast<const __nv_bfloat16*>(d->q);
     a.k = reinterpret_cast<const __nv_bfloat16*>(d->k);

@@ -214,7 +214,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
     if (warp == 0) {
         // ===================================================================== TMA producer
-        if (lane == 0) {
+        {
+            // whole warp in the (uniform) control flow, one elected lane issues: keeps the TMA operands in uniform registers
+            const bool issuer = elect_one();
             int stage = 0;
             uint32_t phase = 0;
             for (int tile = blockIdx.x / CG; tile < num_tiles; tile += gridDim.x / CG) {
@@ -300,27 +302,38 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     }
                 };
                 for (int kb = kb_begin; kb < kb_end; ++kb) {
-                    if (args.pf_dist > 0 && kb + args.pf_dist < kb_end) {   // warm L2 a few k-blocks ahead of the smem ring
+                    if (issuer && args.pf_dist > 0 && kb + args.pf_dist < kb_end) {   // warm L2 a few k-blocks ahead of the smem ring
                         pf_mode = true;
                         issue(kb + args.pf_dist);
                         pf_mode = false;
                     }
                     mbar_wait(&empty_bar[stage], phase ^ 1);
-                    if constexpr (CG == 2) {
-                        if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * (Cfg::A_BYTES + Cfg::B_BYTES));
-                        else mbar_arrive_cluster(&full_bar[stage], 0);
-                    } else {
-                        mbar_arrive_expect_tx(&full_bar[stage], Cfg::A_BYTES + Cfg::B_BYTES);
+                    if (issuer) {
+                        if constexpr (CG == 2) {
+                            if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * (Cfg::A_BYTES + Cfg::B_BYTES));
+                            else mbar_arrive_cluster(&full_bar[stage], 0);
+                        } else {
+                            mbar_arrive_expect_tx(&full_bar[stage], Cfg::A_BYTES + Cfg::B_BYTES);
+                        }
+                        issue(kb);
                     }
-                    issue(kb);
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
             }
         }
     } else if (warp == 1) {
         // ===================================================================== MMA issuer (pair: the leader CTA only)
-        if (lane == 0 && rank == 0) {
+        if (rank == 0) {
+            // The whole warp walks the (warp-uniform) control flow; one elected lane issues.  The loop body is kept to the
+            // minimum instruction count: with 128-cycle MMAs a k-block is only 512 tensor cycles, and a single warp
+            // issuing ~100 dependent uniform-datapath instructions per k-block was itself the bound (ncu: pipe 76 %).
             constexpr uint32_t idesc = make_idesc_bf16(BM * CG, BN, A_MN ? 1u : 0u, B_MN ? 1u : 0u);
+            // descriptor words: lo = start>>4 | LBO>>4 << 16 ; hi = SBO>>4 | version 1 << 14 | SW128 << 29 (same for A and B)
+            constexpr uint32_t desc_hi = (1024u >> 4) | (1u << 14) | (UMMA_LAYOUT_SW128 << 29);
+            constexpr uint32_t a_kstep = (A_MN ? 2048u : 32u) >> 4, b_kstep = (B_MN ? 2048u : 32u) >> 4;
+            const uint32_t a_lo0 = ((smem_u32(smem_a) >> 4) & 0x3FFFu) | (A_MN ? ((8192u >> 4) << 16) : 0u);
+            const uint32_t b_lo0 = ((smem_u32(smem_b) >> 4) & 0x3FFFu) | (B_MN ? ((8192u >> 4) << 16) : 0u);
+            const bool issuer = elect_one();
             int stage = 0;
             uint32_t phase = 0;
             int it = 0;
@@ -331,28 +344,27 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 tc_fence_after();
                 const uint32_t tmem_d = tmem_base + as * BN;
                 const int kb_begin = (tile % splitk) * kb_per, kb_end = min(kb_begin + kb_per, num_kb);
+                uint32_t acc = 0;
                 for (int kb = kb_begin; kb < kb_end; ++kb) {
                     mbar_wait(&full_bar[stage], phase);
                     tc_fence_after();
-                    const uint32_t a_base = smem_u32(smem_a + stage * Cfg::A_BYTES);
-                    const uint32_t b_base = smem_u32(smem_b + stage * Cfg::B_BYTES);
+                    if (issuer) {
+                        const uint32_t a_lo = a_lo0 + stage * (Cfg::A_BYTES >> 4);
+                        const uint32_t b_lo = b_lo0 + stage * (Cfg::B_BYTES >> 4);
 #pragma unroll
-                    for (int k = 0; k < BK / 16; ++k) {
-                        // K-major SW128: rows are 128 B apart, 8-row groups 1024 B apart; +32 B per K=16 step.
-                        // MN-major SW128: 64-wide MN atoms 8 KB apart (LBO), 8-row K groups 1 KB apart (SBO); +2 KB per K=16.
-                        const uint64_t da = A_MN ? make_smem_desc(a_base + k * 2048, 8192, 1024, UMMA_LAYOUT_SW128)
-                                                 : make_smem_desc(a_base + k * 32, 0, 1024, UMMA_LAYOUT_SW128);
-                        const uint64_t db = B_MN ? make_smem_desc(b_base + k * 2048, 8192, 1024, UMMA_LAYOUT_SW128)
-                                                 : make_smem_desc(b_base + k * 32, 0, 1024, UMMA_LAYOUT_SW128);
-                        const uint32_t acc = (kb != kb_begin || k != 0) ? 1u : 0u;
-                        if constexpr (CG == 2) umma_bf16_2sm(tmem_d, da, db, idesc, acc);
-                        else umma_bf16(tmem_d, da, db, idesc, acc);
+                        for (int k = 0; k < BK / 16; ++k) {
+                            // K-major SW128: +32 B per K=16 step inside the 128 B row.  MN-major SW128: 64-wide MN atoms
+                            // 8 KB apart (LBO), 8-row K groups 1 KB apart (SBO); +2 KB per K=16.
+                            if constexpr (CG == 2) umma_bf16_2sm_w(tmem_d, a_lo + k * a_kstep, b_lo + k * b_kstep, desc_hi, idesc, k == 0 ? acc : 1u);
+                            else umma_bf16_w(tmem_d, a_lo + k * a_kstep, b_lo + k * b_kstep, desc_hi, idesc, k == 0 ? acc : 1u);
+                        }
+                        // slot reusable once these MMAs have read it (pair: released in both CTAs)
+                        if constexpr (CG == 2) umma_commit_2sm(&empty_bar[stage]); else umma_commit(&empty_bar[stage]);
+                        if (kb == kb_end - 1) {
+                            if constexpr (CG == 2) umma_commit_2sm(&tmem_full_bar[as]); else umma_commit(&tmem_full_bar[as]);
+                        }
                     }
-                    // slot reusable once these MMAs have read it (pair: released in both CTAs)
-                    if constexpr (CG == 2) umma_commit_2sm(&empty_bar[stage]); else umma_commit(&empty_bar[stage]);
-                    if (kb == kb_end - 1) {
-                        if constexpr (CG == 2) umma_commit_2sm(&tmem_full_bar[as]); else umma_commit(&tmem_full_bar[as]);
-                    }
+                    acc = 1;
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
             }

@@ -190,6 +190,9 @@ def test_gemm_rope_qkv(B, S, D):
     (2, 4, 128, 128, 128, True), (1, 32, 512, 512, 128, True), (2, 3, 175, 175, 128, True),
     (2, 16, 257, 257, 64, False), (3, 16, 64, 320, 64, False), (3, 16, 48, 304, 64, False), (2, 16, 32, 288, 64, False),
     (1, 2, 100, 333, 128, True),
+    # head_dim 128 with >= 128 query rows: tcgen05 kernel (ragged last tiles, Skv != Sq, non-causal, long rows)
+    (2, 4, 512, 512, 128, True), (1, 3, 200, 200, 128, True), (2, 2, 130, 333, 128, True), (1, 2, 256, 300, 128, True),
+    (1, 2, 384, 320, 128, False), (1, 1, 128, 64, 128, False), (1, 2, 2048, 2048, 128, True), (1, 32, 128, 128, 128, True),
 ])
 def test_attention_fwd(B, H, Sq, Skv, hd, causal):
     ops = _ops()
