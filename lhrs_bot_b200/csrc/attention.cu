@@ -4,6 +4,7 @@
 //                                                and the AttnPooler cross-attention (nn.MultiheadAttention, lhrs/models/common_arch.py:302-313)
 // Attention is ~1% of the path's FLOPs at S=512, so this first version uses warp-level mma.sync tiles
 // (cp.async double-buffered K/V, ldmatrix fragments); the dense projections around it are tcgen05.
+#include "attention_common.h"
 #include "host_common.h"
 #include "ptx.cuh"
 
@@ -281,9 +282,7 @@ static int launch_attn(const AttnArgs& a, cudaStream_t stream) {
     return LHRS_OK;
 }
 
-int attention_fwd_tc(const LhrsAttention* d, cudaStream_t stream);   // attention_tc.cu
-
-static bool use_tc_attention() {
+bool use_tc_attention() {
     static int v = -1;
     if (v < 0) { const char* e = getenv("LHRS_ATTN_TC"); v = e ? atoi(e) : 1; }
     return v != 0;

@@ -5,25 +5,12 @@
 //   dK, dV : one CTA per 64-key block, loops over query blocks          (dS^T Q, P^T dO)
 // Two passes recompute S twice but need no atomics, so gradients are deterministic.  Warp-level mma.sync tiles as in
 // attention.cu (attention is a few % of the step; the dense dX/dW contractions around it are tcgen05).
+#include "attention_common.h"
 #include "host_common.h"
 #include "ptx.cuh"
 
 namespace lhrs {
 
-struct AttnBwdArgs {
-    const __nv_bfloat16 *q, *k, *v, *o, *d_o;
-    __nv_bfloat16 *dq, *dk, *dv;
-    const float* lse;    // [B,H,Sq]
-    float* delta;        // [B,H,Sq]
-    const uint8_t* kmask;
-    long long q_bs, q_rs, q_hs, k_bs, k_rs, k_hs, v_bs, v_rs, v_hs;
-    long long o_bs, o_rs, o_hs;        // O and dO share a layout
-    long long dq_bs, dq_rs, dq_hs, dk_bs, dk_rs, dk_hs, dv_bs, dv_rs, dv_hs;
-    int B, H, Sq, Skv;
-    float scale, scale_log2;
-    const float* rope_cos;   // non-null (HD 128 only): inverse RoPE on dQ / dK at store time
-    const float* rope_sin;
-};
 
 // inverse rotate-half on one thread's fragment: tiles i (dims 8i+2t, +1) and i+8 (dims +64) of the same row pair up
 template <int DTILES>
@@ -407,6 +394,15 @@ static int launch_bwd(const AttnBwdArgs& a, cudaStream_t stream) {
     }
     kd<<<dim3(a.Sq, a.B), 256, 0, stream>>>(a);
     LHRS_LAUNCH_CHECK("attn_delta_kernel");
+    bool tma_ok = true;   // TMA views and 16-byte stores need 8-element strides
+    for (long long s : {a.q_bs, a.q_rs, a.q_hs, a.k_bs, a.k_rs, a.k_hs, a.v_bs, a.v_rs, a.v_hs, a.o_bs, a.o_rs, a.o_hs, a.dq_bs, a.dq_rs,
+                        a.dq_hs, a.dk_bs, a.dk_rs, a.dk_hs, a.dv_bs, a.dv_rs, a.dv_hs})
+        tma_ok = tma_ok && (s % 8) == 0;
+    if (HD == 128 && a.Sq >= 128 && a.Skv >= 128 && tma_ok && use_tc_attention()) {   // tcgen05 dQ and dK/dV kernels
+        const int rc = attention_bwd_tc(a, CAUSAL, stream);
+        if (prof) prof_end(stream);
+        return rc;
+    }
     kq<<<dim3((a.Sq + 63) / 64, a.H, a.B), 128, SMEM_DQ, stream>>>(a);
     LHRS_LAUNCH_CHECK("attn_bwd_dq_kernel");
     kkv<<<dim3((a.Skv + 63) / 64, a.H, a.B), 128, SMEM_DKV, stream>>>(a);

@@ -1,0 +1,44 @@
+// Shared between the attention translation units (mma.sync kernels in attention*.cu, tcgen05 kernels in attention*_tc.cu).
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/lhrs_b200.h"
+
+namespace lhrs {
+
+struct AttnBwdArgs {
+    const __nv_bfloat16 *q, *k, *v, *o, *d_o;
+    __nv_bfloat16 *dq, *dk, *dv;
+    const float* lse;    // [B,H,Sq]
+    float* delta;        // [B,H,Sq]
+    const uint8_t* kmask;
+    long long q_bs, q_rs, q_hs, k_bs, k_rs, k_hs, v_bs, v_rs, v_hs;
+    long long o_bs, o_rs, o_hs;        // O and dO share a layout
+    long long dq_bs, dq_rs, dq_hs, dk_bs, dk_rs, dk_hs, dv_bs, dv_rs, dv_hs;
+    int B, H, Sq, Skv;
+    float scale, scale_log2;
+    const float* rope_cos;   // non-null (HD 128 only): inverse RoPE on dQ / dK at store time
+    const float* rope_sin;
+};
+
+// 4-D bf16 TMA view {head_dim, rows | heads (smaller stride first), batch}; box = 64 dims x box_rows rows of one head, SW128.
+// *hfirst tells the kernel which coordinate order the map expects (attention_tc.cu).
+int make_tmap_bshd(CUtensorMap* out, int* hfirst, const void* ptr, int hd, int S, int H, int B, long long rs, long long hs,
+                   long long bs, int box_rows);
+
+bool use_tc_attention();                                                    // LHRS_ATTN_TC (default on)
+int attention_fwd_tc(const LhrsAttention* d, cudaStream_t stream);          // attention_tc.cu
+int attention_bwd_tc(const AttnBwdArgs& a, bool causal, cudaStream_t stream);   // attention_bwd_tc.cu (after the delta kernel)
+
+#ifdef __CUDACC__
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+#endif
+
+}  // namespace lhrs

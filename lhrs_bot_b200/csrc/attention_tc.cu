@@ -16,6 +16,7 @@
 #include <stdint.h>
 
 #include "../../include/lhrs_b200.h"
+#include "attention_common.h"
 #include "host_common.h"
 #include "ptx.cuh"
 
@@ -46,12 +47,6 @@ constexpr int SMEM_BYTES = OFF_BAR + 128;
 constexpr int TMEM_COLS = 256;                // S0 [0,64) | S1 [64,128) | O [128,256)
 constexpr float RESCALE_LOG2 = 8.f;
 }  // namespace atc
-
-__device__ __forceinline__ float ex2(float x) {
-    float y;
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-    return y;
-}
 
 template <bool CAUSAL>
 __global__ void __launch_bounds__(192, 2)
@@ -239,8 +234,8 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
             uint32_t pk[32];
 #pragma unroll
             for (int i = 0; i < 32; ++i) {
-                const float e0 = ex2(fmaf(s[2 * i], c, neg));
-                const float e1 = ex2(fmaf(s[2 * i + 1], c, neg));
+                const float e0 = ex2_approx(fmaf(s[2 * i], c, neg));
+                const float e1 = ex2_approx(fmaf(s[2 * i + 1], c, neg));
                 sum += e0 + e1;
                 pk[i] = pack_bf16(e0, e1);
             }
@@ -335,7 +330,7 @@ static EncodeTiledFn encode_fn() {
 // 4-D bf16 view {head_dim, rows | heads (smaller stride first), batch} with element strides (1, rs, hs, bs); the box is 64 dims x
 // box_rows rows of one head, 128B swizzle.  Rows past S are zero-filled by TMA and a box never crosses into another head or
 // batch entry.  *hfirst tells the kernel which coordinate order the map expects.
-static int make_tmap_bshd(CUtensorMap* out, int* hfirst, const void* ptr, int hd, int S, int H, int B, long long rs, long long hs,
+int make_tmap_bshd(CUtensorMap* out, int* hfirst, const void* ptr, int hd, int S, int H, int B, long long rs, long long hs,
                           long long bs, int box_rows) {
     EncodeTiledFn fn = encode_fn();
     if (fn == nullptr) {

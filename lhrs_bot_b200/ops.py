@@ -285,8 +285,9 @@ def launch_count() -> int:
 
 
 # ---------------------------------------------------------------------------------------------- backward ops
-def attention_bwd(q, k, v, o, lse, d_o, *, causal: bool, scale: Optional[float] = None, key_mask=None):
-    """(B,S,H,hd) views as in ``attention``; returns (dq, dk, dv) contiguous bf16."""
+def attention_bwd(q, k, v, o, lse, d_o, *, causal: bool, scale: Optional[float] = None, key_mask=None, rope=None):
+    """(B,S,H,hd) views as in ``attention``; returns (dq, dk, dv) contiguous bf16.  ``rope=(cos, sin)`` ([max_pos, 64] fp32
+    tables, head_dim 128, Sq == Skv) also undoes the rotary embedding on dq / dk (position = row index)."""
     from ._lib import LhrsAttentionBwd
     B, Sq, H, hd = q.shape
     Skv = k.shape[1]
@@ -310,6 +311,8 @@ def attention_bwd(q, k, v, o, lse, d_o, *, causal: bool, scale: Optional[float] 
     a.dq_bs, a.dq_rs, a.dq_hs = dq.stride(0), dq.stride(1), dq.stride(2)
     a.dk_bs, a.dk_rs, a.dk_hs = dk.stride(0), dk.stride(1), dk.stride(2)
     a.dv_bs, a.dv_rs, a.dv_hs = dv.stride(0), dv.stride(1), dv.stride(2)
+    if rope is not None:
+        a.rope_cos, a.rope_sin = rope[0].data_ptr(), rope[1].data_ptr()
     check(_lib.load().lhrs_attention_bwd(C.byref(a), _stream()), "lhrs_attention_bwd")
     return dq, dk, dv
 

@@ -29,6 +29,9 @@ def _randn(*shape, scale=1.0, seed=0):
 @pytest.mark.parametrize("B,H,Sq,Skv,hd,causal", [
     (2, 2, 128, 128, 128, True), (1, 4, 200, 200, 128, True), (2, 4, 257, 257, 64, False), (2, 2, 64, 320, 64, False),
     (2, 2, 48, 304, 64, False), (1, 2, 32, 288, 64, False), (1, 2, 100, 100, 64, True),
+    # head_dim 128 with >= 128 rows on both sides: tcgen05 dQ and dK/dV kernels
+    (2, 4, 512, 512, 128, True), (1, 2, 384, 320, 128, False), (2, 2, 130, 333, 128, True), (1, 2, 256, 300, 128, True),
+    (1, 3, 1024, 1024, 128, True), (1, 2, 128, 128, 128, False),
 ])
 def test_attention_bwd(B, H, Sq, Skv, hd, causal):
     from lhrs_bot_b200 import ops
@@ -58,6 +61,45 @@ def test_attention_bwd(B, H, Sq, Skv, hd, causal):
     _cmp("dq", dq, qf.grad)
     _cmp("dk", dk, kf.grad)
     _cmp("dv", dv, vf.grad)
+
+
+def test_attention_bwd_tc_unrope_and_packed():
+    """tcgen05 backward on packed [rows, 3*H*hd] projections (strided views, gradients written into a packed buffer) with the
+    fused inverse RoPE, against the same call without it followed by the rotation in fp32."""
+    from lhrs_bot_b200 import ops
+    from oracle.llama import rope_cos_sin
+    B, S, H, hd = 2, 320, 4, 128
+    qkv = _randn(B * S, 3 * H * hd, seed=41)
+    v5 = qkv.view(B, S, 3, H, hd)
+    q, k, v = v5[:, :, 0], v5[:, :, 1], v5[:, :, 2]
+    d_o = _randn(B, S, H, hd, seed=42)
+    mask = torch.ones(B, S, dtype=torch.uint8, device=DEV)
+    mask[1, 250:] = 0
+    o, lse = ops.attention(q, k, v, causal=True, key_mask=mask, return_lse=True)
+    cos, sin = rope_cos_sin(torch.arange(2048), 128)
+    cos_t, sin_t = cos[:, :64].contiguous().float().to(DEV), sin[:, :64].contiguous().float().to(DEV)
+    dq0, dk0, dv0 = ops.attention_bwd(q, k, v, o, lse, d_o, causal=True, key_mask=mask)
+    dq1, dk1, dv1 = ops.attention_bwd(q, k, v, o, lse, d_o, causal=True, key_mask=mask, rope=(cos_t, sin_t))
+    assert torch.equal(dv0, dv1)
+    c, s_ = cos_t[:S][None, :, None, :], sin_t[:S][None, :, None, :]
+
+    def unrot(g):
+        y1, y2 = g.float()[..., :64], g.float()[..., 64:]
+        return torch.cat([y1 * c + y2 * s_, y2 * c - y1 * s_], -1)
+    _cmp("dq unrope", dq1, unrot(dq0), 1e-2)
+    _cmp("dk unrope", dk1, unrot(dk0), 1e-2)
+    # and the plain gradients against autograd
+    qf, kf, vf = (t.float().detach().requires_grad_(True) for t in (q, k, v))
+    sc = (qf.permute(0, 2, 1, 3) @ kf.permute(0, 2, 3, 1)) / math.sqrt(hd)
+    i = torch.arange(S, device=DEV)[:, None]
+    j = torch.arange(S, device=DEV)[None, :]
+    sc = sc.masked_fill(j > i, float("-inf")).masked_fill(mask[:, None, None, :] == 0, float("-inf"))
+    ref = (torch.softmax(sc, -1) @ vf.permute(0, 2, 1, 3)).permute(0, 2, 1, 3)
+    ref.backward(d_o.float())
+    valid = mask.bool()
+    _cmp("dq packed", dq0[valid], qf.grad[valid])
+    _cmp("dk packed", dk0, kf.grad)
+    _cmp("dv packed", dv0, vf.grad)
 
 
 def test_norm_and_elementwise_bwd():
