@@ -223,6 +223,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 int m_blk, n_blk;
                 tile_coords(tile / splitk, num_m, num_n, m_blk, n_blk, args.group_m);
                 const int kb_begin = (tile % splitk) * kb_per, kb_end = min(kb_begin + kb_per, num_kb);
+#ifdef LHRS_GEMM_DEBUG
+                if (args.pf_dist == -3) m_blk = n_blk = 0;   // every cluster streams the same operand tiles (pure L2 hits)
+#endif
                 const int m0 = (m_blk * CG + static_cast<int>(rank)) * BM;
                 const int n0 = n_blk * BN;
                 const int nb0 = n0 + static_cast<int>(rank) * BN_CTA;   // first B row staged by this CTA
@@ -267,6 +270,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                         return;
                     }
                     const int k0 = kb * BK;
+#ifdef LHRS_GEMM_DEBUG   // timing experiments only (results are garbage): -1 skip B loads, -2 skip A loads
+                    if (args.pf_dist == -2) goto load_b;
+#endif
                     if constexpr (!A_MN) {
                         LD(sa, &tmA, k0, m0);  // box {64 k, 128 m}
                     } else {
@@ -274,6 +280,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                         for (int a = 0; a < BM / 64; ++a)  // box {64 m, 64 k} per 128B atom column
                             LD(sa + a * 8192, &tmA, m0 + a * 64, k0);
                     }
+#ifdef LHRS_GEMM_DEBUG
+                load_b:
+                    if (args.pf_dist == -1) return;
+#endif
                     if constexpr (!B_MN) {
                         if constexpr (KIND == LHRS_EPI_SWIGLU) {
                             // tile = [BN/2 gate rows | BN/2 up rows] of the same hidden units
@@ -309,6 +319,16 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     }
                     mbar_wait(&empty_bar[stage], phase ^ 1);
                     if (issuer) {
+#ifdef LHRS_GEMM_DEBUG
+                        if (args.pf_dist < 0) {
+                            const uint32_t by = (args.pf_dist == -2 ? 0 : Cfg::A_BYTES) + (args.pf_dist == -1 ? 0 : Cfg::B_BYTES);
+                            if (CG == 2 && rank != 0) mbar_arrive_cluster(&full_bar[stage], 0);
+                            else mbar_arrive_expect_tx(&full_bar[stage], CG * by);
+                            issue(kb);
+                            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                            continue;
+                        }
+#endif
                         if constexpr (CG == 2) {
                             if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * (Cfg::A_BYTES + Cfg::B_BYTES));
                             else mbar_arrive_cluster(&full_bar[stage], 0);
@@ -800,14 +820,17 @@ extern "C" int lhrs_gemm_bf16(const LhrsGemm* g, void* stream_) {
     GemmArgs a;
     a.ext_k = ext_k; a.ext_kb = ext_kb;
     {
-        static int env_gm = -1, env_pf = -1;
+        static int env_gm = -1, env_pf = -1000;
         if (env_gm < 0) { const char* e = getenv("LHRS_GEMM_GROUP_M"); env_gm = e ? atoi(e) : 0; }
-        if (env_pf < 0) { const char* e = getenv("LHRS_GEMM_PF"); env_pf = e ? atoi(e) : -2; }
+        if (env_pf == -1000) { const char* e = getenv("LHRS_GEMM_PF"); env_pf = e ? atoi(e) : -100; }
         static int env_coal = -1;
         if (env_coal < 0) { const char* e = getenv("LHRS_EPI_COAL"); env_coal = e ? atoi(e) : 1; }
         a.coalesce = env_coal;
         a.group_m = env_gm > 0 ? env_gm : 16;
         a.pf_dist = env_pf >= 0 ? env_pf : 0;
+#ifdef LHRS_GEMM_DEBUG
+        if (env_pf > -100) a.pf_dist = env_pf;
+#endif
     }
     a.splitk = 1;
     if (g->split_k > 1) {

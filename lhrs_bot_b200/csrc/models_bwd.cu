@@ -195,7 +195,7 @@ LlamaBwdBufs llama_bwd_plan(Arena& a, const LhrsLlamaWeights* w, long long M) {
     b.dqkv = a.take<bf16>(M * 3 * D); b.d_o = a.take<bf16>(M * D);
     b.delta = a.take<float>(M * w->heads);
     const bool lora = w->lora_r > 0;
-    b.h = lora ? a.take<bf16>(M * D) : nullptr;
+    b.h = nullptr;   // normalised inputs now come from the stash (h1 / h2)
     b.t = lora ? a.take<bf16>(M * 3 * w->lora_r) : nullptr;
     b.dt = lora ? a.take<bf16>(M * 3 * w->lora_r) : nullptr;
     const long long widest = (3LL * w->dim > 2LL * w->ffn) ? 3LL * w->dim : 2LL * w->ffn;
@@ -255,8 +255,7 @@ extern "C" int lhrs_llama_bwd(const LhrsLlamaWeights* w, void* const* lora_a_gra
             }
         }
         {
-            if (w->lora_r > 0) if ((rc = lhrs_rmsnorm_fwd(t.x_mid, w->ln2_w[l], b.h, nullptr, M, D, w->eps, st))) return rc;
-            LoraBwd L = lora_ctx(w, l, 4, 2, b.h, D, D, b.d_gu, 2 * F, F, M, t.lora_t[2], b.dt, b.skinny);
+            LoraBwd L = lora_ctx(w, l, 4, 2, t.h2, D, D, b.d_gu, 2 * F, F, M, t.lora_t[2], b.dt, b.skinny);
             LhrsGemm g = gemm_desc(M, D, 2 * F, b.d_gu, 2 * F, w->gate_w[l], D, b.dh, D);
             g.b_mn_major = 1; g.B[1] = w->up_w[l]; g.num_b = 2;
             if ((rc = lora_bwd_pre(st, w, lora_a_grads, L, g))) return rc;
@@ -287,8 +286,7 @@ extern "C" int lhrs_llama_bwd(const LhrsLlamaWeights* w, void* const* lora_a_gra
             if ((rc = lhrs_attention_bwd(&ab, st))) return rc;
         }
         {
-            if (w->lora_r > 0) if ((rc = lhrs_rmsnorm_fwd(t.x_in, w->ln1_w[l], b.h, nullptr, M, D, w->eps, st))) return rc;
-            LoraBwd L = lora_ctx(w, l, 0, 3, b.h, D, D, b.dqkv, 3 * D, D, M, t.lora_t[0], b.dt, b.skinny);
+            LoraBwd L = lora_ctx(w, l, 0, 3, t.h1, D, D, b.dqkv, 3 * D, D, M, t.lora_t[0], b.dt, b.skinny);
             LhrsGemm g = gemm_desc(M, D, 3 * D, b.dqkv, 3 * D, w->q_w[l], D, b.dh, D);
             g.b_mn_major = 1; g.B[1] = w->k_w[l]; g.B[2] = w->v_w[l]; g.num_b = 3;
             if ((rc = lora_bwd_pre(st, w, lora_a_grads, L, g))) return rc;

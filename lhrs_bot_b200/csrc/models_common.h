@@ -114,6 +114,7 @@ struct LlamaLayerStash {
     __nv_bfloat16 *x_in, *x_mid, *qkv, *o, *pre_gate, *pre_up, *act;
     float *rstd1, *rstd2, *lse;
     __nv_bfloat16* lora_t[4];   // T = s*x*A^T of the four projection groups {qkv, o, gate/up, down} (LoRA only)
+    __nv_bfloat16 *h1, *h2;     // RMSNorm outputs feeding qkv / gate-up (LoRA only: dA = dT^T h needs them; saves a recompute)
 };
 struct LlamaStash {
     LlamaLayerStash layer[80];
@@ -138,6 +139,8 @@ inline LlamaStash llama_stash_plan(Arena& a, const LhrsLlamaWeights* w, int B, i
         t.lse = a.take<float>(M * w->heads);
         const int np[4] = {3, 1, 2, 1};
         for (int g = 0; g < 4; ++g) t.lora_t[g] = (w->lora_r > 0) ? a.take<__nv_bfloat16>(M * np[g] * w->lora_r) : nullptr;
+        t.h1 = (w->lora_r > 0) ? a.take<__nv_bfloat16>(M * D) : nullptr;
+        t.h2 = (w->lora_r > 0) ? a.take<__nv_bfloat16>(M * D) : nullptr;
     }
     s.x_final = a.take<__nv_bfloat16>(M * D);
     s.rstd_final = a.take<float>(M);

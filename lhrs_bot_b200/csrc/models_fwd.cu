@@ -389,12 +389,14 @@ extern "C" int lhrs_llama_fwd(const LhrsLlamaWeights* w, const void* inputs_embe
         bf16* o = ls ? ls->o : b.o;
         bf16* x_mid = ls ? ls->x_mid : b.x;
         bf16* x_next = !stash ? b.x : (l + 1 < w->num_layers ? st.layer[l + 1].x_in : st.x_final);
-        if ((rc = lhrs_rmsnorm_fwd(x_cur, w->ln1_w[l], b.h, ls ? ls->rstd1 : nullptr, M, D, w->eps, stream))) return rc;
+        bf16* h1 = (ls && ls->h1) ? ls->h1 : b.h;   // normalised inputs go straight into the stash when backward will need them
+        bf16* h2 = (ls && ls->h2) ? ls->h2 : b.h;
+        if ((rc = lhrs_rmsnorm_fwd(x_cur, w->ln1_w[l], h1, ls ? ls->rstd1 : nullptr, M, D, w->eps, stream))) return rc;
         {
-            LhrsGemm g = gemm_desc(M, 3 * D, D, b.h, D, w->q_w[l], D, qkv, 3 * D);
+            LhrsGemm g = gemm_desc(M, 3 * D, D, h1, D, w->q_w[l], D, qkv, 3 * D);
             g.B[1] = w->k_w[l]; g.B[2] = w->v_w[l]; g.num_b = 3; g.seg_rows = D;
             g.epilogue = LHRS_EPI_ROPE; g.rope_cos = w->rope_cos; g.rope_sin = w->rope_sin; g.rope_seq_len = S;
-            if ((rc = lora_attach(g, w, l, 0, 3, b.h, D, M, ls ? ls->lora_t[0] : b.lora_t, b.skinny, stream))) return rc;
+            if ((rc = lora_attach(g, w, l, 0, 3, h1, D, M, ls ? ls->lora_t[0] : b.lora_t, b.skinny, stream))) return rc;
             if ((rc = lhrs_gemm_bf16(&g, stream))) return rc;
         }
         if (kv != nullptr) {
@@ -414,13 +416,13 @@ extern "C" int lhrs_llama_fwd(const LhrsLlamaWeights* w, const void* inputs_embe
             if ((rc = lora_attach(g, w, l, 3, 1, o, D, M, ls ? ls->lora_t[1] : b.lora_t, b.skinny, stream))) return rc;
             if ((rc = lhrs_gemm_bf16(&g, stream))) return rc;
         }
-        if ((rc = lhrs_rmsnorm_fwd(x_mid, w->ln2_w[l], b.h, ls ? ls->rstd2 : nullptr, M, D, w->eps, stream))) return rc;
+        if ((rc = lhrs_rmsnorm_fwd(x_mid, w->ln2_w[l], h2, ls ? ls->rstd2 : nullptr, M, D, w->eps, stream))) return rc;
         bf16* act = ls ? ls->act : b.act;
         {
-            LhrsGemm g = gemm_desc(M, 2 * F, D, b.h, D, w->gate_w[l], D, act, F);
+            LhrsGemm g = gemm_desc(M, 2 * F, D, h2, D, w->gate_w[l], D, act, F);
             g.B[1] = w->up_w[l]; g.num_b = 2; g.seg_rows = F; g.epilogue = LHRS_EPI_SWIGLU;
             if (ls) { g.pre_gate = ls->pre_gate; g.pre_up = ls->pre_up; }
-            if ((rc = lora_attach(g, w, l, 4, 2, b.h, D, M, ls ? ls->lora_t[2] : b.lora_t, b.skinny, stream))) return rc;
+            if ((rc = lora_attach(g, w, l, 4, 2, h2, D, M, ls ? ls->lora_t[2] : b.lora_t, b.skinny, stream))) return rc;
             if ((rc = lhrs_gemm_bf16(&g, stream))) return rc;
         }
         {

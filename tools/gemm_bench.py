@@ -52,6 +52,9 @@ o8 = torch.empty(8192, 8192, device=dev, dtype=torch.bfloat16)
 bench("square 8192^3", lambda: ops.gemm(a8, b8, out=o8), 2 * 8192 ** 3)
 bench("torch.matmul 8192^3 (cuBLAS)", lambda: torch.matmul(a8, b8.t(), out=o8), 2 * 8192 ** 3)
 
+if os.environ.get("MAIN_ONLY"):
+    sys.exit(0)
+
 # ---- skinny LoRA side GEMMs (memory-bound): report GB/s of the big operand
 def bench_bw(name, fn, nbytes, iters=30):
     for _ in range(3):
