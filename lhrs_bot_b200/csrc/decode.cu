@@ -8,6 +8,13 @@
 //   gemv<DOWN>    x += Wd · act
 // then gemv<LMHEAD> (final norm fused) + argmax.  Position, context length and the sampled token live in a device-side
 // state block, so the host enqueues steps back to back without a per-token synchronisation.
+// Every kernel is launched with programmatic dependent launch: before its dependency wait it starts streaming its first weight
+// rows (registers) and prefetches more towards L2, so e.g. the o-projection's weights arrive while the tiny attention runs.
+// (Measured alternative, round 1: ONE persistent cooperative kernel per token with grid barriers between the phases was
+// slower - 5.7 ms vs 3.2 ms per token - because 560 of 592 blocks idle through each attention phase and the row quantisation
+// of every phase lands on a barrier; the dependent-launch chain overlaps exactly those tails.)
+#include <stdlib.h>
+
 #include "host_common.h"
 #include "ptx.cuh"
 #include "models_common.h"
@@ -26,6 +33,7 @@ struct GemvArgs {
     __nv_bfloat16* out;           // QKV: [3*rows]; GATEUP: [rows]; O/DOWN: residual stream [rows] updated in place
     float* logits;                // LMHEAD
     float* part_val; int* part_idx;
+    int pf_bytes_per_warp;        // L2 prefetch budget of each warp's upcoming rows, issued before the dependency wait
 };
 
 __device__ __forceinline__ float dot8(const uint4& w, const uint4& x) {
@@ -57,18 +65,16 @@ __device__ __forceinline__ void prefetch_row(const __nv_bfloat16* row, int nchun
         pre[i] = (c < nchunks) ? ldg_stream(p + c) : make_uint4(0, 0, 0, 0);
     }
 }
-// one weight row against the smem-resident input; `pre` optionally holds the first GV_INFLIGHT chunks (already loaded)
-__device__ __forceinline__ float dot_row(const __nv_bfloat16* row, const uint4* xs, int nchunks, int lane, bool have_pre,
-                                         const uint4 (&pre)[GV_INFLIGHT]) {
+// one weight row against the smem-resident input (per-lane partial sum); `pre` holds the first GV_INFLIGHT chunks, already loaded
+__device__ __forceinline__ float dot_partial(const __nv_bfloat16* row, const uint4* xs, int nchunks, int lane,
+                                             const uint4 (&pre)[GV_INFLIGHT]) {
     const uint4* p = reinterpret_cast<const uint4*>(row);
     float acc = 0.f;
     int c = lane;
-    if (have_pre) {
 #pragma unroll
-        for (int i = 0; i < GV_INFLIGHT; ++i)
-            if (c + i * 32 < nchunks) acc += dot8(pre[i], xs[c + i * 32]);
-        c += GV_INFLIGHT * 32;
-    }
+    for (int i = 0; i < GV_INFLIGHT; ++i)
+        if (c + i * 32 < nchunks) acc += dot8(pre[i], xs[c + i * 32]);
+    c += GV_INFLIGHT * 32;
     for (; c + (GV_INFLIGHT - 1) * 32 < nchunks; c += GV_INFLIGHT * 32) {
         uint4 w[GV_INFLIGHT];
 #pragma unroll
@@ -77,8 +83,9 @@ __device__ __forceinline__ float dot_row(const __nv_bfloat16* row, const uint4* 
         for (int i = 0; i < GV_INFLIGHT; ++i) acc += dot8(w[i], xs[c + i * 32]);
     }
     for (; c < nchunks; c += 32) acc += dot8(ldg_stream(p + c), xs[c]);
-    return warp_red(acc);
+    return acc;
 }
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 template <int MODE>
 __device__ __forceinline__ const __nv_bfloat16* gemv_row(const GemvArgs& a, int n) {
@@ -91,33 +98,53 @@ __device__ __forceinline__ const __nv_bfloat16* gemv_row(const GemvArgs& a, int 
     }
 }
 
+// ---- a GEMV phase in two halves, so both the stand-alone kernels and the persistent whole-token kernel can put a dependency
+// wait / grid barrier between them.
+// gemv_pre: touches only weights (never produced on the device).  Starts streaming the warp's first row into registers and pulls
+// its next rows towards L2 (128-byte lines, budgeted) so HBM keeps streaming while the consumer of the previous phase drains.
 template <int MODE>
-__global__ void __launch_bounds__(256)
-gemv_kernel(const GemvArgs a) {
-    extern __shared__ __align__(16) uint8_t smem[];
-    __nv_bfloat16* xs = reinterpret_cast<__nv_bfloat16*>(smem);
-    __shared__ float red[8];
-    __shared__ float bval[8];
-    __shared__ int bidx[8];
+__device__ __forceinline__ void gemv_pre(const GemvArgs& a, int gw, int nw, int lane, bool regs, uint4 (&pre)[GV_INFLIGHT]) {
+    const int nchunks = a.K / 8;
+    const int total = (MODE == GV_QKV) ? 3 * a.rows : a.rows;
+    if (regs && gw < total) prefetch_row(gemv_row<MODE>(a, gw), nchunks, lane, pre);
+    const int lines_per_row = a.K / 64;   // 128-byte lines in one weight row
+    int budget = a.pf_bytes_per_warp / 128;
+    for (int n = gw; n < total && budget > 0; n += nw) {
+        const char* r0 = reinterpret_cast<const char*>(gemv_row<MODE>(a, n));
+        const int take = min(budget, lines_per_row);
+        for (int l = lane; l < take; l += 32) prefetch_l2(r0 + l * 128);
+        if constexpr (MODE == GV_GATEUP) {
+            const char* r1 = reinterpret_cast<const char*>(a.w1 + static_cast<long long>(n) * a.K);
+            for (int l = lane; l < take; l += 32) prefetch_l2(r1 + l * 128);
+            budget -= take;
+        }
+        budget -= take;
+    }
+}
+
+struct GemvShared {
+    float red[8];
+    float bval[8];
+    int bidx[8];
+};
+
+// gemv_main: stage the input vector in smem (HF RMSNorm fused: w * bf16(x * rstd)), then one weight row per warp trip.
+template <int MODE>
+__device__ __forceinline__ void gemv_main(const GemvArgs& a, __nv_bfloat16* xs, GemvShared& sh, int gw, int nw, int block_id,
+                                          bool have_pre, uint4 (&pre)[GV_INFLIGHT]) {
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int nchunks = a.K / 8;
     const int total = (MODE == GV_QKV) ? 3 * a.rows : a.rows;
-    const int gw = blockIdx.x * 8 + warp, nw = gridDim.x * 8;
-    pdl_launch_dependents();
-    // weights do not depend on the previous kernel: start streaming the first row before waiting for the input vector
-    uint4 pre[GV_INFLIGHT];
-    if (gw < total) prefetch_row(gemv_row<MODE>(a, gw), nchunks, lane, pre);
-    pdl_wait();
-    // ---- stage the input vector (with the HF RMSNorm fused: w * bf16(x * rstd))
+    if (!have_pre && gw < total) prefetch_row(gemv_row<MODE>(a, gw), nchunks, lane, pre);
     if (a.norm_w != nullptr) {
         float ss = 0.f;
         for (int i = tid; i < a.K; i += 256) { const float v = __bfloat162float(a.x[i]); ss += v * v; }
         ss = warp_red(ss);
-        if (lane == 0) red[warp] = ss;
+        if (lane == 0) sh.red[warp] = ss;
         __syncthreads();
         float tot = 0.f;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) tot += red[i];
+        for (int i = 0; i < 8; ++i) tot += sh.red[i];
         const float rstd = rsqrtf(tot / a.K + a.eps);
         for (int i = tid; i < a.K; i += 256)
             xs[i] = __float2bfloat16_rn(__bfloat162float(a.norm_w[i]) * bf16_round(__bfloat162float(a.x[i]) * rstd));
@@ -129,59 +156,92 @@ gemv_kernel(const GemvArgs a) {
 
     float best = -INFINITY;
     int best_i = 0x7fffffff;
-    bool first = true;
-    for (int n = gw; n < total; n += nw, first = false) {
-        const float v0 = dot_row(gemv_row<MODE>(a, n), xv, nchunks, lane, first, pre);
+    // rows are software-pipelined: the first chunks of the next row are requested before this row's warp reduction
+    for (int n = gw; n < total; n += nw) {
+        float acc = dot_partial(gemv_row<MODE>(a, n), xv, nchunks, lane, pre);
         if constexpr (MODE == GV_GATEUP) {
-            const float u0 = dot_row(a.w1 + static_cast<long long>(n) * a.K, xv, nchunks, lane, false, pre);
+            prefetch_row(a.w1 + static_cast<long long>(n) * a.K, nchunks, lane, pre);
+            const float v0 = warp_red(acc);
+            acc = dot_partial(a.w1 + static_cast<long long>(n) * a.K, xv, nchunks, lane, pre);
+            if (n + nw < total) prefetch_row(gemv_row<MODE>(a, n + nw), nchunks, lane, pre);
+            const float u0 = warp_red(acc);
             if (lane == 0) {
                 const float g = bf16_round(v0), u = bf16_round(u0);
                 a.out[n] = __float2bfloat16_rn(bf16_round(g / (1.f + __expf(-g))) * u);
             }
-        } else if (lane == 0) {
-            if constexpr (MODE == GV_QKV) {
-                a.out[n] = __float2bfloat16_rn(v0);
-            } else if constexpr (MODE == GV_O || MODE == GV_DOWN) {
-                a.out[n] = __float2bfloat16_rn(bf16_round(v0) + __bfloat162float(a.out[n]));
-            } else {  // LMHEAD: HF casts the bf16 logits to fp32
-                const float v = bf16_round(v0);
-                a.logits[n] = v;
-                if (v > best || (v == best && n < best_i)) { best = v; best_i = n; }
+        } else {
+            if (n + nw < total) prefetch_row(gemv_row<MODE>(a, n + nw), nchunks, lane, pre);
+            const float v0 = warp_red(acc);
+            if (lane == 0) {
+                if constexpr (MODE == GV_QKV) {
+                    a.out[n] = __float2bfloat16_rn(v0);
+                } else if constexpr (MODE == GV_O || MODE == GV_DOWN) {
+                    a.out[n] = __float2bfloat16_rn(bf16_round(v0) + __bfloat162float(a.out[n]));
+                } else {  // LMHEAD: HF casts the bf16 logits to fp32
+                    const float v = bf16_round(v0);
+                    a.logits[n] = v;
+                    if (v > best || (v == best && n < best_i)) { best = v; best_i = n; }
+                }
             }
         }
     }
     if constexpr (MODE == GV_LMHEAD) {
-        if (lane == 0) { bval[warp] = best; bidx[warp] = best_i; }
+        if (lane == 0) { sh.bval[warp] = best; sh.bidx[warp] = best_i; }
         __syncthreads();
         if (tid == 0) {
             for (int i = 1; i < 8; ++i)
-                if (bval[i] > bval[0] || (bval[i] == bval[0] && bidx[i] < bidx[0])) { bval[0] = bval[i]; bidx[0] = bidx[i]; }
-            a.part_val[blockIdx.x] = bval[0];
-            a.part_idx[blockIdx.x] = bidx[0];
+                if (sh.bval[i] > sh.bval[0] || (sh.bval[i] == sh.bval[0] && sh.bidx[i] < sh.bidx[0])) { sh.bval[0] = sh.bval[i]; sh.bidx[0] = sh.bidx[i]; }
+            a.part_val[block_id] = sh.bval[0];
+            a.part_idx[block_id] = sh.bidx[0];
         }
     }
+    __syncthreads();   // xs / sh are reused by whatever runs next in this block
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(256, 4)
+gemv_kernel(const GemvArgs a) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    __shared__ GemvShared sh;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int gw = blockIdx.x * 8 + warp, nw = gridDim.x * 8;
+    pdl_launch_dependents();
+    uint4 pre[GV_INFLIGHT];
+    gemv_pre<MODE>(a, gw, nw, lane, true, pre);
+    pdl_wait();
+    gemv_main<MODE>(a, reinterpret_cast<__nv_bfloat16*>(smem), sh, gw, nw, blockIdx.x, true, pre);
 }
 
 // state: [0] token to feed next, [1] ctx_len (positions already in the cache), [2] number of tokens emitted, [3] unused
-__global__ void __launch_bounds__(256)
-commit_token_kernel(const float* __restrict__ part_val, const int* __restrict__ part_idx, int nparts, int forced_token,
-                    int* __restrict__ state, int* __restrict__ tokens_out, int max_tokens, int set_ctx,
-                    const __nv_bfloat16* __restrict__ embed, int dim, __nv_bfloat16* __restrict__ xbuf) {
+__device__ __forceinline__ void commit_token_body(const float* __restrict__ part_val, const int* __restrict__ part_idx, int nparts,
+                                                  int forced_token, int* __restrict__ state, int* __restrict__ tokens_out, int max_tokens,
+                                                  int set_ctx, const __nv_bfloat16* __restrict__ embed, int dim,
+                                                  __nv_bfloat16* __restrict__ xbuf) {
     __shared__ int s_tok;
-    pdl_launch_dependents();
-    pdl_wait();
+    __shared__ float s_bv[256];
+    __shared__ int s_bi[256];
+    if (forced_token < 0) {   // argmax over the per-block partials of the lm_head GEMV (ties -> lowest index, like torch.argmax)
+        float bv = -INFINITY;
+        int bi = 0x7fffffff;
+        for (int i = threadIdx.x; i < nparts; i += blockDim.x) {
+            const float v = part_val[i];
+            const int ix = part_idx[i];
+            if (v > bv || (v == bv && ix < bi)) { bv = v; bi = ix; }
+        }
+        s_bv[threadIdx.x] = bv; s_bi[threadIdx.x] = bi;
+        __syncthreads();
+        for (int o = 128; o > 0; o >>= 1) {
+            if (threadIdx.x < o) {
+                const float v = s_bv[threadIdx.x + o];
+                const int ix = s_bi[threadIdx.x + o];
+                if (v > s_bv[threadIdx.x] || (v == s_bv[threadIdx.x] && ix < s_bi[threadIdx.x])) { s_bv[threadIdx.x] = v; s_bi[threadIdx.x] = ix; }
+            }
+            __syncthreads();
+        }
+    }
     if (threadIdx.x == 0) {
         int tok = forced_token;
-        if (tok < 0) {
-            float bv = -INFINITY;
-            int bi = 0x7fffffff;
-            for (int i = 0; i < nparts; ++i) {
-                const float v = part_val[i];
-                const int ix = part_idx[i];
-                if (v > bv || (v == bv && ix < bi)) { bv = v; bi = ix; }
-            }
-            tok = bi;
-        }
+        if (tok < 0) tok = s_bi[0];
         s_tok = tok;
         const int k = state[2];
         if (k < max_tokens) tokens_out[k] = tok;
@@ -195,19 +255,30 @@ commit_token_kernel(const float* __restrict__ part_val, const int* __restrict__ 
     for (int c = threadIdx.x; c < dim / 8; c += blockDim.x) reinterpret_cast<uint4*>(xbuf)[c] = src[c];
 }
 
-// one block per head: RoPE + KV append + attention over the paged cache for the single new query
-// dynamic smem: scores [max_ctx] fp32 | page ids [max_pages] int32
 __global__ void __launch_bounds__(256)
-attn_decode_kernel(const __nv_bfloat16* __restrict__ qkv, int dim, KvGeom kv, int layer, int* __restrict__ state,
-                   const float* __restrict__ cosT, const float* __restrict__ sinT, __nv_bfloat16* __restrict__ obuf, int max_ctx) {
-    extern __shared__ float sc[];            // scores [max_ctx]
-    int* spg = reinterpret_cast<int*>(sc + max_ctx);
-    __shared__ float qs[128];
-    __shared__ float red[8];
-    __shared__ float part[8][128];
-    const int h = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+commit_token_kernel(const float* __restrict__ part_val, const int* __restrict__ part_idx, int nparts, int forced_token,
+                    int* __restrict__ state, int* __restrict__ tokens_out, int max_tokens, int set_ctx,
+                    const __nv_bfloat16* __restrict__ embed, int dim, __nv_bfloat16* __restrict__ xbuf) {
     pdl_launch_dependents();
     pdl_wait();
+    commit_token_body(part_val, part_idx, nparts, forced_token, state, tokens_out, max_tokens, set_ctx, embed, dim, xbuf);
+}
+
+// one block per head: RoPE + KV append + attention over the paged cache for the single new query
+// dynamic smem: scores [max_ctx] fp32 | page ids [max_pages] int32
+struct AttnDecodeShared {
+    float qs[128];
+    float red[8];
+    float part[8][128];
+};
+__device__ __forceinline__ void attn_decode_body(float* sc, AttnDecodeShared& sh, int h, const __nv_bfloat16* __restrict__ qkv, int dim,
+                                                 const KvGeom& kv, int layer, const int* __restrict__ state, const float* __restrict__ cosT,
+                                                 const float* __restrict__ sinT, __nv_bfloat16* __restrict__ obuf, int max_ctx) {
+    int* spg = reinterpret_cast<int*>(sc + max_ctx);
+    float (&qs)[128] = sh.qs;
+    float (&red)[8] = sh.red;
+    float (&part)[8][128] = sh.part;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int pos = state[1];
     const int n = pos + 1;
     const int npages = (n + kv.page_size - 1) / kv.page_size;
@@ -305,6 +376,17 @@ attn_decode_kernel(const __nv_bfloat16* __restrict__ qkv, int dim, KvGeom kv, in
         for (int i = 0; i < 8; ++i) o += part[i][tid];
         obuf[h * 128 + tid] = __float2bfloat16_rn(o * inv);
     }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(256)
+attn_decode_kernel(const __nv_bfloat16* __restrict__ qkv, int dim, KvGeom kv, int layer, int* __restrict__ state,
+                   const float* __restrict__ cosT, const float* __restrict__ sinT, __nv_bfloat16* __restrict__ obuf, int max_ctx) {
+    extern __shared__ float sc[];            // scores [max_ctx] | page ids [max_pages]
+    __shared__ AttnDecodeShared sh;
+    pdl_launch_dependents();
+    pdl_wait();
+    attn_decode_body(sc, sh, blockIdx.x, qkv, dim, kv, layer, state, cosT, sinT, obuf, max_ctx);
 }
 
 // launch with programmatic stream serialization (PDL): the kernel may start while its predecessor drains
@@ -325,11 +407,17 @@ using namespace lhrs;
 typedef __nv_bfloat16 bf16;
 
 template <int MODE>
-static int launch_gemv(const GemvArgs& a, cudaStream_t st) {
-    const int units = (MODE == GV_QKV) ? 3 * a.rows : a.rows;   // one weight row (GATEUP: one gate+up row pair) per warp trip
+static int launch_gemv(const GemvArgs& a_in, cudaStream_t st) {
+    const int units = (MODE == GV_QKV) ? 3 * a_in.rows : a_in.rows;   // one weight row (GATEUP: one gate+up row pair) per warp trip
+    // CTAs per SM: few enough that the successor grid (programmatic dependent launch) becomes co-resident and prefetches
+    static int per_sm = -1, pf_mb = -1;
+    if (per_sm < 0) { const char* e = getenv("LHRS_GEMV_CTAS_PER_SM"); per_sm = e ? atoi(e) : 4; if (per_sm < 1 || per_sm > 8) per_sm = 4; }
+    if (pf_mb < 0) { const char* e = getenv("LHRS_GEMV_PF_MB"); pf_mb = e ? atoi(e) : 24; }
     int grid = (units + 7) / 8;
-    const int cap = num_sms() * 8;
+    const int cap = num_sms() * per_sm;
     if (grid > cap) grid = cap;
+    GemvArgs a = a_in;
+    a.pf_bytes_per_warp = (int)(((long long)pf_mb << 20) / ((long long)grid * 8));
     const size_t smem = (size_t)a.K * 2;
     auto kern = gemv_kernel<MODE>;
     static bool attr = false;
