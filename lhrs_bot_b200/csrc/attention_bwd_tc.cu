@@ -104,11 +104,13 @@ namespace dqk {
 using namespace abt;
 constexpr int OFF_Q = 0;
 constexpr int OFF_DO = OFF_Q + T128;
-constexpr int OFF_K = OFF_DO + T128;         // 2 stages
-constexpr int OFF_V = OFF_K + 2 * T64;       // 2 stages
-constexpr int OFF_DS = OFF_V + 2 * T64;
+constexpr int NST = 4;                       // K/V ring depth: a stage is only free once dQ(j) has read K_j, and the refill
+                                             // takes a TMA round trip, so two stages would expose that latency every step
+constexpr int OFF_K = OFF_DO + T128;         // NST stages
+constexpr int OFF_V = OFF_K + NST * T64;     // NST stages
+constexpr int OFF_DS = OFF_V + NST * T64;
 constexpr int OFF_BAR = OFF_DS + PS;
-constexpr int SMEM_BYTES = OFF_BAR + 128;
+constexpr int SMEM_BYTES = OFF_BAR + 256;
 constexpr int TM_S = 0, TM_DP = 128, TM_DQ = 256;
 }  // namespace dqk
 
@@ -122,13 +124,13 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
     if ((smem_u32(smem) & 1023u) != 0) __trap();
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
     uint64_t* qdo_full = bars;        // 1
-    uint64_t* kv_full = bars + 1;     // 2
-    uint64_t* kv_empty = bars + 3;    // 2
-    uint64_t* sdp_full = bars + 5;    // 2
-    uint64_t* sdp_empty = bars + 7;   // 2
-    uint64_t* ds_full = bars + 9;     // 1
-    uint64_t* dq_done = bars + 10;    // 1
-    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 12);
+    uint64_t* sdp_full = bars + 1;    // 2
+    uint64_t* sdp_empty = bars + 3;   // 2
+    uint64_t* ds_full = bars + 5;     // 1
+    uint64_t* dq_done = bars + 6;     // 1
+    uint64_t* kv_full = bars + 8;     // NST
+    uint64_t* kv_empty = bars + 8 + NST;   // NST
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 8 + 2 * NST);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -142,9 +144,11 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmDO); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV);
         mbar_init(qdo_full, 1);
-        for (int s = 0; s < 2; ++s) {
+        for (int s = 0; s < NST; ++s) {
             mbar_init(&kv_full[s], 1);
             mbar_init(&kv_empty[s], 1);
+        }
+        for (int s = 0; s < 2; ++s) {
             mbar_init(&sdp_full[s], 1);
             mbar_init(&sdp_empty[s], NCOMPUTE);
         }
@@ -172,8 +176,8 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
             load(smem + OFF_DO, &tmDO, qdo_full, 0, q0, pa.o_hfirst);
             load(smem + OFF_DO + T128 / 2, &tmDO, qdo_full, 64, q0, pa.o_hfirst);
             for (int j = 0; j < n; ++j) {
-                const int st = j & 1;
-                mbar_wait(&kv_empty[st], ((j >> 1) & 1) ^ 1);
+                const int st = j % NST;
+                mbar_wait(&kv_empty[st], ((j / NST) & 1) ^ 1);
                 mbar_arrive_expect_tx(&kv_full[st], 2 * T64);
                 uint8_t* sk = smem + OFF_K + st * T64;
                 uint8_t* sv = smem + OFF_V + st * T64;
@@ -195,31 +199,31 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
             const bool issuer = elect_one();
             mbar_wait(qdo_full, 0);
             auto issue_sdp = [&](int j) {
-                const int st = j & 1;
-                mbar_wait(&kv_full[st], (j >> 1) & 1);
-                mbar_wait(&sdp_empty[st], ((j >> 1) & 1) ^ 1);
+                const int st = j % NST, ab = j & 1;      // K/V ring stage, S/dP accumulator buffer
+                mbar_wait(&kv_full[st], (j / NST) & 1);
+                mbar_wait(&sdp_empty[ab], ((j >> 1) & 1) ^ 1);
                 tc_fence_after();
                 if (issuer) {
 #pragma unroll
                     for (int kk = 0; kk < 8; ++kk) {
                         const uint32_t ao = (kk >> 2) * (T128 / 2 >> 4) + (kk & 3) * 2;
                         const uint32_t bo = st * (T64 >> 4) + (kk >> 2) * (T64 / 2 >> 4) + (kk & 3) * 2;
-                        umma_bf16_w(tmem_base + TM_S + st * 64, q_lo + ao, k_lo + bo, DESC_HI, idesc_sdp, kk ? 1u : 0u);
+                        umma_bf16_w(tmem_base + TM_S + ab * 64, q_lo + ao, k_lo + bo, DESC_HI, idesc_sdp, kk ? 1u : 0u);
                     }
 #pragma unroll
                     for (int kk = 0; kk < 8; ++kk) {
                         const uint32_t ao = (kk >> 2) * (T128 / 2 >> 4) + (kk & 3) * 2;
                         const uint32_t bo = st * (T64 >> 4) + (kk >> 2) * (T64 / 2 >> 4) + (kk & 3) * 2;
-                        umma_bf16_w(tmem_base + TM_DP + st * 64, do_lo + ao, v_lo + bo, DESC_HI, idesc_sdp, kk ? 1u : 0u);
+                        umma_bf16_w(tmem_base + TM_DP + ab * 64, do_lo + ao, v_lo + bo, DESC_HI, idesc_sdp, kk ? 1u : 0u);
                     }
-                    umma_commit(&sdp_full[st]);
+                    umma_commit(&sdp_full[ab]);
                 }
                 __syncwarp();
             };
             issue_sdp(0);
             for (int j = 0; j < n; ++j) {
                 if (j + 1 < n) issue_sdp(j + 1);
-                const int st = j & 1;
+                const int st = j % NST;
                 mbar_wait(ds_full, j & 1);
                 tc_fence_after();
                 if (issuer) {
@@ -307,13 +311,14 @@ namespace dkv {
 using namespace abt;
 constexpr int OFF_K = 0;
 constexpr int OFF_V = OFF_K + T128;
-constexpr int OFF_Q = OFF_V + T128;          // 2 stages
-constexpr int OFF_DO = OFF_Q + 2 * T64;      // 2 stages
-constexpr int OFF_PT = OFF_DO + 2 * T64;
+constexpr int NST = 3;                       // Q/dO ring depth (see dqk::NST; three stages is what fits beside K, V, P^T, dS^T)
+constexpr int OFF_Q = OFF_V + T128;          // NST stages
+constexpr int OFF_DO = OFF_Q + NST * T64;    // NST stages
+constexpr int OFF_PT = OFF_DO + NST * T64;
 constexpr int OFF_DST = OFF_PT + PS;
 constexpr int OFF_STAT = OFF_DST + PS;       // [2 stages][lse2 64 | delta 64] fp32
 constexpr int OFF_BAR = OFF_STAT + 2 * 128 * 4;
-constexpr int SMEM_BYTES = OFF_BAR + 128;
+constexpr int SMEM_BYTES = OFF_BAR + 256;
 constexpr int TM_S = 0, TM_DP = 128, TM_DV = 256, TM_DK = 384;
 }  // namespace dkv
 
@@ -327,13 +332,13 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
     if ((smem_u32(smem) & 1023u) != 0) __trap();
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
     uint64_t* kv_full = bars;          // 1
-    uint64_t* qdo_full = bars + 1;     // 2
-    uint64_t* qdo_empty = bars + 3;    // 2
-    uint64_t* sdp_full = bars + 5;     // 2
-    uint64_t* sdp_empty = bars + 7;    // 2
-    uint64_t* ps_full = bars + 9;      // 1
-    uint64_t* dvdk_done = bars + 10;   // 1
-    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 12);
+    uint64_t* sdp_full = bars + 1;     // 2
+    uint64_t* sdp_empty = bars + 3;    // 2
+    uint64_t* ps_full = bars + 5;      // 1
+    uint64_t* dvdk_done = bars + 6;    // 1
+    uint64_t* qdo_full = bars + 8;     // NST
+    uint64_t* qdo_empty = bars + 8 + NST;   // NST
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 8 + 2 * NST);
     float* stat = reinterpret_cast<float*>(smem + OFF_STAT);
 
     const int warp = threadIdx.x >> 5;
@@ -350,9 +355,11 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmDO); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV);
         mbar_init(kv_full, 1);
-        for (int s = 0; s < 2; ++s) {
+        for (int s = 0; s < NST; ++s) {
             mbar_init(&qdo_full[s], 1);
             mbar_init(&qdo_empty[s], 1);
+        }
+        for (int s = 0; s < 2; ++s) {
             mbar_init(&sdp_full[s], 1);
             mbar_init(&sdp_empty[s], NCOMPUTE);
         }
@@ -380,9 +387,9 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
             load(smem + OFF_V, &tmV, kv_full, 0, k0, pa.v_hfirst);
             load(smem + OFF_V + T128 / 2, &tmV, kv_full, 64, k0, pa.v_hfirst);
             for (int t = 0; t < n; ++t) {
-                const int st = t & 1;
+                const int st = t % NST;
                 const int i0 = (i_begin + t) * 64;
-                mbar_wait(&qdo_empty[st], ((t >> 1) & 1) ^ 1);
+                mbar_wait(&qdo_empty[st], ((t / NST) & 1) ^ 1);
                 mbar_arrive_expect_tx(&qdo_full[st], 2 * T64);
                 uint8_t* sq = smem + OFF_Q + st * T64;
                 uint8_t* sd = smem + OFF_DO + st * T64;
@@ -405,31 +412,31 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
             const bool issuer = elect_one();
             mbar_wait(kv_full, 0);
             auto issue_sdp = [&](int t) {
-                const int st = t & 1;
-                mbar_wait(&qdo_full[st], (t >> 1) & 1);
-                mbar_wait(&sdp_empty[st], ((t >> 1) & 1) ^ 1);
+                const int st = t % NST, ab = t & 1;      // Q/dO ring stage, S^T/dP^T accumulator buffer
+                mbar_wait(&qdo_full[st], (t / NST) & 1);
+                mbar_wait(&sdp_empty[ab], ((t >> 1) & 1) ^ 1);
                 tc_fence_after();
                 if (issuer) {
 #pragma unroll
                     for (int kk = 0; kk < 8; ++kk) {   // S^T = K Q^T
                         const uint32_t ao = (kk >> 2) * (T128 / 2 >> 4) + (kk & 3) * 2;
                         const uint32_t bo = st * (T64 >> 4) + (kk >> 2) * (T64 / 2 >> 4) + (kk & 3) * 2;
-                        umma_bf16_w(tmem_base + TM_S + st * 64, k_lo + ao, q_lo + bo, DESC_HI, idesc_sdp, kk ? 1u : 0u);
+                        umma_bf16_w(tmem_base + TM_S + ab * 64, k_lo + ao, q_lo + bo, DESC_HI, idesc_sdp, kk ? 1u : 0u);
                     }
 #pragma unroll
                     for (int kk = 0; kk < 8; ++kk) {   // dP^T = V dO^T
                         const uint32_t ao = (kk >> 2) * (T128 / 2 >> 4) + (kk & 3) * 2;
                         const uint32_t bo = st * (T64 >> 4) + (kk >> 2) * (T64 / 2 >> 4) + (kk & 3) * 2;
-                        umma_bf16_w(tmem_base + TM_DP + st * 64, v_lo + ao, do_lo + bo, DESC_HI, idesc_sdp, kk ? 1u : 0u);
+                        umma_bf16_w(tmem_base + TM_DP + ab * 64, v_lo + ao, do_lo + bo, DESC_HI, idesc_sdp, kk ? 1u : 0u);
                     }
-                    umma_commit(&sdp_full[st]);
+                    umma_commit(&sdp_full[ab]);
                 }
                 __syncwarp();
             };
             issue_sdp(0);
             for (int t = 0; t < n; ++t) {
                 if (t + 1 < n) issue_sdp(t + 1);
-                const int st = t & 1;
+                const int st = t % NST;
                 mbar_wait(ps_full, t & 1);
                 tc_fence_after();
                 if (issuer) {

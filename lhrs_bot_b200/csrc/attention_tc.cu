@@ -57,13 +57,15 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     if ((smem_u32(smem) & 1023u) != 0) __trap();   // SW128 atoms need 1 KB alignment; no slack is budgeted (2 CTAs/SM)
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
     uint64_t* q_full = bars;           // 1
-    uint64_t* kv_full = bars + 1;      // 2
-    uint64_t* kv_empty = bars + 3;     // 2
+    uint64_t* k_full = bars + 1;       // 2   K and V rings are released separately: K_j is dead as soon as S_j has been
+    uint64_t* k_empty = bars + 3;      // 2   computed, a whole softmax + PV step before V_j, so its refill has time to land
     uint64_t* s_full = bars + 5;       // 2
     uint64_t* s_empty = bars + 7;      // 2
     uint64_t* p_full = bars + 9;       // 1
     uint64_t* pv_full = bars + 10;     // 1
-    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 12);
+    uint64_t* v_full = bars + 11;      // 2
+    uint64_t* v_empty = bars + 13;     // 2
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 15);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -80,8 +82,10 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         tma_prefetch_desc(&tmV);
         mbar_init(q_full, 1);
         for (int s = 0; s < 2; ++s) {
-            mbar_init(&kv_full[s], 1);
-            mbar_init(&kv_empty[s], 1);
+            mbar_init(&k_full[s], 1);
+            mbar_init(&k_empty[s], 1);
+            mbar_init(&v_full[s], 1);
+            mbar_init(&v_empty[s], 1);
             mbar_init(&s_full[s], 1);
             mbar_init(&s_empty[s], 128);
         }
@@ -110,14 +114,16 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
             load(smem + OFF_Q + Q_BYTES / 2, &tmQ, q_full, 64, q0, p.q_hfirst);
             for (int j = 0; j < n; ++j) {
                 const int st = j & 1;
-                mbar_wait(&kv_empty[st], ((j >> 1) & 1) ^ 1);
-                mbar_arrive_expect_tx(&kv_full[st], K_BYTES + V_BYTES);
                 uint8_t* sk = smem + OFF_K + st * K_BYTES;
                 uint8_t* sv = smem + OFF_V + st * V_BYTES;
-                load(sk, &tmK, &kv_full[st], 0, j * BKV, p.k_hfirst);
-                load(sk + K_BYTES / 2, &tmK, &kv_full[st], 64, j * BKV, p.k_hfirst);
-                load(sv, &tmV, &kv_full[st], 0, j * BKV, p.v_hfirst);
-                load(sv + V_BYTES / 2, &tmV, &kv_full[st], 64, j * BKV, p.v_hfirst);
+                mbar_wait(&k_empty[st], ((j >> 1) & 1) ^ 1);
+                mbar_arrive_expect_tx(&k_full[st], K_BYTES);
+                load(sk, &tmK, &k_full[st], 0, j * BKV, p.k_hfirst);
+                load(sk + K_BYTES / 2, &tmK, &k_full[st], 64, j * BKV, p.k_hfirst);
+                mbar_wait(&v_empty[st], ((j >> 1) & 1) ^ 1);
+                mbar_arrive_expect_tx(&v_full[st], V_BYTES);
+                load(sv, &tmV, &v_full[st], 0, j * BKV, p.v_hfirst);
+                load(sv + V_BYTES / 2, &tmV, &v_full[st], 64, j * BKV, p.v_hfirst);
             }
         }
     } else if (warp == 1) {
@@ -134,7 +140,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
             mbar_wait(q_full, 0);
             auto issue_s = [&](int j) {
                 const int st = j & 1;
-                mbar_wait(&kv_full[st], (j >> 1) & 1);
+                mbar_wait(&k_full[st], (j >> 1) & 1);
                 mbar_wait(&s_empty[st], ((j >> 1) & 1) ^ 1);
                 tc_fence_after();
                 if (issuer) {
@@ -144,6 +150,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                         const uint32_t bb = k_lo + st * (K_BYTES >> 4) + (kk >> 2) * (K_BYTES / 2 >> 4) + (kk & 3) * 2;
                         umma_bf16_w(tmem_base + st * BKV, a, bb, desc_hi, idesc_s, kk ? 1u : 0u);
                     }
+                    umma_commit(&k_empty[st]);
                     umma_commit(&s_full[st]);
                 }
                 __syncwarp();
@@ -152,6 +159,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
             for (int j = 0; j < n; ++j) {
                 if (j + 1 < n) issue_s(j + 1);
                 const int st = j & 1;
+                mbar_wait(&v_full[st], (j >> 1) & 1);
                 mbar_wait(p_full, j & 1);
                 tc_fence_after();
                 if (issuer) {
@@ -159,7 +167,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                     for (int kk = 0; kk < BKV / 16; ++kk)
                         umma_bf16_w(tmem_base + 2 * BKV, p_lo + kk * 2, v_lo + st * (V_BYTES >> 4) + kk * (2048 >> 4), desc_hi,
                                     idesc_o, (j > 0 || kk > 0) ? 1u : 0u);
-                    umma_commit(&kv_empty[st]);
+                    umma_commit(&v_empty[st]);
                     umma_commit(pv_full);
                 }
                 __syncwarp();
@@ -217,9 +225,10 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                     if (!((w1 >> i) & 1u)) s[32 + i] = -INFINITY;
                 }
             }
-            float mx = s[0];
+            float mx4[4] = {s[0], s[1], s[2], s[3]};   // four independent chains: a single 63-deep fmax chain is pure latency
 #pragma unroll
-            for (int i = 1; i < 64; ++i) mx = fmaxf(mx, s[i]);
+            for (int i = 4; i < 64; ++i) mx4[i & 3] = fmaxf(mx4[i & 3], s[i]);
+            const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
             // ---- lazy running max: raise it only when it would grow by more than 2^RESCALE_LOG2
             const float m_new = fmaxf(m, mx);
             float alpha = 1.f;
@@ -230,16 +239,16 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                 l *= alpha;
             }
             const float neg = (m == -INFINITY) ? 0.f : -m * c;
-            float sum = 0.f;
+            float sum4[4] = {0.f, 0.f, 0.f, 0.f};
             uint32_t pk[32];
 #pragma unroll
             for (int i = 0; i < 32; ++i) {
                 const float e0 = ex2_approx(fmaf(s[2 * i], c, neg));
                 const float e1 = ex2_approx(fmaf(s[2 * i + 1], c, neg));
-                sum += e0 + e1;
+                sum4[i & 3] += e0 + e1;
                 pk[i] = pack_bf16(e0, e1);
             }
-            l += sum;
+            l += (sum4[0] + sum4[1]) + (sum4[2] + sum4[3]);
 
             if (j > 0) {
                 // P smem and the O accumulator are free once the previous step's PV MMAs have completed
