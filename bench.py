@@ -43,8 +43,9 @@ def parse():
     ap.add_argument("--steps", type=int, default=8)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="auto", choices=["auto", "sft_step", "prefill", "decode"])
-    ap.add_argument("--batch", type=int, default=PER_GPU_BATCH)
+    ap.add_argument("--workload", default="auto", choices=["auto", "sft_step", "stage1_step", "prefill", "decode"])
+    ap.add_argument("--batch", type=int, default=None, help="per-GPU batch (default 16; 32 for stage1_step)")
+    ap.add_argument("--seq", type=int, default=None, help="decoder positions per sample (default 512; 256 for stage1_step)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
 
@@ -59,8 +60,9 @@ def peaks():
 
 
 # ------------------------------------------------------------------------------------------------ synthetic workload
-def make_batch(B, seed, device=None, pin=False):
+def make_batch(B, seed, device=None, pin=False, t_text=None):
     g = torch.Generator().manual_seed(seed)
+    T_TEXT = globals()["T_TEXT"] if t_text is None else t_text
     ids = torch.randint(3, 32000, (B, T_TEXT), generator=g)
     ids[:, 0] = 1
     ids[:, 1] = -200                      # plain template: [BOS, <image>, text...]
@@ -311,24 +313,29 @@ def main():
         return run_decode(args, dev, rank, world, local)
     if workload == "auto":
         workload = "sft_step" if training.AVAILABLE else "prefill"
-    B = args.batch
-    cfg = default_config(stage=3 if workload == "sft_step" else 0, local_rank=local, is_distribute=world > 1,
+    # stage1_step = SURVEY 8d config 3: batch 32 per GPU, S = 256, pooler-only gradients (LLaMA and ViT frozen, no LoRA)
+    train = workload in ("sft_step", "stage1_step")
+    B = args.batch if args.batch else (32 if workload == "stage1_step" else PER_GPU_BATCH)
+    SEQ_LEN = args.seq if args.seq else (256 if workload == "stage1_step" else globals()["SEQ_LEN"])
+    t_text = SEQ_LEN - (NUM_QUERY - 1)
+    cfg = default_config(stage=3 if workload == "sft_step" else (1 if workload == "stage1_step" else 0), local_rank=local,
+                         is_distribute=world > 1,
                          lora=dict(enable=workload == "sft_step", lora_r=16, lora_alpha=32, lora_dropout=0.0, lora_bias="none"))
     torch.manual_seed(322 + rank)
     model = build_model(cfg).to(device=dev, dtype=torch.bfloat16)
-    if workload == "sft_step":
-        stepper = training.SftStepper(model, world_size=world)
+    if train:
+        stepper = training.SftStepper(model, world_size=world, max_grad_norm=0.3 if workload == "stage1_step" else 1.0)
     else:
         model.eval()
 
     def step(batch):
-        if workload == "sft_step":
+        if train:
             return stepper.step(batch)
         with torch.no_grad():
             return model(batch)["total_loss"]
 
-    dev_batches = [make_batch(B, seed=1000 * rank + i, device=dev) for i in range(2)]
-    host_batches = [make_batch(B, seed=2000 * rank + i, pin=True) for i in range(2)]
+    dev_batches = [make_batch(B, seed=1000 * rank + i, device=dev, t_text=t_text) for i in range(2)]
+    host_batches = [make_batch(B, seed=2000 * rank + i, pin=True, t_text=t_text) for i in range(2)]
     h2d = batch_bytes(host_batches[0])
 
     def barrier():
@@ -399,8 +406,9 @@ def main():
 
     if rank == 0:
         wl = (f"stage3_sft_step_b{B}_s{SEQ_LEN} (fwd+bwd, LoRA r=16 + pooler grads, allreduce, AdamW)" if workload == "sft_step"
+              else f"stage1_step_b{B}_s{SEQ_LEN} (fwd+bwd, pooler-only grads through the frozen LLaMA, allreduce, AdamW)" if workload == "stage1_step"
               else f"prefill_loss_b{B}_s{SEQ_LEN} (UniBind.forward: ViT-L/14 + pooler + splice + LLaMA-7B + CE)")
-        line = dict(metric="tokens/sec (LLaMA-7B, 224px, seq 512), aggregate", value=value, unit="tokens/s", n_gpus=world,
+        line = dict(metric=f"tokens/sec (LLaMA-7B, 224px, seq {SEQ_LEN}), aggregate", value=value, unit="tokens/s", n_gpus=world,
                     steps=args.steps, warmup=max(args.warmup, 3), ms_per_step=ms / args.steps, higher_is_better=True,
                     scaling="weak", vs_baseline=None, dtype="bf16", data="synthetic",
                     config=dict(workload=wl, per_gpu_batch=B, seq_len=SEQ_LEN, image="224x224", parallelism=f"dp{world}",
