@@ -170,49 +170,125 @@ def _shared_state(cfg, dtype_llama=torch.bfloat16):
     return dict(vit=vit, pooler=pool, llama=ll)
 
 
-def cpu_reference_step(st, cfg, batch):
-    """One pass of the reference's path on the host: UniBind.forward -> loss (oracle restatement, PyTorch eager)."""
+def _trainable_copies(st, workload):
+    """Per-layer trainable leaves for the CPU training step: the pooler's 79.9 M fp32 parameters (own tensors per layer, so the
+    optimizer touches the real parameter count) and, for the SFT step, LoRA r=16 factors on the 7 projections of all 32 layers."""
+    params = []
+    g = torch.Generator().manual_seed(1)
+    pool = {}
+    for k, v in st["pooler"].items():
+        t = v.clone().requires_grad_(True)
+        pool[k] = t
+        params.append(t)
+    st = dict(st, pooler=pool)
+    if workload == "sft_step":
+        ll = dict(st["llama"])
+        d, f, r = 4096, 11008, 16
+        shapes = {"self_attn.q_proj": (d, d), "self_attn.k_proj": (d, d), "self_attn.v_proj": (d, d), "self_attn.o_proj": (d, d),
+                  "mlp.gate_proj": (f, d), "mlp.up_proj": (f, d), "mlp.down_proj": (d, f)}
+        for i in range(32):
+            for n, (o, k) in shapes.items():
+                a = ((torch.rand(r, k, generator=g) * 2 - 1) * (1.0 / k) ** 0.5).to(torch.bfloat16).requires_grad_(True)
+                b = (torch.randn(o, r, generator=g) * 0.02).to(torch.bfloat16).requires_grad_(True)
+                ll[f"model.layers.{i}.{n}.lora_A.weight"], ll[f"model.layers.{i}.{n}.lora_B.weight"] = a, b
+                params += [a, b]
+        st = dict(st, llama=ll)
+    return st, params
+
+
+def cpu_reference_step(st, batch, workload, opt=None):
+    """One pass of the reference's path on the host (oracle restatement, PyTorch eager): UniBind.forward -> loss, and for the
+    training workloads loss.backward() through the frozen LLaMA into the pooler (+ LoRA) followed by the optimizer step."""
     from oracle import llama, pooler, splice, vit
-    with torch.no_grad():
-        feats = vit.vision_encode(batch["rgb"].float(), st["vit"], 24, 16)
+    train = workload in ("sft_step", "stage1_step")
+    with torch.set_grad_enabled(train):
+        with torch.no_grad():
+            feats = vit.vision_encode(batch["rgb"].float(), st["vit"], 24, 16)
         img = pooler.attn_pooler_forward(feats, st["pooler"], 6, 16).to(torch.bfloat16)
         mask, embeds, labels = splice.prepare_inputs_for_multimodal(batch["input_ids"], batch["attention_mask"], batch["labels"],
                                                                     st["llama"]["model.embed_tokens.weight"], img)
-        logits = llama.llama_logits(embeds, st["llama"], 32, 32, 1e-5, mask)
-        return llama.causal_lm_loss(logits, labels)
+        logits = llama.llama_logits(embeds, st["llama"], 32, 32, 1e-5, mask, 2.0 if workload == "sft_step" else 0.0)
+        loss = llama.causal_lm_loss(logits, labels)
+        if train:
+            opt.zero_grad(set_to_none=True)
+            loss.backward()
+            torch.nn.utils.clip_grad_norm_(opt.param_groups[0]["params"], 1.0 if workload == "sft_step" else 0.3)
+            opt.step()
+    return loss.detach()
 
 
-def time_cpu_reference(steps, warmup, sample_batch=1):
-    from lhrs_bot_b200.config import default_config
-    cfg = default_config()
+def cpu_reference_decode(st, n_new):
+    """BASELINE config 2 on the host: image -> pooler -> splice -> prefill (S = 175) -> n_new greedy tokens with a KV cache."""
+    from oracle import llama, pooler, splice, vit
+    g = torch.Generator().manual_seed(0)
+    ids = torch.randint(3, 32000, (1, 32), generator=g)
+    ids[0, 0], ids[0, 5] = 1, -200
+    px = torch.randn(1, 3, 224, 224, generator=g)
+    with torch.no_grad():
+        img = pooler.attn_pooler_forward(vit.vision_encode(px, st["vit"], 24, 16), st["pooler"], 6, 16).to(torch.bfloat16)
+        _, embeds, _ = splice.prepare_inputs_for_multimodal(ids, None, None, st["llama"]["model.embed_tokens.weight"], img)
+        t0 = time.perf_counter()
+        llama.greedy_decode(embeds, st["llama"], 32, 32, 1)
+        t_prefill = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        llama.greedy_decode(embeds, st["llama"], 32, 32, n_new)
+        t_full = time.perf_counter() - t0
+    return (t_full - t_prefill) / (n_new - 1), t_prefill
+
+
+def time_cpu_reference(workload, steps, warmup, seq_len=None, sample_batch=1):
+    """The reference's CPU path on a BOUNDED sample of the GPU arm's workload: `sample_batch` sample(s) per step instead of
+    the per-GPU batch (same sequence length, same trainable set, same optimizer)."""
     torch.set_num_threads(os.cpu_count() or 1)
-    st = _shared_state(cfg)
+    st = _shared_state(None)
+    cores = torch.get_num_threads()
+    if workload == "decode":
+        n_new = 9
+        s_tok, s_pre = cpu_reference_decode(st, n_new)
+        return dict(value=1.0 / s_tok, unit="tokens/s", cores=cores, kind="port",
+                    sample=f"prompt 175 -> {n_new} greedy tokens (of the arm's 128), KV cache, LLaMA-7B bf16, prefill {s_pre * 1e3:.0f} ms, PyTorch eager"), s_tok * 1e3
+    S = seq_len or (256 if workload == "stage1_step" else SEQ_LEN)
+    t_text = S - (NUM_QUERY - 1)
+    opt = None
+    if workload in ("sft_step", "stage1_step"):
+        st, params = _trainable_copies(st, workload)
+        opt = torch.optim.AdamW(params, lr=2e-4, betas=(0.9, 0.95), eps=1e-8, weight_decay=0.0)
     times = []
     for i in range(warmup + steps):
-        batch = make_batch(sample_batch, seed=100 + i)
+        batch = make_batch(sample_batch, seed=100 + i, t_text=t_text)
         t0 = time.perf_counter()
-        loss = cpu_reference_step(st, cfg, batch)
+        loss = cpu_reference_step(st, batch, workload, opt)
         float(loss)
         if i >= warmup:
             times.append(time.perf_counter() - t0)
-    tok = sample_batch * SEQ_LEN
+    tok = sample_batch * S
     mean = sum(times) / len(times)
-    return dict(value=tok / mean, unit="tokens/s", cores=torch.get_num_threads(), kind="port",
-                sample=f"{sample_batch} sample(s) x {SEQ_LEN} positions per step, UniBind.forward->loss (ViT+pooler fp32, LLaMA-7B bf16), "
-                       f"{len(times)} timed step(s) after {warmup} warm-up, PyTorch eager"), mean * 1e3
+    what = {"sft_step": "fwd + bwd (LoRA r=16 + pooler grads) + clip + AdamW", "stage1_step": "fwd + bwd (pooler-only grads) + clip + AdamW",
+            "prefill": "UniBind.forward -> loss"}[workload]
+    return dict(value=tok / mean, unit="tokens/s", cores=cores, kind="port",
+                sample=f"{sample_batch} sample(s) x {S} positions per step (the arm runs the per-GPU batch), {what}; ViT+pooler fp32, "
+                       f"LLaMA-7B bf16, {len(times)} timed step(s) after {warmup} warm-up, PyTorch eager"), mean * 1e3
+
+
+def resolve_workload(args):
+    return "sft_step" if args.workload == "auto" else args.workload
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    workload = resolve_workload(args)
     steps = max(1, min(args.steps, 3))
-    base, ms = time_cpu_reference(steps, 1)
-    line = dict(metric="tokens/sec (LLaMA-7B, 224px, seq 512), aggregate", value=base["value"], unit="tokens/s", n_gpus=args.gpus,
+    base, ms = time_cpu_reference(workload, steps, 1, seq_len=args.seq)
+    S = args.seq or (256 if workload == "stage1_step" else SEQ_LEN)
+    metric = ("decode tokens/sec (LLaMA-7B, 224px, 1 image + 32-token prompt -> 128 greedy tokens), aggregate" if workload == "decode"
+              else f"tokens/sec (LLaMA-7B, 224px, seq {S}), aggregate")
+    line = dict(metric=metric, value=base["value"], unit="tokens/s", n_gpus=args.gpus,
                 steps=steps, warmup=1, ms_per_step=ms, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="bf16",
                 data="synthetic", impl="reference",
-                config=dict(workload="prefill_loss_b1_s512 (reference CPU path, bounded sample of the GPU arm's workload)",
-                            seq_len=SEQ_LEN, image="224x224", inputs_vs_l2="n/a (host)"),
+                config=dict(workload=f"{workload} (reference CPU path: the oracle port of lhrs.models in PyTorch eager, bounded sample of the GPU arm's workload)",
+                            seq_len=S, image="224x224", inputs_vs_l2="n/a (host)"),
                 cpu_baseline=base,
                 e2e=dict(value=base["value"], unit="tokens/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
     print(json.dumps(line), flush=True)
@@ -269,6 +345,12 @@ def run_decode(args, dev, rank, world, local):
     bytes_tok = 2.0 * (32 * (4 * 4096 * 4096 + 3 * 4096 * 11008) + 32000 * 4096) + 2 * 32 * 4096 * 2 * (S + n_new / 2)
     pk = peaks()
     achieved = bytes_tok / (ms_tok * 1e-3) / 1e9
+    cpu_base = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        try:
+            cpu_base, _ = time_cpu_reference("decode", 1, 0)
+        except Exception as e:
+            cpu_base = dict(error=str(e)[:200])
     if rank == 0:
         line = dict(metric="decode tokens/sec (LLaMA-7B, 224px, 1 image + 32-token prompt -> 128 greedy tokens), aggregate",
                     value=world * 1e3 / ms_tok, unit="tokens/s", n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3),
@@ -281,7 +363,7 @@ def run_decode(args, dev, rank, world, local):
                     gpu_launches=int(launches),
                     roofline=dict(bound="hbm", achieved=achieved, peak=pk["hbm"], unit="GB/s", frac=achieved / pk["hbm"], traffic=None,
                                   kernel="gemv_kernel chain (decode step)", peak_source=pk["which"]),
-                    cpu_baseline=None)
+                    cpu_baseline=cpu_base)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -312,7 +394,7 @@ def main():
     if workload == "decode":
         return run_decode(args, dev, rank, world, local)
     if workload == "auto":
-        workload = "sft_step" if training.AVAILABLE else "prefill"
+        workload = "sft_step"
     # stage1_step = SURVEY 8d config 3: batch 32 per GPU, S = 256, pooler-only gradients (LLaMA and ViT frozen, no LoRA)
     train = workload in ("sft_step", "stage1_step")
     B = args.batch if args.batch else (32 if workload == "stage1_step" else PER_GPU_BATCH)
@@ -400,7 +482,7 @@ def main():
     cpu_base = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         try:
-            cpu_base, _ = time_cpu_reference(2, 1)
+            cpu_base, _ = time_cpu_reference(workload, 2, 1, seq_len=SEQ_LEN)
         except Exception as e:   # the baseline is a reported side figure; never let it take the GPU number down
             cpu_base = dict(error=str(e)[:200])
 
