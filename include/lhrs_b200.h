@@ -327,6 +327,15 @@ int lhrs_adamw_step(float* master, float* m, float* v, const void* grad, void* p
                     float lr, float beta1, float beta2, float eps, float weight_decay, int32_t step, const float* gnorm_sq,
                     float max_norm, float grad_scale, void* stream);
 
+/* Adan on flat buffers: the reference's stage-1 optimizer (`optimizer: adanp`, Config/multi_modal_stage1.yaml:89, built by timm
+ * create_optimizer_v2 in lhrs/optimizer/build_optimizer.py:76-86; `adanp` = Adan(no_prox=0), `adanw` = Adan(no_prox=1)).  Betas in
+ * timm's convention (defaults 0.98, 0.92, 0.99).  exp_avg / exp_avg_diff / exp_avg_sq / pre_grad are fp32 state ([n], zero-initialised;
+ * pre_grad is taken from the first gradient when step == 1).  Clipping / grad_scale / decay_mask as in lhrs_adamw_step. */
+int lhrs_adan_step(float* master, float* exp_avg, float* exp_avg_diff, float* exp_avg_sq, float* pre_grad, const void* grad,
+                   void* param_bf16, const float* decay_mask, int64_t n, float lr, float beta1, float beta2, float beta3, float eps,
+                   float weight_decay, int32_t step, int32_t no_prox, const float* gnorm_sq, float max_norm, float grad_scale,
+                   void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Single-sequence decode (HF generate loop reached from TextModal.generate, lhrs/models/text_modal.py:600-612, with the
  * generation-input rule of :36-60).  All buffers are caller-owned device memory (bf16 unless noted):

@@ -163,6 +163,7 @@ SIGNATURES = {
     "lhrs_pooler_bwd": (C.c_int, [C.POINTER(LhrsPoolerWeights), C.POINTER(LhrsPoolerWeights), _P, _I64, _I32, _P, _P, _P, C.c_size_t, _P]),
     "lhrs_grad_sumsq": (C.c_int, [_P, _I64, _P, _P, _P]),
     "lhrs_adamw_step": (C.c_int, [_P, _P, _P, _P, _P, _P, _I64, _F, _F, _F, _F, _F, _I32, _P, _F, _F, _P]),
+    "lhrs_adan_step": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _I64, _F, _F, _F, _F, _F, _F, _I32, _I32, _P, _F, _F, _P]),
 }
 
 _lock = threading.Lock()

@@ -4,7 +4,8 @@ Replaces, for this path, what the reference gets from DeepSpeed ZeRO-2 (main_pre
 hook/deepspeed_hook.py:5-9): the trainable set (pooler 79.9 M, + LoRA) lives in one flat bf16 parameter buffer and one flat
 bf16 gradient buffer; the backward kernels write gradients straight into the flat buffer (``_grad_sink``), a single NCCL
 allreduce (sum) over NVLink follows, and one kernel applies global-norm clipping + AdamW on fp32 master weights.  The frozen
-ViT / LLaMA weights are replicated and never communicated.  LR schedule: linear warm-up + cosine (lr_scheduler_hook.py:243-272).
+ViT / LLaMA weights are replicated and never communicated.  Optimizers: AdamW (stages 2-3) and Adan (stage 1, `adanp`), both
+one fused pass over the flat buffers.  LR schedule: the reference's cosine + warm-up (``reference_lr``, lr_scheduler_hook.py:243-272).
 """
 from __future__ import annotations
 
@@ -23,11 +24,12 @@ def trainable_parameters(model) -> List[torch.nn.Parameter]:
     return [p for p in model.parameters() if p.requires_grad]
 
 
-class FlatAdamW:
-    """Flat-buffer AdamW with global-norm clipping (torch.optim.AdamW semantics, betas (0.9, 0.95) as the reference's
-    DeepSpeed config, main_pretrain_stage1.py:30-41).  1-D parameters and biases get no weight decay (build_optimizer.py:20-46)."""
+class _FlatOptimizer:
+    """Flat buffers shared by the fused optimizers: bf16 params / grads (the tensors the kernels read and write), fp32 master
+    weights, a 0/1 decay mask (1-D parameters and biases get no weight decay, build_optimizer.py:20-46) and the global-norm
+    scratch.  Parameters are re-pointed INTO the flat buffer, so DeepSpeed-style flat collectives need no gather copy."""
 
-    def __init__(self, params: List[torch.nn.Parameter], lr=2e-4, betas=(0.9, 0.95), eps=1e-8, weight_decay=0.0, max_grad_norm=1.0):
+    def __init__(self, params: List[torch.nn.Parameter], lr, weight_decay, max_grad_norm):
         assert params, "no trainable parameters"
         dev = params[0].device
         self.params = params
@@ -35,8 +37,6 @@ class FlatAdamW:
         self.flat_param = torch.empty((self.numel,), device=dev, dtype=torch.bfloat16)
         self.flat_grad = torch.zeros((self.numel,), device=dev, dtype=torch.bfloat16)
         self.master = torch.empty((self.numel,), device=dev, dtype=torch.float32)
-        self.m = torch.zeros((self.numel,), device=dev, dtype=torch.float32)
-        self.v = torch.zeros((self.numel,), device=dev, dtype=torch.float32)
         self.decay_mask = torch.empty((self.numel,), device=dev, dtype=torch.float32) if weight_decay > 0 else None
         self.grad_views: Dict[torch.nn.Parameter, torch.Tensor] = {}
         off = 0
@@ -52,28 +52,82 @@ class FlatAdamW:
                 self.decay_mask[off: off + n] = 0.0 if p.dim() <= 1 else 1.0
             off += n
         self.master.copy_(self.flat_param)
-        self.lr, self.betas, self.eps, self.weight_decay, self.max_grad_norm = lr, betas, eps, weight_decay, max_grad_norm
+        self.lr, self.weight_decay, self.max_grad_norm = lr, weight_decay, max_grad_norm
         self.step_count = 0
         self._sumsq = torch.zeros((1,), device=dev, dtype=torch.float32)
         self._scratch = torch.empty((1024,), device=dev, dtype=torch.float32)
+
+    def _state(self, n: int):
+        return [torch.zeros((self.numel,), device=self.master.device, dtype=torch.float32) for _ in range(n)]
+
+    def _grad_norm_ptr(self, lib, st):
+        if self.max_grad_norm and self.max_grad_norm > 0:
+            check(lib.lhrs_grad_sumsq(self.flat_grad.data_ptr(), self.numel, self._sumsq.data_ptr(), self._scratch.data_ptr(), st),
+                  "lhrs_grad_sumsq")
+            return self._sumsq.data_ptr()
+        return None
+
+    def grad_norm(self) -> float:
+        return float(self._sumsq.sqrt().item())
+
+
+class FlatAdamW(_FlatOptimizer):
+    """Flat-buffer AdamW with global-norm clipping (torch.optim.AdamW semantics, betas (0.9, 0.95) as the reference's
+    DeepSpeed config for stages 2-3, main_pretrain_stage1.py:30-41)."""
+
+    def __init__(self, params: List[torch.nn.Parameter], lr=2e-4, betas=(0.9, 0.95), eps=1e-8, weight_decay=0.0, max_grad_norm=1.0):
+        super().__init__(params, lr, weight_decay, max_grad_norm)
+        self.m, self.v = self._state(2)
+        self.betas, self.eps = betas, eps
 
     def step(self, lr: Optional[float] = None, grad_scale: float = 1.0) -> None:
         lib = _lib.load()
         self.step_count += 1
         st = runtime.stream()
-        gn = None
-        if self.max_grad_norm and self.max_grad_norm > 0:
-            check(lib.lhrs_grad_sumsq(self.flat_grad.data_ptr(), self.numel, self._sumsq.data_ptr(), self._scratch.data_ptr(), st),
-                  "lhrs_grad_sumsq")
-            gn = self._sumsq.data_ptr()
+        gn = self._grad_norm_ptr(lib, st)
         check(lib.lhrs_adamw_step(self.master.data_ptr(), self.m.data_ptr(), self.v.data_ptr(), self.flat_grad.data_ptr(),
                                   self.flat_param.data_ptr(), None if self.decay_mask is None else self.decay_mask.data_ptr(),
                                   self.numel, float(self.lr if lr is None else lr), self.betas[0], self.betas[1], self.eps,
                                   self.weight_decay, self.step_count, gn, float(self.max_grad_norm or 0.0), float(grad_scale), st),
               "lhrs_adamw_step")
 
-    def grad_norm(self) -> float:
-        return float(self._sumsq.sqrt().item())
+
+class FlatAdan(_FlatOptimizer):
+    """Flat-buffer Adan — the reference's stage-1 optimizer (``optimizer: adanp``, Config/multi_modal_stage1.yaml:89-93, built by
+    timm ``create_optimizer_v2`` in lhrs/optimizer/build_optimizer.py:76-86): ``adanp`` = Adan(no_prox=False), ``adanw`` =
+    Adan(no_prox=True); timm defaults betas (0.98, 0.92, 0.99), eps 1e-8.  The reference runs it on the CPU through ZeRO
+    offload (main_pretrain_stage1.py:66-80); here it is one HBM pass over the flat buffers."""
+
+    def __init__(self, params: List[torch.nn.Parameter], lr=2e-4, betas=(0.98, 0.92, 0.99), eps=1e-8, weight_decay=0.0,
+                 max_grad_norm=0.3, no_prox=False):
+        super().__init__(params, lr, weight_decay, max_grad_norm)
+        self.exp_avg, self.exp_avg_diff, self.exp_avg_sq, self.pre_grad = self._state(4)
+        self.betas, self.eps, self.no_prox = betas, eps, bool(no_prox)
+
+    def step(self, lr: Optional[float] = None, grad_scale: float = 1.0) -> None:
+        lib = _lib.load()
+        self.step_count += 1
+        st = runtime.stream()
+        gn = self._grad_norm_ptr(lib, st)
+        check(lib.lhrs_adan_step(self.master.data_ptr(), self.exp_avg.data_ptr(), self.exp_avg_diff.data_ptr(),
+                                 self.exp_avg_sq.data_ptr(), self.pre_grad.data_ptr(), self.flat_grad.data_ptr(),
+                                 self.flat_param.data_ptr(), None if self.decay_mask is None else self.decay_mask.data_ptr(),
+                                 self.numel, float(self.lr if lr is None else lr), self.betas[0], self.betas[1], self.betas[2],
+                                 self.eps, self.weight_decay, self.step_count, int(self.no_prox), gn,
+                                 float(self.max_grad_norm or 0.0), float(grad_scale), st),
+              "lhrs_adan_step")
+
+
+def build_flat_optimizer(name: str, params, lr, weight_decay, max_grad_norm):
+    """``config.optimizer`` -> fused optimizer (build_optimizer.py:76-86 passes the yaml string to timm)."""
+    name = name.lower()
+    if name == "adamw":
+        return FlatAdamW(params, lr=lr, weight_decay=weight_decay, max_grad_norm=max_grad_norm)
+    if name in ("adanp", "adan"):
+        return FlatAdan(params, lr=lr, weight_decay=weight_decay, max_grad_norm=max_grad_norm, no_prox=False)
+    if name == "adanw":
+        return FlatAdan(params, lr=lr, weight_decay=weight_decay, max_grad_norm=max_grad_norm, no_prox=True)
+    raise NotImplementedError(f"optimizer {name!r}: the shipped yamls use adanp (stage 1) and adamw (stages 2-3)")
 
 
 def allreduce_flat_gradients(flat_grad: torch.Tensor, world: int) -> float:
@@ -92,6 +146,25 @@ def cosine_lr(step: int, base_lr: float, warmup: int, total: int, min_lr: float 
     return min_lr + 0.5 * (base_lr - min_lr) * (1.0 + math.cos(math.pi * t))
 
 
+def reference_lr(cur_iter: int, base_lr: float, max_iters: int, min_lr: float = 0.0, warmup_iters: int = 0,
+                 warmup_ratio: float = 0.1, warmup: Optional[str] = "linear") -> float:
+    """The reference's iteration-wise schedule, restated (hook/lr_scheduler_hook.py:243-272 CosineAnnealingLrUpdaterHook.get_lr
+    + :80-99 get_warmup_lr; built from ``config.schedule`` in IterBasedTrainer.py:65-80): the cosine runs over the WHOLE run
+    (progress = cur_iter / max_iters, it is not restarted after the warm-up), and during the first ``warmup_iters`` iterations
+    the regular value is scaled by ``1 - (1 - it/warmup_iters) * (1 - warmup_ratio)`` (linear), ``warmup_ratio`` (constant) or
+    ``warmup_ratio ** (1 - it/warmup_iters)`` (exp).  Shipped stage-1 yaml: min_lr 2e-5, warmup 300 iters, factor 0.1."""
+    regular = min_lr + 0.5 * (base_lr - min_lr) * (math.cos(math.pi * cur_iter / max(1, max_iters)) + 1.0)
+    if warmup is None or warmup_iters <= 0 or cur_iter >= warmup_iters:
+        return regular
+    if warmup == "constant":
+        return regular * warmup_ratio
+    if warmup == "linear":
+        return regular * (1.0 - (1.0 - cur_iter / warmup_iters) * (1.0 - warmup_ratio))
+    if warmup == "exp":
+        return regular * warmup_ratio ** (1.0 - cur_iter / warmup_iters)
+    raise ValueError(f'"{warmup}" is not a supported type for warming up')
+
+
 class SftStepper:
     """One data-parallel training step: ``loss = stepper.step(batch)``.
 
@@ -101,7 +174,8 @@ class SftStepper:
     """
 
     def __init__(self, model, world_size: int = 1, lr: float = 2e-4, weight_decay: float = 0.0, max_grad_norm: float = 1.0,
-                 warmup_steps: int = 0, total_steps: int = 0, prepare: bool = True):
+                 warmup_steps: int = 0, total_steps: int = 0, prepare: bool = True, optimizer: str = "adamw",
+                 min_lr: float = 0.0, warmup_ratio: float = 0.1):
         self.model = model
         self.world = world_size
         if prepare:
@@ -119,11 +193,12 @@ class SftStepper:
         ordered = [a for a, _ in pairs if a.requires_grad] + [b for _, b in pairs if b.requires_grad]
         seen = {id(p) for p in ordered}
         params = [p for p in trainable_parameters(model) if id(p) not in seen] + ordered
-        self.opt = FlatAdamW(params, lr=lr, weight_decay=weight_decay, max_grad_norm=max_grad_norm)
+        self.opt = build_flat_optimizer(optimizer, params, lr, weight_decay, max_grad_norm)
         # the backward kernels write into the flat gradient buffer directly
         model.rgb_pooler._grad_sink = {p: g for p, g in self.opt.grad_views.items()}
         model.text._grad_sink = model.rgb_pooler._grad_sink
         self.base_lr, self.warmup, self.total = lr, warmup_steps, total_steps
+        self.min_lr, self.warmup_ratio = min_lr, warmup_ratio
         self.it = 0
 
     def step(self, batch) -> torch.Tensor:
@@ -131,7 +206,8 @@ class SftStepper:
         loss = out["total_loss"]
         loss.backward()
         scale = allreduce_flat_gradients(self.opt.flat_grad, self.world)
-        lr = cosine_lr(self.it, self.base_lr, self.warmup, self.total) if self.total > 0 else self.base_lr
+        lr = (reference_lr(self.it, self.base_lr, self.total, self.min_lr, self.warmup, self.warmup_ratio)
+              if self.total > 0 else self.base_lr)
         self.opt.step(lr=lr, grad_scale=scale)
         self.it += 1
         return loss.detach()

@@ -274,6 +274,47 @@ def test_adamw_and_stepper(small):
     assert losses[-1] < losses[0] - 0.05 and all(math.isfinite(l) for l in losses)
 
 
+@pytest.mark.parametrize("no_prox,max_norm", [(False, 0.0), (True, 0.0), (False, 0.3)])
+def test_adan_matches_oracle(no_prox, max_norm):
+    """Fused flat-buffer Adan (stage 1's `adanp`) vs the oracle restatement of timm's update rule: fp32 master weights agree to
+    round-off over several steps (incl. the first step, where pre_grad := grad), with weight decay masked off 1-D tensors and
+    with DeepSpeed-style global-norm clipping."""
+    from oracle import optim
+    from lhrs_bot_b200.training import FlatAdan
+    torch.manual_seed(1)
+    ps = [torch.nn.Parameter(torch.randn(96, 40, device=DEV).bfloat16()), torch.nn.Parameter(torch.randn(256, device=DEV).bfloat16())]
+    ref = [p.detach().float().cpu().clone() for p in ps]
+    opt = FlatAdan(ps, lr=2e-3, weight_decay=0.05, max_grad_norm=max_norm, no_prox=no_prox)
+    ropt = optim.Adan(ref, lr=2e-3, weight_decay=0.05, no_prox=no_prox)
+    for it in range(6):
+        gs = [torch.randn(p.shape, device=DEV).bfloat16() for p in ps]
+        for p, g in zip(ps, gs):
+            opt.grad_views[p].copy_(g)
+        opt.step(grad_scale=0.5)
+        gref = [g.float().cpu() * 0.5 for g in gs]
+        c = optim.clip_coef(gref, max_norm)
+        ropt.step([g * c for g in gref], weight_decays=[0.05, 0.0])
+    n0 = ps[0].numel()
+    for p, r, m in zip(ps, ref, (opt.master[:n0], opt.master[n0:])):
+        assert torch.allclose(m.view(r.shape).cpu(), r, atol=2e-5, rtol=2e-5), (m.view(r.shape).cpu() - r).abs().max()
+        assert torch.equal(p.detach(), m.view(r.shape).bfloat16())
+    if max_norm > 0:
+        assert opt.grad_norm() > max_norm   # the clip branch was exercised
+
+
+def test_stage1_stepper_with_adan(small):
+    """Stage-1 recipe end to end: pooler-only grads through the frozen LLaMA, Adan + clip 0.3 + the reference's LR schedule."""
+    from lhrs_bot_b200.training import SftStepper
+    cfg = small_config()
+    model = build_small_model(cfg, DEV, seed=11)
+    stepper = SftStepper(model, world_size=1, lr=2e-3, max_grad_norm=0.3, optimizer="adanp", warmup_steps=2, total_steps=50, min_lr=2e-4)
+    assert all(not p.requires_grad for p in model.text.parameters()) and all(p.requires_grad for p in model.rgb_pooler.parameters())
+    batch = synthetic_batch(4, 24, cfg.text.vocab_size, DEV, seed=25, text_only=(), ragged_mask=False)
+    losses = [stepper.step(batch).item() for _ in range(10)]
+    print("adan stepper losses", [round(l, 4) for l in losses])
+    assert losses[-1] < losses[0] - 0.05 and all(math.isfinite(l) for l in losses)
+
+
 def test_unibind_backward_lora_grouped_flat_layout():
     """Same as above but with the SftStepper's flat parameter layout, which makes A_q/A_k/A_v (and A_gate/A_up) contiguous
     and switches the library to the batched LoRA side-GEMM path (one GEMM per step over all projections of a group)."""

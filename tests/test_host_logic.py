@@ -1,5 +1,6 @@
 """Host-side logic that runs without a GPU: config surface, module construction / state-dict keys (drop-in with the reference's
 checkpoints), freezing rules, tokenizer_image_token, LR schedule, and the data-parallel flat-gradient exchange on gloo (world 2)."""
+import math
 import os
 
 import pytest
@@ -103,6 +104,38 @@ def test_cosine_lr():
     assert cosine_lr(9, 1.0, 10, 100) == pytest.approx(1.0)
     assert cosine_lr(55, 1.0, 10, 100) == pytest.approx(0.5, abs=1e-6)
     assert cosine_lr(100, 1.0, 10, 100) == pytest.approx(0.0, abs=1e-9)
+
+
+def test_reference_lr_schedule():
+    """lr_scheduler_hook.py:243-272 + :80-99 with the shipped stage-1 schedule (min_lr 2e-5, 300 warm-up iters, factor 0.1)."""
+    from lhrs_bot_b200.training import reference_lr
+    base, mn, T, W = 2e-4, 2e-5, 10000, 300
+    cosv = lambda it: mn + 0.5 * (base - mn) * (math.cos(math.pi * it / T) + 1)
+    assert reference_lr(0, base, T, mn, W, 0.1) == pytest.approx(cosv(0) * 0.1)
+    assert reference_lr(150, base, T, mn, W, 0.1) == pytest.approx(cosv(150) * (1 - 0.5 * 0.9))
+    assert reference_lr(300, base, T, mn, W, 0.1) == pytest.approx(cosv(300))
+    assert reference_lr(5000, base, T, mn, W, 0.1) == pytest.approx((base + mn) / 2)
+    assert reference_lr(T, base, T, mn, W, 0.1) == pytest.approx(mn)
+    assert reference_lr(10, base, T, mn, W, 0.1, warmup="constant") == pytest.approx(cosv(10) * 0.1)
+    assert reference_lr(10, base, T, mn, W, 0.1, warmup="exp") == pytest.approx(cosv(10) * 0.1 ** (1 - 10 / W))
+    assert reference_lr(10, base, T, mn, 0, 0.1, warmup=None) == pytest.approx(cosv(10))
+
+
+def test_oracle_adan_first_step_and_prox():
+    """Sanity of the Adan restatement (parity unpinned: timm is absent): first step has zero gradient difference, so
+    update = g / (|g| + eps) * ... = sign(g) up to eps; prox and no-prox forms agree when weight_decay = 0."""
+    from oracle import optim
+    g = torch.tensor([0.5, -2.0, 1e-3])
+    for no_prox in (False, True):
+        p = [torch.zeros(3)]
+        o = optim.Adan(p, lr=0.1, no_prox=no_prox)
+        o.step([g])
+        assert torch.allclose(p[0], -0.1 * torch.sign(g), atol=1e-4)
+    a, b = [torch.ones(4)], [torch.ones(4)]
+    oa, ob = optim.Adan(a, lr=0.01, weight_decay=0.1, no_prox=False), optim.Adan(b, lr=0.01, weight_decay=0.1, no_prox=True)
+    gg = torch.randn(4)
+    oa.step([gg]); ob.step([gg])
+    assert not torch.allclose(a[0], b[0]) and torch.allclose(a[0], b[0], atol=1e-4)
 
 
 def _dp_worker(rank, world, port, out):
