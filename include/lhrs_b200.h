@@ -340,7 +340,7 @@ int lhrs_adan_step(float* master, float* exp_avg, float* exp_avg_diff, float* ex
  * Single-sequence decode (HF generate loop reached from TextModal.generate, lhrs/models/text_modal.py:600-612, with the
  * generation-input rule of :36-60).  All buffers are caller-owned device memory (bf16 unless noted):
  *   xbuf [dim] residual stream of the token being fed, qkv [3*dim], obuf [dim], act [ffn], logits fp32 [vocab],
- *   part_val fp32 / part_idx int32 [>= 8*SMs] argmax partials, state int32[4] = {next token, ctx_len, tokens emitted, -},
+ *   part_val fp32 / part_idx int32 [>= 8*SMs] argmax partials, state int32[4] = {next token, ctx_len, tokens emitted, finished flag},
  *   tokens_out int32 [max_tokens].
  * first_token: logits/argmax of the prefill's last (post-norm) hidden row; sets ctx_len and feeds the token's embedding.
  * decode_step: one token through every layer (5 launches per layer), K/V appended to the paged cache at ctx_len.
@@ -357,6 +357,38 @@ int lhrs_llama_first_token(const LhrsLlamaWeights* w, const void* hidden_last, i
 int lhrs_llama_decode_step(const LhrsLlamaWeights* w, const LhrsKvCache* kv, const LhrsDecodeBuffers* b, int32_t greedy,
                            int32_t max_ctx, void* stream);
 int lhrs_decode_commit_token(const LhrsLlamaWeights* w, const LhrsDecodeBuffers* b, int32_t token, int32_t set_ctx, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Device-side token selection: the HF logits processors the reference's callers enable — repetition penalty,
+ * temperature, top-k, top-p (cli_qa.py:176-186, lhrs_webui.py:206-218, main_vqa.py:205-214) — the multinomial draw, and the
+ * EOS / token-suffix stop test of KeywordsStoppingCriteria (lhrs/utils/eval_utils.py:24-56), all without a host round trip.
+ * Probabilities are handled as 2^-40 fixed-point integers and the draw is Philox4x32-10(seed, counter = draw index), so the
+ * selection is order-independent and restated bit for bit in oracle/sampling.py (csrc/sampling.cuh states the rule).
+ * With state[3] (raised on EOS / stop) the decode kernels of later, already enqueued steps return immediately.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct LhrsSampling {
+    int32_t do_sample;         /* 0: argmax of the repetition-penalised logits (HF greedy); 1: sample                     */
+    float temperature;         /* TemperatureLogitsWarper; <= 0 or 1 disables                                            */
+    int32_t top_k;             /* TopKLogitsWarper; <= 0 disables                                                        */
+    float top_p;               /* TopPLogitsWarper; <= 0 or >= 1 disables                                                */
+    float repetition_penalty;  /* RepetitionPenaltyLogitsProcessor over the tokens generated so far; <= 0 or 1 disables  */
+    int32_t eos_token;         /* -1: none                                                                               */
+    uint64_t seed;             /* Philox key; draw t of a sequence uses counter t                                        */
+    const uint64_t* seed_dev;  /* nullable: device uint64[1] read instead of `seed` (lets a captured CUDA graph be re-seeded) */
+    const int32_t* stop_seqs;  /* device int32 [n_stop, stop_len], right-aligned, left-padded with -1; NULL: none        */
+    int32_t n_stop, stop_len;
+    float* work;               /* device scratch, >= vocab floats                                                        */
+} LhrsSampling;
+/* One selection from fp32 logits [vocab].  history: device int32 [n_history] (penalty set).  token_out: device int32[1].
+ * debug4 (nullable, device uint64[4]): {sum of masses, kept mass, selection key, target} for parity tests. */
+int lhrs_sample_logits(const float* logits, int32_t vocab, const int32_t* history, int32_t n_history, const LhrsSampling* s,
+                       uint64_t draw, int32_t* token_out, uint64_t* debug4, void* stream);
+/* lhrs_llama_first_token / lhrs_llama_decode_step with the selection done on the device by `s` (history = tokens emitted so
+ * far, draw index = their count).  The host polls tokens_out / state[2] / state[3] whenever it likes. */
+int lhrs_llama_first_token_sampled(const LhrsLlamaWeights* w, const void* hidden_last, int32_t ctx_len, const LhrsDecodeBuffers* b,
+                                   const LhrsSampling* s, void* stream);
+int lhrs_llama_decode_step_sampled(const LhrsLlamaWeights* w, const LhrsKvCache* kv, const LhrsDecodeBuffers* b,
+                                   const LhrsSampling* s, int32_t max_ctx, void* stream);
 
 #ifdef __cplusplus
 }

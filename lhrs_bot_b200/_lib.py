@@ -99,6 +99,14 @@ class LhrsDecodeBuffers(C.Structure):
     ]
 
 
+class LhrsSampling(C.Structure):
+    _fields_ = [
+        ("do_sample", C.c_int32), ("temperature", C.c_float), ("top_k", C.c_int32), ("top_p", C.c_float),
+        ("repetition_penalty", C.c_float), ("eos_token", C.c_int32), ("seed", C.c_uint64), ("seed_dev", C.c_void_p),
+        ("stop_seqs", C.c_void_p), ("n_stop", C.c_int32), ("stop_len", C.c_int32), ("work", C.c_void_p),
+    ]
+
+
 class LhrsLlamaWeights(C.Structure):
     _fields_ = [
         ("num_layers", C.c_int32), ("dim", C.c_int32), ("ffn", C.c_int32), ("heads", C.c_int32), ("vocab", C.c_int32),
@@ -147,6 +155,10 @@ SIGNATURES = {
     "lhrs_llama_first_token": (C.c_int, [C.POINTER(LhrsLlamaWeights), _P, _I32, C.POINTER(LhrsDecodeBuffers), _I32, _P]),
     "lhrs_llama_decode_step": (C.c_int, [C.POINTER(LhrsLlamaWeights), C.POINTER(LhrsKvCache), C.POINTER(LhrsDecodeBuffers), _I32, _I32, _P]),
     "lhrs_decode_commit_token": (C.c_int, [C.POINTER(LhrsLlamaWeights), C.POINTER(LhrsDecodeBuffers), _I32, _I32, _P]),
+    "lhrs_sample_logits": (C.c_int, [_P, _I32, _P, _I32, C.POINTER(LhrsSampling), C.c_uint64, _P, _P, _P]),
+    "lhrs_llama_first_token_sampled": (C.c_int, [C.POINTER(LhrsLlamaWeights), _P, _I32, C.POINTER(LhrsDecodeBuffers), C.POINTER(LhrsSampling), _P]),
+    "lhrs_llama_decode_step_sampled": (C.c_int, [C.POINTER(LhrsLlamaWeights), C.POINTER(LhrsKvCache), C.POINTER(LhrsDecodeBuffers),
+                                                 C.POINTER(LhrsSampling), _I32, _P]),
     "lhrs_attention_bwd": (C.c_int, [C.POINTER(LhrsAttentionBwd), _P]),
     "lhrs_rmsnorm_bwd": (C.c_int, [_P, _P, _P, _P, _P, _P, _I64, _I32, _P]),
     "lhrs_layernorm_bwd_scratch_bytes": (C.c_size_t, [_I32]),

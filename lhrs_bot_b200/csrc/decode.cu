@@ -18,6 +18,7 @@
 #include "host_common.h"
 #include "ptx.cuh"
 #include "models_common.h"
+#include "sampling.cuh"
 
 namespace lhrs {
 
@@ -34,6 +35,7 @@ struct GemvArgs {
     float* logits;                // LMHEAD
     float* part_val; int* part_idx;
     int pf_bytes_per_warp;        // L2 prefetch budget of each warp's upcoming rows, issued before the dependency wait
+    const int* done;              // nullable: device flag (decode state[3]); non-zero = the sequence has finished, skip the work
 };
 
 __device__ __forceinline__ float dot8(const uint4& w, const uint4& x) {
@@ -209,6 +211,7 @@ gemv_kernel(const GemvArgs a) {
     uint4 pre[GV_INFLIGHT];
     gemv_pre<MODE>(a, gw, nw, lane, true, pre);
     pdl_wait();
+    if (a.done != nullptr && *a.done != 0) return;   // EOS / stop sequence already hit: the remaining enqueued steps cost nothing
     gemv_main<MODE>(a, reinterpret_cast<__nv_bfloat16*>(smem), sh, gw, nw, blockIdx.x, true, pre);
 }
 
@@ -386,7 +389,44 @@ attn_decode_kernel(const __nv_bfloat16* __restrict__ qkv, int dim, KvGeom kv, in
     __shared__ AttnDecodeShared sh;
     pdl_launch_dependents();
     pdl_wait();
+    if (state[3] != 0) return;
     attn_decode_body(sc, sh, blockIdx.x, qkv, dim, kv, layer, state, cosT, sinT, obuf, max_ctx);
+}
+
+// Device-side selection + commit of the next token (sampling.cuh).  Decode chain: state != nullptr — the history is the tokens
+// generated so far, the draw index is their count, and the token is committed exactly like commit_token_kernel does; state[3] is
+// raised on EOS / a stop sequence.  Stand-alone (state == nullptr): history / n_hist / draw are given, the token goes to token_out.
+__global__ void __launch_bounds__(SMP_THREADS)
+sample_commit_kernel(const float* __restrict__ logits, int V, SampleParams p, float* __restrict__ z, const int* history,
+                     int n_hist, unsigned long long draw, int* state, int* tokens_out, int max_tokens,
+                     int set_ctx, const __nv_bfloat16* __restrict__ embed, int dim, __nv_bfloat16* __restrict__ xbuf,
+                     int* __restrict__ token_out, unsigned long long* __restrict__ dbg) {
+    extern __shared__ unsigned long long smp_hist[];
+    __shared__ SampleShared sh;
+    pdl_launch_dependents();
+    pdl_wait();
+    if (state != nullptr) {
+        if (state[3] != 0) return;
+        n_hist = min(state[2], max_tokens);
+        history = tokens_out;
+        draw = static_cast<unsigned long long>(state[2]);
+    }
+    const int tok = smp_choose(logits, V, p, z, history, n_hist, draw, smp_hist, sh, dbg);
+    if (state == nullptr) {
+        if (threadIdx.x == 0) token_out[0] = tok;
+        return;
+    }
+    if (threadIdx.x == 0) {
+        const int k = state[2];
+        if (k < max_tokens) tokens_out[k] = tok;
+        state[0] = tok;
+        state[2] = k + 1;
+        if (set_ctx >= 0) state[1] = set_ctx;
+        else if (set_ctx == -2) state[1] += 1;
+        if (smp_is_stop(p, tokens_out, min(k + 1, max_tokens), tok)) state[3] = 1;
+    }
+    const uint4* src = reinterpret_cast<const uint4*>(embed + static_cast<long long>(tok) * dim);
+    for (int c = threadIdx.x; c < dim / 8; c += blockDim.x) reinterpret_cast<uint4*>(xbuf)[c] = src[c];
 }
 
 // launch with programmatic stream serialization (PDL): the kernel may start while its predecessor drains
@@ -434,14 +474,41 @@ static int launch_gemv(const GemvArgs& a_in, cudaStream_t st) {
     return grid;
 }
 
+static SampleParams sample_params(const LhrsSampling* s) {
+    SampleParams p;
+    p.do_sample = s->do_sample; p.temperature = s->temperature; p.top_k = s->top_k; p.top_p = s->top_p;
+    p.penalty = s->repetition_penalty; p.eos = s->eos_token; p.seed = s->seed;
+    p.seed_dev = (const unsigned long long*)s->seed_dev;
+    p.stop_seqs = s->stop_seqs; p.n_stop = s->stop_seqs ? s->n_stop : 0; p.stop_len = s->stop_len;
+    return p;
+}
+static int sample_attr() {
+    static bool done = false;
+    if (!done) {
+        LHRS_CUDA(cudaFuncSetAttribute(sample_commit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMP_SMEM_BYTES));
+        done = true;
+    }
+    return LHRS_OK;
+}
+
 static int lm_head_and_commit(const LhrsLlamaWeights* w, const LhrsDecodeBuffers* b, const bf16* x, const bf16* norm_w, int greedy,
-                              int set_ctx, cudaStream_t st) {
+                              int set_ctx, cudaStream_t st, const LhrsSampling* smp = nullptr, bool first = false) {
     GemvArgs a;
     memset(&a, 0, sizeof(a));
     a.w0 = (const bf16*)w->lm_head; a.rows = w->vocab; a.K = w->dim; a.x = x; a.norm_w = norm_w; a.eps = w->eps;
     a.logits = b->logits; a.part_val = b->part_val; a.part_idx = b->part_idx;
+    a.done = first ? nullptr : (const int*)b->state + 3;
     const int grid = launch_gemv<GV_LMHEAD>(a, st);
     if (grid <= 0) return LHRS_ERR_CUDA;
+    if (smp != nullptr) {
+        if (sample_attr()) return LHRS_ERR_CUDA;
+        LHRS_CUDA(launch_pdl(sample_commit_kernel, dim3(1), dim3(SMP_THREADS), SMP_SMEM_BYTES, st, (const float*)b->logits, (int)w->vocab,
+                             sample_params(smp), (float*)smp->work, (const int*)nullptr, 0, 0ull, (int*)b->state, (int*)b->tokens_out,
+                             (int)b->max_tokens, set_ctx, (const bf16*)w->embed, (int)w->dim, (bf16*)b->xbuf, (int*)nullptr,
+                             (unsigned long long*)nullptr));
+        LHRS_LAUNCH_CHECK("sample_commit_kernel");
+        return LHRS_OK;
+    }
     if (greedy) {
         LHRS_CUDA(launch_pdl(commit_token_kernel, dim3(1), dim3(256), 0, st, (const float*)b->part_val, (const int*)b->part_idx, grid, -1,
                              (int*)b->state, (int*)b->tokens_out, (int)b->max_tokens, set_ctx, (const bf16*)w->embed, (int)w->dim, (bf16*)b->xbuf));
@@ -459,15 +526,55 @@ extern "C" int lhrs_decode_commit_token(const LhrsLlamaWeights* w, const LhrsDec
     return LHRS_OK;
 }
 
+static int check_sampling(const LhrsSampling* s, const char* who) {
+    LHRS_CHECK_ARG(s && s->work, "%s: LhrsSampling.work (>= vocab floats of device scratch) is required", who);
+    LHRS_CHECK_ARG(!s->stop_seqs || (s->n_stop > 0 && s->stop_len > 0), "%s: stop_seqs needs n_stop, stop_len > 0", who);
+    return LHRS_OK;
+}
+
+extern "C" int lhrs_sample_logits(const float* logits, int32_t vocab, const int32_t* history, int32_t n_history, const LhrsSampling* s,
+                                  uint64_t draw, int32_t* token_out, uint64_t* debug4, void* stream) {
+    LHRS_CHECK_ARG(logits && vocab > 0 && token_out && (n_history == 0 || history), "lhrs_sample_logits: bad args");
+    if (check_sampling(s, "lhrs_sample_logits")) return LHRS_ERR_INVALID;
+    if (sample_attr()) return LHRS_ERR_CUDA;
+    sample_commit_kernel<<<1, SMP_THREADS, SMP_SMEM_BYTES, (cudaStream_t)stream>>>(
+        logits, vocab, sample_params(s), s->work, (const int*)history, n_history, (unsigned long long)draw, nullptr, nullptr, 0, 0, nullptr, 0,
+        nullptr, (int*)token_out, (unsigned long long*)debug4);
+    LHRS_LAUNCH_CHECK("sample_commit_kernel");
+    return LHRS_OK;
+}
+
 extern "C" int lhrs_llama_first_token(const LhrsLlamaWeights* w, const void* hidden_last, int32_t ctx_len, const LhrsDecodeBuffers* b,
                                       int32_t greedy, void* stream) {
     LHRS_CHECK_ARG(w && hidden_last && b && ctx_len > 0, "lhrs_llama_first_token: bad args");
     LHRS_CUDA(cudaMemsetAsync(b->state, 0, 4 * sizeof(int), (cudaStream_t)stream));
-    return lm_head_and_commit(w, b, (const bf16*)hidden_last, nullptr, greedy, ctx_len, (cudaStream_t)stream);
+    return lm_head_and_commit(w, b, (const bf16*)hidden_last, nullptr, greedy, ctx_len, (cudaStream_t)stream, nullptr, true);
 }
+
+extern "C" int lhrs_llama_first_token_sampled(const LhrsLlamaWeights* w, const void* hidden_last, int32_t ctx_len,
+                                              const LhrsDecodeBuffers* b, const LhrsSampling* s, void* stream) {
+    LHRS_CHECK_ARG(w && hidden_last && b && ctx_len > 0, "lhrs_llama_first_token_sampled: bad args");
+    if (check_sampling(s, "lhrs_llama_first_token_sampled")) return LHRS_ERR_INVALID;
+    LHRS_CUDA(cudaMemsetAsync(b->state, 0, 4 * sizeof(int), (cudaStream_t)stream));
+    return lm_head_and_commit(w, b, (const bf16*)hidden_last, nullptr, 0, ctx_len, (cudaStream_t)stream, s, true);
+}
+
+static int decode_step_impl(const LhrsLlamaWeights* w, const LhrsKvCache* kv, const LhrsDecodeBuffers* b, int32_t greedy,
+                            int32_t max_ctx, const LhrsSampling* smp, void* stream);
 
 extern "C" int lhrs_llama_decode_step(const LhrsLlamaWeights* w, const LhrsKvCache* kv, const LhrsDecodeBuffers* b, int32_t greedy,
                                       int32_t max_ctx, void* stream) {
+    return decode_step_impl(w, kv, b, greedy, max_ctx, nullptr, stream);
+}
+
+extern "C" int lhrs_llama_decode_step_sampled(const LhrsLlamaWeights* w, const LhrsKvCache* kv, const LhrsDecodeBuffers* b,
+                                              const LhrsSampling* s, int32_t max_ctx, void* stream) {
+    if (check_sampling(s, "lhrs_llama_decode_step_sampled")) return LHRS_ERR_INVALID;
+    return decode_step_impl(w, kv, b, 0, max_ctx, s, stream);
+}
+
+static int decode_step_impl(const LhrsLlamaWeights* w, const LhrsKvCache* kv, const LhrsDecodeBuffers* b, int32_t greedy,
+                            int32_t max_ctx, const LhrsSampling* smp, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     LHRS_CHECK_ARG(w && kv && b, "lhrs_llama_decode_step: null");
     LHRS_CHECK_ARG(w->dim / w->heads == 128 && kv->head_dim == 128 && kv->heads == w->heads, "lhrs_llama_decode_step: head_dim must be 128");
@@ -475,30 +582,32 @@ extern "C" int lhrs_llama_decode_step(const LhrsLlamaWeights* w, const LhrsKvCac
     LHRS_CHECK_ARG(max_ctx > 0 && max_ctx <= kv->max_pages * kv->page_size && max_ctx <= w->max_pos, "lhrs_llama_decode_step: max_ctx %d", max_ctx);
     const int D = w->dim, F = w->ffn;
     bf16* x = (bf16*)b->xbuf;
+    const int* done = (const int*)b->state + 3;
     for (int l = 0; l < w->num_layers; ++l) {
         GemvArgs a;
         memset(&a, 0, sizeof(a));
         a.w0 = (const bf16*)w->q_w[l]; a.w1 = (const bf16*)w->k_w[l]; a.w2 = (const bf16*)w->v_w[l];
         a.rows = D; a.K = D; a.x = x; a.norm_w = (const bf16*)w->ln1_w[l]; a.eps = w->eps; a.out = (bf16*)b->qkv;
+        a.done = done;
         if (launch_gemv<GV_QKV>(a, st) <= 0) return LHRS_ERR_CUDA;
         LHRS_CUDA(launch_pdl(attn_decode_kernel, dim3(w->heads), dim3(256), (size_t)max_ctx * sizeof(float) + (size_t)kv->max_pages * sizeof(int), st,
                              (const bf16*)b->qkv, D, *kv, l, (int*)b->state, (const float*)w->rope_cos, (const float*)w->rope_sin, (bf16*)b->obuf,
                              (int)max_ctx));
         LHRS_LAUNCH_CHECK("attn_decode_kernel");
         memset(&a, 0, sizeof(a));
-        a.w0 = (const bf16*)w->o_w[l]; a.rows = D; a.K = D; a.x = (const bf16*)b->obuf; a.out = x;
+        a.w0 = (const bf16*)w->o_w[l]; a.rows = D; a.K = D; a.x = (const bf16*)b->obuf; a.out = x; a.done = done;
         if (launch_gemv<GV_O>(a, st) <= 0) return LHRS_ERR_CUDA;
         memset(&a, 0, sizeof(a));
         a.w0 = (const bf16*)w->gate_w[l]; a.w1 = (const bf16*)w->up_w[l]; a.rows = F; a.K = D; a.x = x;
-        a.norm_w = (const bf16*)w->ln2_w[l]; a.eps = w->eps; a.out = (bf16*)b->act;
+        a.norm_w = (const bf16*)w->ln2_w[l]; a.eps = w->eps; a.out = (bf16*)b->act; a.done = done;
         if (launch_gemv<GV_GATEUP>(a, st) <= 0) return LHRS_ERR_CUDA;
         memset(&a, 0, sizeof(a));
-        a.w0 = (const bf16*)w->down_w[l]; a.rows = D; a.K = F; a.x = (const bf16*)b->act; a.out = x;
+        a.w0 = (const bf16*)w->down_w[l]; a.rows = D; a.K = F; a.x = (const bf16*)b->act; a.out = x; a.done = done;
         if (launch_gemv<GV_DOWN>(a, st) <= 0) return LHRS_ERR_CUDA;
     }
     // the new position is now in the cache for every layer
     {
-        int rc = lm_head_and_commit(w, b, x, (const bf16*)w->norm_w, greedy, -2, st);
+        int rc = lm_head_and_commit(w, b, x, (const bf16*)w->norm_w, greedy, -2, st, smp);
         if (rc) return rc;
     }
     return LHRS_OK;

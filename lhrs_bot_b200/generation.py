@@ -1,20 +1,25 @@
 """Generation loop behind ``TextModal.generate`` / ``UniBind.generate`` (lhrs/models/text_modal.py:528-627, UniBind.py:214-242).
 
-Prefill runs the tensor-core path into a paged KV cache; each later token is one ``lhrs_llama_decode_step`` (HBM-bound
-GEMV chain).  Under greedy search the sampled token, the position and the context length stay on the device, so the host
-enqueues steps without synchronising; EOS is polled every ``eos_poll`` tokens.  With ``do_sample`` (cli_qa.py:176-186 uses
-temperature 0.4) or a ``streamer`` / ``stopping_criteria`` the logits are sampled / inspected per token on the host side.
+Prefill runs the tensor-core path into a paged KV cache; each later token is one ``lhrs_llama_decode_step[_sampled]`` (HBM-bound
+GEMV chain).  The next token is chosen ON THE DEVICE — greedy argmax or the HF logits processors the reference's callers enable
+(repetition penalty, temperature, top-k, top-p; cli_qa.py:176-186, lhrs_webui.py:206-218) plus the draw, the EOS test and the
+token-suffix part of ``KeywordsStoppingCriteria`` (lhrs/utils/eval_utils.py:24-56) — so the host enqueues ``poll`` steps at a time
+without synchronising and then reads the new ids once.  ``streamer`` and arbitrary ``stopping_criteria`` callables are served
+from those polled ids, prefix by prefix, which yields exactly the tokens a per-token loop would (the selection never depends on
+the host); steps enqueued past a stop are skipped on the device (state[3]).  Host-side selection remains for callers that pass a
+``torch.Generator`` or ask for the per-step logits.
 Returns only the NEW token ids, shape (1, n) int64 — HF semantics for prompts given as ``inputs_embeds``.
 """
 from __future__ import annotations
 
 import ctypes as C
-from typing import Optional
+import os
+from typing import List, Optional, Sequence
 
 import torch
 
-from . import _lib, runtime
-from ._lib import LhrsDecodeBuffers, LhrsKvCache, check
+from . import _lib, ops, runtime
+from ._lib import LhrsDecodeBuffers, LhrsKvCache, LhrsSampling, check
 
 PAGE_SIZE = 16
 
@@ -56,9 +61,82 @@ class DecodeBuffers:
         self.desc = d
 
 
+class DecodeSession:
+    """Everything one sequence's decode needs, kept across ``generate`` calls of a model (the web UI / cli_qa loop call it once
+    per turn): the paged KV pool, the per-token buffers, the device-side sampler's scratch / seed / stop table, and — when
+    enabled — a captured CUDA graph of ``poll`` decode steps (all kernel arguments are fixed device pointers; position, token
+    and seed live in device memory, so one graph serves every chunk of every call with the same sampling settings)."""
+
+    def __init__(self, cfg, layers: int, vocab: int, max_len: int, device):
+        hd = cfg.hidden_size // cfg.num_attention_heads
+        self.kv = PagedKvCache(layers, cfg.num_attention_heads, hd, max_len, device)
+        self.buf = DecodeBuffers(cfg.hidden_size, cfg.intermediate_size, vocab, self.kv.capacity, device)
+        self.work = torch.empty((vocab,), device=device, dtype=torch.float32)
+        self.seed = torch.zeros((1,), device=device, dtype=torch.int64)
+        self.stop, self._stop_key = None, None
+        self.smp = LhrsSampling()
+        self.smp.work, self.smp.seed_dev = self.work.data_ptr(), self.seed.data_ptr()
+        self.device = device
+        self._graph, self._graph_key, self._graph_nodes = None, None, 0
+
+    def configure(self, do_sample: bool, temperature: float, top_k: Optional[int], top_p: Optional[float],
+                  repetition_penalty: Optional[float], eos_token_id: Optional[int], stop_seqs: Sequence[Sequence[int]], seed: int):
+        s = self.smp
+        s.do_sample = int(bool(do_sample))
+        s.temperature = float(temperature if temperature else 0.0)
+        s.top_k = int(top_k or 0)
+        s.top_p = float(top_p if top_p is not None else 1.0)
+        s.repetition_penalty = float(repetition_penalty if repetition_penalty else 1.0)
+        s.eos_token = -1 if eos_token_id is None else int(eos_token_id)
+        s.seed = int(seed) & 0x7FFFFFFFFFFFFFFF
+        self.seed.fill_(s.seed)            # the kernels read the seed from device memory (a captured graph can be re-seeded)
+        stop_seqs = [list(map(int, q)) for q in stop_seqs if len(q) > 0]
+        stop_key = tuple(map(tuple, stop_seqs))
+        if stop_key == self._stop_key:
+            pass                           # same table as last time: keep the device tensor (a captured graph points at it)
+        elif stop_seqs:
+            self._stop_key = stop_key
+            L = max(len(q) for q in stop_seqs)
+            table = torch.full((len(stop_seqs), L), -1, dtype=torch.int32)
+            for i, q in enumerate(stop_seqs):
+                table[i, L - len(q):] = torch.tensor(q, dtype=torch.int32)
+            self.stop = table.to(self.device)
+            s.stop_seqs, s.n_stop, s.stop_len = self.stop.data_ptr(), len(stop_seqs), L
+        else:
+            self.stop, self._stop_key = None, stop_key
+            s.stop_seqs, s.n_stop, s.stop_len = None, 0, 0
+        return (s.do_sample, s.temperature, s.top_k, s.top_p, s.repetition_penalty, s.eos_token, stop_key)
+
+    def run_steps(self, lib, w, n: int, poll: int, key, use_graph: bool):
+        """Enqueue n decode steps; whole chunks of ``poll`` steps replay the captured graph when graphs are on."""
+        def eager(k):
+            for _ in range(k):
+                check(lib.lhrs_llama_decode_step_sampled(C.byref(w), C.byref(self.kv.desc), C.byref(self.buf.desc), C.byref(self.smp),
+                                                         self.kv.capacity, runtime.stream()), "lhrs_llama_decode_step_sampled")
+
+        if not use_graph or n < poll:
+            return eager(n)
+        gkey = (key, poll, C.addressof(w))
+        if self._graph is None or self._graph_key != gkey:
+            eager(1)                       # first launch outside capture (function attributes are set lazily); counts as one step
+            n -= 1
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            c0 = lib.lhrs_launch_count()
+            with torch.cuda.graph(g):
+                eager(poll)                # recorded, not executed: no token is consumed by the capture itself
+            self._graph, self._graph_key, self._graph_nodes = g, gkey, int(lib.lhrs_launch_count() - c0)
+            ops.count_graph_replay(-self._graph_nodes)   # the capture bumped the launch counter without launching
+        while n >= poll:
+            self._graph.replay()
+            ops.count_graph_replay(self._graph_nodes)
+            n -= poll
+        eager(n)
+
+
 def _sample(logits: torch.Tensor, temperature: float, top_p: Optional[float], top_k: Optional[int],
             repetition_penalty: Optional[float], history, generator) -> int:
-    """HF logits processors for the options the reference's callers pass (cli_qa.py:176-186, lhrs_webui.py:206-218)."""
+    """Host-side HF logits processors (only for callers that pass a torch.Generator or want the per-step logits)."""
     logits = logits.clone()
     if repetition_penalty and repetition_penalty != 1.0 and history:
         idx = torch.tensor(sorted(set(history)), device=logits.device)
@@ -79,12 +157,45 @@ def _sample(logits: torch.Tensor, temperature: float, top_p: Optional[float], to
     return int(torch.multinomial(probs, 1, generator=generator).item())
 
 
+def _keyword_id_sequences(stopping_criteria) -> List[List[int]]:
+    """Token-id suffixes of KeywordsStoppingCriteria-like objects (attribute ``keyword_ids``: list of 1-D id tensors,
+    eval_utils.py:27-37) — these are matched on the device; every criterion is ALSO evaluated on the host at poll time."""
+    seqs: List[List[int]] = []
+    if stopping_criteria is None:
+        return seqs
+    crits = stopping_criteria if isinstance(stopping_criteria, (list, tuple)) or hasattr(stopping_criteria, "__iter__") else [stopping_criteria]
+    for c in crits:
+        for ids in getattr(c, "keyword_ids", []) or []:
+            seqs.append([int(t) for t in (ids.tolist() if hasattr(ids, "tolist") else ids)])
+    return seqs
+
+
+def _criteria_hit(stopping_criteria, ids: torch.Tensor) -> bool:
+    if stopping_criteria is None:
+        return False
+    if callable(stopping_criteria) and not isinstance(stopping_criteria, (list, tuple)):
+        return bool(stopping_criteria(ids, None))
+    return any(bool(c(ids, None)) for c in stopping_criteria)
+
+
+def _session(text, need_len: int, device) -> DecodeSession:
+    te = text.text_encoder
+    cfg = te.config
+    sess = getattr(text, "_decode_session", None)
+    if sess is None or sess.device != device or sess.kv.capacity < need_len:
+        cap = max(need_len, min(cfg.max_position_embeddings, 2048))
+        sess = DecodeSession(cfg, len(te.model.layers), te.lm_head.out_features, cap, device)
+        text._decode_session = sess
+    return sess
+
+
 @torch.no_grad()
 def generate(text, input_ids: torch.Tensor, image_embedding: Optional[torch.Tensor], do_sample: bool = True,
              temperature: float = 0.2, max_new_tokens: int = 1024, streamer=None, stopping_criteria=None,
              attention_mask=None, top_p: Optional[float] = None, top_k: Optional[int] = None,
              repetition_penalty: Optional[float] = None, num_beams: int = 1, eos_token_id="config", eos_poll: int = 16,
-             generator: Optional[torch.Generator] = None, return_step_logits: bool = False, **unused):
+             generator: Optional[torch.Generator] = None, return_step_logits: bool = False, seed: Optional[int] = None,
+             use_graph: Optional[bool] = None, host_picker=None, **unused):
     lib = _lib.load()
     if input_ids.shape[0] != 1:
         raise NotImplementedError("batched generate: the reference's own batched path is unstable (no position_ids under left "
@@ -108,36 +219,67 @@ def generate(text, input_ids: torch.Tensor, image_embedding: Optional[torch.Tens
     if n_budget <= 0:
         return torch.empty((1, 0), dtype=torch.long, device=input_ids.device)
     dev = embeds.device
-    hd = cfg.hidden_size // cfg.num_attention_heads
-    kv = PagedKvCache(len(te.model.layers), cfg.num_attention_heads, hd, max_len, dev)
-    buf = DecodeBuffers(cfg.hidden_size, cfg.intermediate_size, w.vocab, n_budget, dev)
+    sess = _session(text, max_len, dev)
+    kv, buf = sess.kv, sess.buf
     hidden = text.llama_forward(embeds, None, kv=kv.desc)                 # prefill, K/V of positions 0..S-1 into the pages
     last = hidden[0, S - 1].contiguous()
     st = runtime.stream()
-    host_side = bool(do_sample) or streamer is not None or stopping_criteria is not None or return_step_logits
-    step_logits = []
-    out_tokens = []
 
-    if not host_side:
-        # ---- greedy, device-driven: no per-token synchronisation
-        check(lib.lhrs_llama_first_token(C.byref(w), last.data_ptr(), S, C.byref(buf.desc), 1, st), "lhrs_llama_first_token")
-        done = 1
-        while done < n_budget:
-            n = min(eos_poll, n_budget - done)
-            for _ in range(n):
-                check(lib.lhrs_llama_decode_step(C.byref(w), C.byref(kv.desc), C.byref(buf.desc), 1, kv.capacity, st), "lhrs_llama_decode_step")
-            done += n
-            if eos_token_id is not None:
-                toks = buf.tokens[:done].tolist()                          # D2H poll
-                if eos_token_id in toks:
-                    done = toks.index(eos_token_id) + 1
+    if generator is not None or return_step_logits or host_picker is not None:
+        return _generate_host_side(lib, w, sess, last, S, n_budget, do_sample, temperature, top_p, top_k, repetition_penalty,
+                                   eos_token_id, streamer, stopping_criteria, generator, return_step_logits, dev, host_picker)
+
+    # ---- device-driven: selection, EOS and keyword-suffix stop on the device; the host polls every `eos_poll` tokens
+    if seed is None:
+        seed = int(torch.randint(0, 2 ** 62, (1,)).item()) if do_sample else 0   # follows torch.manual_seed
+    key = sess.configure(do_sample, temperature, top_k, top_p, repetition_penalty, eos_token_id,
+                         _keyword_id_sequences(stopping_criteria), seed)
+    if use_graph is None:
+        use_graph = os.environ.get("LHRS_DECODE_GRAPH", "0") == "1"
+    poll = max(1, int(eos_poll))
+    if streamer is not None:
+        poll = min(poll, 4)              # a streamer wants tokens as they come: 4 tokens = ~13 ms at 300 tok/s
+    check(lib.lhrs_llama_first_token_sampled(C.byref(w), last.data_ptr(), S, C.byref(buf.desc), C.byref(sess.smp), st),
+          "lhrs_llama_first_token_sampled")
+    enq, seen, stop_at = 1, 0, None
+    host_checks = streamer is not None or stopping_criteria is not None
+    while True:
+        n = min(poll, n_budget - enq)
+        if n > 0:
+            sess.run_steps(lib, w, n, poll, key, use_graph)
+            enq += n
+        state = buf.state.tolist()                                         # D2H poll (synchronises)
+        have, finished = min(state[2], n_budget), state[3] != 0
+        if host_checks:
+            toks = buf.tokens[:have].tolist()
+            for i in range(seen, have):
+                if streamer is not None:
+                    streamer.put(torch.tensor([toks[i]]))
+                if _criteria_hit(stopping_criteria, torch.tensor([toks[: i + 1]], dtype=torch.long, device=dev)):
+                    stop_at = i + 1
                     break
-        return buf.tokens[:done].to(torch.long).unsqueeze(0)
+            seen = have
+        if stop_at is not None or finished or enq >= n_budget:
+            break
+    done = stop_at if stop_at is not None else have
+    if streamer is not None:
+        streamer.end()
+    return buf.tokens[:done].to(torch.long).unsqueeze(0)
 
-    # ---- host-side sampling / streaming / stopping criteria: one sync per token
+
+def _generate_host_side(lib, w, sess, last, S, n_budget, do_sample, temperature, top_p, top_k, repetition_penalty, eos_token_id,
+                        streamer, stopping_criteria, generator, return_step_logits, dev, host_picker=None):
+    """One synchronisation per token: fp32 logits are left on the device and the host picks (torch.Generator semantics, or
+    ``host_picker(logits, tokens_so_far) -> id`` — the parity tests plug the oracle's selection rule in here)."""
+    kv, buf = sess.kv, sess.buf
+    st = runtime.stream()
+    step_logits, out_tokens = [], []
+
     def pick() -> int:
         if return_step_logits:
             step_logits.append(buf.logits.clone())
+        if host_picker is not None:
+            return int(host_picker(buf.logits, list(out_tokens)))
         if do_sample:
             return _sample(buf.logits, temperature, top_p, top_k, repetition_penalty, out_tokens, generator)
         return int(torch.argmax(buf.logits).item())
@@ -153,10 +295,8 @@ def generate(text, input_ids: torch.Tensor, image_embedding: Optional[torch.Tens
             break
         if len(out_tokens) >= n_budget:
             break
-        if stopping_criteria is not None:
-            ids = torch.tensor([out_tokens], dtype=torch.long, device=dev)
-            if bool(stopping_criteria(ids, None)):
-                break
+        if _criteria_hit(stopping_criteria, torch.tensor([out_tokens], dtype=torch.long, device=dev)):
+            break
         check(lib.lhrs_decode_commit_token(C.byref(w), C.byref(buf.desc), tok, set_ctx, st), "lhrs_decode_commit_token")
         set_ctx = -2
         check(lib.lhrs_llama_decode_step(C.byref(w), C.byref(kv.desc), C.byref(buf.desc), 0, kv.capacity, st), "lhrs_llama_decode_step")

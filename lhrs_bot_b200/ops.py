@@ -280,8 +280,18 @@ def ce_bwd(logits: torch.Tensor, labels: torch.Tensor, row_lse: torch.Tensor, co
     return out.view(B, S, V)
 
 
+_graph_launches = 0
+
+
 def launch_count() -> int:
-    return int(_lib.load().lhrs_launch_count())
+    """Kernels launched by the library in this process, plus the kernel nodes of CUDA-graph replays (counted by the host
+    mirror: a replay launches exactly what its capture recorded)."""
+    return int(_lib.load().lhrs_launch_count()) + _graph_launches
+
+
+def count_graph_replay(kernel_nodes: int) -> None:
+    global _graph_launches
+    _graph_launches += int(kernel_nodes)
 
 
 # ---------------------------------------------------------------------------------------------- backward ops

@@ -85,6 +85,118 @@ def test_eos_and_sampling_paths(small):
         assert st5[0].tolist() == base[:5]
 
 
+SAMPLING_CASES = [
+    dict(do_sample=True, temperature=0.4),                                                  # cli_qa.py:176-186
+    dict(do_sample=True, temperature=0.7, top_p=0.95, repetition_penalty=1.05),             # lhrs_webui.py:206-218
+    dict(do_sample=True, temperature=1.0, top_k=50, top_p=0.9),
+    dict(do_sample=True, temperature=0.2, top_k=1),
+    dict(do_sample=True, temperature=1.5, top_p=0.5, repetition_penalty=1.3),
+    dict(do_sample=False, repetition_penalty=1.2),                                          # HF greedy keeps the penalty
+]
+
+
+@pytest.mark.parametrize("case", range(len(SAMPLING_CASES)))
+@pytest.mark.parametrize("vocab", [32000, 1024, 50257])
+def test_sample_logits_matches_oracle(case, vocab):
+    """lhrs_sample_logits vs oracle/sampling.py on the same logits / history / seed: the selected id must be identical.  Integer
+    masses may differ where the device expf and numpy exp round differently (1 ulp), which can only move the outcome when the
+    draw lands within a 1e-6 fraction of a CDF boundary — such a draw is reported, everything else must match exactly."""
+    import ctypes as C
+    import numpy as np
+    from oracle import sampling as osmp
+    from lhrs_bot_b200 import _lib, runtime
+    lib = _lib.load()
+    kw = SAMPLING_CASES[case]
+    g = torch.Generator().manual_seed(100 * case + vocab)
+    work = torch.empty(vocab, device=DEV, dtype=torch.float32)
+    out = torch.zeros(1, device=DEV, dtype=torch.int32)
+    dbg = torch.zeros(4, device=DEV, dtype=torch.int64)
+    n_diff = 0
+    for trial in range(12):
+        scale = [0.5, 2.0, 6.0][trial % 3]
+        logits = (torch.randn(vocab, generator=g) * scale).bfloat16().float()     # bf16-valued logits as the LM head emits (ties exist)
+        hist = torch.randint(0, vocab, (trial * 3,), generator=g).to(torch.int32)
+        if trial % 4 == 1 and hist.numel():
+            hist[0] = int(torch.argmax(logits))                                   # penalise the current best id
+        seed, draw = 1234 + trial, trial
+        s = _lib.LhrsSampling()
+        s.do_sample, s.temperature = int(kw.get("do_sample", True)), float(kw.get("temperature", 1.0))
+        s.top_k, s.top_p = int(kw.get("top_k", 0)), float(kw.get("top_p", 1.0))
+        s.repetition_penalty, s.eos_token, s.seed = float(kw.get("repetition_penalty", 1.0)), -1, seed
+        s.work = work.data_ptr()
+        ld, hd = logits.to(DEV), hist.to(DEV)
+        _lib.check(lib.lhrs_sample_logits(ld.data_ptr(), vocab, hd.data_ptr() if hist.numel() else None, hist.numel(), C.byref(s), draw,
+                                          out.data_ptr(), dbg.data_ptr(), runtime.stream()), "lhrs_sample_logits")
+        ours = int(out.item())
+        ref, ex = osmp.select_token(logits.numpy(), history=hist.tolist(), seed=seed, draw=draw, explain=True, **kw)
+        if kw.get("do_sample", True):
+            Z, K, vsel, target = [int(v) for v in dbg.tolist()]
+            assert abs(Z - ex["Z"]) <= 1e-6 * ex["Z"] and abs(K - ex["K"]) <= 1e-6 * ex["K"], (Z, ex["Z"], K, ex["K"])
+            if Z == ex["Z"]:
+                assert (K, vsel & 0xFFFFFFFF, target) == (ex["K"], ex["vsel"], ex["target"])
+        if ours != ref:
+            assert kw.get("do_sample", True) and ex["margin"] < 1e-6, f"trial {trial}: device {ours} vs oracle {ref}, margin {ex['margin']:.3e}"
+            n_diff += 1
+    assert n_diff <= 1
+    print(f"case {kw} vocab {vocab}: {12 - n_diff}/12 identical")
+
+
+def test_device_sampled_generation(small):
+    """Device-driven sampled decoding (no host sync per token) must emit exactly the ids that the oracle's selection rule picks
+    from the same per-step logits (host path with the oracle plugged in as the picker), honour EOS and keyword stop sequences on
+    the device, and be independent of the poll interval and of CUDA-graph replay."""
+    import numpy as np
+    from oracle import sampling as osmp
+    cfg, model, st = small
+    ids, px = _prompt(3)
+    kw = dict(do_sample=True, temperature=0.7, top_p=0.95, repetition_penalty=1.05)
+    with torch.no_grad():
+        a = model.generate(ids, images=px, max_new_tokens=40, eos_token_id=None, seed=77, **kw)
+        b = model.generate(ids, images=px, max_new_tokens=40, eos_token_id=None, seed=77, eos_poll=5, **kw)
+        c = model.generate(ids, images=px, max_new_tokens=40, eos_token_id=None, seed=78, **kw)
+        g = model.generate(ids, images=px, max_new_tokens=40, eos_token_id=None, seed=77, eos_poll=8, use_graph=True, **kw)
+        g2 = model.generate(ids, images=px, max_new_tokens=40, eos_token_id=None, seed=78, eos_poll=8, use_graph=True, **kw)
+
+        def oracle_pick(logits, history):
+            return osmp.select_token(logits.float().cpu().numpy(), history=history, seed=77, draw=len(history), **kw)
+        h = model.generate(ids, images=px, max_new_tokens=40, eos_token_id=None, host_picker=oracle_pick, **kw)
+    assert a.shape == (1, 40) and torch.equal(a, b), "poll interval changed the sampled ids"
+    assert not torch.equal(a, c), "different seeds gave the same 40 ids"
+    assert torch.equal(a, g) and torch.equal(c, g2), "CUDA-graph replay changed the sampled ids"
+    assert torch.equal(a, h), f"device selection differs from the oracle rule: {a[0].tolist()} vs {h[0].tolist()}"
+    base = a[0].tolist()
+    # EOS on the device: stops at and includes the first occurrence
+    eos = base[11]
+    with torch.no_grad():
+        cut = model.generate(ids, images=px, max_new_tokens=40, eos_token_id=eos, seed=77, **kw)[0].tolist()
+    assert cut == base[: base.index(eos) + 1]
+
+    # KeywordsStoppingCriteria-like object (lhrs/utils/eval_utils.py:24-56): token-suffix match runs on the device
+    class Keywords:
+        def __init__(self, seqs):
+            self.keyword_ids = [torch.tensor(q) for q in seqs]
+            self.calls = 0
+
+        def __call__(self, output_ids, scores, **kwargs):
+            self.calls += 1
+            return any(output_ids.shape[1] >= len(k) and output_ids[0, -len(k):].tolist() == k.tolist() for k in self.keyword_ids)
+    stop = base[20:23]
+    first = next(i for i in range(3, 41) if base[i - 3:i] == stop)
+    crit = Keywords([stop, [1023, 1022, 1021, 1020]])
+    with torch.no_grad():
+        out = model.generate(ids, images=px, max_new_tokens=40, eos_token_id=None, seed=77, stopping_criteria=[crit], **kw)[0].tolist()
+    assert out == base[:first] and crit.calls >= 1
+    # a streamer sees every id exactly once, in order
+    class Streamer:
+        def __init__(self): self.got, self.ended = [], False
+        def put(self, t): self.got += t.tolist()
+        def end(self): self.ended = True
+    sm = Streamer()
+    with torch.no_grad():
+        out = model.generate(ids, images=px, max_new_tokens=20, eos_token_id=None, seed=77, streamer=sm, **kw)[0].tolist()
+    assert sm.got == out == base[:20] and sm.ended
+
+
 def test_generate_text_only_and_long_context(small):
     """No image (plain embed path) and a context that crosses many KV pages."""
     from oracle import llama
