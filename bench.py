@@ -406,7 +406,9 @@ def main():
     torch.manual_seed(322 + rank)
     model = build_model(cfg).to(device=dev, dtype=torch.bfloat16)
     if train:
-        stepper = training.SftStepper(model, world_size=world, max_grad_norm=0.3 if workload == "stage1_step" else 1.0)
+        # stage 1: the reference's recipe (Config/multi_modal_stage1.yaml:88-93: adanp, clip 0.3); stage 3: AdamW, clip 1.0
+        stepper = training.SftStepper(model, world_size=world, max_grad_norm=0.3 if workload == "stage1_step" else 1.0,
+                                      optimizer="adanp" if workload == "stage1_step" else "adamw")
     else:
         model.eval()
 
@@ -466,16 +468,30 @@ def main():
     step(dev_batches[0])
     import ctypes as C
     res = {}
-    for kind, name in ((0, "gemm"), (1, "attention")):
+    for kind, name in ((0, "gemm"), (3, "gemm_small"), (1, "attention")):
         t, f, b, n = C.c_double(), C.c_double(), C.c_double(), C.c_int64()
         lib.lhrs_prof_summary(kind, C.byref(t), C.byref(f), C.byref(b), C.byref(n))
         res[name] = dict(ms=t.value, flops=f.value, launches=n.value)
     lib.lhrs_prof_enable(0)
-    gm = res["gemm"]
+    gm, gs = res["gemm"], res["gemm_small"]
     achieved = gm["flops"] / (gm["ms"] * 1e-3) / 1e12 if gm["ms"] > 0 else 0.0
+    all_ms = gm["ms"] + gs["ms"]
+    traffic, traffic_detail = None, None
+    try:   # dram bytes of one launch of the dominant instantiation, from the committed ncu --set full capture
+        with open(os.path.join(ROOT, "profiles", "r1_gemm_traffic.json")) as f:
+            tj = json.load(f)
+        traffic = tj["launches"][tj["dominant"]]["dram_bytes"]
+        traffic_detail = dict(launch=tj["dominant"], algorithmic_bytes=tj["launches"][tj["dominant"]]["algorithmic_bytes"], source=tj["source"])
+    except Exception:
+        pass
     roofline = dict(bound="tensor", achieved=achieved, peak=pk["tflops"], unit="TFLOP/s", frac=achieved / pk["tflops"],
-                    traffic=None, kernel="gemm_bf16_kernel (tcgen05)", peak_source=pk["which"], launches_per_step=gm["launches"],
+                    traffic=traffic, traffic_detail=traffic_detail,
+                    kernel="gemm_bf16_kernel<256,*,*,*,2> (tcgen05, 2-CTA 256x256 tiles: every large projection, fwd and dX)",
+                    peak_source=pk["which"], launches_per_step=gm["launches"],
                     gemm_ms_per_step=gm["ms"], gemm_share_of_step=gm["ms"] / (ms / args.steps),
+                    small_gemm=dict(kernel="gemm_bf16_kernel<128|256,*,*,*,1> (skinny LoRA / pooler / ViT problems)", launches_per_step=gs["launches"],
+                                    ms_per_step=gs["ms"], tflops=(gs["flops"] / (gs["ms"] * 1e-3) / 1e12 if gs["ms"] > 0 else 0.0)),
+                    all_gemm_tflops=((gm["flops"] + gs["flops"]) / (all_ms * 1e-3) / 1e12 if all_ms > 0 else 0.0),
                     attention_ms_per_step=res["attention"]["ms"],
                     attention_tflops=(res["attention"]["flops"] / (res["attention"]["ms"] * 1e-3) / 1e12 if res["attention"]["ms"] > 0 else 0.0))
 
@@ -488,7 +504,7 @@ def main():
 
     if rank == 0:
         wl = (f"stage3_sft_step_b{B}_s{SEQ_LEN} (fwd+bwd, LoRA r=16 + pooler grads, allreduce, AdamW)" if workload == "sft_step"
-              else f"stage1_step_b{B}_s{SEQ_LEN} (fwd+bwd, pooler-only grads through the frozen LLaMA, allreduce, AdamW)" if workload == "stage1_step"
+              else f"stage1_step_b{B}_s{SEQ_LEN} (fwd+bwd, pooler-only grads through the frozen LLaMA, allreduce, Adan)" if workload == "stage1_step"
               else f"prefill_loss_b{B}_s{SEQ_LEN} (UniBind.forward: ViT-L/14 + pooler + splice + LLaMA-7B + CE)")
         line = dict(metric=f"tokens/sec (LLaMA-7B, 224px, seq {SEQ_LEN}), aggregate", value=value, unit="tokens/s", n_gpus=world,
                     steps=args.steps, warmup=max(args.warmup, 3), ms_per_step=ms / args.steps, higher_is_better=True,

@@ -31,7 +31,8 @@ int lhrs_version(void);
 /* Number of kernels this library has launched in this process (bench.py's `gpu_launches`). */
 uint64_t lhrs_launch_count(void);
 /* Optional per-kernel timing for the roofline report: when enabled, CUDA events bracket every launch of the
- * GEMM (kind 0) and attention (kind 1) kernels on their stream.  lhrs_prof_summary synchronises the device and
+ * GEMM (kind 0: the 2-CTA 256x256 instantiations gemm_bf16_kernel<256,*,*,*,2> — the dominant kernel; kind 3: the single-CTA
+ * instantiations used for small / skinny problems), attention (kind 1) and decode GEMV (kind 2) kernels on their stream.  lhrs_prof_summary synchronises the device and
  * returns the summed durations and the summed ALGORITHMIC flops / bytes of the launches recorded since enable. */
 int lhrs_prof_enable(int on);
 int lhrs_prof_summary(int kind, double* ms, double* flops, double* bytes, int64_t* launches);
@@ -357,6 +358,20 @@ int lhrs_llama_first_token(const LhrsLlamaWeights* w, const void* hidden_last, i
 int lhrs_llama_decode_step(const LhrsLlamaWeights* w, const LhrsKvCache* kv, const LhrsDecodeBuffers* b, int32_t greedy,
                            int32_t max_ctx, void* stream);
 int lhrs_decode_commit_token(const LhrsLlamaWeights* w, const LhrsDecodeBuffers* b, int32_t token, int32_t set_ctx, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * CLIP image preprocessing on the device.  Replaces the per-image host work of the reference's input pipeline:
+ * lhrs/Dataset/build_transform.py:43-45 (CLIPImageProcessor for every ViT config), called per sample from
+ * lhrs/Dataset/cap_dataset.py:167-175 and cli_qa.py:119-126 — resize so the shortest edge is out_size (PIL BICUBIC on uint8:
+ * Pillow ImagingResample, antialiased, 22-bit fixed point, horizontal then vertical pass), center crop out_size x out_size,
+ * x/255, (x - mean) / std, channels first.  The uint8 stage is bit-exact with Pillow, the float stage with numpy's float32
+ * arithmetic.  images: device uint8 [B, H, W, 3] (RGB, one geometry per call); out: [B, 3, out_size, out_size] bf16 (or fp32);
+ * mean3 / std3: HOST float[3]; resized_u8: nullable device uint8 [B, out_size, out_size, 3] receiving the cropped resize result.
+ * ---------------------------------------------------------------------------------------------- */
+size_t lhrs_clip_preprocess_workspace_bytes(int32_t B, int32_t H, int32_t W, int32_t out_size);
+int lhrs_clip_preprocess(const uint8_t* images, int32_t B, int32_t H, int32_t W, int32_t out_size, const float* mean3,
+                         const float* std3, void* out, int32_t out_f32, uint8_t* resized_u8, void* workspace, size_t workspace_bytes,
+                         void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Device-side token selection: the HF logits processors the reference's callers enable — repetition penalty,

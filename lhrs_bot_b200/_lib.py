@@ -155,6 +155,8 @@ SIGNATURES = {
     "lhrs_llama_first_token": (C.c_int, [C.POINTER(LhrsLlamaWeights), _P, _I32, C.POINTER(LhrsDecodeBuffers), _I32, _P]),
     "lhrs_llama_decode_step": (C.c_int, [C.POINTER(LhrsLlamaWeights), C.POINTER(LhrsKvCache), C.POINTER(LhrsDecodeBuffers), _I32, _I32, _P]),
     "lhrs_decode_commit_token": (C.c_int, [C.POINTER(LhrsLlamaWeights), C.POINTER(LhrsDecodeBuffers), _I32, _I32, _P]),
+    "lhrs_clip_preprocess_workspace_bytes": (C.c_size_t, [_I32, _I32, _I32, _I32]),
+    "lhrs_clip_preprocess": (C.c_int, [_P, _I32, _I32, _I32, _I32, C.POINTER(C.c_float), C.POINTER(C.c_float), _P, _I32, _P, _P, C.c_size_t, _P]),
     "lhrs_sample_logits": (C.c_int, [_P, _I32, _P, _I32, C.POINTER(LhrsSampling), C.c_uint64, _P, _P, _P]),
     "lhrs_llama_first_token_sampled": (C.c_int, [C.POINTER(LhrsLlamaWeights), _P, _I32, C.POINTER(LhrsDecodeBuffers), C.POINTER(LhrsSampling), _P]),
     "lhrs_llama_decode_step_sampled": (C.c_int, [C.POINTER(LhrsLlamaWeights), C.POINTER(LhrsKvCache), C.POINTER(LhrsDecodeBuffers),

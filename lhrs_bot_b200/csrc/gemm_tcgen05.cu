@@ -675,7 +675,7 @@ static int launch(const CUtensorMap& tA, const CUtensorMap (&tB)[3], const CUten
     const bool prof = prof_on();
     if (prof) {
         const double kk = (double)a.K + (double)a.ext_k;  // algorithmic reduction length (LoRA rank, not its 64-padding)
-        prof_begin(PROF_GEMM, 2.0 * a.M * (double)a.N * kk, 2.0 * ((double)a.M * a.K + (double)a.N * a.K + (double)a.M * a.N), stream);
+        prof_begin(CG == 2 ? PROF_GEMM : PROF_GEMM_SMALL, 2.0 * a.M * (double)a.N * kk, 2.0 * ((double)a.M * a.K + (double)a.N * a.K + (double)a.M * a.N), stream);
     }
     if constexpr (CG == 2) {
         cudaLaunchConfig_t cfg = {};
