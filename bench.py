@@ -47,6 +47,8 @@ def parse():
     ap.add_argument("--batch", type=int, default=None, help="per-GPU batch (default 16; 32 for stage1_step)")
     ap.add_argument("--seq", type=int, default=None, help="decoder positions per sample (default 512; 256 for stage1_step)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--sample", action="store_true", help="decode workload: cli_qa.py's settings (do_sample, temperature 0.4, top_p 0.95, "
+                                                          "repetition_penalty 1.05) selected on the device instead of greedy")
     return ap.parse_args()
 
 
@@ -313,6 +315,9 @@ def run_decode(args, dev, rank, world, local):
 
     def run(n):
         px, idd = px_host.to(dev, non_blocking=True), ids_host.to(dev, non_blocking=True)
+        if args.sample:
+            return model.generate(idd, images=px, do_sample=True, temperature=0.4, top_p=0.95, repetition_penalty=1.05,
+                                  max_new_tokens=n, eos_token_id=None, seed=1234)
         return model.generate(idd, images=px, do_sample=False, max_new_tokens=n, eos_token_id=None)
 
     def timed(n, reps):
@@ -355,7 +360,8 @@ def run_decode(args, dev, rank, world, local):
         line = dict(metric="decode tokens/sec (LLaMA-7B, 224px, 1 image + 32-token prompt -> 128 greedy tokens), aggregate",
                     value=world * 1e3 / ms_tok, unit="tokens/s", n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3),
                     ms_per_step=ms_full, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="bf16", data="synthetic",
-                    config=dict(workload="greedy_decode_b1_prompt175_new128 (cli_qa.py path)", prefill_ms=ms_prefill, ms_per_token=ms_tok,
+                    config=dict(workload=("sampled_decode_b1_prompt175_new128 (cli_qa.py path, device-side temperature/top-p/penalty)" if args.sample
+                                          else "greedy_decode_b1_prompt175_new128 (cli_qa.py path)"), prefill_ms=ms_prefill, ms_per_token=ms_tok,
                                 parallelism=f"replicas{world}", inputs_vs_l2="13.5 GB of weights streamed per token >> 126 MB L2"),
                     clocks=clocks.summary(),
                     e2e=dict(value=world * n_new / (ms_full * 1e-3), unit="tokens/s (incl. image encode + prefill)",
@@ -468,10 +474,10 @@ def main():
     step(dev_batches[0])
     import ctypes as C
     res = {}
-    for kind, name in ((0, "gemm"), (3, "gemm_small"), (1, "attention")):
+    for kind, name in ((0, "gemm"), (3, "gemm_small"), (1, "attention"), (4, "lora_stream")):
         t, f, b, n = C.c_double(), C.c_double(), C.c_double(), C.c_int64()
         lib.lhrs_prof_summary(kind, C.byref(t), C.byref(f), C.byref(b), C.byref(n))
-        res[name] = dict(ms=t.value, flops=f.value, launches=n.value)
+        res[name] = dict(ms=t.value, flops=f.value, bytes=b.value, launches=n.value)
     lib.lhrs_prof_enable(0)
     gm, gs = res["gemm"], res["gemm_small"]
     achieved = gm["flops"] / (gm["ms"] * 1e-3) / 1e12 if gm["ms"] > 0 else 0.0
@@ -492,6 +498,10 @@ def main():
                     small_gemm=dict(kernel="gemm_bf16_kernel<128|256,*,*,*,1> (skinny LoRA / pooler / ViT problems)", launches_per_step=gs["launches"],
                                     ms_per_step=gs["ms"], tflops=(gs["flops"] / (gs["ms"] * 1e-3) / 1e12 if gs["ms"] > 0 else 0.0)),
                     all_gemm_tflops=((gm["flops"] + gs["flops"]) / (all_ms * 1e-3) / 1e12 if all_ms > 0 else 0.0),
+                    lora_stream=dict(kernel="lora_panel_kernel / lora_rowreduce_kernel (HBM-bound rank-16 side products)",
+                                     launches_per_step=res["lora_stream"]["launches"], ms_per_step=res["lora_stream"]["ms"],
+                                     GBps=(res["lora_stream"]["bytes"] / (res["lora_stream"]["ms"] * 1e-3) / 1e9 if res["lora_stream"]["ms"] > 0 else 0.0),
+                                     hbm_peak_GBps=pk["hbm"]),
                     attention_ms_per_step=res["attention"]["ms"],
                     attention_tflops=(res["attention"]["flops"] / (res["attention"]["ms"] * 1e-3) / 1e12 if res["attention"]["ms"] > 0 else 0.0))
 

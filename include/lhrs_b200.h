@@ -32,7 +32,7 @@ int lhrs_version(void);
 uint64_t lhrs_launch_count(void);
 /* Optional per-kernel timing for the roofline report: when enabled, CUDA events bracket every launch of the
  * GEMM (kind 0: the 2-CTA 256x256 instantiations gemm_bf16_kernel<256,*,*,*,2> — the dominant kernel; kind 3: the single-CTA
- * instantiations used for small / skinny problems), attention (kind 1) and decode GEMV (kind 2) kernels on their stream.  lhrs_prof_summary synchronises the device and
+ * instantiations used for small / skinny problems), attention (kind 1), decode GEMV (kind 2) and LoRA streaming (kind 4) kernels.  lhrs_prof_summary synchronises the device and
  * returns the summed durations and the summed ALGORITHMIC flops / bytes of the launches recorded since enable. */
 int lhrs_prof_enable(int on);
 int lhrs_prof_summary(int kind, double* ms, double* flops, double* bytes, int64_t* launches);
@@ -303,6 +303,22 @@ int lhrs_gelu_bwd(void* d /*in place*/, const void* pre, int64_t n, void* stream
 /* inverse rotation, in place on the q and k blocks of a packed [rows, 3*dim] gradient (head_dim 128) */
 int lhrs_rope_bwd(void* dqkv, int64_t ld, int64_t rows, int32_t dim, const float* cos, const float* sin,
                   const int32_t* positions, int32_t seq_len, void* stream);
+
+/* Rank-r side products of LoRA as streaming kernels (HBM-bound: one pass over the large activation; csrc/skinny.cu).  They carry the
+ * arithmetic peft's lora.Linear adds around every wrapped projection (lhrs/models/text_modal.py:133-151) and its autograd:
+ *   lhrs_lora_panel      out[M, n] = alpha * X[M, K] · W,  n in {16, 32, 48}, K % 64 == 0
+ *        w_kn = 0: w[0] = [n, ldw] K-major                     forward   T  = s · x · [A_0;A_1;..]^T
+ *        w_kn = 1: w[s] = [K/nseg, 16], block diagonal          backward  dT_s = s · dy_s · B_s   (B_s = lora_B_s [out, r = 16])
+ *   lhrs_lora_rowreduce  G = P[M, C]^T · Q[M, n_q]  reduced over the M rows, fp32 row-split partials in `scratch`
+ *        transpose = 1, seg_c = 0:  dst[0][j, c] (ld = ldd) = G[c, j], n = n_q            dA = dT^T · x   as [n, in]
+ *        transpose = 0, seg_c > 0:  column block c uses Q columns [16*(c / seg_c), +16), n = 16;
+ *                                   dst[s][c - s*seg_c, j] (ld = ldd)                   dB_s = dy_s^T · T_s as [out, 16]
+ * `w` and `dst` are HOST arrays of device pointers. */
+int lhrs_lora_panel(const void* x, int64_t ldx, int64_t M, int32_t K, const void* const* w, int32_t nseg, int32_t w_kn, int64_t ldw,
+                    int32_t n, float alpha, void* out, int64_t ldo, void* stream);
+size_t lhrs_lora_rowreduce_scratch_bytes(int64_t M, int32_t C, int32_t n);
+int lhrs_lora_rowreduce(const void* p, int64_t ldp, int64_t M, int32_t C, const void* q, int64_t ldq, int32_t n, int32_t seg_c,
+                        int32_t transpose, void* const* dst, int64_t ldd, float alpha, float* scratch, size_t scratch_bytes, void* stream);
 
 /* dX-only backward of the LLaMA stack (weights frozen) + LoRA factor gradients.
  * lora_a_grads / lora_b_grads: arrays [layers*7] of bf16 destinations (entries or the arrays themselves may be NULL).

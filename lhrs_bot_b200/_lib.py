@@ -170,6 +170,9 @@ SIGNATURES = {
     "lhrs_swiglu_bwd": (C.c_int, [_P, _P, _P, _P, _I64, _I32, _P]),
     "lhrs_gelu_bwd": (C.c_int, [_P, _P, _I64, _P]),
     "lhrs_rope_bwd": (C.c_int, [_P, _I64, _I64, _I32, _P, _P, _P, _I32, _P]),
+    "lhrs_lora_panel": (C.c_int, [_P, _I64, _I64, _I32, _PP, _I32, _I32, _I64, _I32, _F, _P, _I64, _P]),
+    "lhrs_lora_rowreduce_scratch_bytes": (C.c_size_t, [_I64, _I32, _I32]),
+    "lhrs_lora_rowreduce": (C.c_int, [_P, _I64, _I64, _I32, _P, _I64, _I32, _I32, _I32, _PP, _I64, _F, _P, C.c_size_t, _P]),
     "lhrs_llama_bwd_workspace_bytes": (C.c_size_t, [C.POINTER(LhrsLlamaWeights), _I32, _I32]),
     "lhrs_llama_bwd": (C.c_int, [C.POINTER(LhrsLlamaWeights), _PP, _PP, _P, _I32, _I32, _P, _P, _P, _P, C.c_size_t, _P]),
     "lhrs_lm_head_bwd": (C.c_int, [C.POINTER(LhrsLlamaWeights), _P, _I64, _P, _P]),

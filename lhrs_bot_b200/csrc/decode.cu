@@ -401,7 +401,7 @@ sample_commit_kernel(const float* __restrict__ logits, int V, SampleParams p, fl
                      int n_hist, unsigned long long draw, int* state, int* tokens_out, int max_tokens,
                      int set_ctx, const __nv_bfloat16* __restrict__ embed, int dim, __nv_bfloat16* __restrict__ xbuf,
                      int* __restrict__ token_out, unsigned long long* __restrict__ dbg) {
-    extern __shared__ unsigned long long smp_hist[];
+    extern __shared__ unsigned smp_hist[];
     __shared__ SampleShared sh;
     pdl_launch_dependents();
     pdl_wait();
@@ -534,7 +534,8 @@ static int check_sampling(const LhrsSampling* s, const char* who) {
 
 extern "C" int lhrs_sample_logits(const float* logits, int32_t vocab, const int32_t* history, int32_t n_history, const LhrsSampling* s,
                                   uint64_t draw, int32_t* token_out, uint64_t* debug4, void* stream) {
-    LHRS_CHECK_ARG(logits && vocab > 0 && token_out && (n_history == 0 || history), "lhrs_sample_logits: bad args");
+    LHRS_CHECK_ARG(logits && vocab > 0 && vocab <= SMP_MAX_VOCAB && token_out && (n_history == 0 || history),
+                   "lhrs_sample_logits: bad args (vocab must be in 1..%d)", SMP_MAX_VOCAB);
     if (check_sampling(s, "lhrs_sample_logits")) return LHRS_ERR_INVALID;
     if (sample_attr()) return LHRS_ERR_CUDA;
     sample_commit_kernel<<<1, SMP_THREADS, SMP_SMEM_BYTES, (cudaStream_t)stream>>>(
@@ -555,6 +556,7 @@ extern "C" int lhrs_llama_first_token_sampled(const LhrsLlamaWeights* w, const v
                                               const LhrsDecodeBuffers* b, const LhrsSampling* s, void* stream) {
     LHRS_CHECK_ARG(w && hidden_last && b && ctx_len > 0, "lhrs_llama_first_token_sampled: bad args");
     if (check_sampling(s, "lhrs_llama_first_token_sampled")) return LHRS_ERR_INVALID;
+    LHRS_CHECK_ARG(w->vocab <= SMP_MAX_VOCAB, "lhrs_llama_first_token_sampled: vocab %d > %d", w->vocab, SMP_MAX_VOCAB);
     LHRS_CUDA(cudaMemsetAsync(b->state, 0, 4 * sizeof(int), (cudaStream_t)stream));
     return lm_head_and_commit(w, b, (const bf16*)hidden_last, nullptr, 0, ctx_len, (cudaStream_t)stream, s, true);
 }

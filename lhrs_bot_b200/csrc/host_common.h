@@ -47,7 +47,7 @@ int num_sms();
 
 // ---- optional per-kernel timing (bench.py's roofline leg): CUDA events around every launch of a kernel family
 namespace lhrs {
-enum ProfKind { PROF_GEMM = 0, PROF_ATTN = 1, PROF_OTHER = 2, PROF_GEMM_SMALL = 3, PROF_KINDS = 4 };
+enum ProfKind { PROF_GEMM = 0, PROF_ATTN = 1, PROF_OTHER = 2, PROF_GEMM_SMALL = 3, PROF_SKINNY = 4, PROF_KINDS = 5 };
 bool prof_on();
 void prof_begin(ProfKind kind, double flops, double bytes, cudaStream_t stream);
 void prof_end(cudaStream_t stream);

@@ -103,7 +103,7 @@ __global__ void lora_extract_diag_kernel(const __nv_bfloat16* __restrict__ full,
 // block-diagonal K-segmented GEMM, `dx += dT A` rides on the main dX GEMM as a K-extension (no extra pass over dx), and
 // dA / dB are one TN GEMM each.  lora_bwd_pre runs before the main dX GEMM `g`, lora_bwd_post after it.
 struct LoraBwd {
-    bool active = false, grouped = false;
+    bool active = false, grouped = false, stream = false;
     int idx0 = 0, nproj = 0, in_dim = 0, out_dim = 0;
     const void* x = nullptr; long long ldx = 0;
     const void* dy[3] = {nullptr, nullptr, nullptr}; long long ldy = 0;
@@ -123,7 +123,11 @@ static int lora_bwd_pre(cudaStream_t st, const LhrsLlamaWeights* w, void* const*
     for (int p = 1; p < n && L.grouped; ++p)
         L.grouped = reinterpret_cast<const __nv_bfloat16*>(L.dy[p]) == reinterpret_cast<const __nv_bfloat16*>(L.dy[0]) + (long long)p * L.out_dim;
     if (!L.grouped) return LHRS_OK;
-    {   // dT = s * [dy_0|dy_1|..] · blockdiag(B_0, B_1, ..)
+    L.stream = lora_stream_ok(w, L.in_dim, L.out_dim, n) && L.ldy % 8 == 0 && L.ldx % 8 == 0;
+    if (L.stream) {   // dT = s * [dy_0|dy_1|..] · blockdiag(B_0, B_1, ..): one streaming pass over dy
+        const void* wb[3] = {w->lora_b[L.idx0], n > 1 ? w->lora_b[L.idx0 + 1] : nullptr, n > 2 ? w->lora_b[L.idx0 + 2] : nullptr};
+        if ((rc = lhrs_lora_panel(L.dy[0], L.ldy, L.M, n * L.out_dim, wb, n, 1, r, n * r, w->lora_scale, L.dt, ldt, st))) return rc;
+    } else {   // dT = s * [dy_0|dy_1|..] · blockdiag(B_0, B_1, ..)
         LhrsGemm d = gemm_desc(L.M, n * r, n * L.out_dim, L.dy[0], L.ldy, w->lora_b[L.idx0], r, L.dt, ldt);
         d.b_mn_major = 1; d.num_b = n; d.alpha = w->lora_scale;
         for (int p = 1; p < n; ++p) d.B[p] = w->lora_b[L.idx0 + p];
@@ -141,6 +145,19 @@ static int lora_bwd_post(cudaStream_t st, const LhrsLlamaWeights* w, void* const
     const int r = w->lora_r, n = L.nproj;
     const long long ldt = (long long)n * r;
     int rc;
+    if (L.grouped && L.stream) {
+        const size_t sb = (size_t)8 * (size_t)(n * L.out_dim > L.in_dim ? n * L.out_dim : L.in_dim) * (size_t)(n * r) * sizeof(float);
+        if (gb != nullptr) {   // dB_p = dy_p^T T_p: one streaming pass over dy, block-diagonal pairing of column blocks and T columns
+            void* dst[3] = {gb[L.idx0], n > 1 ? gb[L.idx0 + 1] : nullptr, n > 2 ? gb[L.idx0 + 2] : nullptr};
+            if (dst[0] != nullptr)
+                if ((rc = lhrs_lora_rowreduce(L.dy[0], L.ldy, L.M, n * L.out_dim, L.T, ldt, r, L.out_dim, 0, dst, r, 1.f, L.scratch, sb, st))) return rc;
+        }
+        if (ga != nullptr && ga[L.idx0]) {   // [dA_0;dA_1;..] = dT^T x: one streaming pass over x
+            void* dst[1] = {ga[L.idx0]};
+            if ((rc = lhrs_lora_rowreduce(L.x, L.ldx, L.M, L.in_dim, L.dt, ldt, n * r, 0, 1, dst, L.in_dim, 1.f, L.scratch, sb, st))) return rc;
+        }
+        return LHRS_OK;
+    }
     if (L.grouped) {
         if (gb != nullptr) {   // [dy_0|dy_1|..]^T T -> diagonal blocks are the dB_p
             if (n == 1) {

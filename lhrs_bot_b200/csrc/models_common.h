@@ -173,7 +173,13 @@ inline long long skinny_scratch_elems(const LhrsLlamaWeights* w, long long M) {
     if (2LL * w->ffn > rows) rows = 2LL * w->ffn;
     if (3LL * w->dim > rows) rows = 3LL * w->dim;
     long long a = rows * 3 * w->lora_r, b = 3LL * w->lora_r * (w->ffn > w->dim ? w->ffn : w->dim);
-    return a > b ? a : b;
+    // the streaming row-reduce kernels (skinny.cu) keep up to 8 row-split partials of [C, n] fp32
+    long long widest = (3LL * w->dim > 2LL * w->ffn) ? 3LL * w->dim : 2LL * w->ffn;
+    long long c = 8 * widest * 3 * w->lora_r;
+    if (b > a) a = b;
+    return a > c ? a : c;
 }
+// LoRA side products on the streaming kernels of skinny.cu (r == 16, dims multiples of 128); LHRS_LORA_STREAM=0 turns them off
+bool lora_stream_ok(const LhrsLlamaWeights* w, int in_dim, int out_dim, int nproj);
 
 }  // namespace lhrs

@@ -4,6 +4,7 @@
 //   lhrs_llama_fwd   LLaMA-2 decoder stack + final norm           (HF LlamaModel via text_modal.py:281-290)
 // Every dense contraction is the tcgen05 GEMM of gemm_tcgen05.cu with its fused epilogues; the rest are the
 // row kernels of elementwise.cu and the flash attention of attention.cu.
+#include <stdlib.h>
 #include "host_common.h"
 #include "ptx.cuh"
 #include "models_common.h"
@@ -101,6 +102,12 @@ int skinny_gemm(LhrsGemm& g, float* scratch, void* stream) {
     return lhrs_cast_f32_bf16(scratch, dst, n, stream);
 }
 
+bool lora_stream_ok(const LhrsLlamaWeights* w, int in_dim, int out_dim, int nproj) {
+    static int on = -1;
+    if (on < 0) { const char* e = getenv("LHRS_LORA_STREAM"); on = e ? atoi(e) : 1; }
+    return on && w->lora_r == 16 && nproj >= 1 && nproj <= 3 && in_dim % 128 == 0 && out_dim % 128 == 0;
+}
+
 int lora_attach(LhrsGemm& g, const LhrsLlamaWeights* w, int layer, int first_proj, int nproj, const void* x, long long ldx,
                 long long M, __nv_bfloat16* t_buf, float* scratch, void* stream) {
     if (w->lora_r <= 0 || w->lora_a == nullptr || w->lora_b == nullptr) return LHRS_OK;
@@ -109,9 +116,14 @@ int lora_attach(LhrsGemm& g, const LhrsLlamaWeights* w, int layer, int first_pro
     int rc;
     if (lora_a_adjacent(w->lora_a, idx, nproj, (long long)r * g.K)) {
         // T = (alpha/r) * x · [A_0; A_1; ..]^T in ONE skinny GEMM (one pass over x)
-        LhrsGemm t = gemm_desc(M, nproj * r, g.K, x, ldx, w->lora_a[idx], g.K, t_buf, (long long)nproj * r);
-        t.alpha = w->lora_scale;
-        if ((rc = skinny_gemm(t, scratch, stream))) return rc;
+        if (lora_stream_ok(w, g.K, 128, nproj) && ldx % 8 == 0) {
+            const void* wa[1] = {w->lora_a[idx]};
+            if ((rc = lhrs_lora_panel(x, ldx, M, g.K, wa, 1, 0, g.K, nproj * r, w->lora_scale, t_buf, (long long)nproj * r, stream))) return rc;
+        } else {
+            LhrsGemm t = gemm_desc(M, nproj * r, g.K, x, ldx, w->lora_a[idx], g.K, t_buf, (long long)nproj * r);
+            t.alpha = w->lora_scale;
+            if ((rc = skinny_gemm(t, scratch, stream))) return rc;
+        }
     } else {
         for (int p = 0; p < nproj; ++p) {
             LhrsGemm t = gemm_desc(M, r, g.K, x, ldx, w->lora_a[idx + p], g.K, t_buf + p * r, (long long)nproj * r);

@@ -19,7 +19,8 @@ namespace lhrs {
 
 constexpr int SMP_THREADS = 1024;
 constexpr int SMP_WARPS = SMP_THREADS / 32;
-constexpr size_t SMP_SMEM_BYTES = (size_t)SMP_WARPS * 256 * sizeof(unsigned long long);
+constexpr size_t SMP_SMEM_BYTES = (size_t)SMP_WARPS * 256 * 2 * sizeof(unsigned);   // per-warp histograms, two 32-bit limbs per bin
+constexpr int SMP_MAX_VOCAB = 65536;   // <= 2048 tokens per warp: the 20-bit limbs of <= 2^40 masses cannot overflow 32 bits
 
 struct SampleParams {
     int do_sample;
@@ -83,30 +84,38 @@ __device__ __forceinline__ unsigned long long smp_block_sum(unsigned long long v
 
 // Ascending radix select over the keys of z[0..V): the smallest key v such that W(key <= v) > thr, with W the sum of per-token
 // weights (COUNT: 1 per token; else the fixed-point mass).  Also returns W(key < v).  Requires thr < W(all).
+// Histograms are per warp and kept as two 32-bit limbs per bin (low 20 bits | the rest), so the adds are native 32-bit
+// shared-memory atomics (a 64-bit shared atomicAdd compiles to a compare-and-swap loop, which crawls when most keys share a digit).
 template <bool COUNT>
 __device__ __forceinline__ void smp_select(const float* __restrict__ z, int V, float m, unsigned long long thr,
-                                           unsigned long long* hist, SampleShared& sh, unsigned& v_out, unsigned long long& below_out) {
+                                           unsigned* hist, SampleShared& sh, unsigned& v_out, unsigned long long& below_out) {
     const int tid = threadIdx.x, warp = tid >> 5;
-    unsigned long long* my = hist + warp * 256;
+    unsigned* my = hist + warp * 512;
     if (tid == 0) { sh.acc = 0ull; sh.prefix = 0u; }
     for (int pass = 0; pass < 4; ++pass) {
         const int shift = 24 - 8 * pass;
-        for (int i = tid; i < SMP_WARPS * 256; i += SMP_THREADS) hist[i] = 0ull;
+        for (int i = tid; i < SMP_WARPS * 512; i += SMP_THREADS) hist[i] = 0u;
         __syncthreads();
         const unsigned prefix = sh.prefix;
         for (int i = tid; i < V; i += SMP_THREADS) {
             const float zi = z[i];
             const unsigned k = smp_key(zi);
             if (pass == 0 || (k >> (shift + 8)) == (prefix >> (shift + 8))) {
-                const unsigned long long w = COUNT ? 1ull : smp_mass(zi, m);
-                if (w) atomicAdd(&my[(k >> shift) & 255u], w);
+                const unsigned bin = ((k >> shift) & 255u) * 2;
+                if (COUNT) {
+                    atomicAdd(&my[bin], 1u);
+                } else {
+                    const unsigned long long w = smp_mass(zi, m);
+                    if (w) { atomicAdd(&my[bin], static_cast<unsigned>(w & 0xFFFFFu)); atomicAdd(&my[bin + 1], static_cast<unsigned>(w >> 20)); }
+                }
             }
         }
         __syncthreads();
         if (tid < 256) {
             unsigned long long t = 0;
 #pragma unroll 8
-            for (int w = 0; w < SMP_WARPS; ++w) t += hist[w * 256 + tid];
+            for (int w = 0; w < SMP_WARPS; ++w)
+                t += static_cast<unsigned long long>(hist[w * 512 + tid * 2]) + (static_cast<unsigned long long>(hist[w * 512 + tid * 2 + 1]) << 20);
             sh.tot[tid] = t;
         }
         __syncthreads();
@@ -131,7 +140,7 @@ __device__ __forceinline__ void smp_select(const float* __restrict__ z, int V, f
 // {sum mass, kept mass, selection key, target} for the parity tests.
 __device__ __forceinline__ int smp_choose(const float* __restrict__ logits, int V, const SampleParams& p, float* __restrict__ z,
                                           const int* history, int n_hist, unsigned long long draw,
-                                          unsigned long long* hist, SampleShared& sh, unsigned long long* dbg) {
+                                          unsigned* hist, SampleShared& sh, unsigned long long* dbg) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const bool t_on = p.do_sample && p.temperature > 0.f && p.temperature != 1.f;
     const bool pen_on = p.penalty > 0.f && p.penalty != 1.f && n_hist > 0;

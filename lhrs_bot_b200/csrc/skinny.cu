@@ -1,0 +1,413 @@
+// Streaming kernels for the rank-r side products of LoRA (text_modal.py:133-151: peft wraps q,k,v,o,gate,up,down of every layer).
+// With r = 16 these products have 16..48 output columns against 4096..22016 input columns: they are HBM-bound (one pass over an
+// activation of 64..360 MB per call), not tensor-bound, so they do not belong on 128-row tcgen05 tiles (which left them at ~1/3 of
+// HBM speed and 13 % of the SFT step).  Two kernels, both built from warp-level mma.sync.m16n8k16 tiles fed by a multi-stage cp.async
+// ring, sized so that every SM keeps >= 48 KB of loads in flight (measured round 1, M = 8192: 2.4-4.4 TB/s, 21.7 ms per SFT step for
+// all 512 side products against 32 ms on the tcgen05 tiles; 128-wide k chunks beat 64-wide ones by 10 %, the L2::256B prefetch hint
+// and 256-column row-reduce blocks change nothing — tools/lora_bench.py, gpurun_out/s2d_lora_variants.txt):
+//   lora_panel_kernel      out[M, n] = alpha * X[M, K] · W          one CTA per 32-row panel, X streamed once, W from L2
+//        W_KN = false:  W = [n, K] K-major (forward  T  = s · x · [A_0;A_1;..]^T)
+//        W_KN = true :  W_s = [kseg, 16] per K segment, block diagonal (backward dT_s = s · dy_s · B_s, B_s = lora_B [out, r])
+//   lora_rowreduce_kernel  G[C, n] = P[M, C]^T · Q[M, n]            one CTA per 128-column block x row split, P streamed once;
+//        per-split fp32 partials are summed, cast and laid out by lora_reduce_store_kernel (no atomics: deterministic)
+//        (backward dA = dT^T · x  -> [n, in];   dB_s = dy_s^T · T_s -> [out, r] per segment)
+#include <stdlib.h>
+
+#include "host_common.h"
+#include "ptx.cuh"
+
+namespace lhrs {
+
+typedef __nv_bfloat16 bf16;
+
+constexpr int SK_THREADS = 128;
+constexpr int PN_BM = 32;                 // panel kernel: 32 rows x BK k per stage
+constexpr int RR_ST = 4;                  // row-reduce kernel: BR rows x BC columns (16 KB) per stage
+
+__device__ __forceinline__ void sk_cp16(uint32_t dst, const void* src, bool valid) {
+    const int sz = valid ? 16 : 0;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(sz) : "memory");
+}
+// same, asking L2 to fetch the whole 256-byte pair of lines: fewer, longer DRAM bursts for streams read 128 bytes per row at a time
+__device__ __forceinline__ void sk_cp16_l2(uint32_t dst, const void* src, bool valid) {
+    const int sz = valid ? 16 : 0;
+    asm volatile("cp.async.cg.shared.global.L2::256B [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void sk_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void sk_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void sk_ldsm(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
+__device__ __forceinline__ void sk_ldsm_t(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
+__device__ __forceinline__ void sk_mma(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+// [rows][COLS] bf16 tile, 16-byte chunks XOR-swizzled by the row within each 128-byte group
+template <int COLS>
+__device__ __forceinline__ uint32_t offsw(int row, int chunk) {
+    return static_cast<uint32_t>(row * (COLS * 2) + (((chunk & ~7) | ((chunk & 7) ^ (row & 7))) << 4));
+}
+
+struct PanelArgs {
+    const bf16* X; long long ldx; int M, K;
+    const bf16* W[3]; long long ldw;   // !W_KN: W[0] = [n, ldw];  W_KN: W[s] = [kseg, ldw] with ldw == 16
+    int kseg;                          // W_KN: K columns per segment (K = nseg * kseg)
+    float alpha;
+    bf16* out; long long ldo;
+};
+
+template <int NT, bool W_KN, int PN_BK, int PN_ST, bool L2H>
+__global__ void __launch_bounds__(SK_THREADS)
+lora_panel_kernel(const PanelArgs a) {
+    constexpr int X_STAGE = PN_BM * PN_BK * 2;
+    constexpr int W_STAGE = W_KN ? PN_BK * 16 * 2 : NT * 8 * PN_BK * 2;
+    constexpr int STAGE = X_STAGE + W_STAGE;
+    constexpr int CPR = PN_BK / 8;                                       // 16-byte chunks per tile row
+    extern __shared__ __align__(128) uint8_t smem[];
+    const uint32_t s0 = smem_u32(smem);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, mat = lane >> 3;
+    const int wr = warp & 1, wk = warp >> 1;
+    const int row0 = blockIdx.x * PN_BM;
+    const int nchunks = a.K / PN_BK;
+
+    auto load = [&](int chunk, int stage) {
+        const uint32_t sx = s0 + stage * STAGE, sw = sx + X_STAGE;
+        const int k0 = chunk * PN_BK;
+#pragma unroll
+        for (int i = 0; i < (PN_BM * CPR) / SK_THREADS; ++i) {
+            const int idx = tid + i * SK_THREADS, r = idx / CPR, c = idx % CPR;
+            const int gr = row0 + r;
+            const bool ok = gr < a.M;
+            const bf16* src = a.X + static_cast<long long>(ok ? gr : 0) * a.ldx + k0 + c * 8;
+            if (L2H) sk_cp16_l2(sx + offsw<PN_BK>(r, c), src, ok); else sk_cp16(sx + offsw<PN_BK>(r, c), src, ok);
+        }
+        if constexpr (W_KN) {
+            const int s = k0 / a.kseg, kin = k0 - s * a.kseg;
+            const bf16* w = a.W[s] + static_cast<long long>(kin) * 16;
+            for (int idx = tid; idx < PN_BK * 2; idx += SK_THREADS) {       // BK k-rows x 2 chunks
+                const int r = idx >> 1, c = idx & 1;
+                sk_cp16(sw + r * 32 + c * 16, w + r * 16 + c * 8, true);
+            }
+        } else {
+            for (int idx = tid; idx < NT * 8 * CPR; idx += SK_THREADS) {
+                const int r = idx / CPR, c = idx % CPR;
+                sk_cp16(sw + offsw<PN_BK>(r, c), a.W[0] + static_cast<long long>(r) * a.ldw + k0 + c * 8, true);
+            }
+        }
+    };
+
+    float acc[NT][4];
+#pragma unroll
+    for (int i = 0; i < NT; ++i) { acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f; }
+
+#pragma unroll
+    for (int s = 0; s < PN_ST - 1; ++s) {
+        if (s < nchunks) load(s, s);
+        sk_commit();
+    }
+    for (int ch = 0; ch < nchunks; ++ch) {
+        sk_wait<PN_ST - 2>();
+        __syncthreads();
+        if (ch + PN_ST - 1 < nchunks) load(ch + PN_ST - 1, (ch + PN_ST - 1) % PN_ST);
+        sk_commit();
+        const uint32_t sx = s0 + (ch % PN_ST) * STAGE, sw = sx + X_STAGE;
+#pragma unroll
+        for (int kk = 0; kk < PN_BK / 32; ++kk) {
+            const int ks = wk * (PN_BK / 32) + kk;                          // this warp's k-steps of the chunk
+            uint32_t af[4];
+            sk_ldsm(sx + offsw<PN_BK>(wr * 16 + (lane & 15), ks * 2 + (lane >> 4)), af[0], af[1], af[2], af[3]);
+            if constexpr (W_KN) {
+                uint32_t b0, b1, b2, b3;
+                sk_ldsm_t(sw + (ks * 16 + (mat & 1) * 8 + (lane & 7)) * 32 + (mat >> 1) * 16, b0, b1, b2, b3);
+                const int s = (ch * PN_BK) / a.kseg;                        // block-uniform: which segment's two n-tiles
+                if (s == 0) { sk_mma(acc[0], af, b0, b1); sk_mma(acc[1], af, b2, b3); }
+                if constexpr (NT >= 4) { if (s == 1) { sk_mma(acc[2], af, b0, b1); sk_mma(acc[3], af, b2, b3); } }
+                if constexpr (NT >= 6) { if (s == 2) { sk_mma(acc[4], af, b0, b1); sk_mma(acc[5], af, b2, b3); } }
+            } else {
+#pragma unroll
+                for (int np = 0; np < NT / 2; ++np) {
+                    uint32_t b0, b1, b2, b3;
+                    sk_ldsm(sw + offsw<PN_BK>(np * 16 + (mat >> 1) * 8 + (lane & 7), ks * 2 + (mat & 1)), b0, b1, b2, b3);
+                    sk_mma(acc[np * 2], af, b0, b1);
+                    sk_mma(acc[np * 2 + 1], af, b2, b3);
+                }
+            }
+        }
+    }
+    sk_wait<0>();
+    __syncthreads();
+    // the two k-halves of each 16-row tile meet in shared memory; warps with wk == 0 finish and store
+    float* red = reinterpret_cast<float*>(smem);                            // [2 row tiles][NT][32 lanes][4]
+    if (wk == 1) {
+#pragma unroll
+        for (int i = 0; i < NT; ++i)
+            *reinterpret_cast<float4*>(red + ((wr * NT + i) * 32 + lane) * 4) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+    }
+    __syncthreads();
+    if (wk == 0) {
+        const int g = lane >> 2, t4 = lane & 3;
+        const int r_lo = row0 + wr * 16 + g, r_hi = r_lo + 8;
+#pragma unroll
+        for (int i = 0; i < NT; ++i) {
+            const float4 o = *reinterpret_cast<const float4*>(red + ((wr * NT + i) * 32 + lane) * 4);
+            const int col = i * 8 + t4 * 2;
+            if (r_lo < a.M)
+                *reinterpret_cast<uint32_t*>(a.out + static_cast<long long>(r_lo) * a.ldo + col) = pack_bf16((acc[i][0] + o.x) * a.alpha, (acc[i][1] + o.y) * a.alpha);
+            if (r_hi < a.M)
+                *reinterpret_cast<uint32_t*>(a.out + static_cast<long long>(r_hi) * a.ldo + col) = pack_bf16((acc[i][2] + o.z) * a.alpha, (acc[i][3] + o.w) * a.alpha);
+        }
+    }
+}
+
+struct ReduceArgs {
+    const bf16* P; long long ldp; int M, C;
+    const bf16* Q; long long ldq;
+    int seg_c;             // > 0: block diagonal — column block c0 belongs to segment c0 / seg_c and uses Q columns [seg*NT*8, +NT*8)
+    int rows_per_split;    // multiple of RR_BR
+    float* partial;        // [nsplit][C][NT*8]
+};
+
+template <int NT, int RR_BC, bool L2H>
+__global__ void __launch_bounds__(SK_THREADS)
+lora_rowreduce_kernel(const ReduceArgs a) {
+    constexpr int RR_BR = 8192 / RR_BC;               // 64 x 128 or 32 x 256
+    constexpr int P_STAGE = RR_BR * RR_BC * 2;        // 16 KB
+    constexpr int Q_STAGE = RR_BR * NT * 16;          // BR rows x NT chunks
+    constexpr int STAGE = P_STAGE + Q_STAGE;
+    constexpr int CPR = RR_BC / 8;
+    constexpr int MT = RR_BC / 64;                    // 16-column tiles per warp
+    extern __shared__ __align__(128) uint8_t smem[];
+    const uint32_t s0 = smem_u32(smem);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, mat = lane >> 3;
+    const int c0 = blockIdx.x * RR_BC;
+    const int split = blockIdx.y;
+    const int m_begin = split * a.rows_per_split;
+    const int m_end = min(a.M, m_begin + a.rows_per_split);
+    const int nchunks = m_end > m_begin ? (m_end - m_begin + RR_BR - 1) / RR_BR : 0;
+    const int qcol0 = a.seg_c > 0 ? (c0 / a.seg_c) * NT * 8 : 0;
+
+    auto load = [&](int chunk, int stage) {
+        const uint32_t sp = s0 + stage * STAGE, sq = sp + P_STAGE;
+        const int m0 = m_begin + chunk * RR_BR;
+#pragma unroll
+        for (int i = 0; i < (RR_BR * CPR) / SK_THREADS; ++i) {
+            const int idx = tid + i * SK_THREADS, r = idx / CPR, c = idx % CPR;
+            const int gm = m0 + r;
+            const bool ok = gm < m_end && c0 + c * 8 < a.C;
+            const bf16* src = a.P + static_cast<long long>(ok ? gm : 0) * a.ldp + (ok ? c0 + c * 8 : 0);
+            if (L2H) sk_cp16_l2(sp + offsw<RR_BC>(r, c), src, ok); else sk_cp16(sp + offsw<RR_BC>(r, c), src, ok);
+        }
+        for (int idx = tid; idx < RR_BR * NT; idx += SK_THREADS) {
+            const int r = idx / NT, c = idx - r * NT;
+            const int gm = m0 + r;
+            const bool ok = gm < m_end;
+            sk_cp16(sq + (r * NT + c) * 16, a.Q + static_cast<long long>(ok ? gm : 0) * a.ldq + qcol0 + c * 8, ok);
+        }
+    };
+
+    float acc[MT][NT][4];
+#pragma unroll
+    for (int t = 0; t < MT; ++t)
+#pragma unroll
+        for (int i = 0; i < NT; ++i) { acc[t][i][0] = acc[t][i][1] = acc[t][i][2] = acc[t][i][3] = 0.f; }
+
+#pragma unroll
+    for (int s = 0; s < RR_ST - 1; ++s) {
+        if (s < nchunks) load(s, s);
+        sk_commit();
+    }
+    for (int ch = 0; ch < nchunks; ++ch) {
+        sk_wait<RR_ST - 2>();
+        __syncthreads();
+        if (ch + RR_ST - 1 < nchunks) load(ch + RR_ST - 1, (ch + RR_ST - 1) % RR_ST);
+        sk_commit();
+        const uint32_t sp = s0 + (ch % RR_ST) * STAGE, sq = sp + P_STAGE;
+#pragma unroll
+        for (int ks = 0; ks < RR_BR / 16; ++ks) {
+            uint32_t bq[NT / 2][4];
+#pragma unroll
+            for (int np = 0; np < NT / 2; ++np)
+                sk_ldsm_t(sq + ((ks * 16 + (mat & 1) * 8 + (lane & 7)) * NT + np * 2 + (mat >> 1)) * 16, bq[np][0], bq[np][1], bq[np][2], bq[np][3]);
+#pragma unroll
+            for (int t = 0; t < MT; ++t) {
+                // A = P^T: fragment rows are the columns of P, fragment k the rows -> transposed 8x8 loads
+                uint32_t af[4];
+                sk_ldsm_t(sp + offsw<RR_BC>(ks * 16 + (mat >> 1) * 8 + (lane & 7), warp * (MT * 2) + t * 2 + (mat & 1)), af[0], af[1], af[2], af[3]);
+#pragma unroll
+                for (int np = 0; np < NT / 2; ++np) {
+                    sk_mma(acc[t][np * 2], af, bq[np][0], bq[np][1]);
+                    sk_mma(acc[t][np * 2 + 1], af, bq[np][2], bq[np][3]);
+                }
+            }
+        }
+    }
+    sk_wait<0>();
+    const int g = lane >> 2, t4 = lane & 3;
+    float* dst = a.partial + static_cast<long long>(split) * a.C * (NT * 8);
+#pragma unroll
+    for (int t = 0; t < MT; ++t) {
+        const int c_lo = c0 + warp * (MT * 16) + t * 16 + g, c_hi = c_lo + 8;
+#pragma unroll
+        for (int i = 0; i < NT; ++i) {
+            const int j = i * 8 + t4 * 2;
+            if (c_lo < a.C) *reinterpret_cast<float2*>(dst + static_cast<long long>(c_lo) * (NT * 8) + j) = make_float2(acc[t][i][0], acc[t][i][1]);
+            if (c_hi < a.C) *reinterpret_cast<float2*>(dst + static_cast<long long>(c_hi) * (NT * 8) + j) = make_float2(acc[t][i][2], acc[t][i][3]);
+        }
+    }
+}
+
+// sum the row-split partials, cast, and lay the result out:
+//   transpose = 1:  dst0[j, c]            (ld = ldd)                      — dA = dT^T x as [n, in]
+//   transpose = 0:  dst_s[c - s*seg_c, j] (ld = ldd), s = c / seg_c       — dB_s = dy_s^T T_s as [out, r] per segment
+__global__ void __launch_bounds__(256)
+lora_reduce_store_kernel(const float* __restrict__ partial, int nsplit, int C, int n, int transpose, int seg_c, bf16* d0, bf16* d1, bf16* d2,
+                         long long ldd, float alpha) {
+    const long long i = blockIdx.x * 256LL + threadIdx.x;
+    if (i >= static_cast<long long>(C) * n) return;
+    int c, j;
+    if (transpose) { j = static_cast<int>(i / C); c = static_cast<int>(i - static_cast<long long>(j) * C); }
+    else { c = static_cast<int>(i / n); j = static_cast<int>(i - static_cast<long long>(c) * n); }
+    float s = 0.f;
+    for (int k = 0; k < nsplit; ++k) s += partial[(static_cast<long long>(k) * C + c) * n + j];
+    s *= alpha;
+    if (transpose) {
+        d0[static_cast<long long>(j) * ldd + c] = __float2bfloat16_rn(s);
+    } else {
+        const int seg = seg_c > 0 ? c / seg_c : 0;
+        bf16* d = seg == 0 ? d0 : (seg == 1 ? d1 : d2);
+        if (d != nullptr) d[static_cast<long long>(c - seg * (seg_c > 0 ? seg_c : 0)) * ldd + j] = __float2bfloat16_rn(s);
+    }
+}
+
+static int env_int(const char* name, int dflt) {
+    const char* e = getenv(name);
+    return e ? atoi(e) : dflt;
+}
+
+template <int NT, bool W_KN, int BK, int ST, bool L2H>
+static int launch_panel_cfg(const PanelArgs& a, cudaStream_t st) {
+    constexpr int STAGE = PN_BM * BK * 2 + (W_KN ? BK * 16 * 2 : NT * 8 * BK * 2);
+    constexpr int SMEM = STAGE * ST;
+    auto kern = lora_panel_kernel<NT, W_KN, BK, ST, L2H>;
+    static bool attr = false;
+    if (!attr) { LHRS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM)); attr = true; }
+    const bool prof = prof_on();
+    if (prof) prof_begin(PROF_SKINNY, 2.0 * a.M * (double)(NT * 8) * (W_KN ? a.kseg : a.K), 2.0 * (double)a.M * a.K, st);
+    kern<<<(a.M + PN_BM - 1) / PN_BM, SK_THREADS, SMEM, st>>>(a);
+    if (prof) prof_end(st);
+    LHRS_LAUNCH_CHECK("lora_panel_kernel");
+    return LHRS_OK;
+}
+template <int NT, bool W_KN>
+static int launch_panel(const PanelArgs& a, cudaStream_t st) {
+    static int bk = -1, l2h = -1;
+    if (bk < 0) { bk = env_int("LHRS_SKINNY_BK", 128); l2h = env_int("LHRS_SKINNY_L2HINT", 0); }
+    if (bk == 128 && a.K % 128 == 0 && (!W_KN || a.kseg % 128 == 0))
+        return l2h ? launch_panel_cfg<NT, W_KN, 128, 5, true>(a, st) : launch_panel_cfg<NT, W_KN, 128, 5, false>(a, st);
+    return l2h ? launch_panel_cfg<NT, W_KN, 64, 8, true>(a, st) : launch_panel_cfg<NT, W_KN, 64, 8, false>(a, st);
+}
+
+template <int NT, int BC, bool L2H>
+static int launch_rowreduce_cfg(const ReduceArgs& a, int nsplit, cudaStream_t st) {
+    constexpr int SMEM = (16384 + (8192 / BC) * NT * 16) * RR_ST;
+    auto kern = lora_rowreduce_kernel<NT, BC, L2H>;
+    static bool attr = false;
+    if (!attr) { LHRS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM)); attr = true; }
+    const bool prof = prof_on();
+    if (prof) prof_begin(PROF_SKINNY, 2.0 * a.M * (double)a.C * (NT * 8), 2.0 * (double)a.M * a.C, st);
+    kern<<<dim3((a.C + BC - 1) / BC, nsplit), SK_THREADS, SMEM, st>>>(a);
+    if (prof) prof_end(st);
+    LHRS_LAUNCH_CHECK("lora_rowreduce_kernel");
+    return LHRS_OK;
+}
+static int rowreduce_bc(int C, int seg_c) {
+    static int bc = -1;
+    if (bc < 0) bc = env_int("LHRS_SKINNY_BC", 128);
+    return (bc == 256 && C % 256 == 0 && (seg_c == 0 || seg_c % 256 == 0)) ? 256 : 128;
+}
+template <int NT>
+static int launch_rowreduce(const ReduceArgs& a, int nsplit, int bc, cudaStream_t st) {
+    static int l2h = -1;
+    if (l2h < 0) l2h = env_int("LHRS_SKINNY_L2HINT", 0);
+    if (bc == 256) return l2h ? launch_rowreduce_cfg<NT, 256, true>(a, nsplit, st) : launch_rowreduce_cfg<NT, 256, false>(a, nsplit, st);
+    return l2h ? launch_rowreduce_cfg<NT, 128, true>(a, nsplit, st) : launch_rowreduce_cfg<NT, 128, false>(a, nsplit, st);
+}
+
+}  // namespace lhrs
+
+using namespace lhrs;
+
+extern "C" int lhrs_lora_panel(const void* x, int64_t ldx, int64_t M, int32_t K, const void* const* w, int32_t nseg, int32_t w_kn,
+                               int64_t ldw, int32_t n, float alpha, void* out, int64_t ldo, void* stream) {
+    LHRS_CHECK_ARG(x && w && w[0] && out && M > 0 && K > 0, "lhrs_lora_panel: null/empty");
+    LHRS_CHECK_ARG(n == 16 || n == 32 || n == 48, "lhrs_lora_panel: n=%d (supported: 16, 32, 48)", n);
+    LHRS_CHECK_ARG(K % 64 == 0 && ldx % 8 == 0 && ldo % 2 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0, "lhrs_lora_panel: K %% 64, ldx %% 8 and 16-byte alignment required");
+    PanelArgs a;
+    memset(&a, 0, sizeof(a));
+    a.X = (const bf16*)x; a.ldx = ldx; a.M = (int)M; a.K = K; a.alpha = alpha; a.out = (bf16*)out; a.ldo = ldo; a.ldw = ldw;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (w_kn) {
+        LHRS_CHECK_ARG(nseg >= 1 && nseg <= 3 && n == nseg * 16 && ldw == 16 && K % nseg == 0 && (K / nseg) % 64 == 0,
+                       "lhrs_lora_panel: block-diagonal form needs r == 16, n == 16*nseg and K/nseg %% 64 == 0");
+        for (int s = 0; s < nseg; ++s) { LHRS_CHECK_ARG(w[s] != nullptr, "lhrs_lora_panel: null segment"); a.W[s] = (const bf16*)w[s]; }
+        a.kseg = K / nseg;
+        if (n == 16) return launch_panel<2, true>(a, st);
+        if (n == 32) return launch_panel<4, true>(a, st);
+        return launch_panel<6, true>(a, st);
+    }
+    LHRS_CHECK_ARG(nseg == 1 && ldw % 8 == 0 && (reinterpret_cast<uintptr_t>(w[0]) & 15) == 0, "lhrs_lora_panel: K-major W must be one [n, ldw] matrix");
+    a.W[0] = (const bf16*)w[0];
+    if (n == 16) return launch_panel<2, false>(a, st);
+    if (n == 32) return launch_panel<4, false>(a, st);
+    return launch_panel<6, false>(a, st);
+}
+
+extern "C" size_t lhrs_lora_rowreduce_scratch_bytes(int64_t M, int32_t C, int32_t n) {
+    (void)M;
+    return (size_t)8 * (size_t)C * (size_t)n * sizeof(float);
+}
+
+extern "C" int lhrs_lora_rowreduce(const void* p, int64_t ldp, int64_t M, int32_t C, const void* q, int64_t ldq, int32_t n, int32_t seg_c,
+                                   int32_t transpose, void* const* dst, int64_t ldd, float alpha, float* scratch, size_t scratch_bytes,
+                                   void* stream) {
+    LHRS_CHECK_ARG(p && q && dst && dst[0] && scratch && M > 0 && C > 0, "lhrs_lora_rowreduce: null/empty");
+    LHRS_CHECK_ARG(n == 16 || n == 32 || n == 48, "lhrs_lora_rowreduce: n=%d (supported: 16, 32, 48)", n);
+    LHRS_CHECK_ARG(C % 8 == 0 && ldp % 8 == 0 && ldq % 8 == 0 && (reinterpret_cast<uintptr_t>(p) & 15) == 0 && (reinterpret_cast<uintptr_t>(q) & 15) == 0,
+                   "lhrs_lora_rowreduce: C, ldp, ldq %% 8 and 16-byte alignment required");
+    LHRS_CHECK_ARG(seg_c == 0 || (seg_c % 128 == 0 && C % seg_c == 0 && C / seg_c <= 3 && !transpose),
+                   "lhrs_lora_rowreduce: block-diagonal form needs seg_c %% 128 == 0 and at most 3 segments");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int bc = rowreduce_bc(C, seg_c);
+    const int RR_BR = 8192 / bc;
+    const int cblocks = (C + bc - 1) / bc;
+    int nsplit = (2 * num_sms() + cblocks - 1) / cblocks;
+    if (nsplit > 8) nsplit = 8;
+    const long long max_by_rows = (M + RR_BR - 1) / RR_BR;
+    if (nsplit > max_by_rows) nsplit = (int)max_by_rows;
+    if (nsplit < 1) nsplit = 1;
+    LHRS_CHECK_ARG(scratch_bytes >= (size_t)nsplit * C * n * sizeof(float), "lhrs_lora_rowreduce: scratch too small");
+    ReduceArgs a;
+    memset(&a, 0, sizeof(a));
+    a.P = (const bf16*)p; a.ldp = ldp; a.M = (int)M; a.C = C; a.Q = (const bf16*)q; a.ldq = ldq; a.seg_c = seg_c; a.partial = scratch;
+    long long rps = (M + nsplit - 1) / nsplit;
+    rps = ((rps + RR_BR - 1) / RR_BR) * RR_BR;
+    a.rows_per_split = (int)rps;
+    nsplit = (int)((M + rps - 1) / rps);
+    int rc;
+    if (n == 16) rc = launch_rowreduce<2>(a, nsplit, bc, st);
+    else if (n == 32) rc = launch_rowreduce<4>(a, nsplit, bc, st);
+    else rc = launch_rowreduce<6>(a, nsplit, bc, st);
+    if (rc) return rc;
+    const long long total = (long long)C * n;
+    const int nseg = seg_c > 0 ? C / seg_c : 1;
+    lora_reduce_store_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(scratch, nsplit, C, n, transpose, seg_c, (bf16*)dst[0],
+                                                                            nseg > 1 ? (bf16*)dst[1] : nullptr, nseg > 2 ? (bf16*)dst[2] : nullptr,
+                                                                            ldd, alpha);
+    LHRS_LAUNCH_CHECK("lora_reduce_store_kernel");
+    return LHRS_OK;
+}

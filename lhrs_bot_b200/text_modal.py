@@ -148,30 +148,57 @@ class CustomLlamaForCausalLM(nn.Module):
         self.peft_config = None
         return self
 
-    def save_pretrained(self, path: str) -> None:
-        """Adapter-only save in peft's key layout (trainer.py:296-300 calls this on text_encoder)."""
+    def save_pretrained(self, path: str, safe_serialization: bool = True) -> None:
+        """Adapter-only save in peft==0.7.1's on-disk layout (trainer.py:296-300 and UniBind.py:79 call this on text_encoder):
+        ``adapter_model.safetensors`` (peft's default; ``adapter_model.bin`` with ``safe_serialization=False``) holding
+        ``base_model.model.<module path>.lora_{A,B}.weight`` and an ``adapter_config.json`` a stock peft can read back."""
         os.makedirs(path, exist_ok=True)
-        sd = {("base_model.model." + k).replace(".default", ""): v.detach().cpu()
+        sd = {("base_model.model." + k).replace(".default", ""): v.detach().cpu().contiguous()
               for k, v in self.state_dict().items() if "lora_" in k}
-        torch.save(sd, os.path.join(path, "adapter_model.bin"))
+        if safe_serialization:
+            from safetensors.torch import save_file
+            save_file(sd, os.path.join(path, "adapter_model.safetensors"), metadata={"format": "pt"})
+        else:
+            torch.save(sd, os.path.join(path, "adapter_model.bin"))
         if self.peft_config is not None:
             import json
             with open(os.path.join(path, "adapter_config.json"), "w") as f:
-                json.dump(dict(peft_type="LORA", r=self.peft_config.r, lora_alpha=self.peft_config.lora_alpha,
-                               lora_dropout=self.peft_config.lora_dropout, target_modules=list(PROJ_NAMES),
-                               bias="none", task_type="CAUSAL_LM"), f)
+                json.dump(dict(peft_type="LORA", task_type="CAUSAL_LM", base_model_name_or_path=None, inference_mode=True,
+                               r=self.peft_config.r, lora_alpha=self.peft_config.lora_alpha,
+                               lora_dropout=self.peft_config.lora_dropout, target_modules=list(PROJ_NAMES), bias="none",
+                               fan_in_fan_out=False, init_lora_weights=True, modules_to_save=None, layers_to_transform=None,
+                               layers_pattern=None, rank_pattern={}, alpha_pattern={}, revision=None), f, indent=2, sort_keys=True)
 
     def load_adapter(self, path: str, is_trainable: bool) -> None:
+        """``PeftModel.from_pretrained(model, path, is_trainable=...)`` for a LoRA adapter (UniBind.py:107-112): reads
+        ``adapter_config.json`` and ``adapter_model.safetensors`` (or the older ``adapter_model.bin``)."""
         import json
         with open(os.path.join(path, "adapter_config.json")) as f:
             ac = json.load(f)
+        if ac.get("peft_type", "LORA") != "LORA":
+            raise NotImplementedError(f"adapter type {ac.get('peft_type')!r}: the reference trains LoRA only (text_modal.py:133-151)")
+        targets = ac.get("target_modules") or list(PROJ_NAMES)
+        if set(targets) != set(PROJ_NAMES):
+            raise NotImplementedError(f"adapter targets {sorted(targets)}: the reference wraps all seven projections (text_modal.py:658-667)")
         self.add_lora(ac["r"], ac["lora_alpha"], ac.get("lora_dropout", 0.0))
-        sd = torch.load(os.path.join(path, "adapter_model.bin"), map_location="cpu")
+        st_path = os.path.join(path, "adapter_model.safetensors")
+        if os.path.exists(st_path):
+            from safetensors.torch import load_file
+            sd = load_file(st_path)
+        else:
+            sd = torch.load(os.path.join(path, "adapter_model.bin"), map_location="cpu")
         own = self.state_dict()
+        loaded = 0
         for k, v in sd.items():
             kk = k.replace("base_model.model.", "", 1).replace("lora_A.weight", "lora_A.default.weight").replace(
                 "lora_B.weight", "lora_B.default.weight")
+            if kk not in own:
+                raise KeyError(f"adapter tensor {k!r} has no counterpart in the model ({kk!r})")
             own[kk].copy_(v)
+            loaded += 1
+        expect = sum(1 for k in own if "lora_" in k)
+        if loaded != expect:
+            raise KeyError(f"adapter holds {loaded} tensors, the model expects {expect}")
         for n, p in self.named_parameters():
             if "lora_" in n:
                 p.requires_grad_(is_trainable)

@@ -69,7 +69,22 @@ def test_checkpoint_roundtrip(tmp_path):
     ck = m.custom_save_checkpoint(str(tmp_path / "FINAL.pt"))
     assert set(ck) == {"rgb_ckpt", "other_ckpt"} and "rgb_pooler" in ck["other_ckpt"]
     torch.save(ck, tmp_path / "FINAL.pt")
-    assert (tmp_path / "TextLoRA" / "adapter_model.bin").exists()
+    assert (tmp_path / "TextLoRA" / "adapter_model.safetensors").exists()      # peft 0.7.1's default serialisation
+    import json
+    from safetensors.torch import load_file
+    ac = json.load(open(tmp_path / "TextLoRA" / "adapter_config.json"))
+    assert ac["peft_type"] == "LORA" and ac["r"] == 16 and ac["lora_alpha"] == 32 and sorted(ac["target_modules"]) == sorted(
+        ["q_proj", "k_proj", "v_proj", "o_proj", "gate_proj", "up_proj", "down_proj"])
+    keys = sorted(load_file(str(tmp_path / "TextLoRA" / "adapter_model.safetensors")))
+    assert keys[0] == "base_model.model.model.layers.0.mlp.down_proj.lora_A.weight" and len(keys) == 2 * 7 * cfg.text.num_hidden_layers
+    # the older .bin layout loads too
+    legacy = tmp_path / "legacy" / "TextLoRA"
+    m.text.text_encoder.save_pretrained(str(legacy), safe_serialization=False)
+    assert (legacy / "adapter_model.bin").exists()
+    torch.save(ck, tmp_path / "legacy" / "FINAL.pt")
+    ml = build_small_model(small_config(stage=3), "cpu", seed=3)
+    ml.custom_load_state_dict(str(tmp_path / "legacy" / "FINAL.pt"))
+    assert torch.equal(ml.text.lora_pairs()[5][1].float(), m.text.lora_pairs()[5][1].float())
     cfg3 = small_config(stage=3)
     m3 = build_small_model(cfg3, "cpu", seed=2)
     m3.custom_load_state_dict(str(tmp_path / "FINAL.pt"))

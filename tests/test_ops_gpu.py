@@ -297,3 +297,77 @@ def test_cross_entropy():
     loss.backward()
     # elementwise: one bf16 rounding of each gradient entry (2^-8 relative)
     torch.testing.assert_close(d.float(), lf.grad, rtol=1.6e-2, atol=1e-8)
+
+
+# ---------------------------------------------------------------------------------------------- LoRA streaming kernels (skinny.cu)
+def _ptrs(tensors):
+    import ctypes as C
+    arr = (C.c_void_p * len(tensors))(*[None if t is None else t.data_ptr() for t in tensors])
+    return C.cast(arr, C.POINTER(C.c_void_p)), arr
+
+
+@pytest.mark.parametrize("M,K,nproj", [(8192, 4096, 3), (489, 256, 3), (1000, 11008, 1), (77, 512, 2), (33, 4096, 1)])
+def test_lora_panel_forward_T(M, K, nproj):
+    """T = s * x · [A_0;A_1;..]^T (text_modal.py:133-151 forward side product), ragged M, x with a leading dimension > K."""
+    from lhrs_bot_b200 import _lib, runtime
+    lib = _lib.load()
+    n = 16 * nproj
+    x = _randn(M, K + 64, seed=1)[:, :K]
+    a = _randn(n, K, scale=K ** -0.5, seed=2)
+    out = torch.full((M, n), 7.0, device=DEV, dtype=torch.bfloat16)
+    wp, keep = _ptrs([a])
+    _lib.check(lib.lhrs_lora_panel(x.data_ptr(), x.stride(0), M, K, wp, 1, 0, K, n, 2.0, out.data_ptr(), n, runtime.stream()), "lhrs_lora_panel")
+    _report(f"lora_panel T M{M} K{K} n{n}", out, 2.0 * (x.float() @ a.float().t()), 1e-2)
+
+
+@pytest.mark.parametrize("M,out_dim,nproj", [(8192, 4096, 3), (489, 256, 3), (2048, 11008, 2), (100, 512, 1)])
+def test_lora_panel_blockdiag_dT(M, out_dim, nproj):
+    """dT_s = s * dy_s · B_s for the projections sharing an input (block-diagonal, B_s = lora_B [out, 16] read in place)."""
+    from lhrs_bot_b200 import _lib, runtime
+    lib = _lib.load()
+    r = 16
+    dy = _randn(M, nproj * out_dim, seed=3)
+    bs = [_randn(out_dim, r, scale=0.1, seed=10 + s) for s in range(nproj)]
+    out = torch.zeros((M, nproj * r), device=DEV, dtype=torch.bfloat16)
+    wp, keep = _ptrs(bs)
+    _lib.check(lib.lhrs_lora_panel(dy.data_ptr(), dy.stride(0), M, nproj * out_dim, wp, nproj, 1, r, nproj * r, 0.5, out.data_ptr(),
+                                   nproj * r, runtime.stream()), "lhrs_lora_panel")
+    ref = torch.cat([0.5 * (dy[:, s * out_dim:(s + 1) * out_dim].float() @ bs[s].float()) for s in range(nproj)], 1)
+    _report(f"lora_panel dT M{M} out{out_dim} x{nproj}", out, ref, 1e-2)
+
+
+@pytest.mark.parametrize("M,C,nproj", [(8192, 4096, 3), (489, 256, 3), (3000, 11008, 1), (64, 512, 2), (8192, 128, 1)])
+def test_lora_rowreduce_dA(M, C, nproj):
+    """[dA_0;dA_1;..] = dT^T · x as [n, in]: reduction over the M rows, partials summed without atomics."""
+    import ctypes as C_
+    from lhrs_bot_b200 import _lib, runtime
+    lib = _lib.load()
+    n = 16 * nproj
+    x = _randn(M, C, seed=4)
+    dt = _randn(M, n, scale=0.3, seed=5)
+    out = torch.zeros((n, C), device=DEV, dtype=torch.bfloat16)
+    nbytes = lib.lhrs_lora_rowreduce_scratch_bytes(M, C, n)
+    scratch = torch.empty(nbytes // 4, device=DEV, dtype=torch.float32)
+    dp, keep = _ptrs([out])
+    _lib.check(lib.lhrs_lora_rowreduce(x.data_ptr(), C, M, C, dt.data_ptr(), n, n, 0, 1, dp, C, 1.0, scratch.data_ptr(), nbytes,
+                                       runtime.stream()), "lhrs_lora_rowreduce")
+    _report(f"lora_rowreduce dA M{M} C{C} n{n}", out, dt.float().t() @ x.float(), 1e-2)
+
+
+@pytest.mark.parametrize("M,out_dim,nproj", [(8192, 4096, 3), (489, 256, 3), (1536, 11008, 2), (64, 128, 1)])
+def test_lora_rowreduce_blockdiag_dB(M, out_dim, nproj):
+    """dB_s = dy_s^T · T_s as [out, 16] per projection: each 128-column block of dy pairs with its own 16 columns of T."""
+    from lhrs_bot_b200 import _lib, runtime
+    lib = _lib.load()
+    r = 16
+    dy = _randn(M, nproj * out_dim, seed=6)
+    t = _randn(M, nproj * r, scale=0.3, seed=7)
+    outs = [torch.zeros((out_dim, r), device=DEV, dtype=torch.bfloat16) for _ in range(nproj)]
+    nbytes = lib.lhrs_lora_rowreduce_scratch_bytes(M, nproj * out_dim, r)
+    scratch = torch.empty(nbytes // 4, device=DEV, dtype=torch.float32)
+    dp, keep = _ptrs(outs)
+    _lib.check(lib.lhrs_lora_rowreduce(dy.data_ptr(), nproj * out_dim, M, nproj * out_dim, t.data_ptr(), nproj * r, r, out_dim, 0, dp, r,
+                                       1.0, scratch.data_ptr(), nbytes, runtime.stream()), "lhrs_lora_rowreduce")
+    for s in range(nproj):
+        ref = dy[:, s * out_dim:(s + 1) * out_dim].float().t() @ t[:, s * r:(s + 1) * r].float()
+        _report(f"lora_rowreduce dB M{M} out{out_dim} seg{s}", outs[s], ref, 1e-2)
