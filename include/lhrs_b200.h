@@ -357,6 +357,7 @@ int lhrs_adan_step(float* master, float* exp_avg, float* exp_avg_diff, float* ex
  * Single-sequence decode (HF generate loop reached from TextModal.generate, lhrs/models/text_modal.py:600-612, with the
  * generation-input rule of :36-60).  All buffers are caller-owned device memory (bf16 unless noted):
  *   xbuf [dim] residual stream of the token being fed, qkv [3*dim], obuf [dim], act [ffn], logits fp32 [vocab],
+ *   attn_part / attn_count: scratch of the split ("flash decoding") attention, 4 context slices per head,
  *   part_val fp32 / part_idx int32 [>= 8*SMs] argmax partials, state int32[4] = {next token, ctx_len, tokens emitted, finished flag},
  *   tokens_out int32 [max_tokens].
  * first_token: logits/argmax of the prefill's last (post-norm) hidden row; sets ctx_len and feeds the token's embedding.
@@ -368,6 +369,8 @@ typedef struct LhrsDecodeBuffers {
     void* xbuf; void* qkv; void* obuf; void* act;
     float* logits; float* part_val; int32_t* part_idx;
     int32_t* state; int32_t* tokens_out; int32_t max_tokens;
+    float* attn_part;    /* fp32 [heads * 4 * 132]: per-slice attention partials (max, sum, un-normalised output) */
+    int32_t* attn_count; /* int32 [heads], ZERO-initialised by the caller; the kernels return it to zero after every use */
 } LhrsDecodeBuffers;
 int lhrs_llama_first_token(const LhrsLlamaWeights* w, const void* hidden_last, int32_t ctx_len, const LhrsDecodeBuffers* b,
                            int32_t greedy, void* stream);

@@ -96,6 +96,7 @@ class LhrsDecodeBuffers(C.Structure):
         ("xbuf", C.c_void_p), ("qkv", C.c_void_p), ("obuf", C.c_void_p), ("act", C.c_void_p),
         ("logits", C.c_void_p), ("part_val", C.c_void_p), ("part_idx", C.c_void_p),
         ("state", C.c_void_p), ("tokens_out", C.c_void_p), ("max_tokens", C.c_int32),
+        ("attn_part", C.c_void_p), ("attn_count", C.c_void_p),
     ]
 
 

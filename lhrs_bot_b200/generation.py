@@ -45,8 +45,11 @@ class PagedKvCache:
 
 
 class DecodeBuffers:
-    def __init__(self, dim: int, ffn: int, vocab: int, max_tokens: int, device):
+    def __init__(self, dim: int, ffn: int, vocab: int, max_tokens: int, device, heads: int = 0):
         bf = dict(device=device, dtype=torch.bfloat16)
+        heads = heads or dim // 128
+        self.attn_part = torch.empty((heads * 4 * 132,), device=device, dtype=torch.float32)
+        self.attn_count = torch.zeros((heads,), device=device, dtype=torch.int32)
         self.xbuf, self.qkv, self.obuf, self.act = (torch.empty((n,), **bf) for n in (dim, 3 * dim, dim, ffn))
         self.logits = torch.empty((vocab,), device=device, dtype=torch.float32)
         nparts = 8 * 256
@@ -58,6 +61,7 @@ class DecodeBuffers:
         d.xbuf, d.qkv, d.obuf, d.act = (t.data_ptr() for t in (self.xbuf, self.qkv, self.obuf, self.act))
         d.logits, d.part_val, d.part_idx = self.logits.data_ptr(), self.part_val.data_ptr(), self.part_idx.data_ptr()
         d.state, d.tokens_out, d.max_tokens = self.state.data_ptr(), self.tokens.data_ptr(), self.tokens.numel()
+        d.attn_part, d.attn_count = self.attn_part.data_ptr(), self.attn_count.data_ptr()
         self.desc = d
 
 
@@ -70,7 +74,7 @@ class DecodeSession:
     def __init__(self, cfg, layers: int, vocab: int, max_len: int, device):
         hd = cfg.hidden_size // cfg.num_attention_heads
         self.kv = PagedKvCache(layers, cfg.num_attention_heads, hd, max_len, device)
-        self.buf = DecodeBuffers(cfg.hidden_size, cfg.intermediate_size, vocab, self.kv.capacity, device)
+        self.buf = DecodeBuffers(cfg.hidden_size, cfg.intermediate_size, vocab, self.kv.capacity, device, cfg.num_attention_heads)
         self.work = torch.empty((vocab,), device=device, dtype=torch.float32)
         self.seed = torch.zeros((1,), device=device, dtype=torch.int64)
         self.stop, self._stop_key = None, None
