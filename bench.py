@@ -340,6 +340,13 @@ def run_decode(args, dev, rank, world, local):
 
     for _ in range(max(args.warmup, 3)):
         run(8)
+    if os.environ.get("LHRS_PROFILE_STEP"):      # ncu --profile-from-start off: capture one short generation, print nothing
+        torch.cuda.synchronize()
+        torch.cuda.profiler.start()
+        run(int(os.environ["LHRS_PROFILE_STEP"]))
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
+        return
     l0 = ops.launch_count()
     with ClockSampler(local) as clocks:
         ms_full = timed(n_new, args.steps)
@@ -450,6 +457,13 @@ def main():
 
     for i in range(max(args.warmup, 3)):
         step(dev_batches[i % 2])
+    if os.environ.get("LHRS_PROFILE_STEP"):      # ncu --profile-from-start off: capture exactly one warm step, print nothing
+        torch.cuda.synchronize()
+        torch.cuda.profiler.start()
+        step(dev_batches[0])
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
+        return
     launches0 = ops.launch_count()
     with ClockSampler(local) as clocks:
         ms = timed(lambda i: step(dev_batches[i % 2]), args.steps)

@@ -439,9 +439,13 @@ __global__ void __launch_bounds__(SMP_THREADS)
 sample_commit_kernel(const float* __restrict__ logits, int V, SampleParams p, float* __restrict__ z, const int* history,
                      int n_hist, unsigned long long draw, int* state, int* tokens_out, int max_tokens,
                      int set_ctx, const __nv_bfloat16* __restrict__ embed, int dim, __nv_bfloat16* __restrict__ xbuf,
-                     int* __restrict__ token_out, unsigned long long* __restrict__ dbg) {
+                     int* __restrict__ token_out, unsigned long long* __restrict__ dbg, int z_in_smem,
+                     const float* __restrict__ part_val, const int* __restrict__ part_idx, int nparts) {
     extern __shared__ unsigned smp_hist[];
     __shared__ SampleShared sh;
+    // the working copy of the scores lives in shared memory when the vocabulary fits next to the histograms (LLaMA: 128 KB):
+    // the ~12 passes of the selection then run at shared-memory latency instead of L2 latency
+    if (z_in_smem) z = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(smp_hist) + SMP_SMEM_BYTES);
     pdl_launch_dependents();
     pdl_wait();
     if (state != nullptr) {
@@ -450,7 +454,33 @@ sample_commit_kernel(const float* __restrict__ logits, int V, SampleParams p, fl
         history = tokens_out;
         draw = static_cast<unsigned long long>(state[2]);
     }
-    const int tok = smp_choose(logits, V, p, z, history, n_hist, draw, smp_hist, sh, dbg);
+    int tok;
+    const bool pen_on = p.penalty > 0.f && p.penalty != 1.f && n_hist > 0;
+    if (!p.do_sample && !pen_on && nparts > 0) {
+        // plain greedy: the lm_head GEMV already reduced every block's rows to (max, argmax); finish over those partials
+        float bv = -INFINITY;
+        int bi = 0x7fffffff;
+        for (int i = threadIdx.x; i < nparts; i += SMP_THREADS) {
+            const float v = part_val[i];
+            const int ix = part_idx[i];
+            if (v > bv || (v == bv && ix < bi)) { bv = v; bi = ix; }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+        }
+        if ((threadIdx.x & 31) == 0) { sh.wmax[threadIdx.x >> 5] = bv; sh.widx[threadIdx.x >> 5] = bi; }
+        __syncthreads();
+        bv = sh.wmax[0]; bi = sh.widx[0];
+#pragma unroll
+        for (int i = 1; i < SMP_WARPS; ++i)
+            if (sh.wmax[i] > bv || (sh.wmax[i] == bv && sh.widx[i] < bi)) { bv = sh.wmax[i]; bi = sh.widx[i]; }
+        tok = bi;
+    } else {
+        tok = smp_choose(logits, V, p, z, history, n_hist, draw, smp_hist, sh, dbg);
+    }
     if (state == nullptr) {
         if (threadIdx.x == 0) token_out[0] = tok;
         return;
@@ -521,10 +551,15 @@ static SampleParams sample_params(const LhrsSampling* s) {
     p.stop_seqs = s->stop_seqs; p.n_stop = s->stop_seqs ? s->n_stop : 0; p.stop_len = s->stop_len;
     return p;
 }
+constexpr size_t SMP_MAX_SMEM = 220 * 1024;   // 227 KB per block minus the static shared variables
+static size_t sample_smem(int vocab) {   // histograms + (if it fits) the fp32 working copy of the scores
+    const size_t with_z = SMP_SMEM_BYTES + (size_t)vocab * sizeof(float);
+    return with_z <= SMP_MAX_SMEM ? with_z : SMP_SMEM_BYTES;
+}
 static int sample_attr() {
     static bool done = false;
     if (!done) {
-        LHRS_CUDA(cudaFuncSetAttribute(sample_commit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMP_SMEM_BYTES));
+        LHRS_CUDA(cudaFuncSetAttribute(sample_commit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMP_MAX_SMEM));
         done = true;
     }
     return LHRS_OK;
@@ -541,10 +576,11 @@ static int lm_head_and_commit(const LhrsLlamaWeights* w, const LhrsDecodeBuffers
     if (grid <= 0) return LHRS_ERR_CUDA;
     if (smp != nullptr) {
         if (sample_attr()) return LHRS_ERR_CUDA;
-        LHRS_CUDA(launch_pdl(sample_commit_kernel, dim3(1), dim3(SMP_THREADS), SMP_SMEM_BYTES, st, (const float*)b->logits, (int)w->vocab,
+        const size_t smem = sample_smem(w->vocab);
+        LHRS_CUDA(launch_pdl(sample_commit_kernel, dim3(1), dim3(SMP_THREADS), smem, st, (const float*)b->logits, (int)w->vocab,
                              sample_params(smp), (float*)smp->work, (const int*)nullptr, 0, 0ull, (int*)b->state, (int*)b->tokens_out,
                              (int)b->max_tokens, set_ctx, (const bf16*)w->embed, (int)w->dim, (bf16*)b->xbuf, (int*)nullptr,
-                             (unsigned long long*)nullptr));
+                             (unsigned long long*)nullptr, (int)(smem > SMP_SMEM_BYTES), (const float*)b->part_val, (const int*)b->part_idx, grid));
         LHRS_LAUNCH_CHECK("sample_commit_kernel");
         return LHRS_OK;
     }
@@ -577,9 +613,10 @@ extern "C" int lhrs_sample_logits(const float* logits, int32_t vocab, const int3
                    "lhrs_sample_logits: bad args (vocab must be in 1..%d)", SMP_MAX_VOCAB);
     if (check_sampling(s, "lhrs_sample_logits")) return LHRS_ERR_INVALID;
     if (sample_attr()) return LHRS_ERR_CUDA;
-    sample_commit_kernel<<<1, SMP_THREADS, SMP_SMEM_BYTES, (cudaStream_t)stream>>>(
+    const size_t smem = sample_smem(vocab);
+    sample_commit_kernel<<<1, SMP_THREADS, smem, (cudaStream_t)stream>>>(
         logits, vocab, sample_params(s), s->work, (const int*)history, n_history, (unsigned long long)draw, nullptr, nullptr, 0, 0, nullptr, 0,
-        nullptr, (int*)token_out, (unsigned long long*)debug4);
+        nullptr, (int*)token_out, (unsigned long long*)debug4, (int)(smem > SMP_SMEM_BYTES), nullptr, nullptr, 0);
     LHRS_LAUNCH_CHECK("sample_commit_kernel");
     return LHRS_OK;
 }

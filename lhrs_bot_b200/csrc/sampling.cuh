@@ -119,15 +119,30 @@ __device__ __forceinline__ void smp_select(const float* __restrict__ z, int V, f
             sh.tot[tid] = t;
         }
         __syncthreads();
-        if (tid == 0) {
-            unsigned long long acc = sh.acc;
-            int d = 0;
-            for (; d < 255; ++d) {
-                if (acc + sh.tot[d] > thr) break;
-                acc += sh.tot[d];
+        if (tid < 32) {   // first warp: each lane owns 8 consecutive bins; find the first bin where the running weight exceeds thr
+            unsigned long long loc[8], mine = 0;
+#pragma unroll
+            for (int b = 0; b < 8; ++b) { loc[b] = sh.tot[tid * 8 + b]; mine += loc[b]; }
+            unsigned long long incl = mine;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned long long t = __shfl_up_sync(0xffffffffu, incl, o);
+                if (tid >= o) incl += t;
             }
-            sh.acc = acc;
-            sh.prefix = prefix | (static_cast<unsigned>(d) << shift);
+            const unsigned long long base = sh.acc + incl - mine;          // weight below this lane's first bin
+            const bool crosses = base + mine > thr;                          // the crossing bin is in this lane's range or an earlier one
+            const unsigned ballot = __ballot_sync(0xffffffffu, crosses);
+            const int owner = ballot ? __ffs(ballot) - 1 : 31;               // no crossing: the last bin (cannot happen when thr < total)
+            if (tid == owner) {
+                unsigned long long acc = base;
+                int d = 0;
+                for (; d < 7; ++d) {
+                    if (acc + loc[d] > thr) break;
+                    acc += loc[d];
+                }
+                sh.acc = acc;
+                sh.prefix = prefix | (static_cast<unsigned>(tid * 8 + d) << shift);
+            }
         }
         __syncthreads();
     }
