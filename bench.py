@@ -356,6 +356,12 @@ def run_decode(args, dev, rank, world, local):
     S = T + 143
     bytes_tok = 2.0 * (32 * (4 * 4096 * 4096 + 3 * 4096 * 11008) + 32000 * 4096) + 2 * 32 * 4096 * 2 * (S + n_new / 2)
     pk = peaks()
+    traffic = None
+    try:   # measured DRAM bytes per token from the committed ncu launch list
+        with open(os.path.join(ROOT, "profiles", "r1s2_decode_traffic.json")) as f:
+            traffic = json.load(f)["per_token_dram_bytes"]
+    except Exception:
+        pass
     achieved = bytes_tok / (ms_tok * 1e-3) / 1e9
     cpu_base = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -374,7 +380,8 @@ def run_decode(args, dev, rank, world, local):
                     e2e=dict(value=world * n_new / (ms_full * 1e-3), unit="tokens/s (incl. image encode + prefill)",
                              h2d_bytes_per_step=int(px_host.numel() * 2 + ids_host.numel() * 8), d2h_bytes_per_step=n_new * 8),
                     gpu_launches=int(launches),
-                    roofline=dict(bound="hbm", achieved=achieved, peak=pk["hbm"], unit="GB/s", frac=achieved / pk["hbm"], traffic=None,
+                    roofline=dict(bound="hbm", achieved=achieved, peak=pk["hbm"], unit="GB/s", frac=achieved / pk["hbm"], traffic=traffic,
+                                  algorithmic_bytes_per_token=bytes_tok, per="token (161 launches: 32 x 5 + lm_head)",
                                   kernel="gemv_kernel chain (decode step)", peak_source=pk["which"]),
                     cpu_baseline=cpu_base)
         print(json.dumps(line), flush=True)
