@@ -47,6 +47,7 @@ def parse():
     ap.add_argument("--batch", type=int, default=None, help="per-GPU batch (default 16; 32 for stage1_step)")
     ap.add_argument("--seq", type=int, default=None, help="decoder positions per sample (default 512; 256 for stage1_step)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--lora-r", type=int, default=16, help="sft_step: LoRA rank (16 = BASELINE config 4; 128 = the shipped stage-2 yaml, alpha 256)")
     ap.add_argument("--sample", action="store_true", help="decode workload: cli_qa.py's settings (do_sample, temperature 0.4, top_p 0.95, "
                                                           "repetition_penalty 1.05) selected on the device instead of greedy")
     return ap.parse_args()
@@ -422,7 +423,7 @@ def main():
     t_text = SEQ_LEN - (NUM_QUERY - 1)
     cfg = default_config(stage=3 if workload == "sft_step" else (1 if workload == "stage1_step" else 0), local_rank=local,
                          is_distribute=world > 1,
-                         lora=dict(enable=workload == "sft_step", lora_r=16, lora_alpha=32, lora_dropout=0.0, lora_bias="none"))
+                         lora=dict(enable=workload == "sft_step", lora_r=args.lora_r, lora_alpha=2 * args.lora_r, lora_dropout=0.0, lora_bias="none"))
     torch.manual_seed(322 + rank)
     model = build_model(cfg).to(device=dev, dtype=torch.bfloat16)
     if train:
@@ -534,7 +535,7 @@ def main():
             cpu_base = dict(error=str(e)[:200])
 
     if rank == 0:
-        wl = (f"stage3_sft_step_b{B}_s{SEQ_LEN} (fwd+bwd, LoRA r=16 + pooler grads, allreduce, AdamW)" if workload == "sft_step"
+        wl = (f"stage3_sft_step_b{B}_s{SEQ_LEN} (fwd+bwd, LoRA r={args.lora_r} + pooler grads, allreduce, AdamW)" if workload == "sft_step"
               else f"stage1_step_b{B}_s{SEQ_LEN} (fwd+bwd, pooler-only grads through the frozen LLaMA, allreduce, Adan)" if workload == "stage1_step"
               else f"prefill_loss_b{B}_s{SEQ_LEN} (UniBind.forward: ViT-L/14 + pooler + splice + LLaMA-7B + CE)")
         line = dict(metric=f"tokens/sec (LLaMA-7B, 224px, seq {SEQ_LEN}), aggregate", value=value, unit="tokens/s", n_gpus=world,

@@ -46,6 +46,14 @@ bench("gate/up swiglu [M,4096]x[22016,4096]", lambda: ops.gemm(x, [wg, wu], out=
 bench("down+res [M,11008]x[4096,11008]", lambda: ops.gemm(xf, wd, out=out_d, residual=res), 2 * M * D * F)
 bench("dX down (MN-major B) N=11008 K=4096", lambda: ops.gemm(x, wd, out=out_f, b_mn_major=True), 2 * M * D * F)
 bench("dX gate/up K-seg N=4096 K=22016", lambda: ops.gemm(dgu, [wg, wu], out=out_d, b_mn_major=True), 2 * M * 2 * F * D)
+dqkv = torch.randn(M, 3 * D, device=dev).bfloat16()
+bench("dX o_proj (MN-major B) N=4096 K=4096", lambda: ops.gemm(x, wo, out=out_d, b_mn_major=True), 2 * M * D * D)
+bench("dX qkv K-seg N=4096 K=12288", lambda: ops.gemm(dqkv, [wq, wk, wv], out=out_d, b_mn_major=True), 2 * M * 3 * D * D)
+wl = w(V, D)
+dlog = torch.randn(M, V, device=dev).bfloat16()
+out_v = torch.empty(M, V, device=dev, dtype=torch.bfloat16)
+bench("lm_head [M,4096]x[32000,4096]", lambda: ops.gemm(x, wl, out=out_v), 2 * M * V * D)
+bench("dX lm_head (MN-major B) N=4096 K=32000", lambda: ops.gemm(dlog, wl, out=out_d, b_mn_major=True), 2 * M * V * D)
 a8 = torch.randn(8192, 8192, device=dev).bfloat16()
 b8 = torch.randn(8192, 8192, device=dev).bfloat16()
 o8 = torch.empty(8192, 8192, device=dev, dtype=torch.bfloat16)
