@@ -353,6 +353,28 @@ int lhrs_adan_step(float* master, float* exp_avg, float* exp_avg_diff, float* ex
                    float weight_decay, int32_t step, int32_t no_prox, const float* gnorm_sq, float max_norm, float grad_scale,
                    void* stream);
 
+/* Gradient exchange + optimizer step over NVLink peer memory — what the reference obtains from DeepSpeed ZeRO-2
+ * (main_pretrain_stage1.py:28-85, 215-220; hook/deepspeed_hook.py:5-9): reduce-scatter of the gradients, optimizer state sharded
+ * over the data-parallel ranks, all-gather of the updated parameters.  grads / params / norm_slots hold, for every rank of the
+ * node, the PEER-MAPPED device pointer of that rank's flat bf16 gradient buffer, flat bf16 parameter buffer and float[world] norm
+ * table (symmetric allocations; entry [rank] is the local buffer).  Rank r owns elements [slice_offset, slice_offset + slice_n).
+ *   lhrs_p2p_reduce_slice  grad_sum[slice_n] (fp32) = sum over ranks of the slice (fixed rank order), and the slice's sum of
+ *                          squares stored into norm_slots[q][rank] of every rank q.          scratch: >= 1024 floats
+ *   lhrs_p2p_adamw_slice   clip by the global norm (sum of this rank's norm table) and grad_scale, AdamW on the slice's fp32
+ *                          master / m / v (local, [slice_n]), bf16 result stored into params[q] of every rank q.
+ * The caller separates the two calls — and brackets the pair — with a cross-rank barrier on the stream. */
+typedef struct LhrsPeerExchange {
+    int32_t world, rank;
+    void* grads[16];
+    void* params[16];
+    float* norm_slots[16];
+    int64_t slice_offset, slice_n;
+} LhrsPeerExchange;
+int lhrs_p2p_reduce_slice(const LhrsPeerExchange* x, float* grad_sum, float* scratch, void* stream);
+int lhrs_p2p_adamw_slice(const LhrsPeerExchange* x, float* master, float* m, float* v, const float* grad_sum, const float* decay_mask,
+                         float lr, float beta1, float beta2, float eps, float weight_decay, int32_t step, float max_norm,
+                         float grad_scale, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Single-sequence decode (HF generate loop reached from TextModal.generate, lhrs/models/text_modal.py:600-612, with the
  * generation-input rule of :36-60).  All buffers are caller-owned device memory (bf16 unless noted):

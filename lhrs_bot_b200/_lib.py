@@ -108,6 +108,13 @@ class LhrsSampling(C.Structure):
     ]
 
 
+class LhrsPeerExchange(C.Structure):
+    _fields_ = [
+        ("world", C.c_int32), ("rank", C.c_int32), ("grads", C.c_void_p * 16), ("params", C.c_void_p * 16),
+        ("norm_slots", C.c_void_p * 16), ("slice_offset", C.c_int64), ("slice_n", C.c_int64),
+    ]
+
+
 class LhrsLlamaWeights(C.Structure):
     _fields_ = [
         ("num_layers", C.c_int32), ("dim", C.c_int32), ("ffn", C.c_int32), ("heads", C.c_int32), ("vocab", C.c_int32),
@@ -181,6 +188,8 @@ SIGNATURES = {
     "lhrs_pooler_bwd": (C.c_int, [C.POINTER(LhrsPoolerWeights), C.POINTER(LhrsPoolerWeights), _P, _I64, _I32, _P, _P, _P, C.c_size_t, _P]),
     "lhrs_grad_sumsq": (C.c_int, [_P, _I64, _P, _P, _P]),
     "lhrs_adamw_step": (C.c_int, [_P, _P, _P, _P, _P, _P, _I64, _F, _F, _F, _F, _F, _I32, _P, _F, _F, _P]),
+    "lhrs_p2p_reduce_slice": (C.c_int, [C.POINTER(LhrsPeerExchange), _P, _P, _P]),
+    "lhrs_p2p_adamw_slice": (C.c_int, [C.POINTER(LhrsPeerExchange), _P, _P, _P, _P, _P, _F, _F, _F, _F, _F, _I32, _F, _F, _P]),
     "lhrs_adan_step": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _I64, _F, _F, _F, _F, _F, _F, _I32, _I32, _P, _F, _F, _P]),
 }
 

@@ -118,6 +118,93 @@ class FlatAdan(_FlatOptimizer):
               "lhrs_adan_step")
 
 
+class PeerShardedAdamW:
+    """ZeRO-style AdamW over NVLink peer memory (csrc/peer_exchange.cu) — the B200-native form of what the reference gets from
+    DeepSpeed ZeRO-2 (main_pretrain_stage1.py:28-85, 215-220): the flat bf16 parameter and gradient buffers are SYMMETRIC
+    allocations (``torch.distributed._symmetric_memory``: every rank maps every peer's buffer), rank r owns slice r of the
+    trainable set — fp32 master weights and Adam moments exist only for that slice — and a step is
+
+        barrier -> lhrs_p2p_reduce_slice (peer loads of the slice from all ranks, fp32 sum, slice norm published to all peers)
+        barrier -> lhrs_p2p_adamw_slice  (global-norm clip, AdamW on the slice, bf16 result stored into every rank's parameters)
+        barrier
+
+    i.e. reduce-scatter + optimizer + all-gather in two kernels, no NCCL call, optimizer state and update work divided by the
+    world size.  Same arithmetic as ``FlatAdamW`` after a summed allreduce (fixed rank order, deterministic)."""
+
+    def __init__(self, params: List[torch.nn.Parameter], world: int, rank: int, group=None, lr=2e-4, betas=(0.9, 0.95), eps=1e-8,
+                 weight_decay=0.0, max_grad_norm=1.0):
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm
+        assert params, "no trainable parameters"
+        dev = params[0].device
+        group = group if group is not None else dist.group.WORLD
+        import warnings
+        with warnings.catch_warnings():      # older releases need the explicit opt-in, newer ones deprecate the call
+            warnings.simplefilter("ignore")
+            try:
+                symm.enable_symm_mem_for_group(group.group_name)
+            except Exception:
+                pass
+        self.params, self.world, self.rank = params, world, rank
+        self.numel = sum(p.numel() for p in params)
+        quantum = 8 * world
+        self.padded = (self.numel + quantum - 1) // quantum * quantum
+        self.slice_n = self.padded // world
+        self.flat_param = symm.empty(self.padded, dtype=torch.bfloat16, device=dev)
+        self.flat_grad = symm.empty(self.padded, dtype=torch.bfloat16, device=dev)
+        self.norm_slots = symm.empty(world, dtype=torch.float32, device=dev)
+        self.flat_param.zero_(); self.flat_grad.zero_(); self.norm_slots.zero_()
+        self.grad_views: Dict[torch.nn.Parameter, torch.Tensor] = {}
+        mask = torch.zeros((self.padded,), device=dev, dtype=torch.float32) if weight_decay > 0 else None
+        off = 0
+        for p in params:
+            runtime.require_bf16_cuda(p, "trainable parameter")
+            n = p.numel()
+            assert off % 8 == 0, "parameter sizes must be multiples of 8 elements"
+            self.flat_param[off: off + n].copy_(p.data.reshape(-1))
+            p.data = self.flat_param[off: off + n].view(p.shape)
+            self.grad_views[p] = self.flat_grad[off: off + n].view(p.shape)
+            if mask is not None:
+                mask[off: off + n] = 0.0 if p.dim() <= 1 else 1.0
+            off += n
+        lo = rank * self.slice_n
+        self.master = self.flat_param[lo: lo + self.slice_n].float()
+        self.m = torch.zeros_like(self.master)
+        self.v = torch.zeros_like(self.master)
+        self.grad_sum = torch.empty_like(self.master)
+        self.decay_mask = None if mask is None else mask[lo: lo + self.slice_n].clone()
+        self._scratch = torch.empty((1024,), device=dev, dtype=torch.float32)
+        self.h_param = symm.rendezvous(self.flat_param, group)
+        self.h_grad = symm.rendezvous(self.flat_grad, group)
+        self.h_norm = symm.rendezvous(self.norm_slots, group)
+        x = _lib.LhrsPeerExchange()
+        x.world, x.rank, x.slice_offset, x.slice_n = world, rank, lo, self.slice_n
+        for r in range(world):
+            x.grads[r], x.params[r], x.norm_slots[r] = self.h_grad.buffer_ptrs[r], self.h_param.buffer_ptrs[r], self.h_norm.buffer_ptrs[r]
+        self.desc = x
+        self.lr, self.betas, self.eps, self.weight_decay, self.max_grad_norm = lr, betas, eps, weight_decay, max_grad_norm
+        self.step_count = 0
+        self.h_param.barrier(channel=0)      # every rank has published its initial parameters and zeroed its tables
+
+    def step(self, lr: Optional[float] = None, grad_scale: Optional[float] = None) -> None:
+        import ctypes as C
+        lib = _lib.load()
+        self.step_count += 1
+        st = runtime.stream()
+        scale = 1.0 / self.world if grad_scale is None else grad_scale
+        self.h_grad.barrier(channel=0)       # all ranks finished writing their gradients
+        check(lib.lhrs_p2p_reduce_slice(C.byref(self.desc), self.grad_sum.data_ptr(), self._scratch.data_ptr(), st), "lhrs_p2p_reduce_slice")
+        self.h_norm.barrier(channel=0)       # every slice norm has landed; every rank has finished READING the gradients
+        check(lib.lhrs_p2p_adamw_slice(C.byref(self.desc), self.master.data_ptr(), self.m.data_ptr(), self.v.data_ptr(),
+                                       self.grad_sum.data_ptr(), None if self.decay_mask is None else self.decay_mask.data_ptr(),
+                                       float(self.lr if lr is None else lr), self.betas[0], self.betas[1], self.eps, self.weight_decay,
+                                       self.step_count, float(self.max_grad_norm or 0.0), float(scale), st), "lhrs_p2p_adamw_slice")
+        self.h_param.barrier(channel=0)      # every rank's parameter buffer holds all updated slices
+
+    def grad_norm(self) -> float:
+        return float(self.norm_slots.sum().sqrt().item())
+
+
 def build_flat_optimizer(name: str, params, lr, weight_decay, max_grad_norm):
     """``config.optimizer`` -> fused optimizer (build_optimizer.py:76-86 passes the yaml string to timm)."""
     name = name.lower()
@@ -175,7 +262,7 @@ class SftStepper:
 
     def __init__(self, model, world_size: int = 1, lr: float = 2e-4, weight_decay: float = 0.0, max_grad_norm: float = 1.0,
                  warmup_steps: int = 0, total_steps: int = 0, prepare: bool = True, optimizer: str = "adamw",
-                 min_lr: float = 0.0, warmup_ratio: float = 0.1):
+                 min_lr: float = 0.0, warmup_ratio: float = 0.1, exchange: str = "auto"):
         self.model = model
         self.world = world_size
         if prepare:
@@ -193,7 +280,26 @@ class SftStepper:
         ordered = [a for a, _ in pairs if a.requires_grad] + [b for _, b in pairs if b.requires_grad]
         seen = {id(p) for p in ordered}
         params = [p for p in trainable_parameters(model) if id(p) not in seen] + ordered
-        self.opt = build_flat_optimizer(optimizer, params, lr, weight_decay, max_grad_norm)
+        # Gradient exchange: "p2p" = reduce-scatter + AdamW + all-gather over NVLink peer memory (PeerShardedAdamW), "nccl" = one
+        # summed NCCL allreduce of the flat buffer + the full-buffer optimizer kernel, "auto" = p2p when it can be set up
+        # (AdamW, world > 1, symmetric memory available on this node), else nccl.  LHRS_EXCHANGE overrides.
+        import os
+        exchange = os.environ.get("LHRS_EXCHANGE", exchange)
+        self.exchange = "nccl"
+        self.opt = None
+        if exchange in ("auto", "p2p") and world_size > 1 and optimizer.lower() == "adamw" and params[0].is_cuda:
+            try:
+                import torch.distributed as dist
+                self.opt = PeerShardedAdamW(params, world_size, dist.get_rank(), lr=lr, weight_decay=weight_decay, max_grad_norm=max_grad_norm)
+                self.exchange = "p2p"
+            except Exception as e:   # no symmetric memory on this node / build: the NCCL schedule is always available
+                if exchange == "p2p":
+                    raise
+                import warnings
+                warnings.warn(f"peer-memory gradient exchange unavailable ({type(e).__name__}: {e}); using the NCCL allreduce")
+                self.opt = None
+        if self.opt is None:
+            self.opt = build_flat_optimizer(optimizer, params, lr, weight_decay, max_grad_norm)
         # the backward kernels write into the flat gradient buffer directly
         model.rgb_pooler._grad_sink = {p: g for p, g in self.opt.grad_views.items()}
         model.text._grad_sink = model.rgb_pooler._grad_sink
@@ -205,9 +311,12 @@ class SftStepper:
         out = self.model(batch)
         loss = out["total_loss"]
         loss.backward()
-        scale = allreduce_flat_gradients(self.opt.flat_grad, self.world)
         lr = (reference_lr(self.it, self.base_lr, self.total, self.min_lr, self.warmup, self.warmup_ratio)
               if self.total > 0 else self.base_lr)
-        self.opt.step(lr=lr, grad_scale=scale)
+        if self.exchange == "p2p":
+            self.opt.step(lr=lr)                                   # exchange and update are one fused schedule
+        else:
+            scale = allreduce_flat_gradients(self.opt.flat_grad, self.world)
+            self.opt.step(lr=lr, grad_scale=scale)
         self.it += 1
         return loss.detach()

@@ -38,7 +38,7 @@ def test_library_exports_every_declared_symbol():
 def test_struct_layouts_match_header():
     from lhrs_bot_b200 import _lib
     structs = ["LhrsGemm", "LhrsAttention", "LhrsAttentionBwd", "LhrsVitWeights", "LhrsPoolerWeights", "LhrsKvCache",
-               "LhrsLlamaWeights", "LhrsDecodeBuffers", "LhrsSampling"]
+               "LhrsLlamaWeights", "LhrsDecodeBuffers", "LhrsSampling", "LhrsPeerExchange"]
     prog = '#include <stdio.h>\n#include "lhrs_b200.h"\nint main(){' + "".join(
         f'printf("{s} %zu\\n", sizeof({s}));' for s in structs) + "return 0;}"
     with tempfile.TemporaryDirectory() as d:
