@@ -369,6 +369,8 @@ typedef struct LhrsPeerExchange {
     void* params[16];
     float* norm_slots[16];
     int64_t slice_offset, slice_n;
+    void* mc_grads;   /* optional NVLS multicast mapping of the gradient buffers: the slice is reduced in the NVSwitch (multimem.ld_reduce) */
+    void* mc_params;  /* optional NVLS multicast mapping of the parameter buffers: the updated slice is broadcast by one multimem.st     */
 } LhrsPeerExchange;
 int lhrs_p2p_reduce_slice(const LhrsPeerExchange* x, float* grad_sum, float* scratch, void* stream);
 int lhrs_p2p_adamw_slice(const LhrsPeerExchange* x, float* master, float* m, float* v, const float* grad_sum, const float* decay_mask,

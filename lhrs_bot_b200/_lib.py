@@ -112,6 +112,7 @@ class LhrsPeerExchange(C.Structure):
     _fields_ = [
         ("world", C.c_int32), ("rank", C.c_int32), ("grads", C.c_void_p * 16), ("params", C.c_void_p * 16),
         ("norm_slots", C.c_void_p * 16), ("slice_offset", C.c_int64), ("slice_n", C.c_int64),
+        ("mc_grads", C.c_void_p), ("mc_params", C.c_void_p),
     ]
 
 

@@ -6,7 +6,9 @@
 //                       rank order -> deterministic), keeps the fp32 sum, and publishes the slice's sum of squares to every peer
 //   p2p_adamw_kernel    global-norm clip from the published partials, AdamW on the slice's fp32 master / moments (state is
 //                       1/world per rank), and the bf16 result stored straight into EVERY rank's flat parameter buffer
-// with a cross-rank barrier (caller's, e.g. torch symmetric-memory signal pads) before, between and after.  Frozen ViT / LLaMA
+// with a cross-rank barrier (caller's, e.g. torch symmetric-memory signal pads) before, between and after.  When the buffers also
+// have NVLS multicast mappings the slice is reduced INSIDE the NVSwitch (multimem.ld_reduce: one load instead of one per peer)
+// and the updated slice is broadcast with one multimem.st.  Frozen ViT / LLaMA
 // weights never move.  Per rank and step at world 8 with 120 M trainable elements: 210 MB in + 210 MB out over NVLink and an
 // optimizer pass over 15 M elements instead of 120 M.
 #include "host_common.h"
@@ -20,9 +22,23 @@ struct PeerPtrs {
     const __nv_bfloat16* grads[16];
     __nv_bfloat16* params[16];
     float* norm_slots[16];
+    const __nv_bfloat16* mc_grads;   // NVLS multicast mappings of the same buffers (or null): one load reduces in the switch,
+    __nv_bfloat16* mc_params;        // one store lands in every rank's copy
     int world, rank;
     long long offset, n;      // this rank's slice, in elements (multiples of 8)
 };
+
+// NVSwitch in-network reduction: ONE load from the multicast address returns the sum over all ranks' copies (fp32 accumulation
+// inside the switch, bf16 result), so a rank receives its slice once instead of once per peer.
+__device__ __forceinline__ uint4 multimem_ld_reduce_bf16x8(const void* mc) {
+    uint4 r;
+    asm volatile("multimem.ld_reduce.relaxed.sys.global.add.acc::f32.v4.bf16x2 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(mc) : "memory");
+    return r;
+}
+__device__ __forceinline__ void multimem_st_bf16x8(void* mc, const uint4& v) {
+    asm volatile("multimem.st.relaxed.sys.global.v4.bf16x2 [%0], {%1,%2,%3,%4};" ::"l"(mc), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
 
 __device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
     f[0] = bf16_lo(u.x); f[1] = bf16_hi(u.x); f[2] = bf16_lo(u.y); f[3] = bf16_hi(u.y);
@@ -36,17 +52,21 @@ p2p_reduce_kernel(const PeerPtrs p, float* __restrict__ gsum, float* __restrict_
     const long long nvec = p.n / 8;
     for (long long i = blockIdx.x * static_cast<long long>(PX_THREADS) + threadIdx.x; i < nvec; i += static_cast<long long>(gridDim.x) * PX_THREADS) {
         float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-        uint4 v[16];
+        if (p.mc_grads != nullptr) {
+            unpack8(multimem_ld_reduce_bf16x8(p.mc_grads + p.offset + i * 8), acc);
+        } else {
+            uint4 v[16];
 #pragma unroll
-        for (int r = 0; r < 16; ++r)                     // all peer loads in flight before the first add
-            if (r < p.world) v[r] = *reinterpret_cast<const uint4*>(p.grads[r] + p.offset + i * 8);
+            for (int r = 0; r < 16; ++r)                     // all peer loads in flight before the first add
+                if (r < p.world) v[r] = *reinterpret_cast<const uint4*>(p.grads[r] + p.offset + i * 8);
 #pragma unroll
-        for (int r = 0; r < 16; ++r) {
-            if (r < p.world) {
-                float f[8];
-                unpack8(v[r], f);
+            for (int r = 0; r < 16; ++r) {
+                if (r < p.world) {
+                    float f[8];
+                    unpack8(v[r], f);
 #pragma unroll
-                for (int e = 0; e < 8; ++e) acc[e] += f[e];
+                    for (int e = 0; e < 8; ++e) acc[e] += f[e];
+                }
             }
         }
         *reinterpret_cast<float4*>(gsum + i * 8) = make_float4(acc[0], acc[1], acc[2], acc[3]);
@@ -113,7 +133,8 @@ p2p_adamw_kernel(const PeerPtrs p, float* __restrict__ master, float* __restrict
         }
         uint4 o;
         o.x = pack_bf16(w8[0], w8[1]); o.y = pack_bf16(w8[2], w8[3]); o.z = pack_bf16(w8[4], w8[5]); o.w = pack_bf16(w8[6], w8[7]);
-        for (int r = 0; r < p.world; ++r) *reinterpret_cast<uint4*>(p.params[r] + p.offset + i * 8) = o;
+        if (p.mc_params != nullptr) multimem_st_bf16x8(p.mc_params + p.offset + i * 8, o);
+        else for (int r = 0; r < p.world; ++r) *reinterpret_cast<uint4*>(p.params[r] + p.offset + i * 8) = o;
     }
     __threadfence_system();
 }
@@ -127,6 +148,8 @@ static int fill(PeerPtrs& p, const LhrsPeerExchange* x, const char* who) {
         LHRS_CHECK_ARG((reinterpret_cast<uintptr_t>(x->grads[r]) & 15) == 0 && (reinterpret_cast<uintptr_t>(x->params[r]) & 15) == 0, "%s: peer buffers must be 16-byte aligned", who);
         p.grads[r] = (const __nv_bfloat16*)x->grads[r]; p.params[r] = (__nv_bfloat16*)x->params[r]; p.norm_slots[r] = x->norm_slots[r];
     }
+    p.mc_grads = (const __nv_bfloat16*)x->mc_grads; p.mc_params = (__nv_bfloat16*)x->mc_params;
+    LHRS_CHECK_ARG((reinterpret_cast<uintptr_t>(x->mc_grads) & 15) == 0 && (reinterpret_cast<uintptr_t>(x->mc_params) & 15) == 0, "%s: multicast mappings must be 16-byte aligned", who);
     p.world = x->world; p.rank = x->rank; p.offset = x->slice_offset; p.n = x->slice_n;
     return LHRS_OK;
 }

@@ -181,6 +181,11 @@ class PeerShardedAdamW:
         x.world, x.rank, x.slice_offset, x.slice_n = world, rank, lo, self.slice_n
         for r in range(world):
             x.grads[r], x.params[r], x.norm_slots[r] = self.h_grad.buffer_ptrs[r], self.h_param.buffer_ptrs[r], self.h_norm.buffer_ptrs[r]
+        # NVLS: multicast mappings let the NVSwitch do the reduction and the broadcast (LHRS_NVLS=0 keeps plain peer loads / stores)
+        import os
+        mc_g, mc_p = int(getattr(self.h_grad, "multicast_ptr", 0) or 0), int(getattr(self.h_param, "multicast_ptr", 0) or 0)
+        self.nvls = bool(mc_g and mc_p) and os.environ.get("LHRS_NVLS", "1") != "0"
+        x.mc_grads, x.mc_params = (mc_g, mc_p) if self.nvls else (None, None)
         self.desc = x
         self.lr, self.betas, self.eps, self.weight_decay, self.max_grad_norm = lr, betas, eps, weight_decay, max_grad_norm
         self.step_count = 0

@@ -9,9 +9,9 @@ import torch
 pytestmark = pytest.mark.gpu
 
 
-def _worker(rank, world, port, max_norm, q):
+def _worker(rank, world, port, max_norm, nvls, q):
     import torch.distributed as dist
-    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), LHRS_NVLS=str(nvls))
     torch.cuda.set_device(rank)
     dev = torch.device("cuda", rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
@@ -52,26 +52,28 @@ def _worker(rank, world, port, max_norm, q):
         dist.all_gather(gathered, opt.flat_param)
         same = all(torch.equal(gathered[0], t) for t in gathered)
         master_ok = torch.equal(opt.master.bfloat16(), opt.flat_param[rank * opt.slice_n:(rank + 1) * opt.slice_n])
-        q.put((rank, ok_ref, close_nccl, same, master_ok, opt.grad_norm()))
+        q.put((rank, ok_ref, close_nccl, same, master_ok, opt.grad_norm(), opt.nvls))
     finally:
         dist.destroy_process_group()
 
 
+@pytest.mark.parametrize("nvls", [0, 1])
 @pytest.mark.parametrize("max_norm", [0.0, 5.0])
-def test_peer_sharded_adamw_two_ranks(max_norm):
+def test_peer_sharded_adamw_two_ranks(max_norm, nvls):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs two GPUs on one node (gpurun --gpus 2)")
     import torch.multiprocessing as mp
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    port = 29600 + int(max_norm)
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, max_norm, q)) for r in range(2)]
+    port = 29600 + int(max_norm) + 10 * nvls
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, max_norm, nvls, q)) for r in range(2)]
     for p in procs:
         p.start()
     res = [q.get(timeout=240) for _ in range(2)]
     for p in procs:
         p.join(timeout=60)
-    for rank, ok_ref, close_nccl, same, master_ok, gn in res:
+    print("NVLS multicast in use:", [r[6] for r in res])
+    for rank, ok_ref, close_nccl, same, master_ok, gn, used_nvls in res:
         assert ok_ref, f"rank {rank}: parameters differ from AdamW on the clipped mean gradient"
         assert close_nccl, f"rank {rank}: peer-memory schedule differs from the NCCL schedule"
         assert same, f"rank {rank}: ranks hold different parameters"
