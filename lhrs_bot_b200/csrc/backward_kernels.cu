@@ -48,6 +48,15 @@ rmsnorm_bwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __r
     const float rs = rstd[row];
     float u[MAXC][8], xh[MAXC][8];
     float dot = 0.f;
+    // the residual-stream gradient does not depend on the row reduction: request it together with x and dy so that the kernel has
+    // one memory round trip before the reduction instead of one before and one after
+    const uint4* rr = dres ? reinterpret_cast<const uint4*>(dres + row * dim) : nullptr;
+    uint4 rraw[MAXC];
+#pragma unroll
+    for (int i = 0; i < MAXC; ++i) {
+        const int c = threadIdx.x + i * BT;
+        rraw[i] = (rr != nullptr && c < nch) ? rr[c] : make_uint4(0, 0, 0, 0);
+    }
 #pragma unroll
     for (int i = 0; i < MAXC; ++i) {
         const int c = threadIdx.x + i * BT;
@@ -59,14 +68,13 @@ rmsnorm_bwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __r
         }
     }
     dot = bsum(dot, red) / dim;
-    const uint4* rr = dres ? reinterpret_cast<const uint4*>(dres + row * dim) : nullptr;
     uint4* o = reinterpret_cast<uint4*>(dx + row * dim);
 #pragma unroll
     for (int i = 0; i < MAXC; ++i) {
         const int c = threadIdx.x + i * BT;
         if (c < nch) {
-            float r[8] = {0, 0, 0, 0, 0, 0, 0, 0}, out[8];
-            if (rr) up8(rr[c], r);
+            float r[8], out[8];
+            up8(rraw[i], r);
 #pragma unroll
             for (int j = 0; j < 8; ++j) out[j] = r[j] + rs * (u[i][j] - xh[i][j] * dot);
             o[c] = pk8(out);

@@ -312,6 +312,21 @@ class SftStepper:
         self.min_lr, self.warmup_ratio = min_lr, warmup_ratio
         self.it = 0
 
+    @classmethod
+    def from_config(cls, model, config, world_size: int = 1, max_iters: int = 0, **kw) -> "SftStepper":
+        """Build the step from the training keys of the reference's yaml (Config/multi_modal_stage{1,2,3}.yaml): ``optimizer``
+        (adanp | adanw | adamw), ``lr``, ``wd``, ``max_grad_norm`` and ``schedule.{name, min_lr, warmup_epochs, warmup_factor,
+        warmup_method}`` — consumed in the reference by build_optimizer.py:76-86, main_pretrain_stage1.py:28-85 and
+        IterBasedTrainer.py:65-80 (``warmup_epochs`` counts ITERATIONS there: warmup_by_epoch=False).  ``max_iters`` = length of the
+        run (the reference takes it from the data loader); 0 keeps the learning rate constant."""
+        sched = config.get("schedule", {}) or {}
+        cosine = str(sched.get("name", "cosine")).lower() == "cosine"
+        return cls(model, world_size=world_size, lr=float(config.get("lr", 2e-4)), weight_decay=float(config.get("wd", 0.0)),
+                   max_grad_norm=float(config.get("max_grad_norm", 1.0) or 0.0), optimizer=str(config.get("optimizer", "adamw")),
+                   warmup_steps=int(sched.get("warmup_epochs", 0)) if sched.get("warmup_method", "linear") else 0,
+                   total_steps=int(max_iters) if cosine else 0, min_lr=float(sched.get("min_lr", 0.0)),
+                   warmup_ratio=float(sched.get("warmup_factor", 0.1)), **kw)
+
     def step(self, batch) -> torch.Tensor:
         out = self.model(batch)
         loss = out["total_loss"]

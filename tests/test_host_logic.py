@@ -136,6 +136,23 @@ def test_reference_lr_schedule():
     assert reference_lr(10, base, T, mn, 0, 0.1, warmup=None) == pytest.approx(cosv(10))
 
 
+def test_stepper_from_reference_yaml_keys(monkeypatch):
+    """SftStepper.from_config maps the yaml's training keys (shipped stage-1 / stage-2 values) onto the fused step."""
+    from lhrs_bot_b200 import training
+    from lhrs_bot_b200.config import ConfigDict
+    seen = {}
+    monkeypatch.setattr(training.SftStepper, "__init__", lambda self, model, **kw: seen.update(kw))
+    stage1 = ConfigDict(dict(optimizer="adanp", lr=2e-4, wd=0.0, max_grad_norm=0.3,
+                             schedule=dict(name="cosine", min_lr=2e-5, warmup_epochs=300, warmup_method="linear", warmup_factor=0.1)))
+    training.SftStepper.from_config(object(), stage1, world_size=8, max_iters=5000)
+    assert seen == dict(world_size=8, lr=2e-4, weight_decay=0.0, max_grad_norm=0.3, optimizer="adanp", warmup_steps=300,
+                        total_steps=5000, min_lr=2e-5, warmup_ratio=0.1)
+    stage2 = ConfigDict(dict(optimizer="adamw", lr=2e-4, wd=0.0, max_grad_norm=1.0,
+                             schedule=dict(name="const", min_lr=8e-5, warmup_epochs=100, warmup_method="linear", warmup_factor=0.01)))
+    training.SftStepper.from_config(object(), stage2, exchange="nccl")
+    assert seen["total_steps"] == 0 and seen["optimizer"] == "adamw" and seen["exchange"] == "nccl" and seen["warmup_ratio"] == 0.01
+
+
 def test_oracle_adan_first_step_and_prox():
     """Sanity of the Adan restatement (parity unpinned: timm is absent): first step has zero gradient difference, so
     update = g / (|g| + eps) * ... = sign(g) up to eps; prox and no-prox forms agree when weight_decay = 0."""
