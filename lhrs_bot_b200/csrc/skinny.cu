@@ -13,6 +13,8 @@
 //        (backward dA = dT^T · x  -> [n, in];   dB_s = dy_s^T · T_s -> [out, r] per segment)
 #include <stdlib.h>
 
+#include <cooperative_groups.h>
+
 #include "host_common.h"
 #include "ptx.cuh"
 
@@ -169,7 +171,15 @@ struct ReduceArgs {
     const bf16* Q; long long ldq;
     int seg_c;             // > 0: block diagonal — column block c0 belongs to segment c0 / seg_c and uses Q columns [seg*NT*8, +NT*8)
     int rows_per_split;    // multiple of RR_BR
-    float* partial;        // [nsplit][C][NT*8]
+    float* partial;        // [nsplit][C][NT*8] (only without the cluster reduction)
+    // cluster reduction: the row splits of one column block form a thread-block cluster (1 x nsplit); their partial tiles meet in
+    // distributed shared memory and every rank sums, scales, casts and stores an interleaved share of the block's result — no scratch,
+    // no second launch (summation order = rank order: deterministic)
+    int cluster;
+    int transpose;         // 1: dst[0][j, c] (ld = ldd);  0: dst[seg][c - seg*seg_c, j] (ld = ldd)
+    bf16* dst[3];
+    long long ldd;
+    float alpha;
 };
 
 template <int NT, int RR_BC, bool L2H>
@@ -248,6 +258,48 @@ lora_rowreduce_kernel(const ReduceArgs a) {
     }
     sk_wait<0>();
     const int g = lane >> 2, t4 = lane & 3;
+    if (a.cluster) {
+        namespace cg = cooperative_groups;
+        cg::cluster_group cluster = cg::this_cluster();
+        constexpr int NQ = NT * 8;
+        __syncthreads();                                   // every warp is done with the pipeline buffers
+        float* red = reinterpret_cast<float*>(smem);       // [RR_BC][NQ] fp32 (<= 48 KB, inside the first stages)
+#pragma unroll
+        for (int t = 0; t < MT; ++t) {
+            const int cl = warp * (MT * 16) + t * 16 + g;
+#pragma unroll
+            for (int i = 0; i < NT; ++i) {
+                const int j = i * 8 + t4 * 2;
+                *reinterpret_cast<float2*>(red + cl * NQ + j) = make_float2(acc[t][i][0], acc[t][i][1]);
+                *reinterpret_cast<float2*>(red + (cl + 8) * NQ + j) = make_float2(acc[t][i][2], acc[t][i][3]);
+            }
+        }
+        cluster.sync();
+        {   // every rank finishes an interleaved share of the block's [RR_BC x NQ] result from all ranks' tiles
+            const unsigned nranks = cluster.num_blocks(), me = cluster.block_rank();
+            const int seg = a.seg_c > 0 ? c0 / a.seg_c : 0;
+            bf16* out = a.dst[a.transpose ? 0 : seg];
+            const float* tiles[8];
+#pragma unroll
+            for (unsigned r = 0; r < 8; ++r) tiles[r] = r < nranks ? cluster.map_shared_rank(red, r) : red;
+            for (int idx = me * SK_THREADS + tid; idx < RR_BC * NQ; idx += nranks * SK_THREADS) {
+                // transpose: consecutive threads walk the columns of one output row; else consecutive elements of [c][j]
+                const int cl = a.transpose ? idx % RR_BC : idx / NQ;
+                const int j = a.transpose ? idx / RR_BC : idx % NQ;
+                float sum = 0.f;
+#pragma unroll
+                for (unsigned r = 0; r < 8; ++r)
+                    if (r < nranks) sum += tiles[r][cl * NQ + j];
+                const int c = c0 + cl;
+                if (c < a.C && out != nullptr) {
+                    if (a.transpose) out[static_cast<long long>(j) * a.ldd + c] = __float2bfloat16_rn(sum * a.alpha);
+                    else out[static_cast<long long>(c - seg * a.seg_c) * a.ldd + j] = __float2bfloat16_rn(sum * a.alpha);
+                }
+            }
+        }
+        cluster.sync();                                    // shared memory stays alive until every rank has read its share
+        return;
+    }
     float* dst = a.partial + static_cast<long long>(split) * a.C * (NT * 8);
 #pragma unroll
     for (int t = 0; t < MT; ++t) {
@@ -320,7 +372,17 @@ static int launch_rowreduce_cfg(const ReduceArgs& a, int nsplit, cudaStream_t st
     if (!attr) { LHRS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM)); attr = true; }
     const bool prof = prof_on();
     if (prof) prof_begin(PROF_SKINNY, 2.0 * a.M * (double)a.C * (NT * 8), 2.0 * (double)a.M * a.C, st);
-    kern<<<dim3((a.C + BC - 1) / BC, nsplit), SK_THREADS, SMEM, st>>>(a);
+    if (a.cluster) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((a.C + BC - 1) / BC, nsplit); cfg.blockDim = dim3(SK_THREADS); cfg.dynamicSmemBytes = SMEM; cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 1; attr[0].val.clusterDim.y = nsplit; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        LHRS_CUDA(cudaLaunchKernelEx(&cfg, kern, a));
+    } else {
+        kern<<<dim3((a.C + BC - 1) / BC, nsplit), SK_THREADS, SMEM, st>>>(a);
+    }
     if (prof) prof_end(st);
     LHRS_LAUNCH_CHECK("lora_rowreduce_kernel");
     return LHRS_OK;
@@ -390,9 +452,18 @@ extern "C" int lhrs_lora_rowreduce(const void* p, int64_t ldp, int64_t M, int32_
     const long long max_by_rows = (M + RR_BR - 1) / RR_BR;
     if (nsplit > max_by_rows) nsplit = (int)max_by_rows;
     if (nsplit < 1) nsplit = 1;
-    LHRS_CHECK_ARG(scratch_bytes >= (size_t)nsplit * C * n * sizeof(float), "lhrs_lora_rowreduce: scratch too small");
+    // Measured (tools/lora_bench.py, M = 8192): the cluster reduction wins 2 us on the [out, 16] block-diagonal form (dB) and loses
+    // 2-10 us on the transposed [n, in] form (dA: 8-block clusters of 90 KB CTAs schedule worse than independent CTAs), so the
+    // default takes it for the former only.  LHRS_SKINNY_CLUSTER = 0 / 1 forces it off / on for both.
+    static int cluster_env = -2;
+    if (cluster_env == -2) cluster_env = env_int("LHRS_SKINNY_CLUSTER", -1);
+    const int use_cluster = cluster_env >= 0 ? cluster_env : (transpose ? 0 : 1);
+    LHRS_CHECK_ARG(use_cluster || scratch_bytes >= (size_t)nsplit * C * n * sizeof(float), "lhrs_lora_rowreduce: scratch too small");
     ReduceArgs a;
     memset(&a, 0, sizeof(a));
+    const int nseg_dst = seg_c > 0 ? C / seg_c : 1;
+    a.cluster = use_cluster; a.transpose = transpose; a.ldd = ldd; a.alpha = alpha;
+    for (int sidx = 0; sidx < nseg_dst && sidx < 3; ++sidx) a.dst[sidx] = (bf16*)dst[sidx];
     a.P = (const bf16*)p; a.ldp = ldp; a.M = (int)M; a.C = C; a.Q = (const bf16*)q; a.ldq = ldq; a.seg_c = seg_c; a.partial = scratch;
     long long rps = (M + nsplit - 1) / nsplit;
     rps = ((rps + RR_BR - 1) / RR_BR) * RR_BR;
@@ -403,6 +474,7 @@ extern "C" int lhrs_lora_rowreduce(const void* p, int64_t ldp, int64_t M, int32_
     else if (n == 32) rc = launch_rowreduce<4>(a, nsplit, bc, st);
     else rc = launch_rowreduce<6>(a, nsplit, bc, st);
     if (rc) return rc;
+    if (use_cluster) return LHRS_OK;
     const long long total = (long long)C * n;
     const int nseg = seg_c > 0 ? C / seg_c : 1;
     lora_reduce_store_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(scratch, nsplit, C, n, transpose, seg_c, (bf16*)dst[0],
