@@ -93,10 +93,13 @@ class InputStager:
         self.batches, self.device, self.pre, self.depth = batches, torch.device(device), preprocessor, max(1, depth)
         self.stream = torch.cuda.Stream(device=self.device)
         self._pinned: List[Dict[str, torch.Tensor]] = [dict() for _ in range(self.depth + 1)]
+        self._copied: List[Optional[torch.cuda.Event]] = [None] * (self.depth + 1)   # per slot: its last H2D copies have executed
 
     def _stage(self, slot: int, batch: Dict[str, torch.Tensor]):
         pin = self._pinned[slot]
         out = {}
+        if self._copied[slot] is not None:
+            self._copied[slot].synchronize()       # the host may run ahead of the GPU: never overwrite pinned bytes still to be copied
         with torch.cuda.stream(self.stream):
             for k, v in batch.items():
                 if not isinstance(v, torch.Tensor):
@@ -111,6 +114,9 @@ class InputStager:
                     pin[k] = buf
                 buf.copy_(v)                                   # pageable -> pinned (host memcpy; DataLoader(pin_memory=True) skips it)
                 out[k] = buf.to(self.device, non_blocking=True)
+            copied = torch.cuda.Event()
+            copied.record(self.stream)
+            self._copied[slot] = copied
             if self.pre is not None and "rgb" in out and out["rgb"].dtype == torch.uint8:
                 out["rgb"] = self.pre.preprocess_device(out["rgb"])
             ev = torch.cuda.Event()
