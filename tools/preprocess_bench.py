@@ -40,13 +40,15 @@ def main():
         cpu = None
         try:
             import PIL.Image as Image
-            from oracle import preprocess as P    # only for the mean / std constants and output-size rule
+            from lhrs_bot_b200.preprocess import OPENAI_CLIP_MEAN, OPENAI_CLIP_STD
             t0 = time.perf_counter()
             for b in range(min(B, 8)):
-                nh, nw = P.resize_output_size(H, W)
+                short, long_ = (W, H) if W <= H else (H, W)
+                nl = int(224 * long_ / short)
+                nh, nw = (nl, 224) if W <= H else (224, nl)
                 r = np.asarray(Image.fromarray(host[b].numpy()).resize((nw, nh), resample=Image.BICUBIC))
                 c = r[(nh - 224) // 2:(nh - 224) // 2 + 224, (nw - 224) // 2:(nw - 224) // 2 + 224]
-                x = ((c * (1 / 255)).astype(np.float32) - np.array(P.CLIP_MEAN, np.float32)) / np.array(P.CLIP_STD, np.float32)
+                x = ((c * (1 / 255)).astype(np.float32) - np.array(OPENAI_CLIP_MEAN, np.float32)) / np.array(OPENAI_CLIP_STD, np.float32)
                 x.transpose(2, 0, 1).copy()
             cpu = (time.perf_counter() - t0) / min(B, 8) * 1e3
         except ImportError:
