@@ -542,9 +542,9 @@ def main():
                     steps=args.steps, warmup=max(args.warmup, 3), ms_per_step=ms / args.steps, higher_is_better=True,
                     scaling="weak", vs_baseline=None, dtype="bf16", data="synthetic",
                     config=dict(workload=wl, per_gpu_batch=B, seq_len=SEQ_LEN, image="224x224", parallelism=f"dp{world}",
-                                gradient_exchange=((("NVLS in-switch reduce-scatter (multimem.ld_reduce) + sharded AdamW + multicast all-gather (no NCCL call)"
+                                gradient_exchange=(((f"NVLS in-switch reduce-scatter (multimem.ld_reduce) + sharded {getattr(stepper.opt, 'kind', 'adamw')} + multicast all-gather (no NCCL call)"
                                                      if getattr(stepper.opt, "nvls", False) else
-                                                     "peer-memory reduce-scatter + sharded AdamW + all-gather (NVLink P2P, no NCCL call)")
+                                                     f"peer-memory reduce-scatter + sharded {getattr(stepper.opt, 'kind', 'adamw')} + all-gather (NVLink P2P, no NCCL call)")
                                                     if getattr(stepper, "exchange", "") == "p2p" else "NCCL allreduce of the flat bf16 gradient buffer")
                                                    if train and world > 1 else "none (single GPU)"),
                                 inputs_vs_l2="13.5 GB of weights + 64 MB activations streamed per step >> 126 MB L2 (no flush needed)"),

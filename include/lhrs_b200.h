@@ -376,6 +376,10 @@ int lhrs_p2p_reduce_slice(const LhrsPeerExchange* x, float* grad_sum, float* scr
 int lhrs_p2p_adamw_slice(const LhrsPeerExchange* x, float* master, float* m, float* v, const float* grad_sum, const float* decay_mask,
                          float lr, float beta1, float beta2, float eps, float weight_decay, int32_t step, float max_norm,
                          float grad_scale, void* stream);
+/* same with the stage-1 optimizer (lhrs_adan_step's update) on the slice */
+int lhrs_p2p_adan_slice(const LhrsPeerExchange* x, float* master, float* exp_avg, float* exp_avg_diff, float* exp_avg_sq, float* pre_grad,
+                        const float* grad_sum, const float* decay_mask, float lr, float beta1, float beta2, float beta3, float eps,
+                        float weight_decay, int32_t step, int32_t no_prox, float max_norm, float grad_scale, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Single-sequence decode (HF generate loop reached from TextModal.generate, lhrs/models/text_modal.py:600-612, with the

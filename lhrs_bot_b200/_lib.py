@@ -191,6 +191,7 @@ SIGNATURES = {
     "lhrs_adamw_step": (C.c_int, [_P, _P, _P, _P, _P, _P, _I64, _F, _F, _F, _F, _F, _I32, _P, _F, _F, _P]),
     "lhrs_p2p_reduce_slice": (C.c_int, [C.POINTER(LhrsPeerExchange), _P, _P, _P]),
     "lhrs_p2p_adamw_slice": (C.c_int, [C.POINTER(LhrsPeerExchange), _P, _P, _P, _P, _P, _F, _F, _F, _F, _F, _I32, _F, _F, _P]),
+    "lhrs_p2p_adan_slice": (C.c_int, [C.POINTER(LhrsPeerExchange), _P, _P, _P, _P, _P, _P, _P, _F, _F, _F, _F, _F, _F, _I32, _I32, _F, _F, _P]),
     "lhrs_adan_step": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _I64, _F, _F, _F, _F, _F, _F, _I32, _I32, _P, _F, _F, _P]),
 }
 

@@ -139,6 +139,49 @@ p2p_adamw_kernel(const PeerPtrs p, float* __restrict__ master, float* __restrict
     __threadfence_system();
 }
 
+// Adan (stage 1, `adanp` / `adanw`; same update as adan_kernel in optimizers.cu) on the rank's slice, result broadcast to every rank
+__global__ void __launch_bounds__(PX_THREADS)
+p2p_adan_kernel(const PeerPtrs p, float* __restrict__ master, float* __restrict__ m, float* __restrict__ d, float* __restrict__ nsq,
+                float* __restrict__ g_prev, const float* __restrict__ gsum, const float* __restrict__ decay_mask, float lr, float b1,
+                float b2, float b3, float eps, float weight_decay, float bc1, float bc2, float sqrt_bc3, int first, int no_prox,
+                float max_norm, float grad_scale) {
+    float clip = grad_scale;
+    if (max_norm > 0.f) {
+        float sq = 0.f;
+        for (int r = 0; r < p.world; ++r) sq += p.norm_slots[p.rank][r];
+        const float norm = sqrtf(sq) * grad_scale;
+        if (norm > max_norm) clip *= max_norm / (norm + 1e-6f);
+    }
+    const long long nvec = p.n / 8;
+    for (long long i = blockIdx.x * static_cast<long long>(PX_THREADS) + threadIdx.x; i < nvec; i += static_cast<long long>(gridDim.x) * PX_THREADS) {
+        float w8[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const long long j = i * 8 + e;
+            const float gi = gsum[j] * clip;
+            const float diff = first ? 0.f : gi - g_prev[j];
+            const float mi = m[j] + (1.f - b1) * (gi - m[j]);
+            const float di = d[j] + (1.f - b2) * (diff - d[j]);
+            const float u = gi + b2 * diff;
+            const float ni = nsq[j] * b3 + (1.f - b3) * u * u;
+            m[j] = mi; d[j] = di; nsq[j] = ni; g_prev[j] = gi;
+            const float denom = sqrtf(ni) / sqrt_bc3 + eps;
+            const float upd = (mi / bc1 + b2 * di / bc2) / denom;
+            const float wd = decay_mask ? decay_mask[j] * weight_decay : weight_decay;
+            float w = master[j];
+            if (no_prox) w = w * (1.f - lr * wd) - lr * upd;
+            else w = (w - lr * upd) / (1.f + lr * wd);
+            master[j] = w;
+            w8[e] = w;
+        }
+        uint4 o;
+        o.x = pack_bf16(w8[0], w8[1]); o.y = pack_bf16(w8[2], w8[3]); o.z = pack_bf16(w8[4], w8[5]); o.w = pack_bf16(w8[6], w8[7]);
+        if (p.mc_params != nullptr) multimem_st_bf16x8(p.mc_params + p.offset + i * 8, o);
+        else for (int r = 0; r < p.world; ++r) *reinterpret_cast<uint4*>(p.params[r] + p.offset + i * 8) = o;
+    }
+    __threadfence_system();
+}
+
 static int fill(PeerPtrs& p, const LhrsPeerExchange* x, const char* who) {
     LHRS_CHECK_ARG(x && x->world >= 1 && x->world <= 16 && x->rank >= 0 && x->rank < x->world, "%s: bad world/rank", who);
     LHRS_CHECK_ARG(x->slice_n > 0 && x->slice_n % 8 == 0 && x->slice_offset % 8 == 0, "%s: the slice must be a multiple of 8 elements", who);
@@ -184,5 +227,23 @@ extern "C" int lhrs_p2p_adamw_slice(const LhrsPeerExchange* x, float* master, fl
     p2p_adamw_kernel<<<(unsigned)blocks, PX_THREADS, 0, (cudaStream_t)stream>>>(p, master, m, v, grad_sum, decay_mask, lr, beta1, beta2, eps,
                                                                                weight_decay, bc1, bc2, max_norm, grad_scale);
     LHRS_LAUNCH_CHECK("p2p_adamw_kernel");
+    return LHRS_OK;
+}
+
+extern "C" int lhrs_p2p_adan_slice(const LhrsPeerExchange* x, float* master, float* exp_avg, float* exp_avg_diff, float* exp_avg_sq,
+                                   float* pre_grad, const float* grad_sum, const float* decay_mask, float lr, float beta1, float beta2,
+                                   float beta3, float eps, float weight_decay, int32_t step, int32_t no_prox, float max_norm,
+                                   float grad_scale, void* stream) {
+    PeerPtrs p;
+    if (fill(p, x, "lhrs_p2p_adan_slice")) return LHRS_ERR_INVALID;
+    LHRS_CHECK_ARG(master && exp_avg && exp_avg_diff && exp_avg_sq && pre_grad && grad_sum && step >= 1, "lhrs_p2p_adan_slice: bad args");
+    const float bc1 = 1.f - powf(beta1, (float)step), bc2 = 1.f - powf(beta2, (float)step), bc3 = 1.f - powf(beta3, (float)step);
+    long long blocks = (p.n / 8 + PX_THREADS - 1) / PX_THREADS;
+    const long long cap = (long long)num_sms() * 8;
+    if (blocks > cap) blocks = cap;
+    p2p_adan_kernel<<<(unsigned)blocks, PX_THREADS, 0, (cudaStream_t)stream>>>(p, master, exp_avg, exp_avg_diff, exp_avg_sq, pre_grad, grad_sum,
+                                                                              decay_mask, lr, beta1, beta2, beta3, eps, weight_decay, bc1, bc2,
+                                                                              sqrtf(bc3), step == 1, no_prox, max_norm, grad_scale);
+    LHRS_LAUNCH_CHECK("p2p_adan_kernel");
     return LHRS_OK;
 }

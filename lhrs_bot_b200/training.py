@@ -119,7 +119,7 @@ class FlatAdan(_FlatOptimizer):
 
 
 class PeerShardedAdamW:
-    """ZeRO-style AdamW over NVLink peer memory (csrc/peer_exchange.cu) — the B200-native form of what the reference gets from
+    """ZeRO-style AdamW (or Adan, ``kind="adanp" | "adanw"``) over NVLink peer memory (csrc/peer_exchange.cu) — the B200-native form of what the reference gets from
     DeepSpeed ZeRO-2 (main_pretrain_stage1.py:28-85, 215-220): the flat bf16 parameter and gradient buffers are SYMMETRIC
     allocations (``torch.distributed._symmetric_memory``: every rank maps every peer's buffer), rank r owns slice r of the
     trainable set — fp32 master weights and Adam moments exist only for that slice — and a step is
@@ -131,8 +131,8 @@ class PeerShardedAdamW:
     i.e. reduce-scatter + optimizer + all-gather in two kernels, no NCCL call, optimizer state and update work divided by the
     world size.  Same arithmetic as ``FlatAdamW`` after a summed allreduce (fixed rank order, deterministic)."""
 
-    def __init__(self, params: List[torch.nn.Parameter], world: int, rank: int, group=None, lr=2e-4, betas=(0.9, 0.95), eps=1e-8,
-                 weight_decay=0.0, max_grad_norm=1.0):
+    def __init__(self, params: List[torch.nn.Parameter], world: int, rank: int, group=None, lr=2e-4, betas=None, eps=1e-8,
+                 weight_decay=0.0, max_grad_norm=1.0, kind: str = "adamw"):
         import torch.distributed as dist
         import torch.distributed._symmetric_memory as symm
         assert params, "no trainable parameters"
@@ -168,9 +168,15 @@ class PeerShardedAdamW:
                 mask[off: off + n] = 0.0 if p.dim() <= 1 else 1.0
             off += n
         lo = rank * self.slice_n
+        kind = kind.lower()
+        assert kind in ("adamw", "adanp", "adan", "adanw"), kind
+        self.kind, self.no_prox = ("adamw" if kind == "adamw" else "adan"), kind == "adanw"
+        betas = betas if betas is not None else ((0.9, 0.95) if self.kind == "adamw" else (0.98, 0.92, 0.99))
         self.master = self.flat_param[lo: lo + self.slice_n].float()
-        self.m = torch.zeros_like(self.master)
+        self.m = torch.zeros_like(self.master)          # AdamW: m, v.   Adan: exp_avg, exp_avg_diff, exp_avg_sq, pre_grad
         self.v = torch.zeros_like(self.master)
+        if self.kind == "adan":
+            self.nsq, self.pre_grad = torch.zeros_like(self.master), torch.zeros_like(self.master)
         self.grad_sum = torch.empty_like(self.master)
         self.decay_mask = None if mask is None else mask[lo: lo + self.slice_n].clone()
         self._scratch = torch.empty((1024,), device=dev, dtype=torch.float32)
@@ -200,10 +206,18 @@ class PeerShardedAdamW:
         self.h_grad.barrier(channel=0)       # all ranks finished writing their gradients
         check(lib.lhrs_p2p_reduce_slice(C.byref(self.desc), self.grad_sum.data_ptr(), self._scratch.data_ptr(), st), "lhrs_p2p_reduce_slice")
         self.h_norm.barrier(channel=0)       # every slice norm has landed; every rank has finished READING the gradients
-        check(lib.lhrs_p2p_adamw_slice(C.byref(self.desc), self.master.data_ptr(), self.m.data_ptr(), self.v.data_ptr(),
-                                       self.grad_sum.data_ptr(), None if self.decay_mask is None else self.decay_mask.data_ptr(),
-                                       float(self.lr if lr is None else lr), self.betas[0], self.betas[1], self.eps, self.weight_decay,
-                                       self.step_count, float(self.max_grad_norm or 0.0), float(scale), st), "lhrs_p2p_adamw_slice")
+        mask = None if self.decay_mask is None else self.decay_mask.data_ptr()
+        if self.kind == "adamw":
+            check(lib.lhrs_p2p_adamw_slice(C.byref(self.desc), self.master.data_ptr(), self.m.data_ptr(), self.v.data_ptr(),
+                                           self.grad_sum.data_ptr(), mask, float(self.lr if lr is None else lr), self.betas[0],
+                                           self.betas[1], self.eps, self.weight_decay, self.step_count,
+                                           float(self.max_grad_norm or 0.0), float(scale), st), "lhrs_p2p_adamw_slice")
+        else:
+            check(lib.lhrs_p2p_adan_slice(C.byref(self.desc), self.master.data_ptr(), self.m.data_ptr(), self.v.data_ptr(),
+                                          self.nsq.data_ptr(), self.pre_grad.data_ptr(), self.grad_sum.data_ptr(), mask,
+                                          float(self.lr if lr is None else lr), self.betas[0], self.betas[1], self.betas[2], self.eps,
+                                          self.weight_decay, self.step_count, int(self.no_prox), float(self.max_grad_norm or 0.0),
+                                          float(scale), st), "lhrs_p2p_adan_slice")
         self.h_param.barrier(channel=0)      # every rank's parameter buffer holds all updated slices
 
     def grad_norm(self) -> float:
@@ -292,10 +306,11 @@ class SftStepper:
         exchange = os.environ.get("LHRS_EXCHANGE", exchange)
         self.exchange = "nccl"
         self.opt = None
-        if exchange in ("auto", "p2p") and world_size > 1 and optimizer.lower() == "adamw" and params[0].is_cuda:
+        if exchange in ("auto", "p2p") and world_size > 1 and optimizer.lower() in ("adamw", "adanp", "adan", "adanw") and params[0].is_cuda:
             try:
                 import torch.distributed as dist
-                self.opt = PeerShardedAdamW(params, world_size, dist.get_rank(), lr=lr, weight_decay=weight_decay, max_grad_norm=max_grad_norm)
+                self.opt = PeerShardedAdamW(params, world_size, dist.get_rank(), lr=lr, weight_decay=weight_decay,
+                                            max_grad_norm=max_grad_norm, kind=optimizer)
                 self.exchange = "p2p"
             except Exception as e:   # no symmetric memory on this node / build: the NCCL schedule is always available
                 if exchange == "p2p":

@@ -80,3 +80,57 @@ def test_peer_sharded_adamw_two_ranks(max_norm, nvls):
         assert master_ok
     if max_norm > 0:
         assert res[0][5] > max_norm          # the clip branch ran
+
+
+def _adan_worker(rank, world, port, q):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    try:
+        from oracle import optim
+        from lhrs_bot_b200.training import PeerShardedAdamW
+        g = torch.Generator().manual_seed(1)
+        shapes = [(80, 24), (128,), (512, 8)]
+        init = [torch.randn(s, generator=g).bfloat16() for s in shapes]
+        ps = [torch.nn.Parameter(t.clone().to(dev)) for t in init]
+        ref = [t.float().clone() for t in init]
+        opt = PeerShardedAdamW(ps, world, rank, lr=2e-3, weight_decay=0.05, max_grad_norm=0.3, kind="adanp")
+        ropt = optim.Adan(ref, lr=2e-3, weight_decay=0.05, no_prox=False)
+        for it in range(5):
+            grads = []
+            for r in range(world):
+                gg = torch.Generator().manual_seed(50 * it + r)
+                grads.append([torch.randn(s, generator=gg).bfloat16() for s in shapes])
+            for p, mine in zip(ps, grads[rank]):
+                opt.grad_views[p].copy_(mine.to(dev))
+            opt.step()
+            mean = [sum(grads[r][i].float() for r in range(world)) / world for i in range(len(shapes))]
+            c = optim.clip_coef(mean, 0.3)
+            ropt.step([m * c for m in mean], weight_decays=[0.05, 0.0, 0.05])
+        torch.cuda.synchronize()
+        ok = all(torch.allclose(p.detach().float().cpu(), r, atol=2e-2, rtol=2e-2) for p, r in zip(ps, ref))
+        gathered = [torch.empty_like(opt.flat_param) for _ in range(world)]
+        dist.all_gather(gathered, opt.flat_param)
+        q.put((rank, ok, all(torch.equal(gathered[0], t) for t in gathered)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_peer_sharded_adan_two_ranks():
+    """Stage-1 recipe (adanp, clip 0.3) on the peer-memory schedule vs the oracle's Adan on the clipped mean gradient."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs on one node (gpurun --gpus 2)")
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_adan_worker, args=(r, 2, 29650, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=240) for _ in range(2)]
+    for p in procs:
+        p.join(timeout=60)
+    for rank, ok, same in res:
+        assert ok, f"rank {rank}: parameters differ from the oracle's Adan"
+        assert same, f"rank {rank}: ranks hold different parameters"
