@@ -216,8 +216,12 @@ def generate(text, input_ids: torch.Tensor, image_embedding: Optional[torch.Tens
     if embeds is None:
         embeds = text.embed(input_ids)
     S = embeds.shape[1]
-    if eos_token_id == "config":
+    if isinstance(eos_token_id, str) and eos_token_id == "config":
         eos_token_id = getattr(cfg, "eos_token_id", None)
+    extra_stops: List[List[int]] = []
+    if isinstance(eos_token_id, (list, tuple)):          # HF accepts several EOS ids: the others become one-token stop sequences
+        ids = [int(t) for t in eos_token_id]
+        eos_token_id, extra_stops = (ids[0] if ids else None), [[t] for t in ids[1:]]
     max_len = min(S + max_new_tokens, cfg.max_position_embeddings)
     n_budget = max_len - S
     if n_budget <= 0:
@@ -231,13 +235,13 @@ def generate(text, input_ids: torch.Tensor, image_embedding: Optional[torch.Tens
 
     if generator is not None or return_step_logits or host_picker is not None:
         return _generate_host_side(lib, w, sess, last, S, n_budget, do_sample, temperature, top_p, top_k, repetition_penalty,
-                                   eos_token_id, streamer, stopping_criteria, generator, return_step_logits, dev, host_picker)
+                                   ([eos_token_id] + [q[0] for q in extra_stops]) if extra_stops else eos_token_id, streamer, stopping_criteria, generator, return_step_logits, dev, host_picker)
 
     # ---- device-driven: selection, EOS and keyword-suffix stop on the device; the host polls every `eos_poll` tokens
     if seed is None:
         seed = int(torch.randint(0, 2 ** 62, (1,)).item()) if do_sample else 0   # follows torch.manual_seed
     key = sess.configure(do_sample, temperature, top_k, top_p, repetition_penalty, eos_token_id,
-                         _keyword_id_sequences(stopping_criteria), seed)
+                         _keyword_id_sequences(stopping_criteria) + extra_stops, seed)
     if use_graph is None:
         use_graph = os.environ.get("LHRS_DECODE_GRAPH", "0") == "1"
     poll = max(1, int(eos_poll))
@@ -295,7 +299,7 @@ def _generate_host_side(lib, w, sess, last, S, n_budget, do_sample, temperature,
         out_tokens.append(tok)
         if streamer is not None:
             streamer.put(torch.tensor([tok]))
-        if eos_token_id is not None and tok == eos_token_id:
+        if eos_token_id is not None and (tok in eos_token_id if isinstance(eos_token_id, (list, tuple)) else tok == eos_token_id):
             break
         if len(out_tokens) >= n_budget:
             break
