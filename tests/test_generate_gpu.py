@@ -70,6 +70,9 @@ def test_eos_and_sampling_paths(small):
         eos = base[9]
         cut = model.generate(ids, images=px, do_sample=False, max_new_tokens=24, eos_token_id=eos)[0].tolist()
         assert cut == base[: base.index(eos) + 1]          # stops at (and includes) EOS, also when polled late
+        both = model.generate(ids, images=px, do_sample=False, max_new_tokens=24, eos_token_id=[eos, base[4]])[0].tolist()
+        first = min(base.index(eos), base.index(base[4]))
+        assert both == base[: first + 1]                   # several EOS ids (HF allows a list): the earliest one wins
         g1 = torch.Generator(device=DEV).manual_seed(5)
         g2 = torch.Generator(device=DEV).manual_seed(5)
         s1 = model.generate(ids, images=px, do_sample=True, temperature=0.4, top_p=0.95, repetition_penalty=1.05,
