@@ -136,6 +136,38 @@ def test_reference_lr_schedule():
     assert reference_lr(10, base, T, mn, 0, 0.1, warmup=None) == pytest.approx(cosv(10))
 
 
+def test_decode_session_sampling_table_and_keyword_extraction():
+    """Host side of the device-driven decode loop: the LhrsSampling block and the right-aligned, -1 padded stop table the
+    kernels read; keyword id sequences are taken from KeywordsStoppingCriteria-like objects (eval_utils.py:24-56)."""
+    from types import SimpleNamespace
+    from lhrs_bot_b200.generation import DecodeSession, _criteria_hit, _keyword_id_sequences
+    cfg = SimpleNamespace(hidden_size=256, num_attention_heads=2, intermediate_size=512)
+    sess = DecodeSession(cfg, layers=2, vocab=1024, max_len=100, device=torch.device("cpu"))
+    assert sess.kv.capacity == 112 and sess.buf.attn_count.numel() == 2 and int(sess.buf.attn_count.abs().sum()) == 0
+    key = sess.configure(True, 0.4, None, 0.95, 1.05, 2, [[5, 6, 7], [9]], seed=(1 << 63) + 5)
+    s = sess.smp
+    assert (s.do_sample, s.top_k, s.eos_token, s.n_stop, s.stop_len) == (1, 0, 2, 2, 3)
+    assert abs(s.temperature - 0.4) < 1e-7 and abs(s.top_p - 0.95) < 1e-7 and abs(s.repetition_penalty - 1.05) < 1e-7
+    assert s.seed == 5 and int(sess.seed.item()) == 5                       # masked to 63 bits; the kernels read the device copy
+    assert sess.stop.tolist() == [[5, 6, 7], [-1, -1, 9]] and s.stop_seqs == sess.stop.data_ptr()
+    ptr = sess.stop.data_ptr()
+    key2 = sess.configure(True, 0.4, None, 0.95, 1.05, 2, [[5, 6, 7], [9]], seed=6)
+    assert key2 == key and sess.stop.data_ptr() == ptr                      # same settings: a captured graph stays valid
+    key3 = sess.configure(False, 0.0, None, None, None, None, [], seed=0)
+    assert key3 != key and sess.smp.stop_seqs is None and sess.smp.eos_token == -1 and sess.smp.do_sample == 0
+
+    class Keywords:
+        def __init__(self):
+            self.keyword_ids = [torch.tensor([11, 12]), torch.tensor([13])]
+
+        def __call__(self, ids, scores, **kw):
+            return ids[0, -1].item() == 13
+    crit = Keywords()
+    assert _keyword_id_sequences([crit, lambda i, s: False]) == [[11, 12], [13]] and _keyword_id_sequences(None) == []
+    assert _criteria_hit([crit], torch.tensor([[1, 13]])) and not _criteria_hit([crit], torch.tensor([[13, 1]]))
+    assert not _criteria_hit(None, torch.tensor([[13]]))
+
+
 def test_stepper_from_reference_yaml_keys(monkeypatch):
     """SftStepper.from_config maps the yaml's training keys (shipped stage-1 / stage-2 values) onto the fused step."""
     from lhrs_bot_b200 import training
