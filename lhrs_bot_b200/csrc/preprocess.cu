@@ -102,7 +102,9 @@ static void resize_dims(int H, int W, int s, int* nh, int* nw) {
 }
 
 static int get_plan(int H, int W, int out, PrePlan* p) {
-    const long long key = ((long long)H << 40) | ((long long)W << 16) | out;
+    int dev = 0;
+    LHRS_CUDA(cudaGetDevice(&dev));                      // the tables live in the memory of the device that was current
+    const long long key = ((long long)(dev & 0xF) << 60) | ((long long)H << 40) | ((long long)W << 16) | out;
     std::lock_guard<std::mutex> lk(g_plan_mu);
     auto it = g_plans.find(key);
     if (it != g_plans.end()) { *p = it->second; return LHRS_OK; }
