@@ -60,6 +60,28 @@ class PoolerFunction(torch.autograd.Function):
         return (None, d_img, *ret)
 
 
+def supervised_rows(new_labels: torch.Tensor):
+    """Rows of the (B*S) hidden matrix whose next-position label is counted by the shifted CE (HF LlamaForCausalLM loss,
+    text_modal.py:281-294): row (b, s) predicts labels[b, s+1]; ignore_index = -100.  Every other row contributes neither loss
+    nor gradient, so the lm_head GEMM (2·rows·4096·32000 flops each way) only needs these rows — typically 30-45 % of a batch
+    (prompt, image and padding positions are never supervised).  Returns (rows int64 [Ms], labels' int64 [1, Ms + 1]) in the
+    layout lhrs_ce_fwd expects for ONE sequence of Ms + 1 positions (row i predicts labels'[i + 1]; the extra last row has no
+    target), or None when compaction is off / pointless.  One small D2H sync (the row count)."""
+    import os
+    if os.environ.get("LHRS_CE_COMPACT", "1") == "0":
+        return None
+    B, S = new_labels.shape
+    tgt = new_labels[:, 1:]
+    idx = (tgt != -100).reshape(-1).nonzero().squeeze(1)          # synchronises: the GEMM's row count is a host value
+    ms = int(idx.numel())
+    if ms == 0 or ms * 10 >= B * S * 9:
+        return None
+    rows = (idx // (S - 1)) * S + idx % (S - 1)
+    lab = torch.full((1, ms + 1), -100, dtype=torch.int64, device=new_labels.device)
+    lab[0, 1:] = tgt.reshape(-1)[idx]
+    return rows, lab
+
+
 class LlamaLossFunction(torch.autograd.Function):
     """splice -> LLaMA stack -> lm_head -> shifted CE, and its backward down to the image features / LoRA factors.
 
@@ -74,11 +96,20 @@ class LlamaLossFunction(torch.autograd.Function):
         B, S, D = embeds.shape
         stash = torch.empty((lib.lhrs_llama_stash_bytes(C.byref(w), B, S),), device=embeds.device, dtype=torch.uint8)
         hidden = text.llama_forward(embeds, new_mask, stash=stash)
-        logits = text.lm_head(hidden)
-        loss_sum, count, row_lse = ops.ce_fwd(logits, new_labels)
+        sel = supervised_rows(new_labels)
+        ctx.rows = None
+        if sel is not None:      # lm_head + CE over the supervised rows only (identical loss and gradients)
+            rows, ce_labels = sel
+            hc = torch.zeros((rows.numel() + 1, D), device=hidden.device, dtype=hidden.dtype)
+            hc[:-1] = hidden.view(B * S, D).index_select(0, rows)
+            logits = text.lm_head(hc).unsqueeze(0)
+            ctx.rows = rows
+        else:
+            logits, ce_labels = text.lm_head(hidden), new_labels
+        loss_sum, count, row_lse = ops.ce_fwd(logits, ce_labels)
         loss = loss_sum[0] / count[0].to(torch.float32)
         km = None if new_mask is None else new_mask.to(torch.uint8).contiguous()
-        ctx.text, ctx.stash, ctx.logits, ctx.labels, ctx.row_lse, ctx.count = text, stash, logits, new_labels, row_lse, count
+        ctx.text, ctx.stash, ctx.logits, ctx.labels, ctx.row_lse, ctx.count = text, stash, logits, ce_labels, row_lse, count
         ctx.km, ctx.row_map, ctx.dims = km, row_map, (B, S, D)
         ctx.img_shape = tuple(image_embedding.shape)
         ctx.need_img = ctx.needs_input_grad[1]
@@ -95,8 +126,15 @@ class LlamaLossFunction(torch.autograd.Function):
         # d_logits overwrites the logits buffer in place (each element is read, then written, by the same thread)
         gs = d_loss.detach().to(torch.float32).reshape(1).contiguous()
         d_logits = ops.ce_bwd(ctx.logits, ctx.labels, ctx.row_lse, ctx.count, 1.0, out=ctx.logits, grad_scale_dev=gs)
-        d_hidden = torch.empty((B * S, D), device=dev, dtype=torch.bfloat16)
-        check(lib.lhrs_lm_head_bwd(C.byref(w), d_logits.data_ptr(), B * S, d_hidden.data_ptr(), runtime.stream()), "lhrs_lm_head_bwd")
+        if ctx.rows is not None:
+            nr = ctx.rows.numel() + 1
+            dhc = torch.empty((nr, D), device=dev, dtype=torch.bfloat16)
+            check(lib.lhrs_lm_head_bwd(C.byref(w), d_logits.data_ptr(), nr, dhc.data_ptr(), runtime.stream()), "lhrs_lm_head_bwd")
+            d_hidden = torch.zeros((B * S, D), device=dev, dtype=torch.bfloat16)
+            d_hidden.index_copy_(0, ctx.rows, dhc[:-1])
+        else:
+            d_hidden = torch.empty((B * S, D), device=dev, dtype=torch.bfloat16)
+            check(lib.lhrs_lm_head_bwd(C.byref(w), d_logits.data_ptr(), B * S, d_hidden.data_ptr(), runtime.stream()), "lhrs_lm_head_bwd")
         # LoRA gradient destinations, in the order of the weight table ([layer*7 + proj])
         lora_grads = []
         ga = gb = None

@@ -430,8 +430,16 @@ class TextModal(BaseModal):
             embeds = self.embed(input_ids)
             new_labels = labels
         hidden = self.llama_forward(embeds, mask)
-        logits = self.lm_head(hidden)
-        loss_sum, count, _ = ops.ce_fwd(logits, new_labels)
+        from .autograd import supervised_rows
+        sel = supervised_rows(new_labels)
+        if sel is not None:      # lm_head + CE over the supervised rows only (identical loss)
+            rows, ce_labels = sel
+            hc = torch.zeros((rows.numel() + 1, hidden.shape[-1]), device=hidden.device, dtype=hidden.dtype)
+            hc[:-1] = hidden.reshape(-1, hidden.shape[-1]).index_select(0, rows)
+            logits = self.lm_head(hc).unsqueeze(0)
+        else:
+            logits, ce_labels = self.lm_head(hidden), new_labels
+        loss_sum, count, _ = ops.ce_fwd(logits, ce_labels)
         return loss_sum[0] / count[0].to(torch.float32)
 
     def embed(self, input_ids: torch.Tensor) -> torch.Tensor:
