@@ -547,6 +547,9 @@ def main():
                                                      f"peer-memory reduce-scatter + sharded {getattr(stepper.opt, 'kind', 'adamw')} + all-gather (NVLink P2P, no NCCL call)")
                                                     if getattr(stepper, "exchange", "") == "p2p" else "NCCL allreduce of the flat bf16 gradient buffer")
                                                    if train and world > 1 else "none (single GPU)"),
+                                loss_rows=("lm_head + CE evaluated on the rows with a counted label only (identical loss and gradients; "
+                                           "LHRS_CE_COMPACT=0 computes all rows)" if os.environ.get("LHRS_CE_COMPACT", "1") != "0"
+                                           else "all rows"),
                                 inputs_vs_l2="13.5 GB of weights + 64 MB activations streamed per step >> 126 MB L2 (no flush needed)"),
                     per_gpu=value / world, clocks=clocks.summary(), e2e=e2e, gpu_launches=int(launches), roofline=roofline,
                     cpu_baseline=cpu_base)
