@@ -220,6 +220,29 @@ def test_generate_text_only_and_long_context(small):
     print("text-only long-context: first diff", first_diff)
 
 
+def test_generate_stops_at_the_context_limit(small):
+    """Maximum size: a prompt that almost fills max_position_embeddings (2048).  HF caps generation at the model's context; the
+    paged cache (128 pages) is filled to its last slot and the tokens up to the cap match the oracle's greedy decode."""
+    from oracle import llama
+    cfg, model, st = small
+    g = torch.Generator().manual_seed(21)
+    ids = torch.randint(3, 1024, (1, 2040), generator=g).to(DEV)
+    with torch.no_grad():
+        out = model.generate(ids, images=None, do_sample=False, max_new_tokens=100, eos_token_id=None)
+        assert out.shape == (1, 8), out.shape                      # 2040 + 8 = 2048 positions
+        emb = st["llama"]["model.embed_tokens.weight"][ids]
+        ref, ref_logits = llama.greedy_decode(emb, st["llama"], cfg.text.num_hidden_layers, cfg.text.num_attention_heads, 8,
+                                              float(cfg.text.rms_norm_eps))
+        assert model.generate(ids[:, :2048 - 0].repeat(1, 1)[:, :2040], images=None, do_sample=False, max_new_tokens=0).shape == (1, 0)
+    ours, refl = out[0].tolist(), ref.tolist()
+    first_diff = next((i for i, (a, b) in enumerate(zip(ours, refl)) if a != b), None)
+    if first_diff is not None:
+        l = ref_logits[first_diff]
+        top2 = torch.topk(l, 2).values
+        assert (top2[0] - top2[1]).item() <= 2e-2 * l.pow(2).mean().sqrt().item(), f"mismatch at {first_diff}"
+    print("context-limit decode: first diff", first_diff)
+
+
 def test_decode_full_width_layer():
     """LLaMA-2-7B widths (4096 / 11008 / 32000, 32 heads), 2 layers: decode-step logits vs the fp32 oracle."""
     from oracle import llama, unibind
