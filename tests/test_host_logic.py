@@ -168,6 +168,23 @@ def test_decode_session_sampling_table_and_keyword_extraction():
     assert not _criteria_hit(None, torch.tensor([[13]]))
 
 
+def test_supervised_rows_match_the_shifted_ce_rule(monkeypatch):
+    """autograd.supervised_rows: exactly the rows (b, s) with labels[b, s+1] != -100 (HF shifted CE), in row-major order, and the
+    label vector in the one-sequence layout the CE kernel expects; off when nothing / almost everything is supervised."""
+    from lhrs_bot_b200.autograd import supervised_rows
+    g = torch.Generator().manual_seed(0)
+    lab = torch.randint(0, 50, (3, 17), generator=g)
+    lab[torch.rand(3, 17, generator=g) < 0.6] = -100
+    rows, ce = supervised_rows(lab)
+    want = [(b * 17 + s, int(lab[b, s + 1])) for b in range(3) for s in range(16) if lab[b, s + 1] != -100]
+    assert rows.tolist() == [r for r, _ in want] and ce.shape == (1, len(want) + 1)
+    assert ce[0, 0] == -100 and ce[0, 1:].tolist() == [t for _, t in want]
+    assert supervised_rows(torch.full((2, 8), -100)) is None                  # nothing counted: the full path reports 0 / 0 like HF
+    assert supervised_rows(torch.ones((2, 8), dtype=torch.long)) is None      # (almost) everything counted: no point compacting
+    monkeypatch.setenv("LHRS_CE_COMPACT", "0")
+    assert supervised_rows(lab) is None
+
+
 def test_stepper_from_reference_yaml_keys(monkeypatch):
     """SftStepper.from_config maps the yaml's training keys (shipped stage-1 / stage-2 values) onto the fused step."""
     from lhrs_bot_b200 import training
