@@ -63,6 +63,41 @@ def test_errors_are_reported_not_swallowed():
         _lib.check(rc, "lhrs_gemm_bf16")
 
 
+def test_argument_validation_of_the_newer_entry_points():
+    """Bad arguments come back as LHRS_ERR_INVALID with a message before any CUDA call is made (runs without a device)."""
+    from lhrs_bot_b200 import _lib
+    lib = _lib.load()
+    one = C.c_void_p(16)      # a non-null, 16-byte aligned dummy pointer: validation fails before it is dereferenced
+    wp = (C.c_void_p * 3)(16, 16, 16)
+    wpp = C.cast(wp, C.POINTER(C.c_void_p))
+    # LoRA streaming kernels: only 16 / 32 / 48 output columns, K % 64 == 0
+    assert lib.lhrs_lora_panel(one, 4096, 128, 4096, wpp, 1, 0, 4096, 20, 1.0, one, 20, None) == 1
+    assert b"n=20" in lib.lhrs_last_error()
+    assert lib.lhrs_lora_panel(one, 4096, 128, 4000, wpp, 1, 0, 4000, 16, 1.0, one, 16, None) == 1
+    assert lib.lhrs_lora_rowreduce(one, 4096, 128, 4096, one, 16, 16, 100, 0, wpp, 16, 1.0, C.cast(one, C.c_void_p), 1 << 20, None) == 1
+    assert b"seg_c" in lib.lhrs_last_error()
+    # sampler: scratch required, vocabulary bounded by the histogram limbs
+    s = _lib.LhrsSampling()
+    assert lib.lhrs_sample_logits(one, 1000, None, 0, C.byref(s), 0, one, None, None) == 1 and b"work" in lib.lhrs_last_error()
+    s.work = 16
+    assert lib.lhrs_sample_logits(one, 70000, None, 0, C.byref(s), 0, one, None, None) == 1 and b"vocab" in lib.lhrs_last_error()
+    # preprocessing: geometry
+    mean = (C.c_float * 3)(0.5, 0.5, 0.5)
+    assert lib.lhrs_clip_preprocess(one, 1, 0, 8, 224, mean, mean, one, 0, None, one, 1 << 20, None) == 1
+    assert b"geometry" in lib.lhrs_last_error()
+    assert lib.lhrs_clip_preprocess_workspace_bytes(2, 512, 512, 224) >= 2 * 512 * 224 * 3
+    # peer exchange: world / rank / slice alignment / null peers
+    x = _lib.LhrsPeerExchange()
+    assert lib.lhrs_p2p_reduce_slice(C.byref(x), one, one, None) == 1 and b"world" in lib.lhrs_last_error()
+    x.world, x.rank, x.slice_offset, x.slice_n = 2, 0, 0, 12
+    assert lib.lhrs_p2p_reduce_slice(C.byref(x), one, one, None) == 1 and b"multiple of 8" in lib.lhrs_last_error()
+    x.slice_n = 16
+    assert lib.lhrs_p2p_adamw_slice(C.byref(x), one, one, one, one, None, 1e-3, 0.9, 0.95, 1e-8, 0.0, 1, 1.0, 0.5, None) == 1
+    assert b"null peer pointer" in lib.lhrs_last_error()
+    # optimizers: step counts from 1
+    assert lib.lhrs_adan_step(one, one, one, one, one, one, one, None, 8, 1e-3, 0.98, 0.92, 0.99, 1e-8, 0.0, 0, 0, None, 0.0, 1.0, None) == 1
+
+
 def test_cpu_tensors_are_rejected():
     import torch
     from lhrs_bot_b200 import ops
