@@ -272,8 +272,10 @@ __device__ __forceinline__ void copy_row16(uint4* dst, const uint4* src, int nch
     for (int c = threadIdx.x; c < nchunks; c += blockDim.x) dst[c] = src[c];
 }
 
-// grid (T + S_out, B). Blocks x < T scatter input token x; blocks x >= T own output position s = x - T
-// (padding rows + the attention mask, which the reference left-extends rather than aligning to tokens).
+// grid (T + S_out + nq, B). Blocks x < T scatter input token x; blocks T <= x < T + S_out own output position s = x - T
+// (padding rows + the attention mask, which the reference left-extends rather than aligning to tokens); blocks x >= T + S_out
+// copy image-feature row q = x - T - S_out of every image token of the sample (one block per row: a single block walking all
+// 144 rows of an image cost 165 us per call).
 __global__ void __launch_bounds__(128)
 splice_fill_kernel(const long long* __restrict__ ids, const long long* __restrict__ labels,
                    const uint8_t* __restrict__ amask, const int* __restrict__ info,
@@ -299,16 +301,23 @@ splice_fill_kernel(const long long* __restrict__ ids, const long long* __restric
         } else {
             const int slot = slot_base + c;
             if (slot < n_slots) {
-                for (int q = 0; q < nq; ++q) {
-                    if (img != nullptr)
-                        copy_row16(reinterpret_cast<uint4*>(embeds + (static_cast<long long>(b) * S_out + dst + q) * dim),
-                                   reinterpret_cast<const uint4*>(img + (static_cast<long long>(slot) * nq + q) * dim), nchunks);
-                }
                 for (int q = threadIdx.x; q < nq; q += blockDim.x) {
                     if (labels_out != nullptr) labels_out[static_cast<long long>(b) * S_out + dst + q] = IGNORE_LABEL;
                     if (row_of_slot != nullptr) row_of_slot[slot * nq + q] = b * S_out + dst + q;
                 }
             }
+        }
+    } else if (static_cast<int>(blockIdx.x) >= T + S_out) {
+        if (img == nullptr) return;
+        const int q = blockIdx.x - T - S_out;
+        for (int t = 0; t < T; ++t) {                       // block-uniform scan: a sample holds very few image tokens
+            if (ids[static_cast<long long>(b) * T + t] != IMAGE_TOKEN) continue;
+            const int c = cnt[b * T + t];
+            const int slot = slot_base + c;
+            if (slot >= n_slots) continue;
+            const int dst = t + c * (nq - 1);
+            copy_row16(reinterpret_cast<uint4*>(embeds + (static_cast<long long>(b) * S_out + dst + q) * dim),
+                       reinterpret_cast<const uint4*>(img + (static_cast<long long>(slot) * nq + q) * dim), nchunks);
         }
     } else {
         const int s = blockIdx.x - T;
@@ -527,7 +536,7 @@ extern "C" int lhrs_splice_fill(const int64_t* input_ids, const int64_t* labels,
     LHRS_CHECK_ARG(dim % 8 == 0 && S_out >= T, "lhrs_splice_fill: dim %d / S_out %d", dim, S_out);
     if (row_of_slot != nullptr && n_slots > 0)
         LHRS_CUDA(cudaMemsetAsync(row_of_slot, 0xFF, sizeof(int32_t) * (size_t)n_slots * num_query, (cudaStream_t)stream));
-    dim3 grid(T + S_out, B);
+    dim3 grid(T + S_out + (image_feats != nullptr ? num_query : 0), B);
     splice_fill_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(
         (const long long*)input_ids, (const long long*)labels, attn_mask, info, (const bf16*)embed_table,
         (const bf16*)image_feats, B, T, S_out, num_query, dim, n_slots, (bf16*)embeds_out, (long long*)labels_out,
