@@ -46,8 +46,14 @@ def parse():
     ap.add_argument("--workload", default="auto", choices=["auto", "sft_step", "stage1_step", "prefill", "decode"])
     ap.add_argument("--batch", type=int, default=None, help="per-GPU batch (default 16; 32 for stage1_step)")
     ap.add_argument("--seq", type=int, default=None, help="decoder positions per sample (default 512; 256 for stage1_step)")
+    ap.add_argument("--uniform", action="store_true", help="sft_step / prefill: the uniform all-image, no-padding batch instead of BASELINE "
+                                                           "config 4 as written (75 %% image / 25 %% text-only samples, ragged lengths)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-gpu-eager", action="store_true", help="skip the PyTorch-eager comparator (oracle modules on this GPU, bf16 autocast)")
+    ap.add_argument("--no-extra", action="store_true", help="skip the extra legs (greedy decode = config 2, stage-1 step = config 3) appended at N=1")
+    ap.add_argument("--no-checks", action="store_true", help="skip the step-0 loss check against the fp32 oracle and the N>1 exchange check")
     ap.add_argument("--lora-r", type=int, default=16, help="sft_step: LoRA rank (16 = BASELINE config 4; 128 = the shipped stage-2 yaml, alpha 256)")
+    ap.add_argument("--lora-dropout", type=float, default=None, help="sft_step: LoRA dropout (default: the shipped yaml's 0.05 when the library models it)")
     ap.add_argument("--sample", action="store_true", help="decode workload: cli_qa.py's settings (do_sample, temperature 0.4, top_p 0.95, "
                                                           "repetition_penalty 1.05) selected on the device instead of greedy")
     return ap.parse_args()
@@ -63,23 +69,50 @@ def peaks():
 
 
 # ------------------------------------------------------------------------------------------------ synthetic workload
-def make_batch(B, seed, device=None, pin=False, t_text=None):
+def make_batch(B, seed, device=None, pin=False, t_text=None, seq_len=None, mixed=False, uint8_images=False):
+    """One collated batch shaped like DataCollatorForSupervisedDataset's output (lhrs/Dataset/cap_dataset.py:792-810).
+
+    mixed=False: every sample is [BOS, <image>, text...] of the same length, no padding (stage-1 captions; round-1 bench).
+    mixed=True : BASELINE config 4 as written — "mixed image/text instructions": every 4th sample is text-only (it still carries
+    a dummy image and consumes an image slot, text_modal.py:321-339), lengths are ragged and right-padded with pad id 0
+    (attention_mask = ids != pad), so the splice takes the reference's padding branch (text_modal.py:440-505): image samples
+    come out at seq_len positions, text-only samples at seq_len - 143 and are padded up.  Sample 0 always has full length."""
     g = torch.Generator().manual_seed(seed)
-    T_TEXT = globals()["T_TEXT"] if t_text is None else t_text
-    ids = torch.randint(3, 32000, (B, T_TEXT), generator=g)
-    ids[:, 0] = 1
-    ids[:, 1] = -200                      # plain template: [BOS, <image>, text...]
+    if seq_len is not None:
+        t_text = seq_len - (NUM_QUERY - 1)
+    T = T_TEXT if t_text is None else t_text
+    ids = torch.randint(3, 32000, (B, T), generator=g)
+    ids[:, 0] = 1                                   # BOS
     labels = ids.clone()
-    n_prompt = int(T_TEXT * 0.6)          # last 40 % of the text positions supervised
-    labels[:, :n_prompt] = -100
-    mask = torch.ones(B, T_TEXT, dtype=torch.bool)
-    rgb = torch.randn(B, 3, 224, 224, generator=g).to(torch.bfloat16)
+    mask = torch.ones(B, T, dtype=torch.bool)
+    for b in range(B):
+        text_only = mixed and (b % 4 == 3)
+        n = T
+        if mixed and b > 0:
+            n = T - int(torch.randint(0, T // 3 if text_only else T // 4, (1,), generator=g))
+        if not text_only:
+            ids[b, 1] = -200                        # plain template: [BOS, <image>, text...]
+        n_prompt = int(n * 0.6)                     # last 40 % of the real text positions supervised (SURVEY 8d config 4)
+        labels[b, :n_prompt] = -100
+        ids[b, n:] = 0
+        labels[b, n:] = -100
+        mask[b, n:] = False
+    labels[ids == -200] = -100
+    if uint8_images:                                # raw tiles as the data loader hands them to the CLIP processor
+        rgb = torch.randint(0, 256, (B, 224, 224, 3), generator=g, dtype=torch.uint8)
+    else:
+        rgb = torch.randn(B, 3, 224, 224, generator=g).to(torch.bfloat16)
     batch = dict(rgb=rgb, input_ids=ids, labels=labels, attention_mask=mask)
     if pin:
         batch = {k: v.pin_memory() for k, v in batch.items()}
     if device is not None:
         batch = {k: v.to(device) for k, v in batch.items()}
     return batch
+
+
+def real_positions(batch):
+    """Decoder positions that carry a token (attention_mask true after the splice): text ids + 143 extra rows per <image>."""
+    return int(batch["attention_mask"].sum().item() + (NUM_QUERY - 1) * (batch["input_ids"] == -200).sum().item())
 
 
 def batch_bytes(batch):
@@ -239,7 +272,7 @@ def cpu_reference_decode(st, n_new):
     return (t_full - t_prefill) / (n_new - 1), t_prefill
 
 
-def time_cpu_reference(workload, steps, warmup, seq_len=None, sample_batch=1):
+def time_cpu_reference(workload, steps, warmup, seq_len=None, sample_batch=1, mixed=False):
     """The reference's CPU path on a BOUNDED sample of the GPU arm's workload: `sample_batch` sample(s) per step instead of
     the per-GPU batch (same sequence length, same trainable set, same optimizer)."""
     torch.set_num_threads(os.cpu_count() or 1)
@@ -258,7 +291,7 @@ def time_cpu_reference(workload, steps, warmup, seq_len=None, sample_batch=1):
         opt = torch.optim.AdamW(params, lr=2e-4, betas=(0.9, 0.95), eps=1e-8, weight_decay=0.0)
     times = []
     for i in range(warmup + steps):
-        batch = make_batch(sample_batch, seed=100 + i, t_text=t_text)
+        batch = make_batch(sample_batch, seed=100 + i, t_text=t_text, mixed=mixed)
         t0 = time.perf_counter()
         loss = cpu_reference_step(st, batch, workload, opt)
         float(loss)
@@ -270,11 +303,16 @@ def time_cpu_reference(workload, steps, warmup, seq_len=None, sample_batch=1):
             "prefill": "UniBind.forward -> loss"}[workload]
     return dict(value=tok / mean, unit="tokens/s", cores=cores, kind="port",
                 sample=f"{sample_batch} sample(s) x {S} positions per step (the arm runs the per-GPU batch), {what}; ViT+pooler fp32, "
-                       f"LLaMA-7B bf16, {len(times)} timed step(s) after {warmup} warm-up, PyTorch eager"), mean * 1e3
+                       f"LLaMA-7B bf16, {len(times)} timed step(s) after {warmup} warm-up, PyTorch eager; every layer of a stack "
+                       f"aliases one seeded tensor set (same arithmetic, friendlier to the host caches than 32 distinct layers)"), mean * 1e3
 
 
 def resolve_workload(args):
     return "sft_step" if args.workload == "auto" else args.workload
+
+
+def is_mixed(args, workload):
+    return workload in ("sft_step", "prefill") and not args.uniform
 
 
 def run_reference(args):
@@ -283,7 +321,7 @@ def run_reference(args):
         return
     workload = resolve_workload(args)
     steps = max(1, min(args.steps, 3))
-    base, ms = time_cpu_reference(workload, steps, 1, seq_len=args.seq)
+    base, ms = time_cpu_reference(workload, steps, 1, seq_len=args.seq, mixed=is_mixed(args, workload))
     S = args.seq or (256 if workload == "stage1_step" else SEQ_LEN)
     metric = ("decode tokens/sec (LLaMA-7B, 224px, 1 image + 32-token prompt -> 128 greedy tokens), aggregate" if workload == "decode"
               else f"tokens/sec (LLaMA-7B, 224px, seq {S}), aggregate")
@@ -297,8 +335,138 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
-# ------------------------------------------------------------------------------------------------ decode workload
-def run_decode(args, dev, rank, world, local):
+# ------------------------------------------------------------------------------------------------ GPU-eager comparator
+def gpu_eager_sft(dev, B, S, mixed, lora_r, steps=10, warmup=3):
+    """What the north star's ">= 6x" is measured against (last row): the reference's path — UniBind.forward
+    (lhrs/models/UniBind.py:178-199) + backward + clip + AdamW — as PyTorch EAGER on this same B200: the oracle modules under bf16
+    autocast, frozen weights in bf16, trainable pooler + LoRA factors in fp32, per-layer activation checkpointing (the
+    reference's operating point, Script/train_stage3.sh `--use-checkpoint`), attention through F.scaled_dot_product_attention
+    (what transformers 4.36.1 selects on torch 2.1.2), `torch.optim.AdamW(fused=True)`.  Same batch shape as the timed arm.
+    No DeepSpeed engine, no fp16 loss scaler, no CPU offload: an optimistic stand-in for the reference."""
+    import torch.nn.functional as F
+    from torch.utils.checkpoint import checkpoint
+    from oracle import llama, pooler, splice, vit
+    bf = torch.bfloat16
+    gen = torch.Generator(device=dev).manual_seed(0)
+
+    def rn(*shape, std=0.02, dt=bf):
+        return (torch.randn(*shape, device=dev, generator=gen) * std).to(dt)
+    ones = lambda n, dt=bf: torch.ones(n, device=dev, dtype=dt)
+    zeros = lambda n, dt=bf: torch.zeros(n, device=dev, dtype=dt)
+    D, Fv = 1024, 4096
+    vsd = {"vision_model.embeddings.class_embedding": rn(D), "vision_model.embeddings.patch_embedding.weight": rn(D, 3, 14, 14),
+           "vision_model.embeddings.position_embedding.weight": rn(257, D),
+           "vision_model.pre_layrnorm.weight": ones(D), "vision_model.pre_layrnorm.bias": zeros(D)}
+    for i in range(24):
+        p = f"vision_model.encoder.layers.{i}."
+        vsd.update({p + "layer_norm1.weight": ones(D), p + "layer_norm1.bias": zeros(D), p + "layer_norm2.weight": ones(D),
+                    p + "layer_norm2.bias": zeros(D), p + "mlp.fc1.weight": rn(Fv, D), p + "mlp.fc1.bias": zeros(Fv),
+                    p + "mlp.fc2.weight": rn(D, Fv), p + "mlp.fc2.bias": zeros(D)})
+        for n in ("q_proj", "k_proj", "v_proj", "out_proj"):
+            vsd[p + f"self_attn.{n}.weight"], vsd[p + f"self_attn.{n}.bias"] = rn(D, D), zeros(D)
+    f32 = torch.float32
+    params = []
+
+    def leaf(t):
+        t = t.to(f32).requires_grad_(True)
+        params.append(t)
+        return t
+    psd = {"query": leaf(rn(1, 144, D, dt=f32)), "out_proj.weight": leaf(rn(4096, D, dt=f32)), "out_proj.bias": leaf(zeros(4096, f32))}
+    for i in range(6):
+        p = f"layers.{i}."
+        for n in ("ln_1", "ln_1_kv", "ln_2"):
+            psd[p + n + ".weight"], psd[p + n + ".bias"] = leaf(ones(D, f32)), leaf(zeros(D, f32))
+        psd[p + "attn.in_proj_weight"], psd[p + "attn.in_proj_bias"] = leaf(rn(3 * D, D, dt=f32)), leaf(zeros(3 * D, f32))
+        psd[p + "attn.out_proj.weight"], psd[p + "attn.out_proj.bias"] = leaf(rn(D, D, dt=f32)), leaf(zeros(D, f32))
+        psd[p + "mlp.c_fc.weight"], psd[p + "mlp.c_fc.bias"] = leaf(rn(Fv, D, dt=f32)), leaf(zeros(Fv, f32))
+        psd[p + "mlp.c_proj.weight"], psd[p + "mlp.c_proj.bias"] = leaf(rn(D, Fv, dt=f32)), leaf(zeros(D, f32))
+    d, f, V, L = 4096, 11008, 32000, 32
+    ll = {"model.embed_tokens.weight": rn(V, d), "lm_head.weight": rn(V, d), "model.norm.weight": ones(d)}
+    shapes = {"self_attn.q_proj": (d, d), "self_attn.k_proj": (d, d), "self_attn.v_proj": (d, d), "self_attn.o_proj": (d, d),
+              "mlp.gate_proj": (f, d), "mlp.up_proj": (f, d), "mlp.down_proj": (d, f)}
+    for i in range(L):
+        p = f"model.layers.{i}."
+        ll[p + "input_layernorm.weight"], ll[p + "post_attention_layernorm.weight"] = ones(d), ones(d)
+        for n, (o, k) in shapes.items():
+            ll[p + n + ".weight"] = rn(o, k)
+            ll[p + n + ".lora_A.weight"] = leaf((torch.rand(lora_r, k, device=dev, generator=gen) * 2 - 1) * (1.0 / k) ** 0.5)
+            ll[p + n + ".lora_B.weight"] = leaf(torch.zeros(o, lora_r, device=dev))
+    opt = torch.optim.AdamW(params, lr=2e-4, betas=(0.9, 0.95), eps=1e-8, weight_decay=0.0, fused=True)
+
+    def step(batch):
+        with torch.autocast("cuda", dtype=bf):
+            with torch.no_grad():
+                feats = vit.vision_encode(batch["rgb"], vsd, 24, 16)
+            img = pooler.attn_pooler_forward(feats, psd, 6, 16).to(bf)
+            mask, embeds, labels = splice.prepare_inputs_for_multimodal(batch["input_ids"], batch["attention_mask"], batch["labels"],
+                                                                        ll["model.embed_tokens.weight"], img)
+            Bq, Sq, _ = embeds.shape
+            cos, sin = llama.rope_cos_sin(torch.arange(Sq, device=dev), 128)
+            add_mask = llama._additive_mask(Bq, Sq, Sq, mask, embeds.dtype, dev)
+            x = embeds
+            for i in range(L):
+                x = checkpoint(lambda x_, i=i: llama.decoder_layer(x_, ll, i, 32, 1e-5, cos, sin, add_mask, 2.0, sdpa=True)[0],
+                               x, use_reentrant=False)
+            x = llama.rms_norm(x, ll["model.norm.weight"], 1e-5)
+            logits = F.linear(x, ll["lm_head.weight"])
+            loss = llama.causal_lm_loss(logits, labels)
+        opt.zero_grad(set_to_none=True)
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(params, 1.0)
+        opt.step()
+        return loss.detach()
+
+    batches = [make_batch(B, seed=300 + i, device=dev, seq_len=S, mixed=mixed) for i in range(2)]
+    for i in range(warmup):
+        step(batches[i % 2])
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        loss = step(batches[i % 2])
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    peak_gb = torch.cuda.max_memory_allocated(dev) / 2 ** 30
+    return dict(value=B * S / (ms * 1e-3), unit="tokens/s", ms_per_step=ms, steps=steps, warmup=warmup, loss=float(loss),
+                peak_mem_GiB=round(peak_gb, 1),
+                what=("PyTorch eager on this GPU: oracle modules (restated lhrs.models / HF LLaMA / CLIP), bf16 autocast, frozen weights bf16, "
+                      f"pooler + LoRA r={lora_r} fp32 trainable, per-layer activation checkpointing (reference: --use-checkpoint), SDPA attention, "
+                      "clip 1.0 + torch.optim.AdamW(fused); same batch shape as the timed arm; no DeepSpeed / loss scaler / offload"))
+
+
+# ------------------------------------------------------------------------------------------------ step-0 loss check
+class _UpcastView:
+    """Read-only view of a bf16 state dict that hands out fp32 copies one tensor at a time (a 7B fp32 clone would be 27 GB)."""
+
+    def __init__(self, sd):
+        self.sd = {k.replace(".base_layer.", ".").replace(".default.", "."): v.detach() for k, v in sd.items()}
+
+    def __getitem__(self, k):
+        return self.sd[k].float()
+
+    def get(self, k, default=None):
+        v = self.sd.get(k)
+        return default if v is None else v.float()
+
+    def __contains__(self, k):
+        return k in self.sd
+
+
+def oracle_loss_fp32(model, cfg, batch):
+    """The fp32 oracle (oracle/unibind.py: the reference's UniBind.forward restated) on the model's CURRENT weights and one device
+    batch — the checker of the step bench.py times, never the thing measured."""
+    from oracle import unibind
+    st = dict(vit=_UpcastView(model.rgb.encoder.state_dict()), pooler=_UpcastView(model.rgb_pooler.state_dict()),
+              llama=_UpcastView(model.text.text_encoder.state_dict()))
+    b32 = dict(batch)
+    b32["rgb"] = batch["rgb"].float()
+    with torch.no_grad():
+        return float(unibind.forward_loss(b32, st, cfg))
+
+
+# ------------------------------------------------------------------------------------------------ decode leg (config 2)
+def measure_decode(args, dev, rank, world, local, steps, warmup, cpu_baseline=True):
     """BASELINE config 2: 1 image + 32-token prompt -> 128 greedy tokens (cli_qa.py path), one sequence per GPU (replicas)."""
     from lhrs_bot_b200.build import build_model
     from lhrs_bot_b200.config import default_config
@@ -339,7 +507,7 @@ def run_decode(args, dev, rank, world, local):
             ms = float(t.item())
         return ms
 
-    for _ in range(max(args.warmup, 3)):
+    for _ in range(max(warmup, 3)):
         run(8)
     if os.environ.get("LHRS_PROFILE_STEP"):      # ncu --profile-from-start off: capture one short generation, print nothing
         torch.cuda.synchronize()
@@ -347,12 +515,12 @@ def run_decode(args, dev, rank, world, local):
         run(int(os.environ["LHRS_PROFILE_STEP"]))
         torch.cuda.synchronize()
         torch.cuda.profiler.stop()
-        return
+        return None
     l0 = ops.launch_count()
     with ClockSampler(local) as clocks:
-        ms_full = timed(n_new, args.steps)
+        ms_full = timed(n_new, steps)
     launches = ops.launch_count() - l0
-    ms_prefill = timed(1, args.steps)
+    ms_prefill = timed(1, steps)
     ms_tok = (ms_full - ms_prefill) / (n_new - 1)
     S = T + 143
     bytes_tok = 2.0 * (32 * (4 * 4096 * 4096 + 3 * 4096 * 11008) + 32000 * 4096) + 2 * 32 * 4096 * 2 * (S + n_new / 2)
@@ -365,29 +533,297 @@ def run_decode(args, dev, rank, world, local):
         pass
     achieved = bytes_tok / (ms_tok * 1e-3) / 1e9
     cpu_base = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    if rank == 0 and world == 1 and cpu_baseline:
         try:
             cpu_base, _ = time_cpu_reference("decode", 1, 0)
         except Exception as e:
             cpu_base = dict(error=str(e)[:200])
-    if rank == 0:
-        line = dict(metric="decode tokens/sec (LLaMA-7B, 224px, 1 image + 32-token prompt -> 128 greedy tokens), aggregate",
-                    value=world * 1e3 / ms_tok, unit="tokens/s", n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3),
-                    ms_per_step=ms_full, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="bf16", data="synthetic",
-                    config=dict(workload=("sampled_decode_b1_prompt175_new128 (cli_qa.py path, device-side temperature/top-p/penalty)" if args.sample
-                                          else "greedy_decode_b1_prompt175_new128 (cli_qa.py path)"), prefill_ms=ms_prefill, ms_per_token=ms_tok,
-                                parallelism=f"replicas{world}", inputs_vs_l2="13.5 GB of weights streamed per token >> 126 MB L2"),
-                    clocks=clocks.summary(),
-                    e2e=dict(value=world * n_new / (ms_full * 1e-3), unit="tokens/s (incl. image encode + prefill)",
-                             h2d_bytes_per_step=int(px_host.numel() * 2 + ids_host.numel() * 8), d2h_bytes_per_step=n_new * 8),
-                    gpu_launches=int(launches),
-                    roofline=dict(bound="hbm", achieved=achieved, peak=pk["hbm"], unit="GB/s", frac=achieved / pk["hbm"], traffic=traffic,
-                                  algorithmic_bytes_per_token=bytes_tok, per="token (161 launches: 32 x 5 + lm_head)",
-                                  kernel="gemv_kernel chain (decode step)", peak_source=pk["which"]),
-                    cpu_baseline=cpu_base)
-        print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    del model
+    _free_gpu()
+    return dict(metric="decode tokens/sec (LLaMA-7B, 224px, 1 image + 32-token prompt -> 128 greedy tokens), aggregate",
+                value=world * 1e3 / ms_tok, unit="tokens/s", n_gpus=world, steps=steps, warmup=max(warmup, 3),
+                ms_per_step=ms_full, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="bf16", data="synthetic",
+                config=dict(workload=("sampled_decode_b1_prompt175_new128 (cli_qa.py path, device-side temperature/top-p/penalty)" if args.sample
+                                      else "greedy_decode_b1_prompt175_new128 (cli_qa.py path)"), prefill_ms=ms_prefill, ms_per_token=ms_tok,
+                            parallelism=f"replicas{world}", inputs_vs_l2="13.5 GB of weights streamed per token >> 126 MB L2"),
+                clocks=clocks.summary(),
+                e2e=dict(value=world * n_new / (ms_full * 1e-3), unit="tokens/s (incl. image encode + prefill)",
+                         h2d_bytes_per_step=int(px_host.numel() * 2 + ids_host.numel() * 8), d2h_bytes_per_step=n_new * 8),
+                gpu_launches=int(launches),
+                roofline=dict(bound="hbm", achieved=achieved, peak=pk["hbm"], unit="GB/s", frac=achieved / pk["hbm"], traffic=traffic,
+                              algorithmic_bytes_per_token=bytes_tok, per="token (161 launches: 32 x 5 + lm_head)",
+                              kernel="gemv_kernel chain (decode step)", peak_source=pk["which"]),
+                cpu_baseline=cpu_base)
+
+
+def _free_gpu():
+    import gc
+    from lhrs_bot_b200 import runtime
+    runtime._workspaces.clear()
+    gc.collect()
+    torch.cuda.empty_cache()
+
+
+# ------------------------------------------------------------------------------------------------ training / prefill legs
+def measure_steps(args, workload, dev, rank, world, local, steps, warmup, B=None, S=None, mixed=False, checks=True,
+                  cpu_baseline=True, e2e_leg=True):
+    """One workload on this rank's GPU: W warm-up steps, K timed steps (barrier + synchronize on both sides, CUDA events, max
+    over ranks), the end-to-end leg from pinned host batches, the per-kernel roofline pass, and the self-checks."""
+    import ctypes as C
+    import torch.distributed as dist
+    from lhrs_bot_b200 import _lib, ops, training
+    from lhrs_bot_b200.build import build_model
+    from lhrs_bot_b200.config import default_config
+    from lhrs_bot_b200.preprocess import ClipPreprocessor, InputStager
+    lib = _lib.load()
+    train = workload in ("sft_step", "stage1_step")
+    B = B or (32 if workload == "stage1_step" else PER_GPU_BATCH)
+    S = S or (256 if workload == "stage1_step" else SEQ_LEN)
+    dropout = 0.0 if args.lora_dropout is None else float(args.lora_dropout)
+    cfg = default_config(stage=3 if workload == "sft_step" else (1 if workload == "stage1_step" else 0), local_rank=local,
+                         is_distribute=world > 1,
+                         lora=dict(enable=workload == "sft_step", lora_r=args.lora_r, lora_alpha=2 * args.lora_r, lora_dropout=dropout,
+                                   lora_bias="none"))
+    torch.manual_seed(322 + rank)          # the reference seeds rank r with seed + r (main_pretrain_stage1.py:282)
+    model = build_model(cfg).to(device=dev, dtype=torch.bfloat16)
+    if train:
+        # stage 1: the reference's recipe (Config/multi_modal_stage1.yaml:88-93: adanp, clip 0.3); stage 3: AdamW, clip 1.0
+        stepper = training.SftStepper(model, world_size=world, max_grad_norm=0.3 if workload == "stage1_step" else 1.0,
+                                      optimizer="adanp" if workload == "stage1_step" else "adamw")
+    else:
+        stepper = None
+        model.eval()
+
+    def step(batch):
+        if train:
+            return stepper.step(batch)
+        with torch.no_grad():
+            return model(batch)["total_loss"]
+
+    dev_batches = [make_batch(B, seed=1000 * rank + i, device=dev, seq_len=S, mixed=mixed) for i in range(2)]
+    host_batches = [make_batch(B, seed=2000 * rank + i, pin=True, seq_len=S, mixed=mixed, uint8_images=True) for i in range(2)]
+    h2d = batch_bytes(host_batches[0])
+    real_tok = sum(real_positions(b) for b in dev_batches) / len(dev_batches)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def gather_ms(ms):
+        """max / min over ranks of a per-rank device time"""
+        if world == 1:
+            return ms, ms
+        t = torch.tensor([ms], device=dev)
+        all_t = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(all_t, t)
+        v = [float(x.item()) for x in all_t]
+        return max(v), min(v)
+
+    def timed(fn, n):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(n):
+            fn(i)
+        e1.record()
+        barrier()
+        return gather_ms(e0.elapsed_time(e1))
+
+    warmup = max(warmup, 3)
+    losses = []
+    for i in range(warmup):
+        losses.append(step(dev_batches[i % 2]))
+    loss_step0 = float(losses[0])
+    if os.environ.get("LHRS_PROFILE_STEP"):      # ncu --profile-from-start off: capture exactly one warm step, print nothing
+        torch.cuda.synchronize()
+        torch.cuda.profiler.start()
+        step(dev_batches[0])
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
+        return None
+
+    # ---- self-check 1: the step that is about to be timed computes the reference's loss.  After the warm-up updates (LoRA B is
+    # no longer zero) the fp32 oracle is evaluated on the CURRENT weights and the next batch, then the real training step runs on
+    # that batch: |loss - oracle| must stay within the parity tests' bar.
+    loss_check = None
+    if checks and rank == 0:
+        ref = oracle_loss_fp32(model, cfg, dev_batches[warmup % 2])
+        _free_gpu()
+    got = float(step(dev_batches[warmup % 2]))
+    if checks and rank == 0:
+        loss_check = dict(loss_step0=loss_step0, step=warmup, loss=got, oracle_fp32=ref, abs_diff=abs(got - ref), tol=2e-2,
+                          ok=bool(abs(got - ref) <= 2e-2 and all(map(lambda v: v == v and abs(v) < 1e4, [loss_step0, got]))))
+        if not loss_check["ok"]:
+            raise SystemExit(f"bench.py: loss check FAILED, refusing to print a throughput line: {json.dumps(loss_check)}")
+
+    launches0 = ops.launch_count()
+    with ClockSampler(local) as clocks:
+        ms, ms_min = timed(lambda i: step(dev_batches[i % 2]), steps)
+    launches = ops.launch_count() - launches0
+    tokens_per_step = B * S * world
+    value = tokens_per_step * steps / (ms * 1e-3)
+
+    # ---- end to end through the public API: pinned HOST batches with raw uint8 tiles -> InputStager (H2D on a side stream +
+    # CLIP preprocessing kernel, double buffered) -> step -> D2H read of the loss, all inside the timed region
+    e2e = None
+    if e2e_leg:
+        pre = ClipPreprocessor()
+
+        def e2e_run(n):
+            it = iter(InputStager((host_batches[i % 2] for i in range(n)), dev, pre))
+            return lambda i: float(step(next(it)))
+        timed(e2e_run(1), 1)
+        ms_e2e, _ = timed(e2e_run(steps), steps)
+        e2e = dict(value=tokens_per_step * steps / (ms_e2e * 1e-3), unit="tokens/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=4,
+                   path="pinned host batch (uint8 224x224x3 tiles + ids/labels/mask) -> InputStager (side-stream H2D + lhrs_clip_preprocess) -> "
+                        + ("SftStepper.step" if train else "UniBind.forward") + " -> float(loss)")
+
+    # ---- exchange attribution (N > 1): CUDA events around the exchange + optimizer part of each step
+    exchange = None
+    if train and world > 1:
+        stepper.time_exchange, stepper.exchange_events = True, []
+        timed(lambda i: step(dev_batches[i % 2]), 4)
+        ex = [a.elapsed_time(b) for a, b in stepper.exchange_events]
+        stepper.time_exchange = False
+        ex_max, ex_min = gather_ms(sum(ex) / len(ex))
+        exchange = dict(exchange_ms_max=ex_max, exchange_ms_min=ex_min,
+                        what="gradient exchange + sharded optimizer + parameter all-gather, events around opt.step, mean of 4 steps, max/min over ranks")
+
+    # ---- self-check 2 (N > 1): the exchange leaves bit-identical parameters on every rank, and the reduce-scatter agrees with NCCL
+    exchange_check = None
+    if train and world > 1 and checks:
+        exchange_check = check_exchange(stepper, model, dev_batches[0], world, rank, dev)
+        if rank == 0 and not exchange_check["ok"]:
+            raise SystemExit(f"bench.py: exchange check FAILED: {json.dumps(exchange_check)}")
+
+    # ---- roofline of the dominant kernel (separate pass: event pairs around every launch of the profiled families)
+    pk = peaks()
+    lib.lhrs_prof_enable(1)
+    step(dev_batches[0])
+    res = {}
+    for kind, name in ((0, "gemm"), (3, "gemm_small"), (1, "attention"), (4, "lora_stream")):
+        t, f, b, n = C.c_double(), C.c_double(), C.c_double(), C.c_int64()
+        lib.lhrs_prof_summary(kind, C.byref(t), C.byref(f), C.byref(b), C.byref(n))
+        res[name] = dict(ms=t.value, flops=f.value, bytes=b.value, launches=n.value)
+    lib.lhrs_prof_enable(0)
+    gm, gs = res["gemm"], res["gemm_small"]
+    achieved = gm["flops"] / (gm["ms"] * 1e-3) / 1e12 if gm["ms"] > 0 else 0.0
+    all_ms = gm["ms"] + gs["ms"]
+    traffic, traffic_detail = None, None
+    try:   # dram bytes of the WORST launch (traffic / algorithmic) of the dominant kernel, from the committed ncu --set full capture
+        with open(os.path.join(ROOT, "profiles", GEMM_TRAFFIC_FILE)) as f:
+            tj = json.load(f)
+        worst = max(tj["launches"], key=lambda k: tj["launches"][k]["dram_bytes"] / tj["launches"][k]["algorithmic_bytes"])
+        traffic = tj["launches"][worst]["dram_bytes"]
+        traffic_detail = dict(launch=worst, algorithmic_bytes=tj["launches"][worst]["algorithmic_bytes"], source=tj["source"],
+                              all={k: dict(dram_bytes=v["dram_bytes"], algorithmic_bytes=v["algorithmic_bytes"]) for k, v in tj["launches"].items()})
+    except Exception:
+        pass
+    step_ms = ms / steps
+    roofline = dict(bound="tensor", achieved=achieved, peak=pk["tflops"], unit="TFLOP/s", frac=achieved / pk["tflops"],
+                    traffic=traffic, traffic_detail=traffic_detail,
+                    kernel="gemm_bf16_kernel<256,*,*,*,2> (tcgen05, 2-CTA 256x256 tiles: every large projection, fwd and dX)",
+                    peak_source=pk["which"], launches_per_step=gm["launches"],
+                    gemm_ms_per_step=gm["ms"], gemm_share_of_step=gm["ms"] / step_ms,
+                    small_gemm=dict(kernel="gemm_bf16_kernel<128|256,*,*,*,1> (skinny LoRA / pooler / ViT problems)", launches_per_step=gs["launches"],
+                                    ms_per_step=gs["ms"], tflops=(gs["flops"] / (gs["ms"] * 1e-3) / 1e12 if gs["ms"] > 0 else 0.0)),
+                    all_gemm_tflops=((gm["flops"] + gs["flops"]) / (all_ms * 1e-3) / 1e12 if all_ms > 0 else 0.0),
+                    lora_stream=dict(kernel="lora_panel_kernel / lora_rowreduce_kernel (HBM-bound rank-16 side products)",
+                                     launches_per_step=res["lora_stream"]["launches"], ms_per_step=res["lora_stream"]["ms"],
+                                     GBps=(res["lora_stream"]["bytes"] / (res["lora_stream"]["ms"] * 1e-3) / 1e9 if res["lora_stream"]["ms"] > 0 else 0.0),
+                                     hbm_peak_GBps=pk["hbm"]),
+                    attention_ms_per_step=res["attention"]["ms"],
+                    attention_tflops=(res["attention"]["flops"] / (res["attention"]["ms"] * 1e-3) / 1e12 if res["attention"]["ms"] > 0 else 0.0))
+    # whole-step fraction of the tensor roofline: algorithmic flops of the step (SURVEY 8d: 14.1 TF per S=512 SFT sample,
+    # 7.09 TF per S=256 stage-1 sample, forward 13.3 GF per position) over the step time
+    step_tf = {"sft_step": 14.1 * S / 512.0, "stage1_step": 7.09 * S / 256.0, "prefill": 13.3e-3 * S}[workload] * B
+    roofline["whole_step"] = dict(algorithmic_TF_per_step=step_tf, tflops=step_tf / (step_ms * 1e-3), frac=step_tf / (step_ms * 1e-3) / pk["tflops"],
+                                  note="padded positions counted (the reference computes them too)")
+
+    cpu_base = None
+    if rank == 0 and world == 1 and cpu_baseline:
+        try:
+            cpu_base, _ = time_cpu_reference(workload, 2, 1, seq_len=S, mixed=mixed)
+        except Exception as e:   # the baseline is a reported side figure; never let it take the GPU number down
+            cpu_base = dict(error=str(e)[:200])
+
+    gx = "none (single GPU)"
+    if train and world > 1:
+        kind = getattr(stepper.opt, "kind", "adamw")
+        if getattr(stepper, "exchange", "") == "p2p":
+            gx = (f"NVLS in-switch reduce-scatter (multimem.ld_reduce) + sharded {kind} + multicast all-gather (no NCCL call)"
+                  if getattr(stepper.opt, "nvls", False) else
+                  f"peer-memory reduce-scatter + sharded {kind} + all-gather (NVLink P2P, no NCCL call)")
+        else:
+            gx = "NCCL allreduce of the flat bf16 gradient buffer"
+    shape = "mixed 75% image / 25% text-only, ragged, padded to S (BASELINE config 4 as written)" if mixed else "uniform all-image, no padding"
+    wl = (f"stage3_sft_step_b{B}_s{S} (fwd+bwd, LoRA r={args.lora_r} dropout {dropout} + pooler grads, allreduce, AdamW; {shape})" if workload == "sft_step"
+          else f"stage1_step_b{B}_s{S} (fwd+bwd, pooler-only grads through the frozen LLaMA, allreduce, Adan; {shape})" if workload == "stage1_step"
+          else f"prefill_loss_b{B}_s{S} (UniBind.forward: ViT-L/14 + pooler + splice + LLaMA-7B + CE; {shape})")
+    line = dict(metric=f"tokens/sec (LLaMA-7B, 224px, seq {S}), aggregate", value=value, unit="tokens/s", n_gpus=world,
+                steps=steps, warmup=warmup, ms_per_step=step_ms, higher_is_better=True,
+                scaling="weak", vs_baseline=None, dtype="bf16", data="synthetic",
+                config=dict(workload=wl, per_gpu_batch=B, seq_len=S, image="224x224", parallelism=f"dp{world}",
+                            positions_per_step=dict(padded=tokens_per_step, real_mean_per_gpu=real_tok,
+                                                    note="`value` counts padded decoder positions B*S (computed by the reference too); "
+                                                         "real = positions with attention_mask true"),
+                            real_tokens_per_s=real_tok * world * steps / (ms * 1e-3),
+                            gradient_exchange=gx,
+                            loss_rows=("lm_head + CE evaluated on the rows with a counted label only (identical loss and gradients; "
+                                       "LHRS_CE_COMPACT=0 computes all rows)" if os.environ.get("LHRS_CE_COMPACT", "1") != "0"
+                                       else "all rows"),
+                            inputs_vs_l2="13.5 GB of weights + 64 MB activations streamed per step >> 126 MB L2 (no flush needed)"),
+                per_gpu=value / world, rank_ms_per_step=dict(max=step_ms, min=ms_min / steps), clocks=clocks.summary(), e2e=e2e,
+                gpu_launches=int(launches), roofline=roofline, cpu_baseline=cpu_base, loss_check=loss_check)
+    if exchange is not None:
+        line["exchange"] = exchange
+    if exchange_check is not None:
+        line["exchange_check"] = exchange_check
+    del model, stepper
+    _free_gpu()
+    return line
+
+
+GEMM_TRAFFIC_FILE = "r1_gemm_traffic.json"
+
+
+def check_exchange(stepper, model, batch, world, rank, dev):
+    """Driver-visible evidence that the N-rank gradient exchange is right:
+    (a) after the timed steps every rank holds BIT-IDENTICAL trainable parameters (two checksums of the flat bf16 buffer);
+    (b) p2p schedule only: one more backward, then the slice sum produced by the repo's reduce-scatter kernel (peer loads or
+        NVLS multimem.ld_reduce) is compared with an NCCL all_reduce(SUM) of the same local gradients in fp32."""
+    import torch.distributed as dist
+    opt = stepper.opt
+    out = dict(schedule=stepper.exchange)
+
+    def checksums():
+        v = opt.flat_param.view(torch.int16).to(torch.int64)
+        w = (torch.arange(v.numel(), device=dev, dtype=torch.int64) % 1021) + 1
+        t = torch.stack([v.sum(), (v * w).sum()])
+        all_t = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(all_t, t)
+        return all(torch.equal(all_t[0], x) for x in all_t)
+    out["params_identical"] = bool(checksums())
+    ok = out["params_identical"]
+    if stepper.exchange == "p2p":
+        loss = model(batch)["total_loss"]
+        loss.backward()
+        expect = opt.flat_grad.float()
+        dist.all_reduce(expect, op=dist.ReduceOp.SUM)
+        opt.step(lr=0.0)                                  # runs the reduce-scatter; lr 0 leaves the parameters where they are
+        torch.cuda.synchronize()
+        lo = opt.rank * opt.slice_n
+        e = expect[lo: lo + opt.slice_n]
+        gsum = opt.grad_sum
+        rel = float((gsum - e).norm() / (e.norm() + 1e-30))
+        out.update(reduce_vs_nccl_rel_l2=rel, reduce_form=("NVLS multimem (bf16-rounded switch sums)" if opt.nvls else "peer loads, fp32 sums"),
+                   reduce_tol=(6e-3 if opt.nvls else 1e-6), params_identical_after=bool(checksums()))
+        t = torch.tensor([1 if (rel <= out["reduce_tol"] and out["params_identical_after"]) else 0], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        ok = ok and bool(t.item())
+    out["ok"] = bool(ok)
+    return out
 
 
 # ------------------------------------------------------------------------------------------------ GPU arm
@@ -405,154 +841,44 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
-    from lhrs_bot_b200 import _lib, ops
-    from lhrs_bot_b200.build import build_model
-    from lhrs_bot_b200.config import default_config
-    from lhrs_bot_b200 import training
-
-    lib = _lib.load()
-    workload = args.workload
+    from lhrs_bot_b200 import _lib
+    _lib.load()                              # fail loudly before anything else if the CUDA library is missing
+    workload = resolve_workload(args)
+    line = None
     if workload == "decode":
-        return run_decode(args, dev, rank, world, local)
-    if workload == "auto":
-        workload = "sft_step"
-    # stage1_step = SURVEY 8d config 3: batch 32 per GPU, S = 256, pooler-only gradients (LLaMA and ViT frozen, no LoRA)
-    train = workload in ("sft_step", "stage1_step")
-    B = args.batch if args.batch else (32 if workload == "stage1_step" else PER_GPU_BATCH)
-    SEQ_LEN = args.seq if args.seq else (256 if workload == "stage1_step" else globals()["SEQ_LEN"])
-    t_text = SEQ_LEN - (NUM_QUERY - 1)
-    cfg = default_config(stage=3 if workload == "sft_step" else (1 if workload == "stage1_step" else 0), local_rank=local,
-                         is_distribute=world > 1,
-                         lora=dict(enable=workload == "sft_step", lora_r=args.lora_r, lora_alpha=2 * args.lora_r, lora_dropout=0.0, lora_bias="none"))
-    torch.manual_seed(322 + rank)
-    model = build_model(cfg).to(device=dev, dtype=torch.bfloat16)
-    if train:
-        # stage 1: the reference's recipe (Config/multi_modal_stage1.yaml:88-93: adanp, clip 0.3); stage 3: AdamW, clip 1.0
-        stepper = training.SftStepper(model, world_size=world, max_grad_norm=0.3 if workload == "stage1_step" else 1.0,
-                                      optimizer="adanp" if workload == "stage1_step" else "adamw")
+        line = measure_decode(args, dev, rank, world, local, args.steps, args.warmup, cpu_baseline=not args.no_cpu_baseline)
     else:
-        model.eval()
-
-    def step(batch):
-        if train:
-            return stepper.step(batch)
-        with torch.no_grad():
-            return model(batch)["total_loss"]
-
-    dev_batches = [make_batch(B, seed=1000 * rank + i, device=dev, t_text=t_text) for i in range(2)]
-    host_batches = [make_batch(B, seed=2000 * rank + i, pin=True, t_text=t_text) for i in range(2)]
-    h2d = batch_bytes(host_batches[0])
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def timed(fn, steps):
-        barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for i in range(steps):
-            fn(i)
-        e1.record()
-        barrier()
-        ms = e0.elapsed_time(e1)
-        if world > 1:
-            t = torch.tensor([ms], device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
-        return ms
-
-    for i in range(max(args.warmup, 3)):
-        step(dev_batches[i % 2])
-    if os.environ.get("LHRS_PROFILE_STEP"):      # ncu --profile-from-start off: capture exactly one warm step, print nothing
-        torch.cuda.synchronize()
-        torch.cuda.profiler.start()
-        step(dev_batches[0])
-        torch.cuda.synchronize()
-        torch.cuda.profiler.stop()
-        return
-    launches0 = ops.launch_count()
-    with ClockSampler(local) as clocks:
-        ms = timed(lambda i: step(dev_batches[i % 2]), args.steps)
-    launches = ops.launch_count() - launches0
-    tokens_per_step = B * SEQ_LEN * world
-    value = tokens_per_step * args.steps / (ms * 1e-3)
-
-    # ---- end to end through the public API with host-resident inputs
-    def e2e_step(i):
-        hb = host_batches[i % 2]
-        db = {k: v.to(dev, non_blocking=True) for k, v in hb.items()}
-        loss = step(db)
-        return float(loss)          # D2H read of the step's result
-
-    e2e_step(0)
-    ms_e2e = timed(e2e_step, args.steps)
-    e2e = dict(value=tokens_per_step * args.steps / (ms_e2e * 1e-3), unit="tokens/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=4)
-
-    # ---- roofline of the dominant kernel (separate pass: event pairs around every GEMM launch)
-    pk = peaks()
-    lib.lhrs_prof_enable(1)
-    step(dev_batches[0])
-    import ctypes as C
-    res = {}
-    for kind, name in ((0, "gemm"), (3, "gemm_small"), (1, "attention"), (4, "lora_stream")):
-        t, f, b, n = C.c_double(), C.c_double(), C.c_double(), C.c_int64()
-        lib.lhrs_prof_summary(kind, C.byref(t), C.byref(f), C.byref(b), C.byref(n))
-        res[name] = dict(ms=t.value, flops=f.value, bytes=b.value, launches=n.value)
-    lib.lhrs_prof_enable(0)
-    gm, gs = res["gemm"], res["gemm_small"]
-    achieved = gm["flops"] / (gm["ms"] * 1e-3) / 1e12 if gm["ms"] > 0 else 0.0
-    all_ms = gm["ms"] + gs["ms"]
-    traffic, traffic_detail = None, None
-    try:   # dram bytes of one launch of the dominant instantiation, from the committed ncu --set full capture
-        with open(os.path.join(ROOT, "profiles", "r1_gemm_traffic.json")) as f:
-            tj = json.load(f)
-        traffic = tj["launches"][tj["dominant"]]["dram_bytes"]
-        traffic_detail = dict(launch=tj["dominant"], algorithmic_bytes=tj["launches"][tj["dominant"]]["algorithmic_bytes"], source=tj["source"])
-    except Exception:
-        pass
-    roofline = dict(bound="tensor", achieved=achieved, peak=pk["tflops"], unit="TFLOP/s", frac=achieved / pk["tflops"],
-                    traffic=traffic, traffic_detail=traffic_detail,
-                    kernel="gemm_bf16_kernel<256,*,*,*,2> (tcgen05, 2-CTA 256x256 tiles: every large projection, fwd and dX)",
-                    peak_source=pk["which"], launches_per_step=gm["launches"],
-                    gemm_ms_per_step=gm["ms"], gemm_share_of_step=gm["ms"] / (ms / args.steps),
-                    small_gemm=dict(kernel="gemm_bf16_kernel<128|256,*,*,*,1> (skinny LoRA / pooler / ViT problems)", launches_per_step=gs["launches"],
-                                    ms_per_step=gs["ms"], tflops=(gs["flops"] / (gs["ms"] * 1e-3) / 1e12 if gs["ms"] > 0 else 0.0)),
-                    all_gemm_tflops=((gm["flops"] + gs["flops"]) / (all_ms * 1e-3) / 1e12 if all_ms > 0 else 0.0),
-                    lora_stream=dict(kernel="lora_panel_kernel / lora_rowreduce_kernel (HBM-bound rank-16 side products)",
-                                     launches_per_step=res["lora_stream"]["launches"], ms_per_step=res["lora_stream"]["ms"],
-                                     GBps=(res["lora_stream"]["bytes"] / (res["lora_stream"]["ms"] * 1e-3) / 1e9 if res["lora_stream"]["ms"] > 0 else 0.0),
-                                     hbm_peak_GBps=pk["hbm"]),
-                    attention_ms_per_step=res["attention"]["ms"],
-                    attention_tflops=(res["attention"]["flops"] / (res["attention"]["ms"] * 1e-3) / 1e12 if res["attention"]["ms"] > 0 else 0.0))
-
-    cpu_base = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        try:
-            cpu_base, _ = time_cpu_reference(workload, 2, 1, seq_len=SEQ_LEN)
-        except Exception as e:   # the baseline is a reported side figure; never let it take the GPU number down
-            cpu_base = dict(error=str(e)[:200])
-
-    if rank == 0:
-        wl = (f"stage3_sft_step_b{B}_s{SEQ_LEN} (fwd+bwd, LoRA r={args.lora_r} + pooler grads, allreduce, AdamW)" if workload == "sft_step"
-              else f"stage1_step_b{B}_s{SEQ_LEN} (fwd+bwd, pooler-only grads through the frozen LLaMA, allreduce, Adan)" if workload == "stage1_step"
-              else f"prefill_loss_b{B}_s{SEQ_LEN} (UniBind.forward: ViT-L/14 + pooler + splice + LLaMA-7B + CE)")
-        line = dict(metric=f"tokens/sec (LLaMA-7B, 224px, seq {SEQ_LEN}), aggregate", value=value, unit="tokens/s", n_gpus=world,
-                    steps=args.steps, warmup=max(args.warmup, 3), ms_per_step=ms / args.steps, higher_is_better=True,
-                    scaling="weak", vs_baseline=None, dtype="bf16", data="synthetic",
-                    config=dict(workload=wl, per_gpu_batch=B, seq_len=SEQ_LEN, image="224x224", parallelism=f"dp{world}",
-                                gradient_exchange=(((f"NVLS in-switch reduce-scatter (multimem.ld_reduce) + sharded {getattr(stepper.opt, 'kind', 'adamw')} + multicast all-gather (no NCCL call)"
-                                                     if getattr(stepper.opt, "nvls", False) else
-                                                     f"peer-memory reduce-scatter + sharded {getattr(stepper.opt, 'kind', 'adamw')} + all-gather (NVLink P2P, no NCCL call)")
-                                                    if getattr(stepper, "exchange", "") == "p2p" else "NCCL allreduce of the flat bf16 gradient buffer")
-                                                   if train and world > 1 else "none (single GPU)"),
-                                loss_rows=("lm_head + CE evaluated on the rows with a counted label only (identical loss and gradients; "
-                                           "LHRS_CE_COMPACT=0 computes all rows)" if os.environ.get("LHRS_CE_COMPACT", "1") != "0"
-                                           else "all rows"),
-                                inputs_vs_l2="13.5 GB of weights + 64 MB activations streamed per step >> 126 MB L2 (no flush needed)"),
-                    per_gpu=value / world, clocks=clocks.summary(), e2e=e2e, gpu_launches=int(launches), roofline=roofline,
-                    cpu_baseline=cpu_base)
+        mixed = is_mixed(args, workload)
+        B = args.batch or (32 if workload == "stage1_step" else PER_GPU_BATCH)
+        S = args.seq or (256 if workload == "stage1_step" else SEQ_LEN)
+        profiling = bool(os.environ.get("LHRS_PROFILE_STEP"))
+        # the comparator the north star's ">= 6x" refers to: PyTorch eager on one GPU, same step — before our model takes the memory
+        eager = None
+        if workload == "sft_step" and world == 1 and rank == 0 and not args.no_gpu_eager and not profiling:
+            try:
+                eager = gpu_eager_sft(dev, B, S, mixed, args.lora_r)
+            except Exception as e:
+                eager = dict(error=f"{type(e).__name__}: {str(e)[:300]}")
+            _free_gpu()
+        line = measure_steps(args, workload, dev, rank, world, local, args.steps, args.warmup, B=B, S=S, mixed=mixed,
+                             checks=not args.no_checks, cpu_baseline=not args.no_cpu_baseline)
+        if line is not None and eager is not None:
+            line["gpu_eager"] = eager
+            if "value" in eager:
+                line["gpu_eager"]["ours_over_eager_1gpu"] = line["value"] / eager["value"]
+        # cheap extra legs on the same driver-run line (N = 1 only): BASELINE config 2 (greedy decode) and config 3 (stage-1 step)
+        if line is not None and args.workload == "auto" and world == 1 and not args.no_extra:
+            extra = {}
+            for name, fn in (("decode_greedy_config2", lambda: measure_decode(args, dev, rank, world, local, 3, 3, cpu_baseline=False)),
+                             ("stage1_step_config3", lambda: measure_steps(args, "stage1_step", dev, rank, world, local, 5, 3, checks=False,
+                                                                           cpu_baseline=False, e2e_leg=False))):
+                try:
+                    r = fn()
+                    extra[name] = {k: r[k] for k in ("metric", "value", "unit", "ms_per_step", "config", "roofline", "clocks", "gpu_launches") if k in r}
+                except Exception as e:
+                    extra[name] = dict(error=f"{type(e).__name__}: {str(e)[:300]}")
+            line["extra"] = extra
+    if rank == 0 and line is not None:
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -50,6 +50,22 @@ class UniBind(nn.Module):
                     checkpoint=getattr(config, "use_checkpoint", False),
                 )
 
+    # ------------------------------------------------------------------ dtype surface
+    def to(self, *args, **kwargs):
+        """``model.to(type_dict[config.dtype])`` is how cli_qa.py:89-90 and the eval drivers cast the model, and every shipped
+        yaml says ``dtype: float16``: a float16 request is served in bfloat16 (``runtime.resolve_compute_dtype``; logged once)."""
+        from . import runtime
+        device, dtype, non_blocking, fmt = torch._C._nn._parse_to(*args, **kwargs)
+        if dtype == torch.float16:
+            dtype = runtime.resolve_compute_dtype(dtype)
+            if device is not None:
+                super().to(device=device, non_blocking=non_blocking)
+            return super().to(dtype=dtype)
+        return super().to(*args, **kwargs)
+
+    def half(self):
+        return self.to(torch.float16)
+
     # ------------------------------------------------------------------ checkpoints (UniBind.py:59-117)
     def load_rgb_encoder(self, path: str):
         assert hasattr(self, "rgb"), "rgb modal is not activated"
@@ -92,8 +108,8 @@ class UniBind(nn.Module):
     def prepare_for_training(self, freeze_vision: bool = False, freeze_text: bool = False, tune_rgb_pooler: bool = False,
                              model_path: str = False, tune_im_start: bool = False,
                              compute_dtype: torch.dtype = torch.float32):
-        if compute_dtype == torch.float16:
-            raise NotImplementedError("compute_dtype=float16: the sm_100a kernels compute in bfloat16 (same tensor-core rate, wider range)")
+        from . import runtime
+        compute_dtype = runtime.resolve_compute_dtype(compute_dtype)   # float16 (every shipped yaml) -> bfloat16, logged once
         self.train()
         for param in self.rgb.parameters():
             param.requires_grad = not freeze_vision

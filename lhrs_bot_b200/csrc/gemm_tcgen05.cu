@@ -712,11 +712,15 @@ extern "C" int lhrs_gemm_bf16(const LhrsGemm* g, void* stream_) {
     const int kind = g->epilogue;
     const bool a_mn = g->a_mn_major != 0, b_mn = g->b_mn_major != 0;
     int bn = 256;
+    // LHRS_GEMM_CG=1/2 forces single-CTA / CTA-pair tiles (read per call: the parity tests flip it between cases so that the
+    // pair kernel and its K-extensions are also exercised on small problems)
+    const char* cg_env = getenv("LHRS_GEMM_CG");
+    const int forced = cg_env ? atoi(cg_env) : 0;
     if (kind == LHRS_EPI_LINEAR) {
         if (g->N <= 128 || (g->N % 256) != 0) bn = 128;
         // small problems: more, smaller tiles fill the 148 SMs better
         const long long tiles256 = (long long)((g->M + BM - 1) / BM) * ((g->N + 255) / 256);
-        if (tiles256 < num_sms() && g->N > 128) bn = 128;
+        if (tiles256 < num_sms() && g->N > 128 && !(forced == 2 && (g->N % 256) == 0)) bn = 128;
         if (g->num_b > 1 && b_mn) {
             // segments stacked along K (each [K/num_b, ldb>=N]); seg_rows is ignored
             LHRS_CHECK_ARG((g->K % g->num_b) == 0 && ((g->K / g->num_b) % BK) == 0 && g->B[1] != nullptr && (g->num_b < 3 || g->B[2] != nullptr),
@@ -740,8 +744,6 @@ extern "C" int lhrs_gemm_bf16(const LhrsGemm* g, void* stream_) {
     // CTA pairs (cta_group::2, 256 x 256 tiles) when the problem has at least one pair-tile per SM pair; LHRS_GEMM_CG=1/2 forces
     int cg = 1;
     {
-        static int forced = -1;
-        if (forced < 0) { const char* e = getenv("LHRS_GEMM_CG"); forced = e ? atoi(e) : 0; }
         const long long pair_tiles = (long long)((g->M + 2 * BM - 1) / (2 * BM)) * ((g->N + 255) / 256);
         if (bn == 256 && (g->N % 256) == 0 && pair_tiles >= num_sms() / 2) cg = 2;
         if (forced == 1) cg = 1;

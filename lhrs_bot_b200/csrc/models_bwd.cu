@@ -257,8 +257,8 @@ extern "C" int lhrs_llama_bwd(const LhrsLlamaWeights* w, void* const* lora_a_gra
             // d_act = dx · W_down (+ LoRA) with the SwiGLU backward applied in the epilogue: writes d_gu = [d_gate | d_up]
             LhrsGemm g = gemm_desc(M, F, D, dx, D, w->down_w[l], F, b.d_gu, 2 * F);
             g.b_mn_major = 1;
-            static int fuse = -1;
-            if (fuse < 0) { const char* e = getenv("LHRS_FUSE_SWIGLU_BWD"); fuse = e ? atoi(e) : 0; }
+            const char* fe = getenv("LHRS_FUSE_SWIGLU_BWD");   // read per call (the parity tests run both forms)
+            const int fuse = fe ? atoi(fe) : 0;
             g.pre_gate = t.pre_gate; g.pre_up = t.pre_up;
             if ((rc = lora_bwd_pre(st, w, lora_a_grads, L, g))) return rc;
             if ((L.active && !L.grouped) || !fuse) {   // un-batched LoRA fallback needs d_act materialised for its read-modify-write pass

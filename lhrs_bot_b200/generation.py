@@ -140,7 +140,9 @@ class DecodeSession:
 
 def _sample(logits: torch.Tensor, temperature: float, top_p: Optional[float], top_k: Optional[int],
             repetition_penalty: Optional[float], history, generator) -> int:
-    """Host-side HF logits processors (only for callers that pass a torch.Generator or want the per-step logits)."""
+    """Host-side HF logits processors — test instrumentation only (``return_step_logits=True`` with sampling: the parity tests
+    want the per-step fp32 logits next to the draw); product callers, including those passing a torch.Generator, select on
+    the device (``sample_commit_kernel``)."""
     logits = logits.clone()
     if repetition_penalty and repetition_penalty != 1.0 and history:
         idx = torch.tensor(sorted(set(history)), device=logits.device)
@@ -233,7 +235,17 @@ def generate(text, input_ids: torch.Tensor, image_embedding: Optional[torch.Tens
     last = hidden[0, S - 1].contiguous()
     st = runtime.stream()
 
-    if generator is not None or return_step_logits or host_picker is not None:
+    if streamer is not None:
+        # HF generate announces the prompt once before the first new token; with inputs_embeds that prompt is an empty (1, 0)
+        # tensor.  TextStreamer(skip_prompt=True) (cli_qa.py:174) consumes its skip flag on this call — without it the first
+        # generated token of every turn would be swallowed from the streamed text.
+        streamer.put(torch.empty((1, 0), dtype=torch.long))
+    if generator is not None and seed is None and not return_step_logits and host_picker is None:
+        # a torch.Generator seeds the DEVICE sampler (Philox key drawn from the generator's stream: reproducible under
+        # generator.manual_seed, advances the generator once per call); no host-side torch.multinomial on the product path
+        seed = int(torch.randint(0, 2 ** 62, (1,), generator=generator, device=generator.device).item())
+        generator = None
+    if return_step_logits or host_picker is not None:
         return _generate_host_side(lib, w, sess, last, S, n_budget, do_sample, temperature, top_p, top_k, repetition_penalty,
                                    ([eos_token_id] + [q[0] for q in extra_stops]) if extra_stops else eos_token_id, streamer, stopping_criteria, generator, return_step_logits, dev, host_picker)
 

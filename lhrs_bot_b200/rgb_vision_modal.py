@@ -177,6 +177,10 @@ class VisionModal(BaseModal):
             raise NotImplementedError(
                 "tune_rgb_bk=True (training the ViT backbone) is outside the hot path: every shipped yaml freezes it "
                 "(Config/multi_modal_stage{1,2,3}.yaml: tune_rgb_bk: False)")
+        if x.is_cuda and x.dtype in (torch.float16, torch.float32):
+            # cli_qa.py:120-126 casts the pixel tensor to type_dict[config.dtype] (float16 in the shipped yamls); HF processors
+            # hand out float32.  Input conversion only — the model itself computes in bfloat16 (runtime.resolve_compute_dtype).
+            x = x.to(torch.bfloat16)
         runtime.require_bf16_cuda(x, "VisionModal input")
         lib = _lib.load()
         w = self.weights()

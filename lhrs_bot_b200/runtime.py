@@ -23,6 +23,41 @@ def workspace(nbytes: int, device: torch.device, tag: str = "fwd") -> torch.Tens
     return buf
 
 
+_warned = set()
+
+
+def warn_once(key: str, msg: str) -> None:
+    """One logged + warned line per process for a documented deviation from the reference's config surface."""
+    if key in _warned:
+        return
+    _warned.add(key)
+    import logging
+    import warnings
+    logging.getLogger("train").warning(msg)
+    warnings.warn(msg, stacklevel=3)
+
+
+def resolve_compute_dtype(dtype) -> torch.dtype:
+    """Map the reference's ``dtype`` / ``compute_dtype`` to what the sm_100a kernels compute in.
+
+    Every shipped yaml says ``dtype: float16`` + ``fp16: True`` (Config/multi_modal_stage{1,2,3}.yaml:75-80,
+    Config/multi_modal_eval.yaml): the reference then autocasts to fp16 with a loss scaler.  tcgen05 runs bf16 at the same
+    rate with fp32's exponent range, so float16 requests are served in **bfloat16** (no loss scaling needed) — the one
+    deliberate numeric deviation of the config surface, logged once.  float32 is refused (there is no fp32 tensor-core path)."""
+    if isinstance(dtype, str):
+        dtype = {"float16": torch.float16, "fp16": torch.float16, "half": torch.float16, "bfloat16": torch.bfloat16,
+                 "bf16": torch.bfloat16, "float32": torch.float32, "fp32": torch.float32}[dtype.lower()]
+    if dtype == torch.float16:
+        warn_once("fp16", "lhrs_bot_b200: float16 was requested (yaml `dtype: float16` / `fp16: True`); the sm_100a kernels "
+                          "compute in bfloat16 with fp32 accumulation (same tensor-core rate, fp32 exponent range, no loss "
+                          "scaling) - documented deviation, see DESIGN.md section 4")
+        return torch.bfloat16
+    if dtype == torch.bfloat16:
+        return torch.bfloat16
+    raise NotImplementedError(f"compute dtype {dtype}: the sm_100a hot path computes in bfloat16 (float16 requests are mapped "
+                              f"to it); there is no fp32 tensor-core path")
+
+
 def stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 

@@ -18,10 +18,22 @@ from . import _lib, runtime
 from ._lib import check
 
 AVAILABLE = True
+LORA_DROPOUT_MODELLED = False     # flipped when the T-panel kernels apply the Philox mask (peft semantics, text_modal.py:136-143)
 
 
 def trainable_parameters(model) -> List[torch.nn.Parameter]:
     return [p for p in model.parameters() if p.requires_grad]
+
+
+def sync_initial_parameters(flat_param: torch.Tensor, src: int = 0) -> None:
+    """Broadcast rank ``src``'s flat trainable set to every data-parallel rank before the fp32 master copy is taken.
+
+    The reference seeds each rank with ``config.seed + rank`` (main_pretrain_stage1.py:282) and relies on
+    ``deepspeed.initialize`` to broadcast rank 0's weights; without this the kaiming-initialised LoRA A factors and the pooler
+    would start different on every rank and the replicas would never agree.  No-op without an initialised process group."""
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.broadcast(flat_param, src=src)
 
 
 class _FlatOptimizer:
@@ -51,6 +63,7 @@ class _FlatOptimizer:
             if self.decay_mask is not None:
                 self.decay_mask[off: off + n] = 0.0 if p.dim() <= 1 else 1.0
             off += n
+        sync_initial_parameters(self.flat_param)      # every data-parallel replica starts from rank 0's trainable set
         self.master.copy_(self.flat_param)
         self.lr, self.weight_decay, self.max_grad_norm = lr, weight_decay, max_grad_norm
         self.step_count = 0
@@ -167,6 +180,7 @@ class PeerShardedAdamW:
             if mask is not None:
                 mask[off: off + n] = 0.0 if p.dim() <= 1 else 1.0
             off += n
+        sync_initial_parameters(self.flat_param)      # replicas start from rank 0's trainable set (see _FlatOptimizer)
         lo = rank * self.slice_n
         kind = kind.lower()
         assert kind in ("adamw", "adanp", "adan", "adanw"), kind
@@ -281,14 +295,18 @@ class SftStepper:
 
     def __init__(self, model, world_size: int = 1, lr: float = 2e-4, weight_decay: float = 0.0, max_grad_norm: float = 1.0,
                  warmup_steps: int = 0, total_steps: int = 0, prepare: bool = True, optimizer: str = "adamw",
-                 min_lr: float = 0.0, warmup_ratio: float = 0.1, exchange: str = "auto"):
+                 min_lr: float = 0.0, warmup_ratio: float = 0.1, exchange: str = "auto", tune_rgb_pooler: bool = True,
+                 model_path=None):
         self.model = model
         self.world = world_size
         if prepare:
-            has_lora = model.text.text_encoder.has_lora()
-            model.prepare_for_training(freeze_vision=True, freeze_text=True, tune_rgb_pooler=True, model_path=None,
-                                       tune_im_start=False, compute_dtype=torch.bfloat16)
-            if has_lora:
+            # the reference's own call (main_pretrain_stage1.py:199-206): ViT and LLaMA frozen, the pooler trainable iff the yaml
+            # says so (stage 3 ships ``tune_rgb_pooler: False`` -> LoRA only), adapters trainable when present
+            model.prepare_for_training(freeze_vision=True, freeze_text=True, tune_rgb_pooler=bool(tune_rgb_pooler),
+                                       model_path=model_path, tune_im_start=False, compute_dtype=torch.bfloat16)
+            # adapters exist either because the yaml enables LoRA (stage 2) or because `model_path` carried a TextLoRA directory
+            # (stage 3 resumes the stage-2 adapters, trainable: UniBind.py:105-112) — look AFTER the checkpoint was loaded
+            if model.text.text_encoder.has_lora():
                 for a, b in model.text.lora_pairs():
                     a.requires_grad_(True)
                     b.requires_grad_(True)
@@ -299,6 +317,12 @@ class SftStepper:
         ordered = [a for a, _ in pairs if a.requires_grad] + [b for _, b in pairs if b.requires_grad]
         seen = {id(p) for p in ordered}
         params = [p for p in trainable_parameters(model) if id(p) not in seen] + ordered
+        if not params:
+            raise ValueError("SftStepper: the model has no trainable parameter (tune_rgb_pooler=False and no LoRA adapters)")
+        pc = model.text.text_encoder.peft_config
+        if pc is not None and float(getattr(pc, "lora_dropout", 0.0) or 0.0) > 0 and ordered and not LORA_DROPOUT_MODELLED:
+            runtime.warn_once("lora_dropout", f"lhrs_bot_b200: lora_dropout={pc.lora_dropout} is not applied by this build: the LoRA branch "
+                                              "trains without peft's input dropout (documented deviation, DESIGN.md section 4)")
         # Gradient exchange: "p2p" = reduce-scatter + AdamW + all-gather over NVLink peer memory (PeerShardedAdamW), "nccl" = one
         # summed NCCL allreduce of the flat buffer + the full-buffer optimizer kernel, "auto" = p2p when it can be set up
         # (AdamW, world > 1, symmetric memory available on this node), else nccl.  LHRS_EXCHANGE overrides.
@@ -307,17 +331,29 @@ class SftStepper:
         self.exchange = "nccl"
         self.opt = None
         if exchange in ("auto", "p2p") and world_size > 1 and optimizer.lower() in ("adamw", "adanp", "adan", "adanw") and params[0].is_cuda:
+            import torch.distributed as dist
+            saved = [p.data for p in params]      # construction re-points p.data into the symmetric buffer: undo on failure
+            opt, err = None, None
             try:
-                import torch.distributed as dist
-                self.opt = PeerShardedAdamW(params, world_size, dist.get_rank(), lr=lr, weight_decay=weight_decay,
-                                            max_grad_norm=max_grad_norm, kind=optimizer)
-                self.exchange = "p2p"
+                opt = PeerShardedAdamW(params, world_size, dist.get_rank(), lr=lr, weight_decay=weight_decay,
+                                       max_grad_norm=max_grad_norm, kind=optimizer)
             except Exception as e:   # no symmetric memory on this node / build: the NCCL schedule is always available
+                err = e
+            # every rank must run the same schedule (a rank on symmetric-memory barriers next to one in an NCCL allreduce is a
+            # hang): agree on the outcome before committing to it
+            ok = torch.tensor([1 if opt is not None else 0], device=params[0].device, dtype=torch.int32)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+            if int(ok.item()) == 1:
+                self.opt, self.exchange = opt, "p2p"
+            else:
+                for p_, d_ in zip(params, saved):
+                    p_.data = d_
+                opt = None
                 if exchange == "p2p":
-                    raise
+                    raise RuntimeError(f"peer-memory gradient exchange unavailable on at least one rank (this rank: {err!r})")
                 import warnings
-                warnings.warn(f"peer-memory gradient exchange unavailable ({type(e).__name__}: {e}); using the NCCL allreduce")
-                self.opt = None
+                warnings.warn(f"peer-memory gradient exchange unavailable on at least one rank (this rank: {err!r}); "
+                              f"every rank uses the NCCL allreduce")
         if self.opt is None:
             self.opt = build_flat_optimizer(optimizer, params, lr, weight_decay, max_grad_norm)
         # the backward kernels write into the flat gradient buffer directly
@@ -326,6 +362,8 @@ class SftStepper:
         self.base_lr, self.warmup, self.total = lr, warmup_steps, total_steps
         self.min_lr, self.warmup_ratio = min_lr, warmup_ratio
         self.it = 0
+        self.time_exchange = False          # bench: record CUDA events around the exchange + optimizer part of each step
+        self.exchange_events = []
 
     @classmethod
     def from_config(cls, model, config, world_size: int = 1, max_iters: int = 0, **kw) -> "SftStepper":
@@ -336,11 +374,19 @@ class SftStepper:
         run (the reference takes it from the data loader); 0 keeps the learning rate constant."""
         sched = config.get("schedule", {}) or {}
         cosine = str(sched.get("name", "cosine")).lower() == "cosine"
-        return cls(model, world_size=world_size, lr=float(config.get("lr", 2e-4)), weight_decay=float(config.get("wd", 0.0)),
-                   max_grad_norm=float(config.get("max_grad_norm", 1.0) or 0.0), optimizer=str(config.get("optimizer", "adamw")),
-                   warmup_steps=int(sched.get("warmup_epochs", 0)) if sched.get("warmup_method", "linear") else 0,
-                   total_steps=int(max_iters) if cosine else 0, min_lr=float(sched.get("min_lr", 0.0)),
-                   warmup_ratio=float(sched.get("warmup_factor", 0.1)), **kw)
+        # trainable set as the reference's entry scripts pass it on (main_pretrain_stage1.py:199-206): tune_rgb_pooler and the
+        # checkpoint to resume from come from the yaml / CLI; tune_rgb_bk=True (a trainable ViT) is outside the hot path
+        if config.get("tune_rgb_bk", False):
+            raise NotImplementedError("tune_rgb_bk=True: the ViT backward is not on the hot path (False in every shipped yaml)")
+        kw.setdefault("tune_rgb_pooler", bool(config.get("tune_rgb_pooler", True)))
+        kw.setdefault("model_path", config.get("model_path", None))
+        args = dict(world_size=world_size, lr=float(config.get("lr", 2e-4)), weight_decay=float(config.get("wd", 0.0)),
+                    max_grad_norm=float(config.get("max_grad_norm", 1.0) or 0.0), optimizer=str(config.get("optimizer", "adamw")),
+                    warmup_steps=int(sched.get("warmup_epochs", 0)) if sched.get("warmup_method", "linear") else 0,
+                    total_steps=int(max_iters) if cosine else 0, min_lr=float(sched.get("min_lr", 0.0)),
+                    warmup_ratio=float(sched.get("warmup_factor", 0.1)))
+        args.update(kw)                      # explicit keyword arguments win over the yaml
+        return cls(model, **args)
 
     def step(self, batch) -> torch.Tensor:
         out = self.model(batch)
@@ -348,10 +394,16 @@ class SftStepper:
         loss.backward()
         lr = (reference_lr(self.it, self.base_lr, self.total, self.min_lr, self.warmup, self.warmup_ratio)
               if self.total > 0 else self.base_lr)
+        if self.time_exchange:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
         if self.exchange == "p2p":
             self.opt.step(lr=lr)                                   # exchange and update are one fused schedule
         else:
             scale = allreduce_flat_gradients(self.opt.flat_grad, self.world)
             self.opt.step(lr=lr, grad_scale=scale)
+        if self.time_exchange:
+            e1.record()
+            self.exchange_events.append((e0, e1))
         self.it += 1
         return loss.detach()

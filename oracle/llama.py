@@ -54,9 +54,11 @@ def _linear(x, sd, name, lora_scale: float):
 
 
 def decoder_layer(x, sd, i: int, n_head: int, eps: float, cos, sin, add_mask, lora_scale: float = 0.0,
-                  past: Optional[Tuple[torch.Tensor, torch.Tensor]] = None):
+                  past: Optional[Tuple[torch.Tensor, torch.Tensor]] = None, sdpa: bool = False):
     """One HF LlamaDecoderLayer.  x (B,S,D); cos/sin (S,hd) for the positions of x; add_mask (B,1,S,S_total) additive.
-    Returns (y, (k, v)) with k/v including ``past``."""
+    Returns (y, (k, v)) with k/v including ``past``.  ``sdpa=True`` evaluates the same attention through
+    ``F.scaled_dot_product_attention`` (transformers 4.36.1 selects LlamaSdpaAttention when torch >= 2.1.1 — the pinned
+    torch 2.1.2 qualifies): same function, library kernel; used by bench.py's GPU-eager comparator."""
     p = f"model.layers.{i}."
     B, S, D = x.shape
     hd = D // n_head
@@ -70,11 +72,15 @@ def decoder_layer(x, sd, i: int, n_head: int, eps: float, cos, sin, add_mask, lo
     if past is not None:
         k = torch.cat([past[0], k], dim=2)
         v = torch.cat([past[1], v], dim=2)
-    att = (q @ k.transpose(-1, -2)) * hd ** -0.5
-    if add_mask is not None:
-        att = att + add_mask
-    att = torch.softmax(att, dim=-1, dtype=torch.float32).to(q.dtype)
-    o = (att @ v).transpose(1, 2).reshape(B, S, D)
+    if sdpa:
+        o = F.scaled_dot_product_attention(q, k, v, attn_mask=None if add_mask is None else add_mask.to(q.dtype))
+        o = o.transpose(1, 2).reshape(B, S, D)
+    else:
+        att = (q @ k.transpose(-1, -2)) * hd ** -0.5
+        if add_mask is not None:
+            att = att + add_mask
+        att = torch.softmax(att, dim=-1, dtype=torch.float32).to(q.dtype)
+        o = (att @ v).transpose(1, 2).reshape(B, S, D)
     x = x + _linear(o, sd, p + "self_attn.o_proj", lora_scale)
     h = rms_norm(x, sd[p + "post_attention_layernorm.weight"], eps)
     g = _linear(h, sd, p + "mlp.gate_proj", lora_scale)

@@ -191,13 +191,40 @@ def test_device_sampled_generation(small):
     assert out == base[:first] and crit.calls >= 1
     # a streamer sees every id exactly once, in order
     class Streamer:
-        def __init__(self): self.got, self.ended = [], False
-        def put(self, t): self.got += t.tolist()
+        def __init__(self): self.got, self.ended, self.prompt_calls = [], False, 0
+        def put(self, t):
+            if t.dim() > 1:                     # HF announces the prompt first: (1, 0) with inputs_embeds
+                assert t.shape == (1, 0) and not self.got
+                self.prompt_calls += 1
+                return
+            self.got += t.tolist()
         def end(self): self.ended = True
     sm = Streamer()
     with torch.no_grad():
         out = model.generate(ids, images=px, max_new_tokens=20, eos_token_id=None, seed=77, streamer=sm, **kw)[0].tolist()
-    assert sm.got == out == base[:20] and sm.ended
+    assert sm.got == out == base[:20] and sm.ended and sm.prompt_calls == 1
+
+    # the stock transformers.TextStreamer(skip_prompt=True) of cli_qa.py:174 must print EVERY generated token: its skip flag is
+    # consumed by the prompt announcement, not by the first new token
+    from transformers import TextStreamer
+
+    class Tok:
+        def decode(self, ids_, **kwargs):
+            return "".join(f"<{int(i)}>" for i in ids_)
+
+    class Capture(TextStreamer):
+        def __init__(self, *a, **k):
+            super().__init__(*a, **k)
+            self.text = ""
+        def on_finalized_text(self, text, stream_end=False):
+            self.text += text
+    for host_side in (False, True):
+        cap = Capture(Tok(), skip_prompt=True)
+        extra = dict(return_step_logits=True) if host_side else {}
+        with torch.no_grad():
+            res = model.generate(ids, images=px, max_new_tokens=8, eos_token_id=None, seed=77, streamer=cap, **kw, **extra)
+        toks = (res[0] if host_side else res)[0].tolist()
+        assert cap.text == "".join(f"<{t}>" for t in toks), (host_side, cap.text, toks)
 
 
 def test_generate_text_only_and_long_context(small):

@@ -1,0 +1,170 @@
+"""Parity at the configuration the headline number is quoted on (BASELINE config 4, per-GPU slice): LLaMA-2-7B WIDTHS
+(hidden 4096, ffn 11008, 32 heads, vocab 32000), M = 16 x 512 = 8192 decoder rows, LoRA on all seven projections + pooler
+trainable, the SftStepper's flat parameter layout.  At this size the library takes the code paths bench.py times and the small
+tests never reach: CTA-pair (cta_group::2) 256x256 GEMM tiles with the LoRA K-extension (incl. the SwiGLU gate/up split across
+the two CTAs), the MN-major dX K-extension, the streaming `lora_panel` / `lora_rowreduce` kernels (r = 16), the tcgen05
+attention forward / backward, and lm_head + CE over the supervised rows only.  Depth is 2 layers (every layer runs the same
+launches) so that the fp32 oracle — autograd through oracle/unibind.py on the GPU — stays in seconds.
+
+Reference semantics: lhrs/models/text_modal.py:133-151 (LoRA wiring), :281-294 (HF forward + shifted CE), UniBind.py:178-199.
+Bars as in test_backward_gpu.py: |loss diff| <= 2e-2, gradients cosine >= 0.999 and rel-L2 <= 5e-2 per tensor.
+"""
+import ctypes as C
+import os
+
+import pytest
+import torch
+
+from helpers import build_small_model, rel_l2, small_config, to_device
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _cmp(name, got, ref, tol=5e-2, cos_min=0.999):
+    got, ref = got.float().flatten(), ref.float().flatten()
+    assert torch.isfinite(got).all(), f"{name}: non-finite gradient"
+    cos = torch.nn.functional.cosine_similarity(got, ref, dim=0).item()
+    e = rel_l2(got, ref)
+    assert cos >= cos_min and e <= tol, f"{name}: cos {cos:.5f} rel-L2 {e:.3e}"
+    return cos, e
+
+
+def headline_config(lora_r, layers=2, dropout=0.0):
+    return small_config(
+        text=dict(vocab_size=32000, hidden_size=4096, intermediate_size=11008, num_hidden_layers=layers, num_attention_heads=32),
+        lora=dict(enable=True, lora_r=lora_r, lora_alpha=2 * lora_r, lora_dropout=dropout, lora_bias="none"), stage=3)
+
+
+def _prof_counts(lib):
+    out = {}
+    for kind, name in ((0, "gemm_pair"), (3, "gemm_single"), (1, "attention"), (4, "lora_stream")):
+        n = C.c_int64()
+        lib.lhrs_prof_summary(kind, None, None, None, C.byref(n))
+        out[name] = n.value
+    return out
+
+
+def _oracle_grads(cfg, st, batch):
+    from oracle import unibind
+    sd = {k: {kk: vv.clone().requires_grad_(vv.is_floating_point() and (k == "pooler" or "lora_" in kk)) for kk, vv in v.items()}
+          for k, v in st.items()}
+    b32 = dict(batch)
+    b32["rgb"] = batch["rgb"].float()
+    loss = unibind.forward_loss(b32, sd, cfg)
+    loss.backward()
+    return loss.detach(), sd
+
+
+@pytest.mark.parametrize("lora_r,mixed", [(16, True), (16, False), (128, True)])
+def test_sft_step_gradients_at_headline_shape(lora_r, mixed):
+    """loss, every LoRA dA / dB and every pooler gradient of ONE stage-3 step at B = 16, S = 512, 7B widths, against the
+    fp32 oracle.  `mixed` = BASELINE config 4 as written (12 image + 4 text-only samples, ragged lengths, the reference's
+    padding branch text_modal.py:440-505); otherwise the uniform all-image batch."""
+    import bench
+    from lhrs_bot_b200 import _lib
+    from lhrs_bot_b200.training import SftStepper
+    from oracle import unibind
+    lib = _lib.load()
+    cfg = headline_config(lora_r)
+    model = build_small_model(cfg, DEV, seed=3)
+    stepper = SftStepper(model, world_size=1, lr=1e-4)
+    st = to_device(unibind.export_state(model), DEV)
+    batch = bench.make_batch(16, seed=5, device=DEV, seq_len=512, mixed=mixed)
+    lib.lhrs_prof_enable(1)
+    out = model(batch)
+    loss = out["total_loss"]
+    loss.backward()
+    torch.cuda.synchronize()
+    counts = _prof_counts(lib)
+    lib.lhrs_prof_enable(0)
+    # the code paths of the headline run were the ones exercised
+    assert counts["gemm_pair"] >= 2 * 8, f"CTA-pair GEMM launches: {counts}"
+    assert counts["attention"] >= 2 * 2, counts
+    if lora_r == 16:
+        assert counts["lora_stream"] >= 2 * 16, f"streaming LoRA side products not engaged: {counts}"
+    else:
+        assert counts["lora_stream"] == 0, counts
+
+    ref_loss, sd = _oracle_grads(cfg, st, batch)
+    print(f"r={lora_r} mixed={mixed}: loss {loss.item():.5f} oracle {ref_loss.item():.5f}; launches {counts}")
+    assert abs(loss.item() - ref_loss.item()) <= 2e-2
+    worst = (1.0, 0.0, "")
+    for name, p in model.text.text_encoder.named_parameters():
+        if "lora_" not in name:
+            assert not p.requires_grad
+            continue
+        key = name.replace(".default.", ".")
+        cos, e = _cmp(f"r{lora_r} {name}", stepper.opt.grad_views[p], sd["llama"][key].grad)
+        if e > worst[1]:
+            worst = (cos, e, name)
+    print(f"  worst LoRA gradient: {worst[2]} cos {worst[0]:.5f} rel-L2 {worst[1]:.3e}")
+    for name, p in model.rgb_pooler.named_parameters():
+        tol = 8e-2 if (p.dim() == 1 or "bias" in name) else 5e-2
+        _cmp(f"r{lora_r} pooler {name}", stepper.opt.grad_views[p], sd["pooler"][name].grad, tol, cos_min=0.998)
+
+
+def test_fused_swiglu_backward_epilogue_at_headline_shape(monkeypatch):
+    """LHRS_FUSE_SWIGLU_BWD=1 (d_act never materialised: the dX GEMM of down_proj applies the SwiGLU backward in its epilogue)
+    gives the same gradients as the separate pass, on the CTA-pair kernel."""
+    import bench
+    from lhrs_bot_b200.training import SftStepper
+    cfg = headline_config(16, layers=1)
+    model = build_small_model(cfg, DEV, seed=4)
+    stepper = SftStepper(model, world_size=1, lr=1e-4)
+    batch = bench.make_batch(16, seed=6, device=DEV, seq_len=512, mixed=False)
+    grads = []
+    for fuse in ("0", "1"):
+        monkeypatch.setenv("LHRS_FUSE_SWIGLU_BWD", fuse)
+        stepper.opt.flat_grad.zero_()
+        model(batch)["total_loss"].backward()
+        torch.cuda.synchronize()
+        grads.append(stepper.opt.flat_grad.clone())
+    _cmp("fused vs separate SwiGLU backward, flat gradient", grads[1], grads[0], 1e-2, cos_min=0.9999)
+
+
+@pytest.mark.parametrize("cg", ["1", "2"])
+def test_small_lora_backward_forced_cta_group(cg, monkeypatch):
+    """The small (hidden 256) LoRA backward test with the GEMM forced onto single-CTA (1) or CTA-pair (2) tiles: the pair
+    kernel's K-extensions are compared with the oracle on a problem where every tile is ragged."""
+    from lhrs_bot_b200.training import SftStepper
+    from helpers import synthetic_batch
+    from oracle import unibind
+    monkeypatch.setenv("LHRS_GEMM_CG", cg)
+    cfg = small_config(lora=dict(enable=True, lora_r=16, lora_alpha=32, lora_dropout=0.0, lora_bias="none"), stage=2)
+    model = build_small_model(cfg, DEV, seed=5)
+    stepper = SftStepper(model, world_size=1, lr=1e-3)
+    st = to_device(unibind.export_state(model), DEV)
+    batch = synthetic_batch(3, 20, cfg.text.vocab_size, DEV, seed=23, text_only=(), ragged_mask=True)
+    loss = model(batch)["total_loss"]
+    loss.backward()
+    ref_loss, sd = _oracle_grads(cfg, st, batch)
+    assert abs(loss.item() - ref_loss.item()) <= 2e-2
+    for name, p in model.text.text_encoder.named_parameters():
+        if "lora_" in name:
+            _cmp(f"cg{cg} {name}", stepper.opt.grad_views[p], sd["llama"][name.replace(".default.", ".")].grad)
+    _cmp(f"cg{cg} pooler out_proj.weight", stepper.opt.grad_views[model.rgb_pooler.out_proj.weight], sd["pooler"]["out_proj.weight"].grad)
+
+
+def test_logits_at_headline_shape():
+    """Forward only, merged-adapter-free path: full-sequence logits at 7B widths, M = 8192 (2 layers) against the fp32 oracle and
+    against the oracle run in bf16 (the 'same-precision eager reference'): ours must be no further from fp32 than 1.5x eager-bf16."""
+    import bench
+    from oracle import llama, unibind
+    cfg = headline_config(16)
+    cfg.lora.enable = False
+    model = build_small_model(cfg, DEV, seed=8)
+    st = to_device(unibind.export_state(model), DEV)
+    batch = bench.make_batch(16, seed=9, device=DEV, seq_len=512, mixed=True)
+    with torch.no_grad():
+        img = model.encode_image(batch["rgb"], pool=False)
+        got = model.text.logits(batch["input_ids"], img, batch["attention_mask"])
+        _, mask, _, embeds, _ = model.text.prepare_inputs_for_multimodal(batch["input_ids"], batch["attention_mask"], batch["labels"], None, img)
+        t = cfg.text
+        ref = llama.llama_logits(embeds.float(), st["llama"], t.num_hidden_layers, t.num_attention_heads, float(t.rms_norm_eps), mask)
+        st16 = {k: v.bfloat16() for k, v in st["llama"].items()}
+        ref16 = llama.llama_logits(embeds, st16, t.num_hidden_layers, t.num_attention_heads, float(t.rms_norm_eps), mask)
+    valid = mask.bool()
+    e, e16 = rel_l2(got[valid], ref[valid]), rel_l2(ref16[valid], ref[valid])
+    print(f"headline logits: ours vs fp32 {e:.3e}; eager-bf16 vs fp32 {e16:.3e}; ours vs eager-bf16 {rel_l2(got[valid], ref16[valid]):.3e}")
+    assert e <= max(2e-2, 1.5 * e16 + 2e-3)

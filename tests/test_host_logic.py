@@ -59,8 +59,13 @@ def test_prepare_for_training_trainable_sets():
     assert not any(p.requires_grad for p in m.rgb_pooler.parameters())
     te = m.text.get_text_encoder()
     assert not te.get_input_embeddings().weight.requires_grad and not te.get_output_embeddings().weight.requires_grad
+    # every shipped yaml says fp16: True -> the entry scripts pass compute_dtype=torch.float16 (main_pretrain_stage1.py:194-206):
+    # served in bfloat16 with one logged deviation, not refused
+    with pytest.warns(UserWarning, match="bfloat16"):
+        m.prepare_for_training(freeze_vision=True, freeze_text=True, tune_rgb_pooler=True, model_path=None, compute_dtype=torch.float16)
+    assert all(p.dtype == torch.bfloat16 for p in m.rgb_pooler.parameters())
     with pytest.raises(NotImplementedError):
-        m.prepare_for_training(compute_dtype=torch.float16)
+        m.prepare_for_training(compute_dtype=torch.float32)
 
 
 def test_checkpoint_roundtrip(tmp_path):
@@ -195,7 +200,12 @@ def test_stepper_from_reference_yaml_keys(monkeypatch):
                              schedule=dict(name="cosine", min_lr=2e-5, warmup_epochs=300, warmup_method="linear", warmup_factor=0.1)))
     training.SftStepper.from_config(object(), stage1, world_size=8, max_iters=5000)
     assert seen == dict(world_size=8, lr=2e-4, weight_decay=0.0, max_grad_norm=0.3, optimizer="adanp", warmup_steps=300,
-                        total_steps=5000, min_lr=2e-5, warmup_ratio=0.1)
+                        total_steps=5000, min_lr=2e-5, warmup_ratio=0.1, tune_rgb_pooler=True, model_path=None)
+    stage3 = ConfigDict(dict(stage1, tune_rgb_pooler=False, model_path="/ckpt/stage2/FINAL.pt"))
+    training.SftStepper.from_config(object(), stage3)
+    assert seen["tune_rgb_pooler"] is False and seen["model_path"] == "/ckpt/stage2/FINAL.pt"   # the yaml's flag is honoured
+    with pytest.raises(NotImplementedError):
+        training.SftStepper.from_config(object(), ConfigDict(dict(stage1, tune_rgb_bk=True)))
     stage2 = ConfigDict(dict(optimizer="adamw", lr=2e-4, wd=0.0, max_grad_norm=1.0,
                              schedule=dict(name="const", min_lr=8e-5, warmup_epochs=100, warmup_method="linear", warmup_factor=0.01)))
     training.SftStepper.from_config(object(), stage2, exchange="nccl")
@@ -249,3 +259,125 @@ def test_flat_gradient_allreduce_world2_gloo():
         p.join(120)
         assert p.exitcode == 0
     assert q.get(timeout=10) is True
+
+
+# ---------------------------------------------------------------------------------------------- shipped yaml surface
+def _shipped_yamls():
+    import json
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "shipped_yamls.json")) as f:
+        return json.load(f)
+
+
+def _shrunk(yaml_dict, **over):
+    """The shipped yaml with ONLY the widths reduced (a 7B random init on the host takes minutes); every other key untouched."""
+    from lhrs_bot_b200.config import ConfigDict, _merge
+    cfg = ConfigDict(yaml_dict)
+    _merge(cfg, dict(random_init=True,
+                     rgb_vision=dict(hidden_size=128, intermediate_size=512, num_hidden_layers=6, num_attention_heads=2,
+                                     attn_pooler=dict(num_query=144, num_attn_heads=2, num_layers=2)),
+                     text=dict(vocab_size=1024, hidden_size=256, intermediate_size=512, num_hidden_layers=2, num_attention_heads=2)))
+    _merge(cfg, over)
+    return cfg
+
+
+class _FakeFlat:
+    def __init__(self, params):
+        self.grad_views = {p: torch.zeros_like(p) for p in params}
+
+
+@pytest.mark.parametrize("name", ["multi_modal_stage1.yaml", "multi_modal_stage2.yaml", "multi_modal_stage3.yaml", "multi_modal_eval.yaml"])
+def test_shipped_yamls_are_accepted_unchanged(name, monkeypatch, tmp_path):
+    """Config/*.yaml as shipped (fixture generated by tests/golden/make_yaml_fixture.py): `dtype: float16` everywhere and
+    `bits: 8` in stages 2-3 build a bf16 model with logged deviations instead of raising, and SftStepper.from_config picks the
+    trainable set the reference's entry script would (stage 1: pooler; stage 2: pooler + LoRA r=128; stage 3: the LoRA adapters
+    resumed from the stage-2 checkpoint only — `tune_rgb_pooler: False`)."""
+    import warnings
+    from lhrs_bot_b200 import rgb_vision_modal, runtime, training
+    from lhrs_bot_b200.build import build_model
+    y = _shipped_yamls()[name]
+    assert y["dtype"] == "float16"
+    cfg = _shrunk(y)
+    runtime._warned.clear()
+    monkeypatch.setitem(rgb_vision_modal.VisionModal.EMBEDDING_DIM, "vit_large", 128)
+    with warnings.catch_warnings(record=True) as rec:
+        warnings.simplefilter("always")
+        model = build_model(cfg)
+        model = model.to(runtime.resolve_compute_dtype(cfg.dtype))
+    msgs = " | ".join(str(w.message) for w in rec)
+    assert "float16 was requested" in msgs
+    assert ("bits=8" in msgs) == (y["bits"] == 8)
+    assert all(p.dtype == torch.bfloat16 for p in model.parameters())
+    assert model.text.text_encoder.has_lora() == bool(y["lora"]["enable"])
+    if y["stage"] == 0:
+        return
+    if y["stage"] == 3:
+        # stage 3 resumes stage 2's FINAL.pt + TextLoRA/ (Script/train_stage3.sh MODEL_PATH): make one with the stage-2 yaml
+        m2 = build_model(_shrunk(_shipped_yamls()["multi_modal_stage2.yaml"])).to(torch.bfloat16)
+        torch.save(m2.custom_save_checkpoint(str(tmp_path / "FINAL.pt")), tmp_path / "FINAL.pt")
+        cfg.model_path = str(tmp_path / "FINAL.pt")
+    monkeypatch.setattr(training, "build_flat_optimizer", lambda name, params, lr, wd, mg: _FakeFlat(params))
+    stepper = training.SftStepper.from_config(model, cfg, world_size=1, max_iters=1000)
+    pool = any(p.requires_grad for p in model.rgb_pooler.parameters())
+    lora = [a.requires_grad and b.requires_grad for a, b in model.text.lora_pairs()]
+    body = [p.requires_grad for n, p in model.text.named_parameters() if "lora_" not in n]
+    assert pool == bool(y["tune_rgb_pooler"]) and not any(body) and not any(p.requires_grad for p in model.rgb.parameters())
+    assert (len(lora) > 0 and all(lora)) == (y["stage"] >= 2)
+    if y["stage"] >= 2:
+        assert model.text.text_encoder.peft_config.r == 128 and model.text.text_encoder.peft_config.lora_dropout == 0.05
+    assert stepper.base_lr == float(y["lr"]) and stepper.min_lr == float(y["schedule"]["min_lr"])
+    assert set(stepper.opt.grad_views) == {p for p in model.parameters() if p.requires_grad}
+
+
+def test_float16_requests_are_served_in_bfloat16():
+    """cli_qa.py:89-90 does `model.to(type_dict[config.dtype])` with the yaml's float16; `.half()` likewise."""
+    from lhrs_bot_b200 import runtime
+    cfg = small_config()
+    m = build_small_model(cfg, "cpu")
+    runtime._warned.clear()
+    with pytest.warns(UserWarning, match="float16 was requested"):
+        m2 = m.to(torch.float16)
+    assert m2 is m and all(p.dtype == torch.bfloat16 for p in m.parameters())
+    assert all(p.dtype == torch.bfloat16 for p in m.half().parameters())
+    assert runtime.resolve_compute_dtype("bfloat16") == torch.bfloat16 and runtime.resolve_compute_dtype(torch.float16) == torch.bfloat16
+    with pytest.raises(NotImplementedError):
+        runtime.resolve_compute_dtype(torch.float32)
+
+
+def test_bench_mixed_batch_is_config4_as_written():
+    """bench.make_batch(mixed=True): 75 % image / 25 % text-only samples, ragged right-padded lengths -> the oracle's splice
+    takes the reference's padding branch (text_modal.py:440-505) and comes out at exactly seq_len positions."""
+    import bench
+    from oracle import splice
+    b = bench.make_batch(16, seed=5, seq_len=512, mixed=True)
+    ids, mask, labels = b["input_ids"], b["attention_mask"], b["labels"]
+    n_img = (ids == -200).sum(1)
+    assert n_img.tolist() == [0 if i % 4 == 3 else 1 for i in range(16)]
+    assert torch.equal(mask, ids != 0) and int(mask[0].sum()) == ids.shape[1] and int(mask.sum(1).min()) < ids.shape[1]
+    assert bool((labels[~mask] == -100).all()) and bool((labels[ids == -200] == -100).all())
+    table = torch.zeros(32000, 8)
+    img = torch.zeros(16, 144, 8)
+    new_mask, embeds, new_labels = splice.prepare_inputs_for_multimodal(ids, mask, labels, table, img)
+    assert embeds.shape[:2] == (16, 512) and new_mask.shape == (16, 512)
+    assert int(new_mask.sum()) == bench.real_positions(b) < 16 * 512
+    assert int((new_labels != -100).sum()) == int((labels != -100).sum())
+    u = bench.make_batch(4, seed=1, seq_len=512, mixed=False, uint8_images=True)
+    assert u["rgb"].dtype == torch.uint8 and u["rgb"].shape == (4, 224, 224, 3) and bool(u["attention_mask"].all())
+
+
+def test_oracle_sdpa_branch_equals_written_out_attention():
+    """oracle/llama.py `sdpa=True` (used only by bench.py's GPU-eager comparator) is the same function as the explicit softmax."""
+    from oracle import llama
+    torch.manual_seed(0)
+    D, H, S, B = 256, 2, 24, 2
+    sd = {"model.layers.0.input_layernorm.weight": torch.ones(D), "model.layers.0.post_attention_layernorm.weight": torch.ones(D)}
+    for n, (o, k) in {"self_attn.q_proj": (D, D), "self_attn.k_proj": (D, D), "self_attn.v_proj": (D, D), "self_attn.o_proj": (D, D),
+                      "mlp.gate_proj": (512, D), "mlp.up_proj": (512, D), "mlp.down_proj": (D, 512)}.items():
+        sd[f"model.layers.0.{n}.weight"] = torch.randn(o, k) * 0.05
+    x = torch.randn(B, S, D)
+    km = torch.ones(B, S, dtype=torch.bool)
+    km[1, 17:] = False
+    cos, sin = llama.rope_cos_sin(torch.arange(S), D // H)
+    am = llama._additive_mask(B, S, S, km, x.dtype)
+    a, _ = llama.decoder_layer(x, sd, 0, H, 1e-5, cos, sin, am)
+    b, _ = llama.decoder_layer(x, sd, 0, H, 1e-5, cos, sin, am, sdpa=True)
+    assert torch.allclose(a, b, atol=1e-5, rtol=1e-5)
