@@ -41,7 +41,7 @@ class _FlatOptimizer:
     weights, a 0/1 decay mask (1-D parameters and biases get no weight decay, build_optimizer.py:20-46) and the global-norm
     scratch.  Parameters are re-pointed INTO the flat buffer, so DeepSpeed-style flat collectives need no gather copy."""
 
-    def __init__(self, params: List[torch.nn.Parameter], lr, weight_decay, max_grad_norm):
+    def __init__(self, params: List[torch.nn.Parameter], lr, weight_decay, max_grad_norm, sync: bool = True):
         assert params, "no trainable parameters"
         dev = params[0].device
         self.params = params
@@ -63,7 +63,8 @@ class _FlatOptimizer:
             if self.decay_mask is not None:
                 self.decay_mask[off: off + n] = 0.0 if p.dim() <= 1 else 1.0
             off += n
-        sync_initial_parameters(self.flat_param)      # every data-parallel replica starts from rank 0's trainable set
+        if sync:
+            sync_initial_parameters(self.flat_param)  # every data-parallel replica starts from rank 0's trainable set
         self.master.copy_(self.flat_param)
         self.lr, self.weight_decay, self.max_grad_norm = lr, weight_decay, max_grad_norm
         self.step_count = 0
@@ -88,8 +89,9 @@ class FlatAdamW(_FlatOptimizer):
     """Flat-buffer AdamW with global-norm clipping (torch.optim.AdamW semantics, betas (0.9, 0.95) as the reference's
     DeepSpeed config for stages 2-3, main_pretrain_stage1.py:30-41)."""
 
-    def __init__(self, params: List[torch.nn.Parameter], lr=2e-4, betas=(0.9, 0.95), eps=1e-8, weight_decay=0.0, max_grad_norm=1.0):
-        super().__init__(params, lr, weight_decay, max_grad_norm)
+    def __init__(self, params: List[torch.nn.Parameter], lr=2e-4, betas=(0.9, 0.95), eps=1e-8, weight_decay=0.0, max_grad_norm=1.0,
+                 sync: bool = True):
+        super().__init__(params, lr, weight_decay, max_grad_norm, sync)
         self.m, self.v = self._state(2)
         self.betas, self.eps = betas, eps
 
@@ -112,8 +114,8 @@ class FlatAdan(_FlatOptimizer):
     offload (main_pretrain_stage1.py:66-80); here it is one HBM pass over the flat buffers."""
 
     def __init__(self, params: List[torch.nn.Parameter], lr=2e-4, betas=(0.98, 0.92, 0.99), eps=1e-8, weight_decay=0.0,
-                 max_grad_norm=0.3, no_prox=False):
-        super().__init__(params, lr, weight_decay, max_grad_norm)
+                 max_grad_norm=0.3, no_prox=False, sync: bool = True):
+        super().__init__(params, lr, weight_decay, max_grad_norm, sync)
         self.exp_avg, self.exp_avg_diff, self.exp_avg_sq, self.pre_grad = self._state(4)
         self.betas, self.eps, self.no_prox = betas, eps, bool(no_prox)
 
@@ -238,15 +240,16 @@ class PeerShardedAdamW:
         return float(self.norm_slots.sum().sqrt().item())
 
 
-def build_flat_optimizer(name: str, params, lr, weight_decay, max_grad_norm):
-    """``config.optimizer`` -> fused optimizer (build_optimizer.py:76-86 passes the yaml string to timm)."""
+def build_flat_optimizer(name: str, params, lr, weight_decay, max_grad_norm, sync: bool = True):
+    """``config.optimizer`` -> fused optimizer (build_optimizer.py:76-86 passes the yaml string to timm).  ``sync``: broadcast
+    rank 0's parameters first when a process group is up (False for a single-replica stepper inside a distributed job)."""
     name = name.lower()
     if name == "adamw":
-        return FlatAdamW(params, lr=lr, weight_decay=weight_decay, max_grad_norm=max_grad_norm)
+        return FlatAdamW(params, lr=lr, weight_decay=weight_decay, max_grad_norm=max_grad_norm, sync=sync)
     if name in ("adanp", "adan"):
-        return FlatAdan(params, lr=lr, weight_decay=weight_decay, max_grad_norm=max_grad_norm, no_prox=False)
+        return FlatAdan(params, lr=lr, weight_decay=weight_decay, max_grad_norm=max_grad_norm, no_prox=False, sync=sync)
     if name == "adanw":
-        return FlatAdan(params, lr=lr, weight_decay=weight_decay, max_grad_norm=max_grad_norm, no_prox=True)
+        return FlatAdan(params, lr=lr, weight_decay=weight_decay, max_grad_norm=max_grad_norm, no_prox=True, sync=sync)
     raise NotImplementedError(f"optimizer {name!r}: the shipped yamls use adanp (stage 1) and adamw (stages 2-3)")
 
 
@@ -355,7 +358,7 @@ class SftStepper:
                 warnings.warn(f"peer-memory gradient exchange unavailable on at least one rank (this rank: {err!r}); "
                               f"every rank uses the NCCL allreduce")
         if self.opt is None:
-            self.opt = build_flat_optimizer(optimizer, params, lr, weight_decay, max_grad_norm)
+            self.opt = build_flat_optimizer(optimizer, params, lr, weight_decay, max_grad_norm, world_size > 1)
         # the backward kernels write into the flat gradient buffer directly
         model.rgb_pooler._grad_sink = {p: g for p, g in self.opt.grad_views.items()}
         model.text._grad_sink = model.rgb_pooler._grad_sink

@@ -241,6 +241,16 @@ def _dp_worker(rank, world, port, out):
     dist.all_gather(gathered, local)
     expect = sum(gathered) * scale
     ok = torch.allclose(g * scale, expect, atol=1e-6) and scale == pytest.approx(1.0 / world)
+    # replicas seeded with seed + rank (main_pretrain_stage1.py:282) start from rank 0's trainable set after the broadcast
+    from lhrs_bot_b200.training import sync_initial_parameters
+    flat = torch.randn(257).bfloat16()
+    mine = flat.clone()
+    sync_initial_parameters(flat)
+    everyone = [torch.zeros_like(flat) for _ in range(world)]
+    dist.all_gather(everyone, flat)
+    firsts = [torch.zeros_like(mine) for _ in range(world)]
+    dist.all_gather(firsts, mine)
+    ok = ok and all(torch.equal(everyone[0], t) for t in everyone) and torch.equal(everyone[0], firsts[0]) and not torch.equal(firsts[0], firsts[1])
     if rank == 0:
         out.put(bool(ok))
     dist.destroy_process_group()
@@ -315,7 +325,7 @@ def test_shipped_yamls_are_accepted_unchanged(name, monkeypatch, tmp_path):
         m2 = build_model(_shrunk(_shipped_yamls()["multi_modal_stage2.yaml"])).to(torch.bfloat16)
         torch.save(m2.custom_save_checkpoint(str(tmp_path / "FINAL.pt")), tmp_path / "FINAL.pt")
         cfg.model_path = str(tmp_path / "FINAL.pt")
-    monkeypatch.setattr(training, "build_flat_optimizer", lambda name, params, lr, wd, mg: _FakeFlat(params))
+    monkeypatch.setattr(training, "build_flat_optimizer", lambda name, params, lr, wd, mg, sync=True: _FakeFlat(params))
     stepper = training.SftStepper.from_config(model, cfg, world_size=1, max_iters=1000)
     pool = any(p.requires_grad for p in model.rgb_pooler.parameters())
     lora = [a.requires_grad and b.requires_grad for a, b in model.text.lora_pairs()]

@@ -134,3 +134,89 @@ def test_peer_sharded_adan_two_ranks():
     for rank, ok, same in res:
         assert ok, f"rank {rank}: parameters differ from the oracle's Adan"
         assert same, f"rank {rank}: ranks hold different parameters"
+
+
+# ---------------------------------------------------------------------------------------------- model-level data parallelism
+def _dp_model_worker(rank, world, port, exchange, q):
+    """N ranks, each seeded differently (seed + rank, as the reference does) and fed its own slice of a
+    global batch, must (a) start from rank 0's trainable set, (b) reduce to the gradient a single rank computes on the
+    concatenated batch, (c) hold bit-identical parameters after the step."""
+    import sys
+    import torch.distributed as dist
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    try:
+        from helpers import build_small_model, rel_l2, small_config, synthetic_batch
+        from lhrs_bot_b200.training import SftStepper
+        cfg = small_config(lora=dict(enable=True, lora_r=16, lora_alpha=32, lora_dropout=0.0, lora_bias="none"), stage=2)
+        # frozen weights identical everywhere (a shared pretrained checkpoint); trainable set deliberately different per rank
+        model = build_small_model(cfg, dev, seed=0)
+        torch.manual_seed(1000 + rank)
+        with torch.no_grad():
+            for p in list(model.rgb_pooler.parameters()) + [t for pair in model.text.lora_pairs() for t in pair]:
+                p.add_(0.02 * torch.randn_like(p.float()).to(p.dtype))
+        stepper = SftStepper(model, world_size=world, lr=1e-3, exchange=exchange)
+        flat0 = stepper.opt.flat_param.clone()
+        g0 = [torch.empty_like(flat0) for _ in range(world)]
+        dist.all_gather(g0, flat0)
+        start_same = all(torch.equal(g0[0], t) for t in g0)
+        per = 2
+        full = synthetic_batch(per * world, 24, cfg.text.vocab_size, dev, seed=77, text_only=(), ragged_mask=False)
+        mine = {k: v[rank * per:(rank + 1) * per] for k, v in full.items()}
+        # the single-rank reference: same starting weights (rank 0's), the whole batch, no exchange
+        ref_model = build_small_model(cfg, dev, seed=0)
+        ref_stepper = SftStepper(ref_model, world_size=1, lr=1e-3)
+        ref_stepper.opt.flat_param[: stepper.opt.numel].copy_(g0[0][: stepper.opt.numel])
+        ref_model(full)["total_loss"].backward()
+        ref_grad = ref_stepper.opt.flat_grad[: stepper.opt.numel].float().clone()
+        # this rank's local gradient, then the library's exchange
+        model(mine)["total_loss"].backward()
+        local = stepper.opt.flat_grad[: stepper.opt.numel].float().clone()
+        summed = local.clone()
+        dist.all_reduce(summed, op=dist.ReduceOp.SUM)
+        grad_err = rel_l2(summed / world, ref_grad)
+        if stepper.exchange == "p2p":
+            stepper.opt.step(lr=1e-3)
+            lo = rank * stepper.opt.slice_n
+            hi = min(lo + stepper.opt.slice_n, stepper.opt.numel)
+            red_err = rel_l2(stepper.opt.grad_sum[: hi - lo], summed[lo:hi]) if hi > lo else 0.0
+        else:
+            from lhrs_bot_b200.training import allreduce_flat_gradients
+            scale = allreduce_flat_gradients(stepper.opt.flat_grad, world)
+            red_err = rel_l2(stepper.opt.flat_grad[: stepper.opt.numel].float(), summed)
+            stepper.opt.step(lr=1e-3, grad_scale=scale)
+        torch.cuda.synchronize()
+        g1 = [torch.empty_like(flat0) for _ in range(world)]
+        dist.all_gather(g1, stepper.opt.flat_param)
+        end_same = all(torch.equal(g1[0], t) for t in g1)
+        moved = not torch.equal(g1[0], g0[0])
+        q.put((rank, stepper.exchange, start_same, grad_err, red_err, end_same, moved))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("exchange", ["p2p", "nccl"])
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_data_parallel_step_equals_concatenated_batch(world, exchange):
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs on one node (gpurun --gpus {world})")
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29700 + world + (50 if exchange == "nccl" else 0)
+    procs = [ctx.Process(target=_dp_model_worker, args=(r, world, port, exchange, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=600) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=120)
+    for rank, used, start_same, grad_err, red_err, end_same, moved in sorted(res):
+        print(f"rank {rank} [{used}]: mean-of-ranks gradient vs concatenated-batch gradient rel-L2 {grad_err:.3e}; library reduce vs NCCL fp32 sum {red_err:.3e}")
+        assert used == exchange
+        assert start_same, f"rank {rank}: replicas did not start from the same trainable set (seed + rank init must be broadcast)"
+        assert grad_err <= 3e-2, f"rank {rank}: data-parallel mean gradient differs from the concatenated-batch gradient ({grad_err:.3e})"
+        assert red_err <= 6e-3, f"rank {rank}: the library's reduction differs from an fp32 NCCL sum ({red_err:.3e})"
+        assert end_same and moved, f"rank {rank}: parameters after the step differ across ranks (or did not move)"
