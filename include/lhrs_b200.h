@@ -127,7 +127,9 @@ typedef struct LhrsAttention {
 int lhrs_attention_fwd(const LhrsAttention* a, void* stream);
 
 /* Backward of lhrs_attention_fwd (recompute-based; needs the forward's O and lse).  dQ/dK/dV are bf16 with their own
- * (batch,row,head) strides so they can land in a packed [rows, 3*H*hd] buffer.  delta: fp32 scratch [B,H,Sq]. */
+ * (batch,row,head) strides so they can land in a packed [rows, 3*H*hd] buffer.  delta: fp32 scratch of
+ * lhrs_attention_bwd_scratch_floats(B, H, Sq, Skv) elements ([B,H,Sq] row sums of dO*O, then the key mask packed to bits). */
+int64_t lhrs_attention_bwd_scratch_floats(int32_t B, int32_t H, int32_t Sq, int32_t Skv);
 typedef struct LhrsAttentionBwd {
     LhrsAttention fwd;   /* the forward problem: q,k,v,o,lse,key_mask,strides,sizes */
     const void* d_o;     /* same layout as fwd.o */

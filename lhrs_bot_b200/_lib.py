@@ -10,7 +10,7 @@ import os
 import threading
 
 LIB_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib")
-LIB_PATH = os.path.join(LIB_DIR, "liblhrs_b200.so")
+LIB_PATH = os.environ.get("LHRS_LIB_PATH") or os.path.join(LIB_DIR, "liblhrs_b200.so")   # override: instrumented debug builds (tools/)
 
 
 class LhrsLibraryError(RuntimeError):
@@ -171,6 +171,7 @@ SIGNATURES = {
     "lhrs_llama_decode_step_sampled": (C.c_int, [C.POINTER(LhrsLlamaWeights), C.POINTER(LhrsKvCache), C.POINTER(LhrsDecodeBuffers),
                                                  C.POINTER(LhrsSampling), _I32, _P]),
     "lhrs_attention_bwd": (C.c_int, [C.POINTER(LhrsAttentionBwd), _P]),
+    "lhrs_attention_bwd_scratch_floats": (C.c_int64, [_I32, _I32, _I32, _I32]),
     "lhrs_rmsnorm_bwd": (C.c_int, [_P, _P, _P, _P, _P, _P, _I64, _I32, _P]),
     "lhrs_layernorm_bwd_scratch_bytes": (C.c_size_t, [_I32]),
     "lhrs_layernorm_bwd": (C.c_int, [_P, _I64, _P, _P, _P, _P, _P, _P, _P, _P, _I32, _P, _I64, _I32, _P]),

@@ -6,6 +6,7 @@
 // Two passes recompute S twice but need no atomics, so gradients are deterministic.  Warp-level mma.sync tiles as in
 // attention.cu (attention is a few % of the step; the dense dX/dW contractions around it are tcgen05).
 #include "attention_common.h"
+#include <stdlib.h>
 #include "host_common.h"
 #include "ptx.cuh"
 
@@ -92,6 +93,13 @@ __global__ void __launch_bounds__(256) attn_delta_kernel(const AttnBwdArgs p) {
 #pragma unroll
         for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
         if (lane == 0) p.delta[(static_cast<long long>(b) * p.H + h) * p.Sq + s] = acc;
+    }
+    // the same pre-pass packs the key-padding mask to bits for the tcgen05 kernels: block (s, b) writes word s of batch row b
+    if (p.kbits != nullptr && s < p.kbits_w && warp == 0) {
+        const int key = s * 32 + lane;
+        const bool on = key < p.Skv && p.kmask[static_cast<long long>(b) * p.Skv + key] != 0;
+        const uint32_t bits = __ballot_sync(0xffffffffu, on);
+        if (lane == 0) p.kbits[static_cast<long long>(b) * p.kbits_w + s] = bits;
     }
 }
 
@@ -399,7 +407,9 @@ static int launch_bwd(const AttnBwdArgs& a, cudaStream_t stream) {
                         a.dq_hs, a.dk_bs, a.dk_rs, a.dk_hs, a.dv_bs, a.dv_rs, a.dv_hs})
         tma_ok = tma_ok && (s % 8) == 0;
     if (HD == 128 && a.Sq >= 128 && a.Skv >= 128 && tma_ok && use_tc_attention()) {   // tcgen05 dQ and dK/dV kernels
-        const int rc = attention_bwd_tc(a, CAUSAL, stream);
+        const char* pe = getenv("LHRS_ATTN_BWD_PERSIST");   // 0: one CTA per tile (attention_bwd_tc.cu); read per call for A/B runs
+        const bool persist = (pe == nullptr || atoi(pe) != 0) && attention_bwd_tcp_ok(a) && (a.kmask == nullptr || a.kbits != nullptr);
+        const int rc = persist ? attention_bwd_tcp(a, CAUSAL, stream) : attention_bwd_tc(a, CAUSAL, stream);
         if (prof) prof_end(stream);
         return rc;
     }
@@ -414,6 +424,10 @@ static int launch_bwd(const AttnBwdArgs& a, cudaStream_t stream) {
 }  // namespace lhrs
 
 using namespace lhrs;
+
+extern "C" int64_t lhrs_attention_bwd_scratch_floats(int32_t B, int32_t H, int32_t Sq, int32_t Skv) {
+    return static_cast<int64_t>(B) * H * Sq + static_cast<int64_t>(B) * 2 * ((Skv + 63) / 64);
+}
 
 extern "C" int lhrs_attention_bwd(const LhrsAttentionBwd* d, void* stream_) {
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
@@ -430,6 +444,10 @@ extern "C" int lhrs_attention_bwd(const LhrsAttentionBwd* d, void* stream_) {
     a.o = (const __nv_bfloat16*)f->o; a.d_o = (const __nv_bfloat16*)d->d_o;
     a.dq = (__nv_bfloat16*)d->dq; a.dk = (__nv_bfloat16*)d->dk; a.dv = (__nv_bfloat16*)d->dv;
     a.lse = f->lse; a.delta = d->delta; a.kmask = f->key_mask;
+    // mask bits live behind the delta values in the caller's scratch (lhrs_attention_bwd_scratch_floats)
+    a.kbits_w = 2 * ((f->Skv + 63) / 64);
+    a.kbits = (f->key_mask != nullptr && f->head_dim == 128 && a.kbits_w <= f->Sq)
+                  ? reinterpret_cast<uint32_t*>(d->delta + static_cast<long long>(f->B) * f->H * f->Sq) : nullptr;
     a.q_bs = f->q_bs; a.q_rs = f->q_rs; a.q_hs = f->q_hs; a.k_bs = f->k_bs; a.k_rs = f->k_rs; a.k_hs = f->k_hs;
     a.v_bs = f->v_bs; a.v_rs = f->v_rs; a.v_hs = f->v_hs; a.o_bs = f->o_bs; a.o_rs = f->o_rs; a.o_hs = f->o_hs;
     a.dq_bs = d->dq_bs; a.dq_rs = d->dq_rs; a.dq_hs = d->dq_hs; a.dk_bs = d->dk_bs; a.dk_rs = d->dk_rs; a.dk_hs = d->dk_hs;

@@ -15,6 +15,8 @@ struct AttnBwdArgs {
     const float* lse;    // [B,H,Sq]
     float* delta;        // [B,H,Sq]
     const uint8_t* kmask;
+    uint32_t* kbits;     // kmask packed to bits by the delta pre-pass: [B, kbits_w] words, word t = keys [32t, 32t+32) (tcgen05 path)
+    int kbits_w;         // words per batch row (even, >= ceil(Skv / 32))
     long long q_bs, q_rs, q_hs, k_bs, k_rs, k_hs, v_bs, v_rs, v_hs;
     long long o_bs, o_rs, o_hs;        // O and dO share a layout
     long long dq_bs, dq_rs, dq_hs, dk_bs, dk_rs, dk_hs, dv_bs, dv_rs, dv_hs;
@@ -32,6 +34,8 @@ int make_tmap_bshd(CUtensorMap* out, int* hfirst, const void* ptr, int hd, int S
 bool use_tc_attention();                                                    // LHRS_ATTN_TC (default on)
 int attention_fwd_tc(const LhrsAttention* d, cudaStream_t stream);          // attention_tc.cu
 int attention_bwd_tc(const AttnBwdArgs& a, bool causal, cudaStream_t stream);   // attention_bwd_tc.cu (after the delta kernel)
+bool attention_bwd_tcp_ok(const AttnBwdArgs& a);                                // attention_bwd_tcp.cu: persistent, tile-pipelined
+int attention_bwd_tcp(const AttnBwdArgs& a, bool causal, cudaStream_t stream);  //   form of the same two passes (default)
 
 #ifdef __CUDACC__
 __device__ __forceinline__ float ex2_approx(float x) {

@@ -210,7 +210,7 @@ LlamaBwdBufs llama_bwd_plan(Arena& a, const LhrsLlamaWeights* w, long long M) {
     b.dxa = a.take<bf16>(M * D); b.dxb = a.take<bf16>(M * D); b.dh = a.take<bf16>(M * D);
     b.d_act = a.take<bf16>(M * F); b.d_gu = a.take<bf16>(M * 2 * F);
     b.dqkv = a.take<bf16>(M * 3 * D); b.d_o = a.take<bf16>(M * D);
-    b.delta = a.take<float>(M * w->heads);
+    b.delta = a.take<float>(M * w->heads + M);   // + the key mask as bits (lhrs_attention_bwd_scratch_floats; M >= B * 2 * ceil(S/64))
     const bool lora = w->lora_r > 0;
     b.h = nullptr;   // normalised inputs now come from the stash (h1 / h2)
     b.t = lora ? a.take<bf16>(M * 3 * w->lora_r) : nullptr;
@@ -328,7 +328,7 @@ PoolBwdBufs pool_bwd_plan(Arena& a, const LhrsPoolerWeights* w, int B, const Poo
     p.dx = a.take<bf16>(RQ * D); p.dx2 = a.take<bf16>(RQ * D);
     p.d_f = a.take<bf16>(RQ * F); p.dh = a.take<bf16>(RQ * D); p.d_ao = a.take<bf16>(RQ * D); p.dqp = a.take<bf16>(RQ * D);
     p.dkvp = a.take<bf16>(RKV * 2 * D); p.dkvn = a.take<bf16>(RKV * D); p.dkv_raw = a.take<bf16>(RKV * D);
-    p.delta = a.take<float>(RQ * w->heads);
+    p.delta = a.take<float>(RQ * w->heads + RQ);
     const int widest = F > w->out_dim ? F : w->out_dim;
     p.scratch = a.take<float>((long long)2 * 296 * (widest > 2 * D ? widest : 2 * D));
     return p;

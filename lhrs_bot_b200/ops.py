@@ -303,7 +303,7 @@ def attention_bwd(q, k, v, o, lse, d_o, *, causal: bool, scale: Optional[float] 
     Skv = k.shape[1]
     dq, dk, dv = torch.empty_like(q, memory_format=torch.contiguous_format), torch.empty(k.shape, device=k.device, dtype=k.dtype), \
         torch.empty(v.shape, device=v.device, dtype=v.dtype)
-    delta = torch.empty((B, H, Sq), device=q.device, dtype=torch.float32)
+    delta = torch.empty((int(_lib.load().lhrs_attention_bwd_scratch_floats(B, H, Sq, k.shape[1])),), device=q.device, dtype=torch.float32)
     d_o = d_o.contiguous()
     if not o.is_contiguous():
         o = o.contiguous()

@@ -63,6 +63,39 @@ def test_attention_bwd(B, H, Sq, Skv, hd, causal):
     _cmp("dv", dv, vf.grad)
 
 
+@pytest.mark.parametrize("B,H,Sq,Skv,causal", [(2, 4, 512, 512, True), (3, 5, 640, 640, True), (1, 2, 384, 320, False), (2, 2, 130, 333, True),
+                                               (1, 3, 1024, 1024, True), (1, 2, 256, 128, True), (40, 8, 256, 256, True)])
+def test_attention_bwd_persistent_equals_per_tile(B, H, Sq, Skv, causal, monkeypatch):
+    """The persistent, tile-pipelined tcgen05 backward (attention_bwd_tcp.cu, default) runs the same MMAs in the same order as
+    the one-CTA-per-tile form (attention_bwd_tc.cu): the gradients must be BIT-IDENTICAL, with a key mask, with ragged last
+    tiles, with more items than SMs (every CTA walks several items: ring indices and barrier parities carry across them) and
+    with key tiles no query sees (Sq > Skv under the causal offset)."""
+    from lhrs_bot_b200 import ops
+    q, k, v = _randn(B, Sq, H, 128, seed=31), _randn(B, Skv, H, 128, seed=32), _randn(B, Skv, H, 128, seed=33)
+    d_o = _randn(B, Sq, H, 128, seed=34)
+    mask = torch.ones(B, Skv, dtype=torch.uint8, device=DEV)
+    mask[B - 1, Skv - 21:] = 0
+    if B > 2:
+        mask[1, Skv // 2:] = 0
+    o, lse = ops.attention(q, k, v, causal=causal, key_mask=mask, return_lse=True)
+    outs = []
+    for persist in ("0", "1", "1"):
+        monkeypatch.setenv("LHRS_ATTN_BWD_PERSIST", persist)
+        outs.append(ops.attention_bwd(q, k, v, o, lse, d_o, causal=causal, key_mask=mask))
+    torch.cuda.synchronize()
+    for name, a, b, c in zip(("dq", "dk", "dv"), *outs):
+        assert torch.isfinite(b.float()).all(), name
+        assert torch.equal(a, b), f"{name}: persistent kernel differs from the per-tile kernel (max |diff| {(a.float() - b.float()).abs().max().item():.3e})"
+        assert torch.equal(b, c), f"{name}: the persistent kernel is not deterministic"
+    # and without a mask
+    outs = []
+    for persist in ("0", "1"):
+        monkeypatch.setenv("LHRS_ATTN_BWD_PERSIST", persist)
+        outs.append(ops.attention_bwd(q, k, v, o, lse, d_o, causal=causal, key_mask=None))
+    for name, a, b in zip(("dq", "dk", "dv"), *outs):
+        assert torch.equal(a, b), f"{name} (no mask): persistent kernel differs from the per-tile kernel"
+
+
 def test_attention_bwd_tc_unrope_and_packed():
     """tcgen05 backward on packed [rows, 3*H*hd] projections (strided views, gradients written into a packed buffer) with the
     fused inverse RoPE, against the same call without it followed by the rotation in fp32."""
