@@ -453,16 +453,16 @@ class _UpcastView:
         return k in self.sd
 
 
-def oracle_loss_fp32(model, cfg, batch):
+def oracle_loss_fp32(model, cfg, batch, lora_dropout=None):
     """The fp32 oracle (oracle/unibind.py: the reference's UniBind.forward restated) on the model's CURRENT weights and one device
-    batch — the checker of the step bench.py times, never the thing measured."""
+    batch — the checker of the step bench.py times, never the thing measured.  lora_dropout = (p, seed of the coming call)."""
     from oracle import unibind
     st = dict(vit=_UpcastView(model.rgb.encoder.state_dict()), pooler=_UpcastView(model.rgb_pooler.state_dict()),
               llama=_UpcastView(model.text.text_encoder.state_dict()))
     b32 = dict(batch)
     b32["rgb"] = batch["rgb"].float()
     with torch.no_grad():
-        return float(unibind.forward_loss(b32, st, cfg))
+        return float(unibind.forward_loss(b32, st, cfg, lora_dropout=lora_dropout))
 
 
 # ------------------------------------------------------------------------------------------------ decode leg (config 2)
@@ -579,6 +579,8 @@ def measure_steps(args, workload, dev, rank, world, local, steps, warmup, B=None
     train = workload in ("sft_step", "stage1_step")
     B = B or (32 if workload == "stage1_step" else PER_GPU_BATCH)
     S = S or (256 if workload == "stage1_step" else SEQ_LEN)
+    # BASELINE config 4 does not name a dropout (round 1 ran 0.0: kept for comparability); the shipped stage-2/3 yamls say 0.05
+    # (Config/multi_modal_stage2.yaml:85) — `--lora-dropout 0.05` times that, and the default line reports it as a side figure
     dropout = 0.0 if args.lora_dropout is None else float(args.lora_dropout)
     cfg = default_config(stage=3 if workload == "sft_step" else (1 if workload == "stage1_step" else 0), local_rank=local,
                          is_distribute=world > 1,
@@ -648,7 +650,11 @@ def measure_steps(args, workload, dev, rank, world, local, steps, warmup, B=None
     # that batch: |loss - oracle| must stay within the parity tests' bar.
     loss_check = None
     if checks and rank == 0:
-        ref = oracle_loss_fp32(model, cfg, dev_batches[warmup % 2])
+        drop = None
+        if train and model.text.lora_dropout_p() > 0:      # the masks the coming training forward will draw
+            from lhrs_bot_b200.text_modal import dropout_call_seed
+            drop = (model.text.lora_dropout_p(), dropout_call_seed(model.text._drop_base, model.text._drop_calls + 1))
+        ref = oracle_loss_fp32(model, cfg, dev_batches[warmup % 2], lora_dropout=drop)
         _free_gpu()
     got = float(step(dev_batches[warmup % 2]))
     if checks and rank == 0:
@@ -869,6 +875,16 @@ def main():
         # cheap extra legs on the same driver-run line (N = 1 only): BASELINE config 2 (greedy decode) and config 3 (stage-1 step)
         if line is not None and args.workload == "auto" and world == 1 and not args.no_extra:
             extra = {}
+            if args.lora_dropout is None:
+                try:      # the same step with the shipped yamls' LoRA dropout (peft train-mode input dropout, csrc/dropout.cuh)
+                    args.lora_dropout = 0.05
+                    r = measure_steps(args, workload, dev, rank, world, local, 5, 3, B=B, S=S, mixed=mixed, checks=not args.no_checks,
+                                      cpu_baseline=False, e2e_leg=False)
+                    extra["sft_step_with_lora_dropout_0.05"] = {k: r[k] for k in ("value", "unit", "ms_per_step", "loss_check") if k in r}
+                except Exception as e:
+                    extra["sft_step_with_lora_dropout_0.05"] = dict(error=f"{type(e).__name__}: {str(e)[:300]}")
+                finally:
+                    args.lora_dropout = None
             for name, fn in (("decode_greedy_config2", lambda: measure_decode(args, dev, rank, world, local, 3, 3, cpu_baseline=False)),
                              ("stage1_step_config3", lambda: measure_steps(args, "stage1_step", dev, rank, world, local, 5, 3, checks=False,
                                                                            cpu_baseline=False, e2e_leg=False))):

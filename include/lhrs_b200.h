@@ -96,6 +96,10 @@ typedef struct LhrsGemm {
     /* split_k > 1: split the K loop over that many CTAs per output tile (skinny problems that would otherwise occupy few
      * SMs).  Partial sums are added with fp32 atomics: D must be fp32 (d_f32) and zero-initialised; plain LINEAR epilogue. */
     int32_t split_k;
+    /* LINEAR epilogue, drop_t > 0: zero the accumulator elements the LoRA dropout mask of drop_key drops (row = output row,
+     * column = output column, ld = N; see lhrs_lora_dropout_mask) before the residual is added.  N % 32 == 0. */
+    uint32_t drop_key;
+    int32_t drop_t;
 } LhrsGemm;
 
 int lhrs_gemm_bf16(const LhrsGemm* g, void* stream);
@@ -274,6 +278,10 @@ typedef struct LhrsLlamaWeights {
     /* LoRA (all NULL when disabled).  Index [layer*7 + p], p in {q,k,v,o,gate,up,down}. */
     int32_t lora_r; float lora_scale;
     const void* const* lora_a; const void* const* lora_b;
+    /* peft's input dropout of the LoRA branch for THIS call (training forward and its backward: same seed); 0 = off (eval).
+     * The mask is a pure function of (lora_seed, layer * 7 + projection, row, column): lhrs_lora_dropout_mask. */
+    float lora_dropout;
+    uint64_t lora_seed;
 } LhrsLlamaWeights;
 
 size_t lhrs_llama_workspace_bytes(const LhrsLlamaWeights* w, int32_t B, int32_t S);
@@ -299,6 +307,23 @@ int lhrs_layernorm_bwd(const void* x, int64_t ldx, const void* w, const float* m
                        int32_t dim, void* stream);
 size_t lhrs_colsum_scratch_bytes(int32_t n);
 int lhrs_colsum(const void* a, int64_t ld, int64_t rows, int32_t n, void* out, int32_t accumulate, float* scratch, void* stream);
+/* LoRA input dropout (peft lora.Linear, text_modal.py:136-143): out = x with the dropped elements zeroed (survivors NOT scaled;
+ * callers fold 256 / (256 - T) into the product that consumes it).  keep(row, col) is the counter-based hash documented in
+ * csrc/dropout.cuh: drop probability T / 256 with T = round(p * 256); module = layer * 7 + {q,k,v,o,gate,up,down}. */
+int lhrs_lora_dropout_mask(const void* x, int64_t ldx, int64_t rows, int32_t cols, uint64_t seed, int32_t module, float p,
+                           void* out, int64_t ldo, void* stream);
+/* Fused-mask forms of the rank-16 streaming side products (no masked copy of the activation is written):
+ *   out[M, n] = alpha * 256/(256-T) * [ (mask_p o x) · w_p^T ]_p      w = [n, ldw] = lora_A of n/16 projections stacked
+ *   dst[n, C] = 256/(256-T) * [ q_p^T · (mask_p o x) ]_p               q = dT [M, n]  (dA of the n/16 projections, stacked) */
+int lhrs_lora_panel_dropout(const void* x, int64_t ldx, int64_t M, int32_t K, const void* w, int64_t ldw, int32_t n, float alpha,
+                            uint64_t seed, int32_t module0, float p, void* out, int64_t ldo, void* stream);
+int lhrs_lora_rowreduce_dropout(const void* x, int64_t ldx, int64_t M, int32_t C, const void* q, int64_t ldq, int32_t n, void* dst,
+                                int64_t ldd, uint64_t seed, int32_t module0, float p, float* scratch, size_t scratch_bytes,
+                                void* stream);
+/* dx[M, C] += 256/(256-T) * sum_p mask_p o (dT[:, 16p:16p+16] · lora_a[p][16, C]): the LoRA branch's input gradient under
+ * dropout (rank 16; module of projection p = module0 + p).  One streaming read-modify-write pass over dx. */
+int lhrs_lora_dx_dropout(void* dx, int64_t ldx, int64_t M, int32_t C, const void* dT, int64_t ldt, const void* const* lora_a,
+                         int32_t nproj, uint64_t seed, int32_t module0, float p, void* stream);
 /* d_gu[rows, 2f] = [d_gate | d_up] from d_act and the stashed pre-activations (HF LlamaMLP backward) */
 int lhrs_swiglu_bwd(const void* d_act, const void* pre_gate, const void* pre_up, void* d_gu, int64_t rows, int32_t f, void* stream);
 int lhrs_gelu_bwd(void* d /*in place*/, const void* pre, int64_t n, void* stream);

@@ -31,7 +31,7 @@ class LhrsGemm(C.Structure):
         ("rope_seq_len", C.c_int32),
         ("pre_gate", C.c_void_p), ("pre_up", C.c_void_p),
         ("A2", C.c_void_p), ("lda2", C.c_int64), ("B2", C.c_void_p * 3), ("ldb2", C.c_int64), ("ext_k", C.c_int32),
-        ("b_seg_nshift", C.c_int32), ("split_k", C.c_int32),
+        ("b_seg_nshift", C.c_int32), ("split_k", C.c_int32), ("drop_key", C.c_uint32), ("drop_t", C.c_int32),
     ]
 
 
@@ -125,6 +125,7 @@ class LhrsLlamaWeights(C.Structure):
         ("norm_w", C.c_void_p), ("lm_head", C.c_void_p), ("embed", C.c_void_p),
         ("rope_cos", C.c_void_p), ("rope_sin", C.c_void_p),
         ("lora_r", C.c_int32), ("lora_scale", C.c_float), ("lora_a", _PP), ("lora_b", _PP),
+        ("lora_dropout", C.c_float), ("lora_seed", C.c_uint64),
     ]
 
 
@@ -172,6 +173,10 @@ SIGNATURES = {
                                                  C.POINTER(LhrsSampling), _I32, _P]),
     "lhrs_attention_bwd": (C.c_int, [C.POINTER(LhrsAttentionBwd), _P]),
     "lhrs_attention_bwd_scratch_floats": (C.c_int64, [_I32, _I32, _I32, _I32]),
+    "lhrs_lora_dropout_mask": (C.c_int, [_P, _I64, _I64, _I32, C.c_uint64, _I32, _F, _P, _I64, _P]),
+    "lhrs_lora_dx_dropout": (C.c_int, [_P, _I64, _I64, _I32, _P, _I64, _PP, _I32, C.c_uint64, _I32, _F, _P]),
+    "lhrs_lora_panel_dropout": (C.c_int, [_P, _I64, _I64, _I32, _P, _I64, _I32, _F, C.c_uint64, _I32, _F, _P, _I64, _P]),
+    "lhrs_lora_rowreduce_dropout": (C.c_int, [_P, _I64, _I64, _I32, _P, _I64, _I32, _P, _I64, C.c_uint64, _I32, _F, _P, C.c_size_t, _P]),
     "lhrs_rmsnorm_bwd": (C.c_int, [_P, _P, _P, _P, _P, _P, _I64, _I32, _P]),
     "lhrs_layernorm_bwd_scratch_bytes": (C.c_size_t, [_I32]),
     "lhrs_layernorm_bwd": (C.c_int, [_P, _I64, _P, _P, _P, _P, _P, _P, _P, _P, _I32, _P, _I64, _I32, _P]),

@@ -95,7 +95,16 @@ class LlamaLossFunction(torch.autograd.Function):
         embeds, new_labels, new_mask, row_map, _ = text._splice(input_ids, attention_mask, labels, image_embedding)
         B, S, D = embeds.shape
         stash = torch.empty((lib.lhrs_llama_stash_bytes(C.byref(w), B, S),), device=embeds.device, dtype=torch.uint8)
-        hidden = text.llama_forward(embeds, new_mask, stash=stash)
+        # peft's input dropout on the LoRA branch: one seed per training forward, kept for the backward (same masks)
+        ctx.drop = (0.0, 0)
+        p_drop = text.lora_dropout_p() if lora_params and any(p.requires_grad for p in lora_params) else 0.0
+        if p_drop > 0.0:
+            ctx.drop = (p_drop, text.next_lora_dropout_seed())
+        w.lora_dropout, w.lora_seed = ctx.drop
+        try:
+            hidden = text.llama_forward(embeds, new_mask, stash=stash)
+        finally:
+            w.lora_dropout, w.lora_seed = 0.0, 0
         sel = supervised_rows(new_labels)
         ctx.rows = None
         if sel is not None:      # lm_head + CE over the supervised rows only (identical loss and gradients)
@@ -156,11 +165,15 @@ class LlamaLossFunction(torch.autograd.Function):
             keep += [pa, pb, a_list, b_list]
             ga, gb = pa.ptr(), pb.ptr()
         d_embeds = torch.empty((B, S, D), device=dev, dtype=torch.bfloat16)
-        ws_bytes = lib.lhrs_llama_bwd_workspace_bytes(C.byref(w), B, S)
-        ws = runtime.workspace(ws_bytes, dev, "bwd")
-        check(lib.lhrs_llama_bwd(C.byref(w), ga, gb, d_hidden.data_ptr(), B, S, None if ctx.km is None else ctx.km.data_ptr(),
-                                 ctx.stash.data_ptr(), d_embeds.data_ptr(), ws.data_ptr(), ws.numel(), runtime.stream()),
-              "lhrs_llama_bwd")
+        w.lora_dropout, w.lora_seed = ctx.drop          # the forward's masks
+        try:
+            ws_bytes = lib.lhrs_llama_bwd_workspace_bytes(C.byref(w), B, S)
+            ws = runtime.workspace(ws_bytes, dev, "bwd")
+            check(lib.lhrs_llama_bwd(C.byref(w), ga, gb, d_hidden.data_ptr(), B, S, None if ctx.km is None else ctx.km.data_ptr(),
+                                     ctx.stash.data_ptr(), d_embeds.data_ptr(), ws.data_ptr(), ws.numel(), runtime.stream()),
+                  "lhrs_llama_bwd")
+        finally:
+            w.lora_dropout, w.lora_seed = 0.0, 0
         d_img = None
         if ctx.need_img:
             d_img = ops.splice_bwd(d_embeds, ctx.row_map, ctx.img_shape[0], ctx.img_shape[1])

@@ -3,6 +3,7 @@
 // SwiGLU / GELU / RoPE backward, column sums for bias gradients, global grad-norm and AdamW on flat buffers.
 #include "host_common.h"
 #include "ptx.cuh"
+#include "dropout.cuh"
 
 namespace lhrs {
 
@@ -339,6 +340,38 @@ extern "C" int lhrs_colsum(const void* a, int64_t ld, int64_t rows, int32_t n, v
     LHRS_LAUNCH_CHECK("colsum_partial_kernel");
     colsum_final_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(scratch, ny, n, (bf16*)out, accumulate);
     LHRS_LAUNCH_CHECK("colsum_final_kernel");
+    return LHRS_OK;
+}
+
+// out = x with the elements dropped by the LoRA dropout mask of `key` zeroed (survivors unscaled: the callers fold 1/keep into
+// the alpha of the product that consumes it).  One thread per 8 columns: four 2 x 2 blocks, one mask word each.
+__global__ void __launch_bounds__(BT)
+lora_dropout_mask_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, long long rows, int cols, uint32_t key, int t,
+                         __nv_bfloat16* __restrict__ out, long long ldo) {
+    const int cpr = cols / 8;
+    const long long total = rows * cpr;
+    for (long long i = blockIdx.x * static_cast<long long>(BT) + threadIdx.x; i < total; i += static_cast<long long>(gridDim.x) * BT) {
+        const long long r = i / cpr;
+        const int c0 = static_cast<int>(i - r * cpr) * 8;
+        uint4 v = *reinterpret_cast<const uint4*>(x + r * ldx + c0);
+        uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const uint32_t word = drop_word(key, static_cast<uint32_t>(r), static_cast<uint32_t>(c0 + 2 * j), static_cast<uint32_t>(cols));
+            if (!drop_keep(word, static_cast<uint32_t>(r), 0u, t)) w[j] &= 0xffff0000u;
+            if (!drop_keep(word, static_cast<uint32_t>(r), 1u, t)) w[j] &= 0x0000ffffu;
+        }
+        *reinterpret_cast<uint4*>(out + r * ldo + c0) = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+}
+
+extern "C" int lhrs_lora_dropout_mask(const void* x, int64_t ldx, int64_t rows, int32_t cols, uint64_t seed, int32_t module, float p,
+                                      void* out, int64_t ldo, void* stream) {
+    LHRS_CHECK_ARG(x && out && rows > 0 && cols > 0 && cols % 8 == 0 && ldx % 8 == 0 && ldo % 8 == 0 && p >= 0.f && p < 1.f,
+                   "lhrs_lora_dropout_mask: bad args (cols, ldx, ldo must be multiples of 8; 0 <= p < 1)");
+    lora_dropout_mask_kernel<<<grid_for(rows * (cols / 8), BT), BT, 0, (cudaStream_t)stream>>>(
+        (const bf16*)x, ldx, rows, cols, drop_key(seed, static_cast<uint32_t>(module)), drop_threshold(p), (bf16*)out, ldo);
+    LHRS_LAUNCH_CHECK("lora_dropout_mask_kernel");
     return LHRS_OK;
 }
 

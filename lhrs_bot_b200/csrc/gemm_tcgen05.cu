@@ -15,6 +15,7 @@
 
 #include "host_common.h"
 #include "ptx.cuh"
+#include "dropout.cuh"
 
 namespace lhrs {
 
@@ -47,6 +48,8 @@ struct GemmArgs {
     int splitk;  // >1: the K loop is split over `splitk` CTAs per tile; partial sums are added with fp32 atomics into D
     int ext_k;   // LoRA K-extension: columns of A2 per B segment (0 = none)
     int ext_kb;  // extra 64-wide k-blocks appended after the main K loop
+    uint32_t drop_key;  // LINEAR: LoRA dropout mask applied to the accumulator (drop_t > 0), see dropout.cuh
+    int drop_t;
 };
 
 // CG = 1: one CTA per 128 x BN tile.  CG = 2: a CTA pair (cluster of 2, tcgen05 cta_group::2) owns a 256 x BN tile; each CTA
@@ -419,6 +422,63 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 const int bseg = (args.num_b > 1) ? (n_tile0 / args.seg_rows) : 0;
                 const __nv_bfloat16* bias_seg = (bseg == 0) ? args.bias[0] : (bseg == 1 ? args.bias[1] : args.bias[2]);
                 const __nv_bfloat16* bias = (bias_seg != nullptr) ? bias_seg - bseg * args.seg_rows : nullptr;  // index by global n
+                if (args.pre_up != nullptr && coal) {
+                    // SwiGLU backward fused into the dX GEMM of down_proj (acc = d_act; D = d_gu = [d_gate | d_up], d_act is never
+                    // stored).  The stashed pre-activations g, u are 2 x 16 KB per warp and tile: their loads for chunk c+1 are
+                    // issued BEFORE chunk c is processed, so the ~1 us global latency sits under a chunk of math and stores.
+                    // (Unpipelined — load, wait, compute, store per chunk — this epilogue took longer than the K = 4096 mainloop
+                    // and the fused form lost 2 ms per step to the separate swiglu_bwd pass, gpurun_out/s2b_sft_fuse.json.)
+                    const int cc = lane & 3;
+                    uint4 gq[4], uq[4];
+                    auto issue = [&](int n0) {
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const int rr = (lane >> 2) + 8 * i;
+                            gq[i] = make_uint4(0, 0, 0, 0); uq[i] = make_uint4(0, 0, 0, 0);
+                            if (rr < nvalid && n0 + 32 <= args.N) {
+                                gq[i] = __ldg(reinterpret_cast<const uint4*>(args.pre_gate + (row_w0 + rr) * args.N + n0 + cc * 8));
+                                uq[i] = __ldg(reinterpret_cast<const uint4*>(args.pre_up + (row_w0 + rr) * args.N + n0 + cc * 8));
+                            }
+                        }
+                    };
+                    auto transpose_in = [&](const uint4 (&q4)[4], float (&out)[32]) {   // 8 rows x 64 B pieces -> this lane's row
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) *reinterpret_cast<uint4*>(slab + ((lane >> 2) + 8 * i) * 80 + cc * 16) = q4[i];
+                        __syncwarp();
+                        const uint4* mine = reinterpret_cast<const uint4*>(slab + lane * 80);
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const uint4 u4 = mine[i];
+                            out[i * 8 + 0] = bf16_lo(u4.x); out[i * 8 + 1] = bf16_hi(u4.x); out[i * 8 + 2] = bf16_lo(u4.y); out[i * 8 + 3] = bf16_hi(u4.y);
+                            out[i * 8 + 4] = bf16_lo(u4.z); out[i * 8 + 5] = bf16_hi(u4.z); out[i * 8 + 6] = bf16_lo(u4.w); out[i * 8 + 7] = bf16_hi(u4.w);
+                        }
+                        __syncwarp();
+                    };
+                    issue(n_tile0);
+#pragma unroll 1
+                    for (int c = 0; c < BN / 32; ++c) {
+                        const int n0 = n_tile0 + c * 32;
+                        if (n0 + 32 > args.N) break;
+                        float g[32], u[32];
+                        transpose_in(gq, g);
+                        transpose_in(uq, u);
+                        if (c + 1 < BN / 32) issue(n0 + 32);      // in flight under this chunk's TMEM read, math and stores
+                        uint32_t r[32];
+                        tmem_ld_32x32(taddr + c * 32, r);
+                        tmem_ld_wait();
+                        float dg[32], du[32];
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            const float da = bf16_round(__uint_as_float(r[j]) * args.alpha);
+                            const float sg = 1.f / (1.f + __expf(-g[j]));
+                            dg[j] = da * u[j] * sg * (1.f + g[j] * (1.f - sg));
+                            du[j] = da * g[j] * sg;
+                        }
+                        __nv_bfloat16* d = reinterpret_cast<__nv_bfloat16*>(args.D) + row_w0 * args.ldd + n0;
+                        tile_store(slab, dg, d, args.ldd, nvalid, lane);
+                        tile_store(slab, du, d + args.N, args.ldd, nvalid, lane);
+                    }
+                } else
 #pragma unroll 1
                 for (int c = 0; c < BN / 32; ++c) {
                     const int n0 = n_tile0 + c * 32;
@@ -484,6 +544,15 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                         if (args.act != LHRS_ACT_NONE) {
 #pragma unroll
                             for (int j = 0; j < 32; ++j) v[j] = act_apply(bf16_round(v[j]), args.act);
+                        }
+                        if (args.drop_t > 0) {   // LoRA dropout on the dX correction dT·A: one mask word per 2 x 2 block
+#pragma unroll
+                            for (int j = 0; j < 32; j += 2) {
+                                const uint32_t word = drop_word(args.drop_key, static_cast<uint32_t>(row), static_cast<uint32_t>(n0 + j),
+                                                                static_cast<uint32_t>(args.N));
+                                if (!drop_keep(word, static_cast<uint32_t>(row), 0u, args.drop_t)) v[j] = 0.f;
+                                if (!drop_keep(word, static_cast<uint32_t>(row), 1u, args.drop_t)) v[j + 1] = 0.f;
+                            }
                         }
                         if (args.residual != nullptr) {
                             float rr[32];
@@ -857,6 +926,10 @@ extern "C" int lhrs_gemm_bf16(const LhrsGemm* g, void* stream_) {
     a.rope_cos = g->rope_cos; a.rope_sin = g->rope_sin; a.positions = g->positions; a.rope_seq_len = g->rope_seq_len;
     a.pre_gate = reinterpret_cast<__nv_bfloat16*>(g->pre_gate);
     a.pre_up = reinterpret_cast<__nv_bfloat16*>(g->pre_up);
+    a.drop_key = g->drop_key; a.drop_t = g->drop_t;
+    if (g->drop_t > 0)
+        LHRS_CHECK_ARG(kind == LHRS_EPI_LINEAR && (g->N % 32) == 0 && g->drop_t < 256 && g->split_k <= 1 && !g->pre_up,
+                       "lhrs_gemm_bf16: the dropout mask needs a LINEAR epilogue with N %% 32 == 0");
 
     if (cg == 2) {
         if (kind == LHRS_EPI_SWIGLU) return launch<256, LHRS_EPI_SWIGLU, false, false, 2>(tA, tB, tA2, tE, a, stream);

@@ -7,6 +7,7 @@
 #include <stdlib.h>
 #include "host_common.h"
 #include "ptx.cuh"
+#include "dropout.cuh"
 #include "models_common.h"
 
 namespace lhrs {
@@ -110,6 +111,8 @@ struct LoraBwd {
     const __nv_bfloat16* T = nullptr;   // [M, nproj*r] from the forward stash
     __nv_bfloat16* dt = nullptr;        // [M, nproj*r]
     float* scratch = nullptr;           // fp32 split-K accumulator for the skinny side GEMMs
+    __nv_bfloat16* drop_x = nullptr;    // [M, in_dim] masked copy of x (LoRA dropout only)
+    int drop_t = 0;
     long long M = 0;
 };
 
@@ -134,8 +137,9 @@ static int lora_bwd_pre(cudaStream_t st, const LhrsLlamaWeights* w, void* const*
         if (n > 1) d.b_seg_nshift = r;
         if ((rc = skinny_gemm(d, L.scratch, st))) return rc;
     }
-    // dx += dT · [A_0;A_1;..] accumulates in the main GEMM's TMEM tile
-    g.A2 = L.dt; g.lda2 = ldt; g.B2[0] = w->lora_a[L.idx0]; g.ldb2 = L.in_dim; g.ext_k = n * r;
+    // dx += dT · [A_0;A_1;..] accumulates in the main GEMM's TMEM tile — unless dropout masks each projection's term
+    // separately (then lora_bwd_post adds mask_p o (dT_p · A_p) per projection)
+    if (L.drop_t == 0) { g.A2 = L.dt; g.lda2 = ldt; g.B2[0] = w->lora_a[L.idx0]; g.ldb2 = L.in_dim; g.ext_k = n * r; }
     return LHRS_OK;
 }
 
@@ -145,6 +149,54 @@ static int lora_bwd_post(cudaStream_t st, const LhrsLlamaWeights* w, void* const
     const int r = w->lora_r, n = L.nproj;
     const long long ldt = (long long)n * r;
     int rc;
+    if (L.drop_t > 0 && L.grouped) {
+        // peft input dropout (mask_p per LoRA module, regenerated from the call seed):
+        //   dx  += (1/keep) * mask_p o (dT_p · A_p)        a K = r GEMM per projection with the mask in its epilogue
+        //   dA_p = (1/keep) * dT_p^T · (mask_p o x)        from a masked copy of x
+        //   dB_p = dy_p^T · T_p                            unchanged (T already carries the mask)
+        const float inv = drop_inv_keep(L.drop_t);
+        LHRS_CHECK_ARG(dx != nullptr && L.drop_x != nullptr, "lora_bwd_post: dropout needs the materialised dX and the masked-input scratch");
+        const size_t sb = (size_t)8 * (size_t)(n * L.out_dim > L.in_dim ? n * L.out_dim : L.in_dim) * (size_t)(n * r) * sizeof(float);
+        if (r == 16) {   // one streaming pass over dx for all projections of the group
+            if ((rc = lhrs_lora_dx_dropout(dx, lddx, L.M, L.in_dim, L.dt, ldt, w->lora_a + L.idx0, n, w->lora_seed, L.idx0, w->lora_dropout, st))) return rc;
+        }
+        bool da_done = false;
+        if (L.stream && ga != nullptr && ga[L.idx0]) {   // [dA_0;dA_1;..] = (1/keep) dT^T (mask_p o x): one pass over x, masks on the fragments
+            if ((rc = lhrs_lora_rowreduce_dropout(L.x, L.ldx, L.M, L.in_dim, L.dt, ldt, n * r, ga[L.idx0], L.in_dim, w->lora_seed, L.idx0,
+                                                  w->lora_dropout, L.scratch, sb, st))) return rc;
+            da_done = true;
+        }
+        for (int p = 0; p < n; ++p) {
+            const int idx = L.idx0 + p;
+            if (r != 16) {
+                LhrsGemm c = gemm_desc(L.M, L.in_dim, r, L.dt + p * r, ldt, w->lora_a[idx], L.in_dim, dx, lddx);
+                c.b_mn_major = 1; c.alpha = inv; c.residual = dx; c.ldr = lddx;
+                c.drop_key = drop_key(w->lora_seed, (uint32_t)idx); c.drop_t = L.drop_t;
+                if ((rc = lhrs_gemm_bf16(&c, st))) return rc;
+            }
+            if (!da_done && ga != nullptr && ga[idx]) {
+                if ((rc = lhrs_lora_dropout_mask(L.x, L.ldx, L.M, L.in_dim, w->lora_seed, idx, w->lora_dropout, L.drop_x, L.in_dim, st))) return rc;
+                if (L.stream) {
+                    void* dst[1] = {ga[idx]};
+                    if ((rc = lhrs_lora_rowreduce(L.drop_x, L.in_dim, L.M, L.in_dim, L.dt + p * r, ldt, r, 0, 1, dst, L.in_dim, inv, L.scratch, sb, st))) return rc;
+                } else {
+                    if ((rc = gemm_dw(st, r, L.in_dim, L.M, L.dt + p * r, ldt, L.drop_x, L.in_dim, ga[idx], L.in_dim, inv, L.scratch))) return rc;
+                }
+            }
+        }
+        if (gb != nullptr) {
+            if (L.stream) {
+                void* dst[3] = {gb[L.idx0], n > 1 ? gb[L.idx0 + 1] : nullptr, n > 2 ? gb[L.idx0 + 2] : nullptr};
+                if (dst[0] != nullptr)
+                    if ((rc = lhrs_lora_rowreduce(L.dy[0], L.ldy, L.M, n * L.out_dim, L.T, ldt, r, L.out_dim, 0, dst, r, 1.f, L.scratch, sb, st))) return rc;
+            } else {
+                for (int p = 0; p < n; ++p)
+                    if (gb[L.idx0 + p]) if ((rc = gemm_dw(st, L.out_dim, r, L.M, L.dy[p], L.ldy, L.T + p * r, ldt, gb[L.idx0 + p], r))) return rc;
+            }
+        }
+        return LHRS_OK;
+    }
+    LHRS_CHECK_ARG(L.drop_t == 0, "lora backward with dropout needs the grouped (flat, SftStepper) LoRA parameter layout");
     if (L.grouped && L.stream) {
         const size_t sb = (size_t)8 * (size_t)(n * L.out_dim > L.in_dim ? n * L.out_dim : L.in_dim) * (size_t)(n * r) * sizeof(float);
         if (gb != nullptr) {   // dB_p = dy_p^T T_p: one streaming pass over dy, block-diagonal pairing of column blocks and T columns
@@ -186,9 +238,11 @@ static int lora_bwd_post(cudaStream_t st, const LhrsLlamaWeights* w, void* const
 
 static LoraBwd lora_ctx(const LhrsLlamaWeights* w, int layer, int first, int nproj, const void* x, long long ldx, int in_dim,
                         const void* dy0, long long ldy, int out_dim, long long M, const __nv_bfloat16* T, __nv_bfloat16* dt,
-                        float* scratch) {
+                        float* scratch, __nv_bfloat16* drop_x = nullptr) {
     LoraBwd L;
     L.scratch = scratch;
+    L.drop_x = drop_x;
+    L.drop_t = (w->lora_r > 0) ? drop_threshold(w->lora_dropout) : 0;
     L.active = w->lora_r > 0 && w->lora_a != nullptr && w->lora_b != nullptr;
     L.idx0 = layer * 7 + first; L.nproj = nproj; L.in_dim = in_dim; L.out_dim = out_dim;
     L.x = x; L.ldx = ldx; L.ldy = ldy; L.M = M; L.T = T; L.dt = dt;
@@ -203,7 +257,7 @@ typedef __nv_bfloat16 bf16;
 
 // ================================================================================================ LLaMA backward
 namespace {
-struct LlamaBwdBufs { bf16 *dxa, *dxb, *dh, *d_act, *d_gu, *dqkv, *d_o, *h, *t, *dt, *diag; float *delta, *skinny; };
+struct LlamaBwdBufs { bf16 *dxa, *dxb, *dh, *d_act, *d_gu, *dqkv, *d_o, *h, *t, *dt, *diag, *drop_x; float *delta, *skinny; };
 LlamaBwdBufs llama_bwd_plan(Arena& a, const LhrsLlamaWeights* w, long long M) {
     LlamaBwdBufs b;
     const int D = w->dim, F = w->ffn;
@@ -218,6 +272,7 @@ LlamaBwdBufs llama_bwd_plan(Arena& a, const LhrsLlamaWeights* w, long long M) {
     const long long widest = (3LL * w->dim > 2LL * w->ffn) ? 3LL * w->dim : 2LL * w->ffn;
     b.diag = lora ? a.take<bf16>(widest * 3 * w->lora_r) : nullptr;
     b.skinny = lora ? a.take<float>(skinny_scratch_elems(w, M)) : nullptr;
+    b.drop_x = (lora && w->lora_dropout > 0.f) ? a.take<bf16>(M * (F > D ? F : D)) : nullptr;
     return b;
 }
 }  // namespace
@@ -253,7 +308,7 @@ extern "C" int lhrs_llama_bwd(const LhrsLlamaWeights* w, void* const* lora_a_gra
         const LlamaLayerStash& t = s.layer[l];
         // ---- MLP: x_out = x_mid + down(silu(gate(h2)) * up(h2)),  h2 = rmsnorm(x_mid)
         {
-            LoraBwd L = lora_ctx(w, l, 6, 1, t.act, F, F, dx, D, D, M, t.lora_t[3], b.dt, b.skinny);
+            LoraBwd L = lora_ctx(w, l, 6, 1, t.act, F, F, dx, D, D, M, t.lora_t[3], b.dt, b.skinny, b.drop_x);
             // d_act = dx · W_down (+ LoRA) with the SwiGLU backward applied in the epilogue: writes d_gu = [d_gate | d_up]
             LhrsGemm g = gemm_desc(M, F, D, dx, D, w->down_w[l], F, b.d_gu, 2 * F);
             g.b_mn_major = 1;
@@ -261,7 +316,7 @@ extern "C" int lhrs_llama_bwd(const LhrsLlamaWeights* w, void* const* lora_a_gra
             const int fuse = fe ? atoi(fe) : 0;
             g.pre_gate = t.pre_gate; g.pre_up = t.pre_up;
             if ((rc = lora_bwd_pre(st, w, lora_a_grads, L, g))) return rc;
-            if ((L.active && !L.grouped) || !fuse) {   // un-batched LoRA fallback needs d_act materialised for its read-modify-write pass
+            if ((L.active && !L.grouped) || !fuse || L.drop_t > 0) {   // un-batched LoRA fallback needs d_act materialised for its read-modify-write pass
                 g.D = b.d_act; g.ldd = F; g.pre_gate = nullptr; g.pre_up = nullptr;
                 if ((rc = lhrs_gemm_bf16(&g, st))) return rc;
                 if ((rc = lora_bwd_post(st, w, lora_a_grads, lora_b_grads, L, b.d_act, F, b.diag))) return rc;
@@ -272,7 +327,7 @@ extern "C" int lhrs_llama_bwd(const LhrsLlamaWeights* w, void* const* lora_a_gra
             }
         }
         {
-            LoraBwd L = lora_ctx(w, l, 4, 2, t.h2, D, D, b.d_gu, 2 * F, F, M, t.lora_t[2], b.dt, b.skinny);
+            LoraBwd L = lora_ctx(w, l, 4, 2, t.h2, D, D, b.d_gu, 2 * F, F, M, t.lora_t[2], b.dt, b.skinny, b.drop_x);
             LhrsGemm g = gemm_desc(M, D, 2 * F, b.d_gu, 2 * F, w->gate_w[l], D, b.dh, D);
             g.b_mn_major = 1; g.B[1] = w->up_w[l]; g.num_b = 2;
             if ((rc = lora_bwd_pre(st, w, lora_a_grads, L, g))) return rc;
@@ -283,7 +338,7 @@ extern "C" int lhrs_llama_bwd(const LhrsLlamaWeights* w, void* const* lora_a_gra
         { bf16* tmp = dx; dx = dx_other; dx_other = tmp; }   // dx = grad wrt x_mid
         // ---- attention: x_mid = x_in + o_proj(attn(rope(q), rope(k), v)),  q,k,v = proj(h1), h1 = rmsnorm(x_in)
         {
-            LoraBwd L = lora_ctx(w, l, 3, 1, t.o, D, D, dx, D, D, M, t.lora_t[1], b.dt, b.skinny);
+            LoraBwd L = lora_ctx(w, l, 3, 1, t.o, D, D, dx, D, D, M, t.lora_t[1], b.dt, b.skinny, b.drop_x);
             LhrsGemm g = gemm_desc(M, D, D, dx, D, w->o_w[l], D, b.d_o, D);
             g.b_mn_major = 1;
             if ((rc = lora_bwd_pre(st, w, lora_a_grads, L, g))) return rc;
@@ -303,7 +358,7 @@ extern "C" int lhrs_llama_bwd(const LhrsLlamaWeights* w, void* const* lora_a_gra
             if ((rc = lhrs_attention_bwd(&ab, st))) return rc;
         }
         {
-            LoraBwd L = lora_ctx(w, l, 0, 3, t.h1, D, D, b.dqkv, 3 * D, D, M, t.lora_t[0], b.dt, b.skinny);
+            LoraBwd L = lora_ctx(w, l, 0, 3, t.h1, D, D, b.dqkv, 3 * D, D, M, t.lora_t[0], b.dt, b.skinny, b.drop_x);
             LhrsGemm g = gemm_desc(M, D, 3 * D, b.dqkv, 3 * D, w->q_w[l], D, b.dh, D);
             g.b_mn_major = 1; g.B[1] = w->k_w[l]; g.B[2] = w->v_w[l]; g.num_b = 3;
             if ((rc = lora_bwd_pre(st, w, lora_a_grads, L, g))) return rc;

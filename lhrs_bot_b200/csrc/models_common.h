@@ -160,7 +160,7 @@ __host__ __device__ inline __nv_bfloat16* kv_ptr(const KvGeom& kv, int layer, in
 // LoRA: compute T = scale * x · A^T for `nproj` projections sharing the input x and attach the K-extension
 // (A2 = T, B2 = lora_B) to the parent GEMM so that B·T accumulates into the same TMEM tile.  No-op when LoRA is off.
 int lora_attach(LhrsGemm& g, const LhrsLlamaWeights* w, int layer, int first_proj, int nproj, const void* x, long long ldx,
-                long long M, __nv_bfloat16* t_buf, float* scratch, void* stream);
+                long long M, __nv_bfloat16* t_buf, float* scratch, __nv_bfloat16* drop_x, void* stream);
 
 bool lora_a_adjacent(const void* const* arr, int idx, int nproj, long long elems_each);
 

@@ -7,6 +7,7 @@
 #include <stdlib.h>
 #include "host_common.h"
 #include "ptx.cuh"
+#include "dropout.cuh"
 #include "models_common.h"
 
 namespace lhrs {
@@ -109,11 +110,34 @@ bool lora_stream_ok(const LhrsLlamaWeights* w, int in_dim, int out_dim, int npro
 }
 
 int lora_attach(LhrsGemm& g, const LhrsLlamaWeights* w, int layer, int first_proj, int nproj, const void* x, long long ldx,
-                long long M, __nv_bfloat16* t_buf, float* scratch, void* stream) {
+                long long M, __nv_bfloat16* t_buf, float* scratch, __nv_bfloat16* drop_x, void* stream) {
     if (w->lora_r <= 0 || w->lora_a == nullptr || w->lora_b == nullptr) return LHRS_OK;
     const int r = w->lora_r;
     const int idx = layer * 7 + first_proj;
     int rc;
+    const int drop_t = drop_threshold(w->lora_dropout);
+    if (drop_t > 0) {
+        // training forward with peft's input dropout: every LoRA module draws its own mask of the shared input, so the
+        // projections of a group no longer share one pass: T_p = (s / keep) * (mask_p o x) · A_p^T from a masked copy of x
+        LHRS_CHECK_ARG(drop_x != nullptr && ldx % 8 == 0, "lora_attach: dropout needs the masked-input scratch");
+        const float alpha = w->lora_scale * drop_inv_keep(drop_t);
+        if (lora_stream_ok(w, g.K, 128, nproj) && lora_a_adjacent(w->lora_a, idx, nproj, (long long)r * g.K)) {
+            // rank 16, flat parameter layout: ONE pass over x for the whole group, masks applied to the mma fragments
+            if ((rc = lhrs_lora_panel_dropout(x, ldx, M, g.K, w->lora_a[idx], g.K, nproj * r, w->lora_scale, w->lora_seed, idx,
+                                              w->lora_dropout, t_buf, (long long)nproj * r, stream))) return rc;
+        } else
+        for (int p = 0; p < nproj; ++p) {
+            if ((rc = lhrs_lora_dropout_mask(x, ldx, M, g.K, w->lora_seed, idx + p, w->lora_dropout, drop_x, g.K, stream))) return rc;
+            if (lora_stream_ok(w, g.K, 128, 1)) {
+                const void* wa[1] = {w->lora_a[idx + p]};
+                if ((rc = lhrs_lora_panel(drop_x, g.K, M, g.K, wa, 1, 0, g.K, r, alpha, t_buf + p * r, (long long)nproj * r, stream))) return rc;
+            } else {
+                LhrsGemm t = gemm_desc(M, r, g.K, drop_x, g.K, w->lora_a[idx + p], g.K, t_buf + p * r, (long long)nproj * r);
+                t.alpha = alpha;
+                if ((rc = lhrs_gemm_bf16(&t, stream))) return rc;
+            }
+        }
+    } else
     if (lora_a_adjacent(w->lora_a, idx, nproj, (long long)r * g.K)) {
         // T = (alpha/r) * x · [A_0; A_1; ..]^T in ONE skinny GEMM (one pass over x)
         if (lora_stream_ok(w, g.K, 128, nproj) && ldx % 8 == 0) {
@@ -347,7 +371,7 @@ extern "C" int lhrs_pooler_fwd(const LhrsPoolerWeights* w, const void* image_emb
 
 // ================================================================================================ LLaMA
 namespace {
-struct LlamaBufs { bf16 *x, *h, *qkv, *o, *act, *lora_t; float* skinny; };
+struct LlamaBufs { bf16 *x, *h, *qkv, *o, *act, *lora_t, *drop_x; float* skinny; };
 LlamaBufs llama_plan(Arena& a, const LhrsLlamaWeights* w, long long M, bool have_stash) {
     LlamaBufs b;
     b.x = a.take<bf16>(M * w->dim);
@@ -357,6 +381,7 @@ LlamaBufs llama_plan(Arena& a, const LhrsLlamaWeights* w, long long M, bool have
     b.act = have_stash ? nullptr : a.take<bf16>(M * w->ffn);
     b.lora_t = (w->lora_r > 0) ? a.take<bf16>(M * 3 * w->lora_r) : nullptr;
     b.skinny = (w->lora_r > 0) ? a.take<float>(skinny_scratch_elems(w, M)) : nullptr;
+    b.drop_x = (w->lora_r > 0 && w->lora_dropout > 0.f) ? a.take<bf16>(M * (w->ffn > w->dim ? w->ffn : w->dim)) : nullptr;
     return b;
 }
 }  // namespace
@@ -408,7 +433,7 @@ extern "C" int lhrs_llama_fwd(const LhrsLlamaWeights* w, const void* inputs_embe
             LhrsGemm g = gemm_desc(M, 3 * D, D, h1, D, w->q_w[l], D, qkv, 3 * D);
             g.B[1] = w->k_w[l]; g.B[2] = w->v_w[l]; g.num_b = 3; g.seg_rows = D;
             g.epilogue = LHRS_EPI_ROPE; g.rope_cos = w->rope_cos; g.rope_sin = w->rope_sin; g.rope_seq_len = S;
-            if ((rc = lora_attach(g, w, l, 0, 3, h1, D, M, ls ? ls->lora_t[0] : b.lora_t, b.skinny, stream))) return rc;
+            if ((rc = lora_attach(g, w, l, 0, 3, h1, D, M, ls ? ls->lora_t[0] : b.lora_t, b.skinny, b.drop_x, stream))) return rc;
             if ((rc = lhrs_gemm_bf16(&g, stream))) return rc;
         }
         if (kv != nullptr) {
@@ -425,7 +450,7 @@ extern "C" int lhrs_llama_fwd(const LhrsLlamaWeights* w, const void* inputs_embe
         {
             LhrsGemm g = gemm_desc(M, D, D, o, D, w->o_w[l], D, x_mid, D);
             g.residual = x_cur; g.ldr = D;
-            if ((rc = lora_attach(g, w, l, 3, 1, o, D, M, ls ? ls->lora_t[1] : b.lora_t, b.skinny, stream))) return rc;
+            if ((rc = lora_attach(g, w, l, 3, 1, o, D, M, ls ? ls->lora_t[1] : b.lora_t, b.skinny, b.drop_x, stream))) return rc;
             if ((rc = lhrs_gemm_bf16(&g, stream))) return rc;
         }
         if ((rc = lhrs_rmsnorm_fwd(x_mid, w->ln2_w[l], h2, ls ? ls->rstd2 : nullptr, M, D, w->eps, stream))) return rc;
@@ -434,13 +459,13 @@ extern "C" int lhrs_llama_fwd(const LhrsLlamaWeights* w, const void* inputs_embe
             LhrsGemm g = gemm_desc(M, 2 * F, D, h2, D, w->gate_w[l], D, act, F);
             g.B[1] = w->up_w[l]; g.num_b = 2; g.seg_rows = F; g.epilogue = LHRS_EPI_SWIGLU;
             if (ls) { g.pre_gate = ls->pre_gate; g.pre_up = ls->pre_up; }
-            if ((rc = lora_attach(g, w, l, 4, 2, h2, D, M, ls ? ls->lora_t[2] : b.lora_t, b.skinny, stream))) return rc;
+            if ((rc = lora_attach(g, w, l, 4, 2, h2, D, M, ls ? ls->lora_t[2] : b.lora_t, b.skinny, b.drop_x, stream))) return rc;
             if ((rc = lhrs_gemm_bf16(&g, stream))) return rc;
         }
         {
             LhrsGemm g = gemm_desc(M, D, F, act, F, w->down_w[l], F, x_next, D);
             g.residual = x_mid; g.ldr = D;
-            if ((rc = lora_attach(g, w, l, 6, 1, act, F, M, ls ? ls->lora_t[3] : b.lora_t, b.skinny, stream))) return rc;
+            if ((rc = lora_attach(g, w, l, 6, 1, act, F, M, ls ? ls->lora_t[3] : b.lora_t, b.skinny, b.drop_x, stream))) return rc;
             if ((rc = lhrs_gemm_bf16(&g, stream))) return rc;
         }
         x_cur = x_next;

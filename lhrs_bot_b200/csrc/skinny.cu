@@ -17,6 +17,7 @@
 
 #include "host_common.h"
 #include "ptx.cuh"
+#include "dropout.cuh"
 
 namespace lhrs {
 
@@ -61,7 +62,24 @@ struct PanelArgs {
     int kseg;                          // W_KN: K columns per segment (K = nseg * kseg)
     float alpha;
     bf16* out; long long ldo;
+    // !W_KN, drop_t > 0: peft input dropout — the 16 output columns of projection p see X masked by key[p] (dropout.cuh);
+    // the survivors' 1/keep is folded into alpha by the caller
+    uint32_t key[3];
+    int drop_t;
 };
+
+// zero the halves of a 2 x bf16 register whose elements (row, col) and (row, col + 1) the mask word drops (col even)
+// (the four byte draws of the word are compared at once: __vcmpgeu4 gives 0xff per surviving byte; a byte permute then widens
+//  the two bytes of interest to the two bf16 halves — 4 integer instructions per register instead of 10)
+__device__ __forceinline__ uint32_t drop_pair_cols(uint32_t v, uint32_t word, uint32_t row, int t) {
+    const uint32_t k4 = __vcmpgeu4(word, static_cast<uint32_t>(t) * 0x01010101u);       // byte i: 0xff = keep draw i
+    return v & __byte_perm(k4, 0u, (row & 1u) ? 0x3322u : 0x1100u);                     // draws 2r, 2r+1 -> low / high half
+}
+// same for a register holding (row, col) and (row + 1, col) (row even): the transposed fragments of the row-reduce kernel
+__device__ __forceinline__ uint32_t drop_pair_rows(uint32_t v, uint32_t word, uint32_t col, int t) {
+    const uint32_t k4 = __vcmpgeu4(word, static_cast<uint32_t>(t) * 0x01010101u);
+    return v & __byte_perm(k4, 0u, (col & 1u) ? 0x3311u : 0x2200u);                     // draws c, 2 + c -> low / high half
+}
 
 template <int NT, bool W_KN, int PN_BK, int PN_ST, bool L2H>
 __global__ void __launch_bounds__(SK_THREADS)
@@ -135,8 +153,21 @@ lora_panel_kernel(const PanelArgs a) {
                 for (int np = 0; np < NT / 2; ++np) {
                     uint32_t b0, b1, b2, b3;
                     sk_ldsm(sw + offsw<PN_BK>(np * 16 + (mat >> 1) * 8 + (lane & 7), ks * 2 + (mat & 1)), b0, b1, b2, b3);
-                    sk_mma(acc[np * 2], af, b0, b1);
-                    sk_mma(acc[np * 2 + 1], af, b2, b3);
+                    if (a.drop_t > 0) {
+                        // fragment elements: af[0] (r_lo, k..k+1), af[1] (r_hi, k..k+1), af[2] (r_lo, k+8..), af[3] (r_hi, k+8..)
+                        const uint32_t r_lo = static_cast<uint32_t>(row0 + wr * 16 + (lane >> 2)), r_hi = r_lo + 8;
+                        const uint32_t kc = static_cast<uint32_t>(ch * PN_BK + ks * 16 + (lane & 3) * 2);
+                        uint32_t m[4];
+                        m[0] = drop_pair_cols(af[0], drop_word(a.key[np], r_lo, kc, static_cast<uint32_t>(a.K)), r_lo, a.drop_t);
+                        m[1] = drop_pair_cols(af[1], drop_word(a.key[np], r_hi, kc, static_cast<uint32_t>(a.K)), r_hi, a.drop_t);
+                        m[2] = drop_pair_cols(af[2], drop_word(a.key[np], r_lo, kc + 8, static_cast<uint32_t>(a.K)), r_lo, a.drop_t);
+                        m[3] = drop_pair_cols(af[3], drop_word(a.key[np], r_hi, kc + 8, static_cast<uint32_t>(a.K)), r_hi, a.drop_t);
+                        sk_mma(acc[np * 2], m, b0, b1);
+                        sk_mma(acc[np * 2 + 1], m, b2, b3);
+                    } else {
+                        sk_mma(acc[np * 2], af, b0, b1);
+                        sk_mma(acc[np * 2 + 1], af, b2, b3);
+                    }
                 }
             }
         }
@@ -180,6 +211,9 @@ struct ReduceArgs {
     bf16* dst[3];
     long long ldd;
     float alpha;
+    // drop_t > 0 (dA form, seg_c == 0): the 16 Q columns of projection p contract with P masked by key[p] (ld of the mask = C)
+    uint32_t key[3];
+    int drop_t;
 };
 
 template <int NT, int RR_BC, bool L2H>
@@ -248,10 +282,28 @@ lora_rowreduce_kernel(const ReduceArgs a) {
                 // A = P^T: fragment rows are the columns of P, fragment k the rows -> transposed 8x8 loads
                 uint32_t af[4];
                 sk_ldsm_t(sp + offsw<RR_BC>(ks * 16 + (mat >> 1) * 8 + (lane & 7), warp * (MT * 2) + t * 2 + (mat & 1)), af[0], af[1], af[2], af[3]);
+                if (a.drop_t > 0) {
+                    // transposed fragments: af[i] holds P[m, c] (low) and P[m + 1, c] (high), m even:
+                    //   m = chunk row0 + ks*16 + (i >> 1)*8 + 2*t4,  c = c0 + (warp*MT*2 + t*2 + (i & 1))*8 + g
+                    const uint32_t mb = static_cast<uint32_t>(m_begin + ch * RR_BR + ks * 16 + (lane & 3) * 2);
+                    const uint32_t cb = static_cast<uint32_t>(c0 + (warp * (MT * 2) + t * 2) * 8 + (lane >> 2));
 #pragma unroll
-                for (int np = 0; np < NT / 2; ++np) {
-                    sk_mma(acc[t][np * 2], af, bq[np][0], bq[np][1]);
-                    sk_mma(acc[t][np * 2 + 1], af, bq[np][2], bq[np][3]);
+                    for (int np = 0; np < NT / 2; ++np) {
+                        uint32_t m[4];
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const uint32_t mr = mb + (i >> 1) * 8, cc = cb + (i & 1) * 8;
+                            m[i] = drop_pair_rows(af[i], drop_word(a.key[np], mr, cc, static_cast<uint32_t>(a.C)), cc, a.drop_t);
+                        }
+                        sk_mma(acc[t][np * 2], m, bq[np][0], bq[np][1]);
+                        sk_mma(acc[t][np * 2 + 1], m, bq[np][2], bq[np][3]);
+                    }
+                } else {
+#pragma unroll
+                    for (int np = 0; np < NT / 2; ++np) {
+                        sk_mma(acc[t][np * 2], af, bq[np][0], bq[np][1]);
+                        sk_mma(acc[t][np * 2 + 1], af, bq[np][2], bq[np][3]);
+                    }
                 }
             }
         }
@@ -400,9 +452,133 @@ static int launch_rowreduce(const ReduceArgs& a, int nsplit, int bc, cudaStream_
     return l2h ? launch_rowreduce_cfg<NT, 128, true>(a, nsplit, st) : launch_rowreduce_cfg<NT, 128, false>(a, nsplit, st);
 }
 
+// ------------------------------------------------------------------------------------------------ dX correction under dropout
+// dx[M, C] += inv * sum_p mask_p o (dT_p[M, 16] · A_p[16, C]) — the LoRA branch's input gradient when peft's input dropout is on.
+// Without dropout this term rides on the dX GEMM as a K-extension; with it every projection's rank-16 product has its own
+// elementwise mask, so it is one streaming read-modify-write pass over dx (HBM-bound: 2 bytes in, 2 out per element) with the
+// products on mma.sync and the mask bits regenerated from the call seed (dropout.cuh).  CTA = 64 rows x 128 columns.
+struct DxDropArgs {
+    bf16* dx; long long ldx; int M, C;
+    const bf16* dT; long long ldt;
+    const bf16* A[3];              // lora_A of the projections, [16, C] each
+    uint32_t key[3];
+    int t;
+    float inv;
+};
+
+template <int NP>
+__global__ void __launch_bounds__(SK_THREADS)
+lora_dx_dropout_kernel(const DxDropArgs a) {
+    constexpr int TR = 64, TC = 128;
+    // operands first, then (after a barrier) the fp32 result tile in the same bytes
+    __shared__ __align__(128) uint8_t s_buf[TR * (TC + 4) * 4];
+    uint8_t* s_dt = s_buf;                                          // [64][NP*16] bf16, 16-byte chunks XOR-swizzled by row (<= 6 KB)
+    uint8_t* s_a = s_buf + 6144;                                    // [NP][16][128] bf16, offsw<128> (<= 12 KB)
+    float* s_acc = reinterpret_cast<float*>(s_buf);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, mat = lane >> 3;
+    const int c0 = blockIdx.x * TC, row0 = blockIdx.y * TR;
+    const uint32_t sdt = smem_u32(s_dt), sa = smem_u32(s_a);
+    // stage dT rows (NP*2 chunks of 16 B per row) and the A tiles (16 rows x 16 chunks per projection)
+    for (int idx = tid; idx < TR * NP * 2; idx += SK_THREADS) {
+        const int r = idx / (NP * 2), c = idx - r * (NP * 2);
+        const bool ok = row0 + r < a.M;
+        sk_cp16(sdt + r * (NP * 32) + ((c ^ (r & 1)) << 4), a.dT + static_cast<long long>(ok ? row0 + r : 0) * a.ldt + c * 8, ok);
+    }
+    for (int idx = tid; idx < NP * 16 * 16; idx += SK_THREADS) {
+        const int p = idx >> 8, r = (idx >> 4) & 15, c = idx & 15;
+        const bool ok = c0 + c * 8 < a.C;
+        sk_cp16(sa + p * (16 * TC * 2) + offsw<TC>(r, c), a.A[p] + static_cast<long long>(r) * a.C + (ok ? c0 + c * 8 : 0), ok);
+    }
+    sk_commit();
+    sk_wait<0>();
+    __syncthreads();
+    const int g = lane >> 2, t4 = lane & 3;
+    const uint32_t r_lo = static_cast<uint32_t>(row0 + warp * 16 + g), r_hi = r_lo + 8;
+    float acc[16][4];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) { acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f; }
+#pragma unroll
+    for (int p = 0; p < NP; ++p) {
+        uint32_t af[4];
+        {   // A fragment of the 16 x 16 dT_p tile: rows warp*16 + (lane & 15), 16-byte chunk p*2 + (lane >> 4)
+            const int r = warp * 16 + (lane & 15), c = p * 2 + (lane >> 4);
+            sk_ldsm(sdt + r * (NP * 32) + ((c ^ (r & 1)) << 4), af[0], af[1], af[2], af[3]);
+        }
+#pragma unroll
+        for (int np = 0; np < 8; ++np) {                       // two 8-column tiles per transposed x4 load
+            uint32_t b0, b1, b2, b3;
+            sk_ldsm_t(sa + p * (16 * TC * 2) + offsw<TC>((mat & 1) * 8 + (lane & 7), np * 2 + (mat >> 1)), b0, b1, b2, b3);
+            float c1[4] = {0.f, 0.f, 0.f, 0.f}, c2[4] = {0.f, 0.f, 0.f, 0.f};
+            sk_mma(c1, af, b0, b1);
+            sk_mma(c2, af, b2, b3);
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const float* cc = h ? c2 : c1;
+                const int nt = np * 2 + h;
+                const uint32_t col = static_cast<uint32_t>(c0 + nt * 8 + t4 * 2);
+                const uint32_t w_lo = drop_word(a.key[p], r_lo, col, static_cast<uint32_t>(a.C));
+                const uint32_t w_hi = drop_word(a.key[p], r_hi, col, static_cast<uint32_t>(a.C));
+                if (drop_keep(w_lo, r_lo, 0u, a.t)) acc[nt][0] += cc[0];
+                if (drop_keep(w_lo, r_lo, 1u, a.t)) acc[nt][1] += cc[1];
+                if (drop_keep(w_hi, r_hi, 0u, a.t)) acc[nt][2] += cc[2];
+                if (drop_keep(w_hi, r_hi, 1u, a.t)) acc[nt][3] += cc[3];
+            }
+        }
+    }
+    // through shared memory so that the read-modify-write of dx moves whole 16-byte pieces
+    __syncthreads();                                               // every warp has read its operand fragments
+#pragma unroll
+    for (int nt = 0; nt < 16; ++nt) {
+        const int col = nt * 8 + t4 * 2;
+        *reinterpret_cast<float2*>(s_acc + (warp * 16 + g) * (TC + 4) + col) = make_float2(acc[nt][0], acc[nt][1]);
+        *reinterpret_cast<float2*>(s_acc + (warp * 16 + g + 8) * (TC + 4) + col) = make_float2(acc[nt][2], acc[nt][3]);
+    }
+    __syncthreads();
+    for (int idx = tid; idx < TR * (TC / 8); idx += SK_THREADS) {
+        const int r = idx / (TC / 8), c = idx - r * (TC / 8);
+        if (row0 + r >= a.M || c0 + c * 8 >= a.C) continue;
+        bf16* ptr = a.dx + static_cast<long long>(row0 + r) * a.ldx + c0 + c * 8;
+        uint4 v = *reinterpret_cast<const uint4*>(ptr);
+        const float* s = s_acc + r * (TC + 4) + c * 8;
+        uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            w[j] = pack_bf16(bf16_lo(w[j]) + a.inv * s[2 * j], bf16_hi(w[j]) + a.inv * s[2 * j + 1]);
+        *reinterpret_cast<uint4*>(ptr) = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+}
+
 }  // namespace lhrs
 
 using namespace lhrs;
+
+extern "C" int lhrs_lora_dx_dropout(void* dx, int64_t ldx, int64_t M, int32_t C, const void* dT, int64_t ldt, const void* const* lora_a,
+                                    int32_t nproj, uint64_t seed, int32_t module0, float p, void* stream) {
+    LHRS_CHECK_ARG(dx && dT && lora_a && M > 0 && C > 0 && nproj >= 1 && nproj <= 3, "lhrs_lora_dx_dropout: null/empty");
+    LHRS_CHECK_ARG(C % 8 == 0 && ldx % 8 == 0 && ldt % 8 == 0 && p > 0.f && p < 1.f && (reinterpret_cast<uintptr_t>(dx) & 15) == 0 &&
+                       (reinterpret_cast<uintptr_t>(dT) & 15) == 0,
+                   "lhrs_lora_dx_dropout: C, ldx, ldt %% 8, 16-byte alignment and 0 < p < 1 required (rank 16)");
+    DxDropArgs a;
+    memset(&a, 0, sizeof(a));
+    a.dx = (bf16*)dx; a.ldx = ldx; a.M = (int)M; a.C = C; a.dT = (const bf16*)dT; a.ldt = ldt;
+    a.t = drop_threshold(p); a.inv = drop_inv_keep(a.t);
+    for (int i = 0; i < nproj; ++i) {
+        LHRS_CHECK_ARG(lora_a[i] != nullptr && (reinterpret_cast<uintptr_t>(lora_a[i]) & 15) == 0, "lhrs_lora_dx_dropout: lora_a[%d] null/unaligned", i);
+        a.A[i] = (const bf16*)lora_a[i];
+        a.key[i] = drop_key(seed, (uint32_t)(module0 + i));
+    }
+    if (a.t == 0) return LHRS_OK;
+    const dim3 grid((C + 127) / 128, (unsigned)((M + 63) / 64));
+    cudaStream_t st = (cudaStream_t)stream;
+    const bool prof = prof_on();
+    if (prof) prof_begin(PROF_SKINNY, 2.0 * M * (double)C * 16 * nproj, 4.0 * M * (double)C, st);
+    if (nproj == 1) lora_dx_dropout_kernel<1><<<grid, SK_THREADS, 0, st>>>(a);
+    else if (nproj == 2) lora_dx_dropout_kernel<2><<<grid, SK_THREADS, 0, st>>>(a);
+    else lora_dx_dropout_kernel<3><<<grid, SK_THREADS, 0, st>>>(a);
+    if (prof) prof_end(st);
+    LHRS_LAUNCH_CHECK("lora_dx_dropout_kernel");
+    return LHRS_OK;
+}
 
 extern "C" int lhrs_lora_panel(const void* x, int64_t ldx, int64_t M, int32_t K, const void* const* w, int32_t nseg, int32_t w_kn,
                                int64_t ldw, int32_t n, float alpha, void* out, int64_t ldo, void* stream) {
@@ -429,14 +605,55 @@ extern "C" int lhrs_lora_panel(const void* x, int64_t ldx, int64_t M, int32_t K,
     return launch_panel<6, false>(a, st);
 }
 
+extern "C" int lhrs_lora_panel_dropout(const void* x, int64_t ldx, int64_t M, int32_t K, const void* w, int64_t ldw, int32_t n,
+                                       float alpha, uint64_t seed, int32_t module0, float p, void* out, int64_t ldo, void* stream) {
+    LHRS_CHECK_ARG(x && w && out && M > 0 && K > 0, "lhrs_lora_panel_dropout: null/empty");
+    LHRS_CHECK_ARG(n == 16 || n == 32 || n == 48, "lhrs_lora_panel_dropout: n=%d (supported: 16, 32, 48)", n);
+    LHRS_CHECK_ARG(K % 64 == 0 && ldx % 8 == 0 && ldo % 2 == 0 && ldw % 8 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 &&
+                       (reinterpret_cast<uintptr_t>(w) & 15) == 0 && p >= 0.f && p < 1.f,
+                   "lhrs_lora_panel_dropout: K %% 64, ldx / ldw %% 8, 16-byte alignment and 0 <= p < 1 required");
+    PanelArgs a;
+    memset(&a, 0, sizeof(a));
+    a.X = (const bf16*)x; a.ldx = ldx; a.M = (int)M; a.K = K; a.out = (bf16*)out; a.ldo = ldo; a.ldw = ldw;
+    a.W[0] = (const bf16*)w;
+    a.drop_t = drop_threshold(p);
+    a.alpha = alpha * drop_inv_keep(a.drop_t);
+    for (int i = 0; i < n / 16; ++i) a.key[i] = drop_key(seed, (uint32_t)(module0 + i));
+    cudaStream_t st = (cudaStream_t)stream;
+    if (n == 16) return launch_panel<2, false>(a, st);
+    if (n == 32) return launch_panel<4, false>(a, st);
+    return launch_panel<6, false>(a, st);
+}
+
 extern "C" size_t lhrs_lora_rowreduce_scratch_bytes(int64_t M, int32_t C, int32_t n) {
     (void)M;
     return (size_t)8 * (size_t)C * (size_t)n * sizeof(float);
 }
 
+static int rowreduce_impl(const void* p, int64_t ldp, int64_t M, int32_t C, const void* q, int64_t ldq, int32_t n, int32_t seg_c,
+                          int32_t transpose, void* const* dst, int64_t ldd, float alpha, float* scratch, size_t scratch_bytes,
+                          void* stream, int drop_t, const uint32_t* keys);
+
 extern "C" int lhrs_lora_rowreduce(const void* p, int64_t ldp, int64_t M, int32_t C, const void* q, int64_t ldq, int32_t n, int32_t seg_c,
                                    int32_t transpose, void* const* dst, int64_t ldd, float alpha, float* scratch, size_t scratch_bytes,
                                    void* stream) {
+    return rowreduce_impl(p, ldp, M, C, q, ldq, n, seg_c, transpose, dst, ldd, alpha, scratch, scratch_bytes, stream, 0, nullptr);
+}
+
+extern "C" int lhrs_lora_rowreduce_dropout(const void* p, int64_t ldp, int64_t M, int32_t C, const void* q, int64_t ldq, int32_t n,
+                                           void* dst, int64_t ldd, uint64_t seed, int32_t module0, float p_drop, float* scratch,
+                                           size_t scratch_bytes, void* stream) {
+    LHRS_CHECK_ARG(p_drop >= 0.f && p_drop < 1.f && (n == 16 || n == 32 || n == 48), "lhrs_lora_rowreduce_dropout: bad p / n");
+    const int t = drop_threshold(p_drop);
+    uint32_t keys[3] = {0, 0, 0};
+    for (int i = 0; i < n / 16; ++i) keys[i] = drop_key(seed, (uint32_t)(module0 + i));
+    void* d[1] = {dst};
+    return rowreduce_impl(p, ldp, M, C, q, ldq, n, 0, 1, d, ldd, drop_inv_keep(t), scratch, scratch_bytes, stream, t, keys);
+}
+
+static int rowreduce_impl(const void* p, int64_t ldp, int64_t M, int32_t C, const void* q, int64_t ldq, int32_t n, int32_t seg_c,
+                          int32_t transpose, void* const* dst, int64_t ldd, float alpha, float* scratch, size_t scratch_bytes,
+                          void* stream, int drop_t, const uint32_t* keys) {
     LHRS_CHECK_ARG(p && q && dst && dst[0] && scratch && M > 0 && C > 0, "lhrs_lora_rowreduce: null/empty");
     LHRS_CHECK_ARG(n == 16 || n == 32 || n == 48, "lhrs_lora_rowreduce: n=%d (supported: 16, 32, 48)", n);
     LHRS_CHECK_ARG(C % 8 == 0 && ldp % 8 == 0 && ldq % 8 == 0 && (reinterpret_cast<uintptr_t>(p) & 15) == 0 && (reinterpret_cast<uintptr_t>(q) & 15) == 0,
@@ -463,6 +680,8 @@ extern "C" int lhrs_lora_rowreduce(const void* p, int64_t ldp, int64_t M, int32_
     memset(&a, 0, sizeof(a));
     const int nseg_dst = seg_c > 0 ? C / seg_c : 1;
     a.cluster = use_cluster; a.transpose = transpose; a.ldd = ldd; a.alpha = alpha;
+    a.drop_t = drop_t;
+    if (drop_t > 0 && keys != nullptr) { a.key[0] = keys[0]; a.key[1] = keys[1]; a.key[2] = keys[2]; }
     for (int sidx = 0; sidx < nseg_dst && sidx < 3; ++sidx) a.dst[sidx] = (bf16*)dst[sidx];
     a.P = (const bf16*)p; a.ldp = ldp; a.M = (int)M; a.C = C; a.Q = (const bf16*)q; a.ldq = ldq; a.seg_c = seg_c; a.partial = scratch;
     long long rps = (M + nsplit - 1) / nsplit;

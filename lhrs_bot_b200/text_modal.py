@@ -204,6 +204,11 @@ class CustomLlamaForCausalLM(nn.Module):
                 p.requires_grad_(is_trainable)
 
 
+def dropout_call_seed(base: int, call: int) -> int:
+    """Seed of the `call`-th training forward (1-based) under base seed `base` — one mask set per forward, reused by its backward."""
+    return (int(base) + 0x9E3779B97F4A7C15 * int(call)) & 0xFFFFFFFFFFFFFFFF
+
+
 def find_all_linear_names(model) -> List[str]:
     """text_modal.py:658-667"""
     names = set()
@@ -371,8 +376,29 @@ class TextModal(BaseModal):
             w.lora_a, w.lora_b = pa.ptr(), pb.ptr()
         else:
             w.lora_r, w.lora_scale = 0, 0.0
+        w.lora_dropout, w.lora_seed = 0.0, 0          # set per training call by autograd.LlamaLossFunction
         self._table, self._table_sig = (w, keep), sig
         return w
+
+    # ------------------------------------------------------------------ LoRA dropout (peft lora.Linear input dropout)
+    def lora_dropout_p(self) -> float:
+        """Dropout probability of the LoRA branch for the NEXT training forward: peft applies nn.Dropout(lora_dropout) to the
+        branch input while the module is in train mode (the trainer calls model.train(), IterBasedTrainer.py:87)."""
+        pc = self.text_encoder.peft_config
+        if pc is None or not self.training:
+            return 0.0
+        return float(getattr(pc, "lora_dropout", 0.0) or 0.0)
+
+    def set_lora_dropout_seed(self, seed: int) -> None:
+        """Base seed of the dropout masks (default: drawn from torch's generator at first use, so it follows
+        torch.manual_seed and differs per rank under the reference's seed + rank rule)."""
+        self._drop_base, self._drop_calls = int(seed) & ((1 << 62) - 1), 0
+
+    def next_lora_dropout_seed(self) -> int:
+        if getattr(self, "_drop_base", None) is None:
+            self.set_lora_dropout_seed(int(torch.randint(0, 2 ** 62, (1,)).item()))
+        self._drop_calls += 1
+        return dropout_call_seed(self._drop_base, self._drop_calls)
 
     def lora_pairs(self):
         """[(lora_A.weight, lora_B.weight)] in weight-table order [layer*7 + proj]; empty without LoRA."""

@@ -18,7 +18,7 @@ from . import _lib, runtime
 from ._lib import check
 
 AVAILABLE = True
-LORA_DROPOUT_MODELLED = False     # flipped when the T-panel kernels apply the Philox mask (peft semantics, text_modal.py:136-143)
+LORA_DROPOUT_MODELLED = True      # csrc/dropout.cuh: counter-based mask on the LoRA branch input (peft semantics, text_modal.py:136-143)
 
 
 def trainable_parameters(model) -> List[torch.nn.Parameter]:
@@ -313,6 +313,8 @@ class SftStepper:
                 for a, b in model.text.lora_pairs():
                     a.requires_grad_(True)
                     b.requires_grad_(True)
+        if prepare:
+            model.train()      # the reference's trainer does this once before its loop (IterBasedTrainer.py:87): peft's LoRA dropout is live
         # Flat layout: pooler, then every LoRA A factor in [layer][q,k,v,o,gate,up,down] order, then the B factors.  Keeping
         # A_q/A_k/A_v (and A_gate/A_up) back to back makes [A_q;A_k;A_v] one contiguous [3r, in] matrix, which lets the
         # library batch the LoRA side GEMMs of projections that share an input (lora_a_adjacent in csrc/models_fwd.cu).

@@ -10,7 +10,8 @@ published formulae: RMSNorm with fp32 statistics and eps 1e-5, rotate-half RoPE 
 mask and scale hd^-0.5, SwiGLU MLP, untied lm_head, loss = mean CE over labels != -100 after shifting by one.
 LoRA (peft==0.7.1, pyproject.toml:23; absent everywhere) follows its published definition
 h = W x + (alpha/r) * B(A(x)) on the seven projections of every layer (text_modal.py:133-151, :658-667); dropout is
-the identity in eval and is not modelled.
+the identity in eval; in train mode peft drops the LoRA branch INPUT per module: `lora_dropout=(p, seed)` reproduces the
+mask function of csrc/dropout.cuh (torch's own dropout stream depends on its kernel's launch geometry and cannot be restated).
 
 State dict uses HF names: ``model.embed_tokens.weight``, ``model.layers.N.{input_layernorm,post_attention_layernorm}.weight``,
 ``model.layers.N.self_attn.{q,k,v,o}_proj.weight``, ``model.layers.N.mlp.{gate,up,down}_proj.weight``, ``model.norm.weight``,
@@ -45,16 +46,76 @@ def rotate_half(x: torch.Tensor) -> torch.Tensor:
     return torch.cat([-x[..., h:], x[..., :h]], dim=-1)
 
 
-def _linear(x, sd, name, lora_scale: float):
+def _mix32(h):
+    """murmur3 32-bit finaliser on numpy uint32 arrays (csrc/dropout.cuh: mix32)."""
+    import numpy as np
+    h = h.astype(np.uint32)
+    h ^= h >> np.uint32(16); h = (h * np.uint32(0x85EBCA6B)).astype(np.uint32)
+    h ^= h >> np.uint32(13); h = (h * np.uint32(0xC2B2AE35)).astype(np.uint32)
+    h ^= h >> np.uint32(16)
+    return h
+
+
+def lora_dropout_threshold(p: float) -> int:
+    return max(0, min(255, int(p * 256.0 + 0.5)))
+
+
+def _mix32_t(h: torch.Tensor) -> torch.Tensor:
+    """the same finaliser on int64 tensors holding uint32 values (any device)"""
+    m = 0xFFFFFFFF
+    h = h ^ (h >> 16); h = (h * 0x85EBCA6B) & m
+    h = h ^ (h >> 13); h = (h * 0xC2B2AE35) & m
+    return h ^ (h >> 16)
+
+
+def lora_dropout_mask(seed: int, module: int, rows: int, cols: int, p: float, device=None) -> torch.Tensor:
+    """keep-mask (rows, cols) bool of peft's LoRA input dropout as THIS repo defines it (csrc/dropout.cuh; torch's own dropout
+    stream cannot be reproduced): one hashed word per 2 x 2 block, one byte per element, keep = byte >= round(256 p).
+    With `device` the same arithmetic runs in torch on that device (int64 lanes masked to 32 bits) — identical bits
+    (tests/test_oracle.py), used for full-size checks."""
+    if device is not None and torch.device(device).type != "cpu":
+        m = 0xFFFFFFFF
+        seed = int(seed) & 0xFFFFFFFFFFFFFFFF
+        one = lambda v: torch.tensor([v & m], dtype=torch.int64, device=device)
+        inner = _mix32_t(one((seed >> 32) + module * 0x9E3779B9))
+        key = _mix32_t(one(seed & m) ^ inner)
+        r = torch.arange(rows, dtype=torch.int64, device=device)[:, None]
+        c = torch.arange(cols, dtype=torch.int64, device=device)[None, :]
+        group = ((r >> 1) * (cols >> 1) + (c >> 1)) & m
+        word = _mix32_t((key + group * 0x9E3779B1) & m)
+        byte = (word >> (8 * (2 * (r & 1) + (c & 1)))) & 255
+        return byte >= lora_dropout_threshold(p)
+    import numpy as np
+    with np.errstate(over="ignore"):
+        seed = int(seed) & 0xFFFFFFFFFFFFFFFF
+        lo, hi = np.uint32(seed & 0xFFFFFFFF), np.uint32(seed >> 32)
+        inner = _mix32(np.array([(int(hi) + module * 0x9E3779B9) & 0xFFFFFFFF], dtype=np.uint32))
+        key = _mix32(np.array([int(lo) ^ int(inner[0])], dtype=np.uint32))[0]
+        r = np.arange(rows, dtype=np.uint32)[:, None]
+        c = np.arange(cols, dtype=np.uint32)[None, :]
+        group = ((r >> np.uint32(1)) * np.uint32(cols >> 1) + (c >> np.uint32(1))).astype(np.uint32)
+        word = _mix32((np.uint32(key) + group * np.uint32(0x9E3779B1)).astype(np.uint32))
+        shift = (np.uint32(8) * (np.uint32(2) * (r & np.uint32(1)) + (c & np.uint32(1)))).astype(np.uint32)
+        byte = (word >> shift) & np.uint32(255)
+    return torch.from_numpy(byte.astype(np.int32) >= lora_dropout_threshold(p))
+
+
+def _linear(x, sd, name, lora_scale: float, drop=None, module: int = 0):
+    """y = W x + (alpha/r) B(A(dropout(x)));  drop = (p, seed) enables peft's train-mode input dropout on the LoRA branch."""
     y = F.linear(x, sd[name + ".weight"])
     a = sd.get(name + ".lora_A.weight")
     if a is not None:
-        y = y + lora_scale * F.linear(F.linear(x, a), sd[name + ".lora_B.weight"])
+        xl = x
+        if drop is not None and drop[0] > 0:
+            t = lora_dropout_threshold(drop[0])
+            keep = lora_dropout_mask(drop[1], module, x.numel() // x.shape[-1], x.shape[-1], drop[0], device=x.device).to(x.device).view(x.shape)
+            xl = x * keep.to(x.dtype) * (256.0 / (256 - t))
+        y = y + lora_scale * F.linear(F.linear(xl, a), sd[name + ".lora_B.weight"])
     return y
 
 
 def decoder_layer(x, sd, i: int, n_head: int, eps: float, cos, sin, add_mask, lora_scale: float = 0.0,
-                  past: Optional[Tuple[torch.Tensor, torch.Tensor]] = None, sdpa: bool = False):
+                  past: Optional[Tuple[torch.Tensor, torch.Tensor]] = None, sdpa: bool = False, lora_dropout=None):
     """One HF LlamaDecoderLayer.  x (B,S,D); cos/sin (S,hd) for the positions of x; add_mask (B,1,S,S_total) additive.
     Returns (y, (k, v)) with k/v including ``past``.  ``sdpa=True`` evaluates the same attention through
     ``F.scaled_dot_product_attention`` (transformers 4.36.1 selects LlamaSdpaAttention when torch >= 2.1.1 — the pinned
@@ -63,9 +124,9 @@ def decoder_layer(x, sd, i: int, n_head: int, eps: float, cos, sin, add_mask, lo
     B, S, D = x.shape
     hd = D // n_head
     h = rms_norm(x, sd[p + "input_layernorm.weight"], eps)
-    q = _linear(h, sd, p + "self_attn.q_proj", lora_scale).view(B, S, n_head, hd).transpose(1, 2)
-    k = _linear(h, sd, p + "self_attn.k_proj", lora_scale).view(B, S, n_head, hd).transpose(1, 2)
-    v = _linear(h, sd, p + "self_attn.v_proj", lora_scale).view(B, S, n_head, hd).transpose(1, 2)
+    q = _linear(h, sd, p + "self_attn.q_proj", lora_scale, lora_dropout, i * 7 + 0).view(B, S, n_head, hd).transpose(1, 2)
+    k = _linear(h, sd, p + "self_attn.k_proj", lora_scale, lora_dropout, i * 7 + 1).view(B, S, n_head, hd).transpose(1, 2)
+    v = _linear(h, sd, p + "self_attn.v_proj", lora_scale, lora_dropout, i * 7 + 2).view(B, S, n_head, hd).transpose(1, 2)
     c, s = cos[None, None].to(q.dtype), sin[None, None].to(q.dtype)
     q = q * c + rotate_half(q) * s
     k = k * c + rotate_half(k) * s
@@ -81,11 +142,11 @@ def decoder_layer(x, sd, i: int, n_head: int, eps: float, cos, sin, add_mask, lo
             att = att + add_mask
         att = torch.softmax(att, dim=-1, dtype=torch.float32).to(q.dtype)
         o = (att @ v).transpose(1, 2).reshape(B, S, D)
-    x = x + _linear(o, sd, p + "self_attn.o_proj", lora_scale)
+    x = x + _linear(o, sd, p + "self_attn.o_proj", lora_scale, lora_dropout, i * 7 + 3)
     h = rms_norm(x, sd[p + "post_attention_layernorm.weight"], eps)
-    g = _linear(h, sd, p + "mlp.gate_proj", lora_scale)
-    u = _linear(h, sd, p + "mlp.up_proj", lora_scale)
-    x = x + _linear(F.silu(g) * u, sd, p + "mlp.down_proj", lora_scale)
+    g = _linear(h, sd, p + "mlp.gate_proj", lora_scale, lora_dropout, i * 7 + 4)
+    u = _linear(h, sd, p + "mlp.up_proj", lora_scale, lora_dropout, i * 7 + 5)
+    x = x + _linear(F.silu(g) * u, sd, p + "mlp.down_proj", lora_scale, lora_dropout, i * 7 + 6)
     return x, (k, v)
 
 
@@ -102,7 +163,7 @@ def _additive_mask(B: int, Sq: int, Skv: int, key_mask: Optional[torch.Tensor], 
 
 def llama_hidden(inputs_embeds: torch.Tensor, sd: Dict[str, torch.Tensor], num_layers: int, n_head: int, eps: float = 1e-5,
                  attention_mask: Optional[torch.Tensor] = None, lora_scale: float = 0.0, theta: float = 10000.0,
-                 return_kv: bool = False):
+                 return_kv: bool = False, lora_dropout=None):
     B, S, D = inputs_embeds.shape
     dev = inputs_embeds.device
     cos, sin = rope_cos_sin(torch.arange(S, device=dev), D // n_head, theta)
@@ -110,14 +171,15 @@ def llama_hidden(inputs_embeds: torch.Tensor, sd: Dict[str, torch.Tensor], num_l
     x = inputs_embeds
     kvs = []
     for i in range(num_layers):
-        x, kv = decoder_layer(x, sd, i, n_head, eps, cos, sin, add_mask, lora_scale)
+        x, kv = decoder_layer(x, sd, i, n_head, eps, cos, sin, add_mask, lora_scale, lora_dropout=lora_dropout)
         kvs.append(kv)
     x = rms_norm(x, sd["model.norm.weight"], eps)
     return (x, kvs) if return_kv else x
 
 
-def llama_logits(inputs_embeds, sd, num_layers, n_head, eps=1e-5, attention_mask=None, lora_scale=0.0):
-    return F.linear(llama_hidden(inputs_embeds, sd, num_layers, n_head, eps, attention_mask, lora_scale), sd["lm_head.weight"])
+def llama_logits(inputs_embeds, sd, num_layers, n_head, eps=1e-5, attention_mask=None, lora_scale=0.0, lora_dropout=None):
+    return F.linear(llama_hidden(inputs_embeds, sd, num_layers, n_head, eps, attention_mask, lora_scale, lora_dropout=lora_dropout),
+                    sd["lm_head.weight"])
 
 
 def causal_lm_loss(logits: torch.Tensor, labels: torch.Tensor) -> torch.Tensor:

@@ -36,14 +36,14 @@ def lora_scale(cfg) -> float:
     return float(cfg.lora.lora_alpha) / float(cfg.lora.lora_r) if cfg.lora.enable else 0.0
 
 
-def forward_loss(data: Dict[str, torch.Tensor], st, cfg, return_logits: bool = False):
-    """UniBind.forward -> text_loss (fp32 scalar)."""
+def forward_loss(data: Dict[str, torch.Tensor], st, cfg, return_logits: bool = False, lora_dropout=None):
+    """UniBind.forward -> text_loss (fp32 scalar).  lora_dropout = (p, seed): train-mode LoRA input dropout (oracle/llama.py)."""
     img = encode_image(data["rgb"], st, cfg)
     mask, embeds, labels = splice.prepare_inputs_for_multimodal(
         data["input_ids"], data.get("attention_mask"), data.get("labels"), st["llama"]["model.embed_tokens.weight"], img)
     t = cfg.text
     logits = llama.llama_logits(embeds, st["llama"], t.num_hidden_layers, t.num_attention_heads, float(t.rms_norm_eps),
-                                mask, lora_scale(cfg))
+                                mask, lora_scale(cfg), lora_dropout=lora_dropout)
     loss = llama.causal_lm_loss(logits, labels) if labels is not None else None
     return (loss, logits, labels, mask) if return_logits else loss
 

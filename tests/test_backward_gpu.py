@@ -369,3 +369,108 @@ def test_unibind_backward_lora_grouped_flat_layout():
         if "lora_" in name and ("layers.0." in name or "layers.1.mlp" in name):
             _cmp(f"grouped {name}", stepper.opt.grad_views[p], sd["llama"][name.replace(".default.", ".")].grad, 5e-2)
     _cmp("grouped pooler out_proj.weight", stepper.opt.grad_views[model.rgb_pooler.out_proj.weight], sd["pooler"]["out_proj.weight"].grad, 5e-2)
+
+
+# ---------------------------------------------------------------------------------------------- LoRA dropout (peft lora.Linear)
+def test_lora_dropout_mask_kernel_matches_oracle():
+    """lhrs_lora_dropout_mask (csrc/dropout.cuh) vs the numpy restatement in oracle/llama.py: bit for bit, for several modules,
+    probabilities and shapes (incl. a leading dimension larger than the row)."""
+    import ctypes as C
+    from lhrs_bot_b200 import _lib, runtime
+    from oracle import llama
+    lib = _lib.load()
+    for rows, cols, ld, p, module, seed in [(64, 256, 256, 0.05, 0, 1), (37, 128, 384, 0.25, 13, 0xDEADBEEFCAFE1234), (130, 1024, 1024, 0.5, 223, 7)]:
+        x = _randn(rows, ld, seed=rows)
+        out = torch.full((rows, cols), 7.0, device=DEV, dtype=torch.bfloat16)
+        rc = lib.lhrs_lora_dropout_mask(x.data_ptr(), ld, rows, cols, C.c_uint64(seed), module, C.c_float(p), out.data_ptr(), cols, runtime.stream())
+        assert rc == 0, lib.lhrs_last_error()
+        keep = llama.lora_dropout_mask(seed, module, rows, cols, p).to(DEV)
+        assert torch.equal(keep, llama.lora_dropout_mask(seed, module, rows, cols, p, device=DEV)), "torch (device) form of the oracle mask differs"
+        want = torch.where(keep, x[:, :cols], torch.zeros((), device=DEV, dtype=torch.bfloat16))
+        assert torch.equal(out, want), f"mask differs for {(rows, cols, ld, p, module)}"
+        rate = 1.0 - keep.float().mean().item()
+        assert abs(rate - llama.lora_dropout_threshold(p) / 256.0) < 0.02
+
+
+@pytest.mark.parametrize("r,p", [(16, 0.25), (128, 0.05)])
+def test_unibind_backward_lora_with_dropout(r, p):
+    """Stage-2 step in train mode with peft's LoRA input dropout (the shipped yamls: lora_dropout 0.05; 0.25 makes a missed
+    mask obvious): loss and every dA / dB / pooler gradient against the oracle evaluated with the SAME masks
+    (oracle/llama.py restates the mask function; the seed of the call is `dropout_call_seed(base, 1)`).  r = 16 takes the
+    streaming kernels, r = 128 the tcgen05 side GEMMs; both go through the masked dX-correction GEMM epilogue."""
+    from oracle import unibind
+    from lhrs_bot_b200.text_modal import dropout_call_seed
+    from lhrs_bot_b200.training import SftStepper
+    cfg = small_config(lora=dict(enable=True, lora_r=r, lora_alpha=2 * r, lora_dropout=p, lora_bias="none"), stage=2)
+    model = build_small_model(cfg, DEV, seed=5)
+    stepper = SftStepper(model, world_size=1, lr=1e-3)
+    assert model.text.training and model.text.lora_dropout_p() == p
+    model.text.set_lora_dropout_seed(4242)
+    st = to_device(unibind.export_state(model), DEV)
+    batch = synthetic_batch(3, 20, cfg.text.vocab_size, DEV, seed=23, text_only=(), ragged_mask=True)
+    out = model(batch)
+    out["total_loss"].backward()
+    seed = dropout_call_seed(4242, 1)
+    sd = {k: {kk: vv.clone().requires_grad_(vv.is_floating_point()) for kk, vv in v.items()} for k, v in st.items()}
+    b32 = dict(batch)
+    b32["rgb"] = batch["rgb"].float()
+    ref_loss = unibind.forward_loss(b32, sd, cfg, lora_dropout=(p, seed))
+    ref_loss.backward()
+    no_drop = unibind.forward_loss(b32, {k: dict(v) for k, v in st.items()}, cfg)
+    print(f"r={r} p={p}: loss {out['total_loss'].item():.5f} oracle(with masks) {ref_loss.item():.5f} oracle(no dropout) {no_drop.item():.5f}")
+    assert abs(out["total_loss"].item() - ref_loss.item()) <= 2e-2
+    for name, prm in model.text.text_encoder.named_parameters():
+        if "lora_" in name:
+            _cmp(f"dropout {name}", stepper.opt.grad_views[prm], sd["llama"][name.replace(".default.", ".")].grad, 5e-2)
+    _cmp("dropout pooler out_proj.weight", stepper.opt.grad_views[model.rgb_pooler.out_proj.weight], sd["pooler"]["out_proj.weight"].grad, 5e-2)
+    # a second forward draws new masks; eval mode draws none
+    l2 = model(batch)["total_loss"].item()
+    assert abs(l2 - out["total_loss"].item()) > 1e-6
+    model.eval()
+    with torch.no_grad():
+        le = model(batch)["total_loss"].item()
+    assert abs(le - no_drop.item()) <= 2e-2
+
+
+@pytest.mark.parametrize("nproj", [1, 2, 3])
+def test_lora_fused_dropout_kernels(nproj):
+    """The rank-16 streaming kernels with the dropout mask applied on their mma fragments (no masked copy of the activation):
+    forward T panel, backward dA row-reduce and the dX correction pass, against torch with the oracle's masks."""
+    import ctypes as C
+    from lhrs_bot_b200 import _lib, runtime
+    from oracle import llama
+    lib = _lib.load()
+    M, K, r, p, seed, mod0 = 200, 512, 16, 0.25, 0xABCDEF0123456789, 11
+    n = nproj * r
+    x = _randn(M, K, seed=51)
+    A = _randn(n, K, scale=0.05, seed=52)
+    t = llama.lora_dropout_threshold(p)
+    inv = 256.0 / (256 - t)
+    masks = [llama.lora_dropout_mask(seed, mod0 + i, M, K, p, device=DEV) for i in range(nproj)]
+    st = runtime.stream()
+    # forward: T = alpha / keep * (mask_p o x) A_p^T
+    T = torch.empty(M, n, device=DEV, dtype=torch.bfloat16)
+    rc = lib.lhrs_lora_panel_dropout(x.data_ptr(), K, M, K, A.data_ptr(), K, n, C.c_float(2.0), C.c_uint64(seed), mod0, C.c_float(p),
+                                     T.data_ptr(), n, st)
+    assert rc == 0, lib.lhrs_last_error()
+    ref = torch.cat([2.0 * inv * ((x.float() * masks[i]) @ A[i * r:(i + 1) * r].float().t()) for i in range(nproj)], 1)
+    assert rel_l2(T, ref) < 1e-2, rel_l2(T, ref)
+    # backward dA: [n, K] = 1/keep * dT_p^T (mask_p o x)
+    dT = _randn(M, n, seed=53)
+    dA = torch.empty(n, K, device=DEV, dtype=torch.bfloat16)
+    sb = lib.lhrs_lora_rowreduce_scratch_bytes(M, K, n)
+    scratch = torch.empty(sb // 4, device=DEV, dtype=torch.float32)
+    rc = lib.lhrs_lora_rowreduce_dropout(x.data_ptr(), K, M, K, dT.data_ptr(), n, n, dA.data_ptr(), K, C.c_uint64(seed), mod0, C.c_float(p),
+                                         scratch.data_ptr(), sb, st)
+    assert rc == 0, lib.lhrs_last_error()
+    ref = torch.cat([inv * (dT[:, i * r:(i + 1) * r].float().t() @ (x.float() * masks[i])) for i in range(nproj)], 0)
+    assert rel_l2(dA, ref) < 1e-2, rel_l2(dA, ref)
+    # dX correction: dx += 1/keep * sum_p mask_p o (dT_p A_p)
+    dx0 = _randn(M, K, seed=54)
+    dx = dx0.clone()
+    ptrs = (C.c_void_p * 3)(*[A[i * r:(i + 1) * r].data_ptr() if i < nproj else None for i in range(3)])
+    rc = lib.lhrs_lora_dx_dropout(dx.data_ptr(), K, M, K, dT.data_ptr(), n, C.cast(ptrs, C.POINTER(C.c_void_p)), nproj, C.c_uint64(seed), mod0,
+                                  C.c_float(p), st)
+    assert rc == 0, lib.lhrs_last_error()
+    ref = dx0.float() + inv * sum(masks[i] * (dT[:, i * r:(i + 1) * r].float() @ A[i * r:(i + 1) * r].float()) for i in range(nproj))
+    assert rel_l2(dx, ref) < 1e-2, rel_l2(dx, ref)
