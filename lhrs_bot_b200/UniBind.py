@@ -76,10 +76,22 @@ class UniBind(nn.Module):
         logger.info(f"Loading RGB Model: {msg}")
 
     def custom_save_checkpoint(self, file_name: str):
-        """Returns ``{rgb_ckpt, other_ckpt}`` in the reference's FINAL.pt layout (UniBind.py:68-81).  The reference
-        first folds a DeepSpeed ZeRO checkpoint into fp32; here the live parameters are read directly (no ZeRO)."""
-        rgb_ckpt = {k: v.detach().float().cpu() for k, v in self.rgb.state_dict().items()}
-        other_ckpt = {"rgb_pooler": {k: v.detach().float().cpu() for k, v in self.rgb_pooler.state_dict().items()}}
+        """Returns ``{rgb_ckpt, other_ckpt}`` in the reference's FINAL.pt layout (UniBind.py:68-81).  Given a DeepSpeed ZeRO
+        checkpoint directory it folds that to fp32 like the reference; given a file name it reads the live parameters (this
+        package's trainer keeps no ZeRO shards on disk)."""
+        if os.path.isdir(str(file_name)) and os.path.isfile(os.path.join(str(file_name), "latest")):
+            # the reference's own call: a DeepSpeed ZeRO checkpoint directory is folded to fp32 (UniBind.py:68-70, 275-302)
+            from .zero_checkpoint import get_fp32_state_dict_from_zero_checkpoint
+            fp32 = get_fp32_state_dict_from_zero_checkpoint(str(file_name))
+            rgb_ckpt = {k[len("rgb."):]: v.cpu() for k, v in fp32.items() if k.startswith("rgb.")}
+            other_ckpt = dict(rgb_pooler={}, text_proj={}, embed_tokens={}, lm_head={})
+            for k, v in fp32.items():
+                for name in ("rgb_pooler", "embed_tokens"):
+                    if name in k:
+                        other_ckpt[name][k.split(name + ".")[-1]] = v
+        else:
+            rgb_ckpt = {k: v.detach().float().cpu() for k, v in self.rgb.state_dict().items()}
+            other_ckpt = {"rgb_pooler": {k: v.detach().float().cpu() for k, v in self.rgb_pooler.state_dict().items()}}
         if self.stage >= 2 and self.text.text_encoder.has_lora():
             file_name = pathlib.Path(file_name)
             lora_dir = (file_name.parent if file_name.suffix else file_name) / "TextLoRA"
@@ -88,8 +100,13 @@ class UniBind(nn.Module):
 
     def custom_load_state_dict(self, state_dict_path, strict=False):
         if os.path.isdir(state_dict_path):
-            raise NotImplementedError("loading a DeepSpeed ZeRO checkpoint directory (UniBind.py:84-88) is outside the hot path; "
-                                      "pass the exported FINAL.pt file")
+            # a DeepSpeed ZeRO checkpoint directory (UniBind.py:84-88): merged without DeepSpeed (zero_checkpoint.py), adapters
+            # folded into the base weights as the reference does for a PeftModel
+            from .zero_checkpoint import load_state_dict_from_zero_checkpoint
+            load_state_dict_from_zero_checkpoint(self, state_dict_path)
+            if self.text.text_encoder.has_lora():
+                self.text.text_encoder = self.text.text_encoder.merge_and_unload()
+            return None
         ckpt = torch.load(state_dict_path, map_location="cpu")
         if "model" in ckpt.keys():
             ckpt = ckpt["model"]

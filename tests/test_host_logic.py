@@ -391,3 +391,55 @@ def test_oracle_sdpa_branch_equals_written_out_attention():
     a, _ = llama.decoder_layer(x, sd, 0, H, 1e-5, cos, sin, am)
     b, _ = llama.decoder_layer(x, sd, 0, H, 1e-5, cos, sin, am, sdpa=True)
     assert torch.allclose(a, b, atol=1e-5, rtol=1e-5)
+
+
+# ---------------------------------------------------------------------------------------------- DeepSpeed ZeRO directories
+def test_zero2_checkpoint_directory_roundtrip(tmp_path):
+    """UniBind.custom_load_state_dict(<dir>) / custom_save_checkpoint(<dir>) on a DeepSpeed ZeRO-2 checkpoint directory
+    (UniBind.py:68-70, 84-88), read without DeepSpeed: `latest` tag file, mp_rank_00_model_states.pt (param_shapes, frozen
+    fragments, buffers) and one zero_pp_rank_<r> optimizer-state file per rank whose fp32 slices concatenate — with the 2 * world
+    alignment padding — to the trainable parameters in param_shapes order."""
+    from lhrs_bot_b200 import zero_checkpoint as zc
+    cfg = small_config()
+    src = build_small_model(cfg, "cpu", seed=3)
+    src.prepare_for_training(freeze_vision=True, freeze_text=True, tune_rgb_pooler=True, model_path=None, compute_dtype=torch.bfloat16)
+    for world in (1, 3, 8):
+        d = tmp_path / f"ds_w{world}"
+        tag_dir = zc.write_zero2_checkpoint(src, str(d), tag="global_step7", world=world)
+        assert (d / "latest").read_text() == "global_step7"
+        assert sorted(os.listdir(tag_dir)) == sorted(["mp_rank_00_model_states.pt"] + [f"zero_pp_rank_{r}_mp_rank_00_optim_states.pt" for r in range(world)])
+        parts = [torch.load(os.path.join(tag_dir, f"zero_pp_rank_{r}_mp_rank_00_optim_states.pt"), weights_only=False)["optimizer_state_dict"]
+                 for r in range(world)]
+        n_train = sum(p.numel() for p in src.parameters() if p.requires_grad)
+        assert all(p["zero_stage"] == 2 and p["partition_count"] == world for p in parts)
+        total = sum(p["single_partition_of_fp32_groups"][0].numel() for p in parts)
+        assert total % (2 * world) == 0 and 0 <= total - n_train < 2 * world
+        fp32 = zc.get_fp32_state_dict_from_zero_checkpoint(str(d))
+        assert set(fp32) == set(src.state_dict()) and all(v.dtype == torch.float32 for v in fp32.values())
+        for k, v in src.state_dict().items():
+            assert torch.equal(fp32[k], v.float()), k
+        dst = build_small_model(cfg, "cpu", seed=9)
+        assert not torch.equal(dst.rgb_pooler.query, src.rgb_pooler.query)
+        assert dst.custom_load_state_dict(str(d)) is None
+        for (k, a), (_, b) in zip(dst.state_dict().items(), src.state_dict().items()):
+            assert torch.equal(a, b), k
+        ck = dst.custom_save_checkpoint(str(d))              # the reference's export path: fold the directory into FINAL.pt form
+        assert set(ck) == {"rgb_ckpt", "other_ckpt"} and torch.equal(ck["other_ckpt"]["rgb_pooler"]["query"], src.rgb_pooler.query.float())
+        assert "encoder.vision_model.embeddings.class_embedding" in ck["rgb_ckpt"]
+    with pytest.raises(FileNotFoundError):
+        zc.get_fp32_state_dict_from_zero_checkpoint(str(tmp_path / "nothing_here"))
+    # adapters: the reference's PeftModel prefixes the LLaMA tree with base_model.model.; the loader maps it back and creates
+    # the adapters from the saved shapes
+    cfg2 = small_config(stage=2, lora=dict(enable=True, lora_r=16, lora_alpha=32, lora_dropout=0.05, lora_bias="none"))
+    m2 = build_small_model(cfg2, "cpu", seed=4)
+    for a, b in m2.text.lora_pairs():
+        a.requires_grad_(True); b.requires_grad_(True)
+    d2 = tmp_path / "ds_lora"
+    zc.write_zero2_checkpoint(m2, str(d2), world=2)
+    raw = zc.get_fp32_state_dict_from_zero_checkpoint(str(d2))
+    assert "text.text_encoder.base_model.model.model.layers.0.self_attn.q_proj.lora_A.default.weight" in raw
+    m3 = build_small_model(small_config(stage=3), "cpu", seed=5)
+    assert not m3.text.text_encoder.has_lora()
+    zc.load_state_dict_from_zero_checkpoint(m3, str(d2))
+    assert m3.text.text_encoder.has_lora() and m3._zero_load_report["unexpected"] == []
+    assert torch.equal(m3.text.lora_pairs()[9][1], m2.text.lora_pairs()[9][1])

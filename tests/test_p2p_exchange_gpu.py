@@ -166,12 +166,16 @@ def _dp_model_worker(rank, world, port, exchange, q):
         per = 2
         full = synthetic_batch(per * world, 24, cfg.text.vocab_size, dev, seed=77, text_only=(), ragged_mask=False)
         mine = {k: v[rank * per:(rank + 1) * per] for k, v in full.items()}
-        # the single-rank reference: same starting weights (rank 0's), the whole batch, no exchange
+        # the single-rank reference: same starting weights (rank 0's), EVERY rank's slice in turn, gradients averaged — data
+        # parallelism averages the per-rank mean losses (DeepSpeed / DDP semantics), which is the concatenated-batch loss when
+        # the slices carry equal numbers of supervised tokens
         ref_model = build_small_model(cfg, dev, seed=0)
         ref_stepper = SftStepper(ref_model, world_size=1, lr=1e-3)
         ref_stepper.opt.flat_param[: stepper.opt.numel].copy_(g0[0][: stepper.opt.numel])
-        ref_model(full)["total_loss"].backward()
-        ref_grad = ref_stepper.opt.flat_grad[: stepper.opt.numel].float().clone()
+        ref_grad = torch.zeros(stepper.opt.numel, device=dev)
+        for r in range(world):
+            ref_model({k: v[r * per:(r + 1) * per] for k, v in full.items()})["total_loss"].backward()
+            ref_grad += ref_stepper.opt.flat_grad[: stepper.opt.numel].float() / world
         # this rank's local gradient, then the library's exchange
         model(mine)["total_loss"].backward()
         local = stepper.opt.flat_grad[: stepper.opt.numel].float().clone()
