@@ -129,6 +129,9 @@ typedef struct LhrsAttention {
 } LhrsAttention;
 
 int lhrs_attention_fwd(const LhrsAttention* a, void* stream);
+/* n (1..3) problems that share B, H, head_dim 64 and the causal flag as ONE launch: the three query groups of the AttnPooler's
+ * cross-attention (common_arch.py:159-166).  Falls back to n single launches when the problems cannot be grouped. */
+int lhrs_attention_fwd_grouped(const LhrsAttention* a, int32_t n, void* stream);
 
 /* Backward of lhrs_attention_fwd (recompute-based; needs the forward's O and lse).  dQ/dK/dV are bf16 with their own
  * (batch,row,head) strides so they can land in a packed [rows, 3*H*hd] buffer.  delta: fp32 scratch of
@@ -146,6 +149,8 @@ typedef struct LhrsAttentionBwd {
     const float* rope_sin;
 } LhrsAttentionBwd;
 int lhrs_attention_bwd(const LhrsAttentionBwd* a, void* stream);
+/* grouped form (see lhrs_attention_fwd_grouped): delta, dQ and dK/dV of up to three problems as one launch each */
+int lhrs_attention_bwd_grouped(const LhrsAttentionBwd* a, int32_t n, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Row-wise normalisations and small fused elementwise steps (HBM-bound, one pass each).

@@ -190,6 +190,17 @@ class UniBind(nn.Module):
                  temperature: float = 0.2, max_new_tokens: int = 1024, streamer=None, use_cache: bool = True,
                  stopping_criteria=None, **kwargs):
         assert hasattr(self, "text"), "text modal is not activate"
+        if (images is not None and hasattr(self, "rgb_pooler") and input_ids is not None and input_ids.shape[0] == 1 and
+                input_ids.shape[1] > 1 and os.environ.get("LHRS_SCATTER_SPLICE", "1") != "0"):
+            # generation fast path: the splice plan is made first (text rows + row map), and the AttnPooler's out_proj epilogue
+            # writes its 144 rows per image straight into inputs_embeds (scatter epilogue of lhrs_gemm_bf16; common_arch.py:167-173
+            # followed by text_modal.py:340-407 without the dense intermediate)
+            feats = self.rgb.encode(images)
+            embeds, row_map = self.text.splice_for_scatter(input_ids, feats.shape[0], self.rgb_pooler.num_query)
+            self.rgb_pooler(feats, scatter_into=embeds.view(-1, embeds.shape[-1]), row_map=row_map)
+            return self.text.generate(input_ids=input_ids, image_embedding=None, inputs_embeds=embeds, do_sample=do_sample,
+                                      temperature=temperature, max_new_tokens=max_new_tokens, streamer=streamer,
+                                      use_cache=use_cache, stopping_criteria=stopping_criteria, **kwargs)
         image_embedding = self.encode_image(images, pool=False) if images is not None else None
         return self.text.generate(input_ids=input_ids, image_embedding=image_embedding, do_sample=do_sample,
                                   temperature=temperature, max_new_tokens=max_new_tokens, streamer=streamer,

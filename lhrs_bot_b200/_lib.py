@@ -172,6 +172,8 @@ SIGNATURES = {
     "lhrs_llama_decode_step_sampled": (C.c_int, [C.POINTER(LhrsLlamaWeights), C.POINTER(LhrsKvCache), C.POINTER(LhrsDecodeBuffers),
                                                  C.POINTER(LhrsSampling), _I32, _P]),
     "lhrs_attention_bwd": (C.c_int, [C.POINTER(LhrsAttentionBwd), _P]),
+    "lhrs_attention_bwd_grouped": (C.c_int, [C.POINTER(LhrsAttentionBwd), _I32, _P]),
+    "lhrs_attention_fwd_grouped": (C.c_int, [C.POINTER(LhrsAttention), _I32, _P]),
     "lhrs_attention_bwd_scratch_floats": (C.c_int64, [_I32, _I32, _I32, _I32]),
     "lhrs_lora_dropout_mask": (C.c_int, [_P, _I64, _I64, _I32, C.c_uint64, _I32, _F, _P, _I64, _P]),
     "lhrs_lora_dx_dropout": (C.c_int, [_P, _I64, _I64, _I32, _P, _I64, _PP, _I32, C.c_uint64, _I32, _F, _P]),

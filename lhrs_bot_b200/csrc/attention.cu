@@ -72,10 +72,20 @@ __device__ __forceinline__ void load_tile(uint32_t smem_base, const __nv_bfloat1
     }
 }
 
+// Up to three problems that share (B, H) in ONE launch: blockIdx.z = group * B + batch.  The AttnPooler's three query groups
+// (64/48/32 queries against 320/304/288 keys, common_arch.py:159-166) run as one grid instead of three.
+struct AttnArgsG {
+    AttnArgs a[3];
+    int n;
+};
+
 template <int HD, bool CAUSAL>
 __global__ void __launch_bounds__(128)
-attn_fwd_kernel(const AttnArgs p) {
+attn_fwd_kernel(const AttnArgsG G) {
     constexpr int BQ = 64, BKV = 64, THREADS = 128;
+    const int gi = static_cast<int>(blockIdx.z) / G.a[0].B;
+    const AttnArgs p = (gi == 0) ? G.a[0] : (gi == 1 ? G.a[1] : G.a[2]);
+    if (static_cast<int>(blockIdx.x) * BQ >= p.Sq) return;     // shorter groups own fewer query blocks
     constexpr int KSTEPS = HD / 16;   // k-steps of QK^T
     constexpr int DTILES = HD / 8;    // n-tiles of the output
     extern __shared__ __align__(128) uint8_t smem[];
@@ -85,7 +95,7 @@ attn_fwd_kernel(const AttnArgs p) {
     __shared__ uint8_t sMask[2][BKV];   // key-padding mask of the current / next key tile
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int qb = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+    const int qb = blockIdx.x, h = blockIdx.y, b = static_cast<int>(blockIdx.z) - gi * p.B;
     const int q0 = qb * BQ;
 
     const __nv_bfloat16* qg = p.q + b * p.q_bs + h * p.q_hs;
@@ -262,7 +272,8 @@ attn_fwd_kernel(const AttnArgs p) {
 }
 
 template <int HD, bool CAUSAL>
-static int launch_attn(const AttnArgs& a, cudaStream_t stream) {
+static int launch_attn(const AttnArgsG& G, cudaStream_t stream) {
+    const AttnArgs& a = G.a[0];
     constexpr int SMEM = (64 + 4 * 64) * HD * 2;
     auto kern = attn_fwd_kernel<HD, CAUSAL>;
     static bool attr_set = false;
@@ -270,13 +281,17 @@ static int launch_attn(const AttnArgs& a, cudaStream_t stream) {
         LHRS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
         attr_set = true;
     }
-    dim3 grid((a.Sq + 63) / 64, a.H, a.B);
-    const bool prof = prof_on();
-    if (prof) {
-        const double pairs = CAUSAL ? 0.5 * a.Sq * (double)a.Skv : (double)a.Sq * a.Skv;  // causal counted at half
-        prof_begin(PROF_ATTN, 4.0 * a.B * a.H * pairs * HD, 2.0 * a.B * a.H * HD * (2.0 * a.Sq + 2.0 * a.Skv), stream);
+    int max_sq = 0;
+    double pairs = 0, rows = 0;
+    for (int i = 0; i < G.n; ++i) {
+        max_sq = G.a[i].Sq > max_sq ? G.a[i].Sq : max_sq;
+        pairs += CAUSAL ? 0.5 * G.a[i].Sq * (double)G.a[i].Skv : (double)G.a[i].Sq * G.a[i].Skv;  // causal counted at half
+        rows += 2.0 * G.a[i].Sq + 2.0 * G.a[i].Skv;
     }
-    kern<<<grid, 128, SMEM, stream>>>(a);
+    dim3 grid((max_sq + 63) / 64, a.H, a.B * G.n);
+    const bool prof = prof_on();
+    if (prof) prof_begin(PROF_ATTN, 4.0 * a.B * a.H * pairs * HD, 2.0 * a.B * a.H * HD * rows, stream);
+    kern<<<grid, 128, SMEM, stream>>>(G);
     if (prof) prof_end(stream);
     LHRS_LAUNCH_CHECK("attn_fwd_kernel");
     return LHRS_OK;
@@ -301,7 +316,9 @@ extern "C" int lhrs_attention_fwd(const LhrsAttention* d, void* stream_) {
     for (long long s : strides) LHRS_CHECK_ARG((s % 8) == 0, "lhrs_attention_fwd: strides must be multiples of 8 elements");
     // head_dim 128 with at least one full 128-row query tile runs on the tcgen05 kernel (attention_tc.cu)
     if (d->head_dim == 128 && d->Sq >= 128 && use_tc_attention()) return attention_fwd_tc(d, stream);
-    AttnArgs a;
+    AttnArgsG G;
+    G.n = 1;
+    AttnArgs& a = G.a[0];
     a.q = reinterpret_cast<const __nv_bfloat16*>(d->q);
     a.k = reinterpret_cast<const __nv_bfloat16*>(d->k);
     a.v = reinterpret_cast<const __nv_bfloat16*>(d->v);
@@ -315,6 +332,37 @@ extern "C" int lhrs_attention_fwd(const LhrsAttention* d, void* stream_) {
     a.B = d->B; a.H = d->H; a.Sq = d->Sq; a.Skv = d->Skv;
     a.scale = d->scale;
     a.scale_log2 = d->scale * 1.4426950408889634f;
-    if (d->head_dim == 128) return d->causal ? launch_attn<128, true>(a, stream) : launch_attn<128, false>(a, stream);
-    return d->causal ? launch_attn<64, true>(a, stream) : launch_attn<64, false>(a, stream);
+    G.a[1] = a; G.a[2] = a;
+    if (d->head_dim == 128) return d->causal ? launch_attn<128, true>(G, stream) : launch_attn<128, false>(G, stream);
+    return d->causal ? launch_attn<64, true>(G, stream) : launch_attn<64, false>(G, stream);
+}
+
+// n (<= 3) forward problems with the same B, H, head_dim 64 and causal flag in one launch (the AttnPooler's query groups)
+extern "C" int lhrs_attention_fwd_grouped(const LhrsAttention* d, int32_t n, void* stream_) {
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    LHRS_CHECK_ARG(d != nullptr && n >= 1 && n <= 3, "lhrs_attention_fwd_grouped: 1..3 problems");
+    bool same = true;
+    for (int i = 0; i < n; ++i) {
+        LHRS_CHECK_ARG(d[i].q && d[i].k && d[i].v && d[i].o && d[i].B > 0 && d[i].H > 0 && d[i].Sq > 0 && d[i].Skv > 0, "lhrs_attention_fwd_grouped: null/empty problem %d", i);
+        same = same && d[i].B == d[0].B && d[i].H == d[0].H && d[i].head_dim == 64 && d[i].causal == d[0].causal;
+        const long long strides[] = {d[i].q_bs, d[i].q_rs, d[i].q_hs, d[i].k_bs, d[i].k_rs, d[i].k_hs, d[i].v_bs, d[i].v_rs, d[i].v_hs, d[i].o_rs, d[i].o_hs, d[i].o_bs};
+        for (long long s : strides) LHRS_CHECK_ARG((s % 8) == 0, "lhrs_attention_fwd_grouped: strides must be multiples of 8 elements");
+    }
+    if (!same || n == 1) {       // not groupable: one launch each
+        for (int i = 0; i < n; ++i) { const int rc = lhrs_attention_fwd(&d[i], stream_); if (rc) return rc; }
+        return LHRS_OK;
+    }
+    AttnArgsG G;
+    G.n = n;
+    for (int i = 0; i < 3; ++i) {
+        const LhrsAttention& s = d[i < n ? i : 0];
+        AttnArgs& a = G.a[i];
+        a.q = reinterpret_cast<const __nv_bfloat16*>(s.q); a.k = reinterpret_cast<const __nv_bfloat16*>(s.k);
+        a.v = reinterpret_cast<const __nv_bfloat16*>(s.v); a.o = reinterpret_cast<__nv_bfloat16*>(s.o);
+        a.lse = s.lse; a.kmask = s.key_mask;
+        a.q_bs = s.q_bs; a.q_rs = s.q_rs; a.q_hs = s.q_hs; a.k_bs = s.k_bs; a.k_rs = s.k_rs; a.k_hs = s.k_hs;
+        a.v_bs = s.v_bs; a.v_rs = s.v_rs; a.v_hs = s.v_hs; a.o_bs = s.o_bs; a.o_rs = s.o_rs; a.o_hs = s.o_hs;
+        a.B = s.B; a.H = s.H; a.Sq = s.Sq; a.Skv = s.Skv; a.scale = s.scale; a.scale_log2 = s.scale * 1.4426950408889634f;
+    }
+    return d[0].causal ? launch_attn<64, true>(G, stream) : launch_attn<64, false>(G, stream);
 }

@@ -76,9 +76,18 @@ __device__ __forceinline__ void load_rows(uint32_t smem_base, const __nv_bfloat1
 }
 
 // ------------------------------------------------------------------ delta = rowsum(dO * O), layout [B,H,Sq]
+// up to three problems that share (B, H) in one launch (the AttnPooler's query groups): block index = group * B + batch
+struct AttnBwdArgsG {
+    AttnBwdArgs a[3];
+    int n;
+};
+
 template <int HD>
-__global__ void __launch_bounds__(256) attn_delta_kernel(const AttnBwdArgs p) {
-    const int s = blockIdx.x, b = blockIdx.y;
+__global__ void __launch_bounds__(256) attn_delta_kernel(const AttnBwdArgsG G) {
+    const int gi = static_cast<int>(blockIdx.y) / G.a[0].B;
+    const AttnBwdArgs p = (gi == 0) ? G.a[0] : (gi == 1 ? G.a[1] : G.a[2]);
+    if (static_cast<int>(blockIdx.x) >= p.Sq) return;
+    const int s = blockIdx.x, b = static_cast<int>(blockIdx.y) - gi * p.B;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     for (int h = warp; h < p.H; h += 8) {
         const __nv_bfloat16* o = p.o + b * p.o_bs + static_cast<long long>(s) * p.o_rs + h * p.o_hs;
@@ -105,8 +114,11 @@ __global__ void __launch_bounds__(256) attn_delta_kernel(const AttnBwdArgs p) {
 
 // ------------------------------------------------------------------ dQ
 template <int HD, bool CAUSAL>
-__global__ void __launch_bounds__(128) attn_bwd_dq_kernel(const AttnBwdArgs p) {
+__global__ void __launch_bounds__(128) attn_bwd_dq_kernel(const AttnBwdArgsG G) {
     constexpr int BQ = 64, BKV = 64, THREADS = 128, KSTEPS = HD / 16, DTILES = HD / 8;
+    const int gi = static_cast<int>(blockIdx.z) / G.a[0].B;
+    const AttnBwdArgs p = (gi == 0) ? G.a[0] : (gi == 1 ? G.a[1] : G.a[2]);
+    if (static_cast<int>(blockIdx.x) * BQ >= p.Sq) return;
     extern __shared__ __align__(128) uint8_t smem[];
     const uint32_t sQ = smem_u32(smem);
     const uint32_t sdO = sQ + BQ * HD * 2;
@@ -114,7 +126,7 @@ __global__ void __launch_bounds__(128) attn_bwd_dq_kernel(const AttnBwdArgs p) {
     const uint32_t sV = sK + 2 * BKV * HD * 2;
     __shared__ uint8_t sMask[2][BKV];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t4 = lane & 3;
-    const int qb = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+    const int qb = blockIdx.x, h = blockIdx.y, b = static_cast<int>(blockIdx.z) - gi * p.B;
     const int q0 = qb * BQ;
     const __nv_bfloat16* qg = p.q + b * p.q_bs + h * p.q_hs;
     const __nv_bfloat16* kg = p.k + b * p.k_bs + h * p.k_hs;
@@ -237,8 +249,11 @@ __global__ void __launch_bounds__(128) attn_bwd_dq_kernel(const AttnBwdArgs p) {
 
 // ------------------------------------------------------------------ dK, dV
 template <int HD, int BQ, bool CAUSAL>
-__global__ void __launch_bounds__(128) attn_bwd_dkv_kernel(const AttnBwdArgs p) {
+__global__ void __launch_bounds__(128) attn_bwd_dkv_kernel(const AttnBwdArgsG G) {
     constexpr int BKV = 64, THREADS = 128, KSTEPS = HD / 16, DTILES = HD / 8;
+    const int gi = static_cast<int>(blockIdx.z) / G.a[0].B;
+    const AttnBwdArgs p = (gi == 0) ? G.a[0] : (gi == 1 ? G.a[1] : G.a[2]);
+    if (static_cast<int>(blockIdx.x) * BKV >= p.Skv) return;
     extern __shared__ __align__(128) uint8_t smem[];
     const uint32_t sK = smem_u32(smem);
     const uint32_t sV = sK + BKV * HD * 2;
@@ -246,7 +261,7 @@ __global__ void __launch_bounds__(128) attn_bwd_dkv_kernel(const AttnBwdArgs p) 
     const uint32_t sdO = sQ + 2 * BQ * HD * 2;        // 2 buffers of BQ rows
     float* sStat = reinterpret_cast<float*>(smem + (2 * BKV + 4 * BQ) * HD * 2);  // [2 buf][2 (lse2, delta)][BQ]
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t4 = lane & 3;
-    const int kblk = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+    const int kblk = blockIdx.x, h = blockIdx.y, b = static_cast<int>(blockIdx.z) - gi * p.B;
     const int k0 = kblk * BKV;
     const __nv_bfloat16* qg = p.q + b * p.q_bs + h * p.q_hs;
     const __nv_bfloat16* kg = p.k + b * p.k_bs + h * p.k_hs;
@@ -382,7 +397,8 @@ __global__ void __launch_bounds__(128) attn_bwd_dkv_kernel(const AttnBwdArgs p) 
 }
 
 template <int HD, bool CAUSAL>
-static int launch_bwd(const AttnBwdArgs& a, cudaStream_t stream) {
+static int launch_bwd(const AttnBwdArgsG& G, cudaStream_t stream) {
+    const AttnBwdArgs& a = G.a[0];
     constexpr int BQ2 = (HD == 128) ? 32 : 64;
     constexpr int SMEM_DQ = (2 * 64 + 4 * 64) * HD * 2;
     constexpr int SMEM_DKV = (2 * 64 + 4 * BQ2) * HD * 2 + 4 * BQ2 * 4;
@@ -396,26 +412,30 @@ static int launch_bwd(const AttnBwdArgs& a, cudaStream_t stream) {
         attr_set = true;
     }
     const bool prof = prof_on();
-    if (prof) {
-        const double pairs = CAUSAL ? 0.5 * a.Sq * (double)a.Skv : (double)a.Sq * a.Skv;
-        prof_begin(PROF_ATTN, 10.0 * a.B * a.H * pairs * HD, 0.0, stream);  // 5 contractions of 2*pairs*HD (algorithmic)
+    int max_sq = 0, max_skv = 0;
+    double pairs = 0;
+    for (int i = 0; i < G.n; ++i) {
+        max_sq = G.a[i].Sq > max_sq ? G.a[i].Sq : max_sq;
+        max_skv = G.a[i].Skv > max_skv ? G.a[i].Skv : max_skv;
+        pairs += CAUSAL ? 0.5 * G.a[i].Sq * (double)G.a[i].Skv : (double)G.a[i].Sq * G.a[i].Skv;
     }
-    kd<<<dim3(a.Sq, a.B), 256, 0, stream>>>(a);
+    if (prof) prof_begin(PROF_ATTN, 10.0 * a.B * a.H * pairs * HD, 0.0, stream);  // 5 contractions of 2*pairs*HD (algorithmic)
+    kd<<<dim3(max_sq, a.B * G.n), 256, 0, stream>>>(G);
     LHRS_LAUNCH_CHECK("attn_delta_kernel");
     bool tma_ok = true;   // TMA views and 16-byte stores need 8-element strides
     for (long long s : {a.q_bs, a.q_rs, a.q_hs, a.k_bs, a.k_rs, a.k_hs, a.v_bs, a.v_rs, a.v_hs, a.o_bs, a.o_rs, a.o_hs, a.dq_bs, a.dq_rs,
                         a.dq_hs, a.dk_bs, a.dk_rs, a.dk_hs, a.dv_bs, a.dv_rs, a.dv_hs})
         tma_ok = tma_ok && (s % 8) == 0;
-    if (HD == 128 && a.Sq >= 128 && a.Skv >= 128 && tma_ok && use_tc_attention()) {   // tcgen05 dQ and dK/dV kernels
+    if (G.n == 1 && HD == 128 && a.Sq >= 128 && a.Skv >= 128 && tma_ok && use_tc_attention()) {   // tcgen05 dQ and dK/dV kernels
         const char* pe = getenv("LHRS_ATTN_BWD_PERSIST");   // 0: one CTA per tile (attention_bwd_tc.cu); read per call for A/B runs
         const bool persist = (pe == nullptr || atoi(pe) != 0) && attention_bwd_tcp_ok(a) && (a.kmask == nullptr || a.kbits != nullptr);
         const int rc = persist ? attention_bwd_tcp(a, CAUSAL, stream) : attention_bwd_tc(a, CAUSAL, stream);
         if (prof) prof_end(stream);
         return rc;
     }
-    kq<<<dim3((a.Sq + 63) / 64, a.H, a.B), 128, SMEM_DQ, stream>>>(a);
+    kq<<<dim3((max_sq + 63) / 64, a.H, a.B * G.n), 128, SMEM_DQ, stream>>>(G);
     LHRS_LAUNCH_CHECK("attn_bwd_dq_kernel");
-    kkv<<<dim3((a.Skv + 63) / 64, a.H, a.B), 128, SMEM_DKV, stream>>>(a);
+    kkv<<<dim3((max_skv + 63) / 64, a.H, a.B * G.n), 128, SMEM_DKV, stream>>>(G);
     if (prof) prof_end(stream);
     LHRS_LAUNCH_CHECK("attn_bwd_dkv_kernel");
     return LHRS_OK;
@@ -429,8 +449,7 @@ extern "C" int64_t lhrs_attention_bwd_scratch_floats(int32_t B, int32_t H, int32
     return static_cast<int64_t>(B) * H * Sq + static_cast<int64_t>(B) * 2 * ((Skv + 63) / 64);
 }
 
-extern "C" int lhrs_attention_bwd(const LhrsAttentionBwd* d, void* stream_) {
-    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+static int fill_bwd_args(const LhrsAttentionBwd* d, AttnBwdArgs& a) {
     LHRS_CHECK_ARG(d != nullptr, "lhrs_attention_bwd: null descriptor");
     const LhrsAttention* f = &d->fwd;
     LHRS_CHECK_ARG(f->q && f->k && f->v && f->o && f->lse && d->d_o && d->dq && d->dk && d->dv && d->delta,
@@ -439,7 +458,6 @@ extern "C" int lhrs_attention_bwd(const LhrsAttentionBwd* d, void* stream_) {
     const long long strides[] = {f->q_bs, f->q_rs, f->q_hs, f->k_bs, f->k_rs, f->k_hs, f->v_bs, f->v_rs, f->v_hs, f->o_bs, f->o_rs, f->o_hs,
                                  d->dq_bs, d->dq_rs, d->dq_hs, d->dk_bs, d->dk_rs, d->dk_hs, d->dv_bs, d->dv_rs, d->dv_hs};
     for (long long s : strides) LHRS_CHECK_ARG((s % 2) == 0, "lhrs_attention_bwd: odd stride");
-    AttnBwdArgs a;
     a.q = (const __nv_bfloat16*)f->q; a.k = (const __nv_bfloat16*)f->k; a.v = (const __nv_bfloat16*)f->v;
     a.o = (const __nv_bfloat16*)f->o; a.d_o = (const __nv_bfloat16*)d->d_o;
     a.dq = (__nv_bfloat16*)d->dq; a.dk = (__nv_bfloat16*)d->dk; a.dv = (__nv_bfloat16*)d->dv;
@@ -457,6 +475,37 @@ extern "C" int lhrs_attention_bwd(const LhrsAttentionBwd* d, void* stream_) {
     a.rope_cos = d->rope_cos; a.rope_sin = d->rope_sin;
     LHRS_CHECK_ARG(a.rope_cos == nullptr || (f->head_dim == 128 && a.rope_sin != nullptr && f->Sq == f->Skv),
                    "lhrs_attention_bwd: fused un-RoPE needs head_dim 128, both tables and Sq == Skv");
-    if (f->head_dim == 128) return f->causal ? launch_bwd<128, true>(a, stream) : launch_bwd<128, false>(a, stream);
-    return f->causal ? launch_bwd<64, true>(a, stream) : launch_bwd<64, false>(a, stream);
+    return LHRS_OK;
+}
+
+extern "C" int lhrs_attention_bwd(const LhrsAttentionBwd* d, void* stream_) {
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    AttnBwdArgsG G;
+    G.n = 1;
+    const int rc = fill_bwd_args(d, G.a[0]);
+    if (rc) return rc;
+    G.a[1] = G.a[0]; G.a[2] = G.a[0];
+    const LhrsAttention* f = &d->fwd;
+    if (f->head_dim == 128) return f->causal ? launch_bwd<128, true>(G, stream) : launch_bwd<128, false>(G, stream);
+    return f->causal ? launch_bwd<64, true>(G, stream) : launch_bwd<64, false>(G, stream);
+}
+
+// n (<= 3) backward problems with the same B, H, head_dim 64 and causal flag: delta, dQ and dK/dV each as ONE launch
+extern "C" int lhrs_attention_bwd_grouped(const LhrsAttentionBwd* d, int32_t n, void* stream_) {
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    LHRS_CHECK_ARG(d != nullptr && n >= 1 && n <= 3, "lhrs_attention_bwd_grouped: 1..3 problems");
+    AttnBwdArgsG G;
+    G.n = n;
+    bool same = true;
+    for (int i = 0; i < n; ++i) {
+        const int rc = fill_bwd_args(&d[i], G.a[i]);
+        if (rc) return rc;
+        same = same && d[i].fwd.B == d[0].fwd.B && d[i].fwd.H == d[0].fwd.H && d[i].fwd.head_dim == 64 && d[i].fwd.causal == d[0].fwd.causal;
+    }
+    if (!same || n == 1) {
+        for (int i = 0; i < n; ++i) { const int rc = lhrs_attention_bwd(&d[i], stream_); if (rc) return rc; }
+        return LHRS_OK;
+    }
+    for (int i = n; i < 3; ++i) G.a[i] = G.a[0];
+    return d[0].fwd.causal ? launch_bwd<64, true>(G, stream) : launch_bwd<64, false>(G, stream);
 }

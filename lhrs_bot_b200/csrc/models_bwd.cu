@@ -441,10 +441,11 @@ extern "C" int lhrs_pooler_bwd(const LhrsPoolerWeights* w, const LhrsPoolerWeigh
         if (gr->ao_w && gr->ao_w[l]) if ((rc = gemm_dw(st, D, D, RQ, dx, D, t.ao, D, G(gr->ao_w[l]), D))) return rc;
         if (gr->ao_b && gr->ao_b[l]) if ((rc = lhrs_colsum(dx, D, RQ, D, G(gr->ao_b[l]), 0, p.scratch, st))) return rc;
         if ((rc = gemm_dx(st, RQ, D, D, dx, D, w->ao_w[l], D, p.d_ao, D))) return rc;
+        LhrsAttentionBwd abs_[4];
         for (int g = 0; g < geo.G; ++g) {
             const int Lq = geo.stage[g], Lkv = geo.stage[g] + geo.split[g];
             const long long qo = (long long)B * geo.q_off[g], ko = (long long)B * geo.kv_off[g];
-            LhrsAttentionBwd ab;
+            LhrsAttentionBwd& ab = abs_[g];
             memset(&ab, 0, sizeof(ab));
             ab.fwd = attn_desc(t.qp + qo * D, t.kvp + ko * 2 * D, t.kvp + ko * 2 * D + D, D, (long long)Lq * D, t.ao + qo * D, D,
                                (long long)Lq * D, B, w->heads, Lq, Lkv, 64, 0);
@@ -454,7 +455,11 @@ extern "C" int lhrs_pooler_bwd(const LhrsPoolerWeights* w, const LhrsPoolerWeigh
             ab.dq = p.dqp + qo * D; ab.dq_rs = D; ab.dq_bs = (long long)Lq * D; ab.dq_hs = 64;
             ab.dk = p.dkvp + ko * 2 * D; ab.dv = p.dkvp + ko * 2 * D + D;
             ab.dk_rs = ab.dv_rs = 2 * D; ab.dk_bs = ab.dv_bs = (long long)Lkv * 2 * D; ab.dk_hs = ab.dv_hs = 64;
-            if ((rc = lhrs_attention_bwd(&ab, st))) return rc;
+        }
+        if (geo.G <= 3) {      // delta, dQ and dK/dV of all query groups: three launches instead of nine
+            if ((rc = lhrs_attention_bwd_grouped(abs_, geo.G, st))) return rc;
+        } else {
+            for (int g = 0; g < geo.G; ++g) if ((rc = lhrs_attention_bwd(&abs_[g], st))) return rc;
         }
         // q projection (in_proj rows [0, D)) and k/v projection (rows [D, 3D))
         if (g_in_w) if ((rc = gemm_dw(st, D, D, RQ, p.dqp, D, t.hq, D, g_in_w, D))) return rc;

@@ -329,15 +329,22 @@ extern "C" int lhrs_pooler_fwd(const LhrsPoolerWeights* w, const void* image_emb
             gq.bias[0] = in_b;
             if ((rc = lhrs_gemm_bf16(&gq, stream))) return rc;
         }
-        for (int g = 0; g < geo.G; ++g) {
-            const int Lq = geo.stage[g], Lkv = geo.stage[g] + geo.split[g];
-            const bf16* q = qp + (long long)B * geo.q_off[g] * D;
-            const bf16* k = kvp + (long long)B * geo.kv_off[g] * 2 * D;
-            bf16* o = ao + (long long)B * geo.q_off[g] * D;
-            LhrsAttention at = attn_desc(q, k, k + D, D, (long long)Lq * D, o, D, (long long)Lq * D, B, w->heads, Lq, Lkv, 64, 0);
-            at.k_rs = at.v_rs = 2 * D; at.k_bs = at.v_bs = (long long)Lkv * 2 * D;
-            if (ls) at.lse = ls->lse + (long long)B * geo.q_off[g] * w->heads;
-            if ((rc = lhrs_attention_fwd(&at, stream))) return rc;
+        {   // the cross-attention of all query groups as ONE launch (group-major rows: each group is its own (B, Lq) x (B, Lkv) problem)
+            LhrsAttention at[4];
+            for (int g = 0; g < geo.G; ++g) {
+                const int Lq = geo.stage[g], Lkv = geo.stage[g] + geo.split[g];
+                const bf16* q = qp + (long long)B * geo.q_off[g] * D;
+                const bf16* k = kvp + (long long)B * geo.kv_off[g] * 2 * D;
+                bf16* o = ao + (long long)B * geo.q_off[g] * D;
+                at[g] = attn_desc(q, k, k + D, D, (long long)Lq * D, o, D, (long long)Lq * D, B, w->heads, Lq, Lkv, 64, 0);
+                at[g].k_rs = at[g].v_rs = 2 * D; at[g].k_bs = at[g].v_bs = (long long)Lkv * 2 * D;
+                if (ls) at[g].lse = ls->lse + (long long)B * geo.q_off[g] * w->heads;
+            }
+            if (geo.G <= 3) {
+                if ((rc = lhrs_attention_fwd_grouped(at, geo.G, stream))) return rc;
+            } else {
+                for (int g = 0; g < geo.G; ++g) if ((rc = lhrs_attention_fwd(&at[g], stream))) return rc;
+            }
         }
         {
             LhrsGemm g = gemm_desc(RQ, D, D, ao, D, w->ao_w[l], D, p.xq, D);

@@ -201,7 +201,7 @@ def generate(text, input_ids: torch.Tensor, image_embedding: Optional[torch.Tens
              attention_mask=None, top_p: Optional[float] = None, top_k: Optional[int] = None,
              repetition_penalty: Optional[float] = None, num_beams: int = 1, eos_token_id="config", eos_poll: int = 16,
              generator: Optional[torch.Generator] = None, return_step_logits: bool = False, seed: Optional[int] = None,
-             use_graph: Optional[bool] = None, host_picker=None, **unused):
+             use_graph: Optional[bool] = None, host_picker=None, inputs_embeds: Optional[torch.Tensor] = None, **unused):
     lib = _lib.load()
     if input_ids.shape[0] != 1:
         raise NotImplementedError("batched generate: the reference's own batched path is unstable (no position_ids under left "
@@ -214,9 +214,12 @@ def generate(text, input_ids: torch.Tensor, image_embedding: Optional[torch.Tens
                            "(the reference merges for evaluation, UniBind.py:114-115)")
     cfg = te.config
     w = text.weights()
-    _, _, _, embeds, _ = text.prepare_inputs_for_multimodal(input_ids, None, None, None, image_embedding)
-    if embeds is None:
-        embeds = text.embed(input_ids)
+    if inputs_embeds is not None:           # spliced by the caller (UniBind.generate: pooler rows scattered in place)
+        embeds = inputs_embeds
+    else:
+        _, _, _, embeds, _ = text.prepare_inputs_for_multimodal(input_ids, None, None, None, image_embedding)
+        if embeds is None:
+            embeds = text.embed(input_ids)
     S = embeds.shape[1]
     if isinstance(eos_token_id, str) and eos_token_id == "config":
         eos_token_id = getattr(cfg, "eos_token_id", None)

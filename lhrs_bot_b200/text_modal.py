@@ -426,13 +426,21 @@ class TextModal(BaseModal):
         embeds, new_labels, new_mask, _, _ = self._splice(input_ids, attention_mask, labels, image_embedding)
         return None, new_mask, past_key_values, embeds, new_labels
 
-    def _splice(self, input_ids, attention_mask, labels, image_embedding, fill_image: bool = True):
-        runtime.require_bf16_cuda(image_embedding, "image_embedding")
+    def splice_for_scatter(self, input_ids, n_images: int, num_query: int):
+        """Text half of the splice for the generation path: inputs_embeds with the text rows filled and a row map telling where
+        row (slot, i) of the pooler output belongs — ``AttnPooler.forward(scatter_into=embeds, row_map=...)`` then writes the image
+        rows straight from its out_proj epilogue (no dense (B, 144, 4096) tensor, no splice copy of it)."""
+        embeds, _, _, row_map, _ = self._splice(input_ids, None, None, None, fill_image=False, nq=num_query, n_slots=n_images)
+        return embeds, row_map
+
+    def _splice(self, input_ids, attention_mask, labels, image_embedding, fill_image: bool = True, nq: int = 0, n_slots: int = 0):
         table = self.text_encoder.model.embed_tokens.weight
         runtime.require_bf16_cuda(table, "embed_tokens.weight")
         B, T = input_ids.shape
-        nq = image_embedding.shape[1]
-        n_slots = image_embedding.shape[0]
+        if image_embedding is not None:
+            runtime.require_bf16_cuda(image_embedding, "image_embedding")
+            nq = image_embedding.shape[1]
+            n_slots = image_embedding.shape[0]
         info = ops.splice_scan(input_ids, nq)
         head = info[: (B + 1) * 4].cpu().view(B + 1, 4)      # the one D2H sync of the splice (B+1 small rows)
         total_slots, s_out = int(head[B, 0]), int(head[B, 1])
@@ -517,6 +525,7 @@ class TextModal(BaseModal):
     def generate(self, image_embedding: torch.Tensor = None, prompt=None, input_ids: Optional[torch.LongTensor] = None,
                  do_sample: bool = True, temperature: float = 0.2, max_new_tokens: int = 1024, streamer=None,
                  use_cache: bool = True, stopping_criteria=None, attention_mask=None, **kwargs):
+        """``inputs_embeds=`` (extension, used by UniBind.generate): the already spliced prompt (see ``splice_for_scatter``)."""
         from .generation import generate as _generate
         if input_ids is None:
             raise NotImplementedError("caption-prompt generation (text_modal.py:543-579) needs the tokenizer files; pass input_ids")

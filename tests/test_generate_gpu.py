@@ -288,3 +288,30 @@ def test_decode_full_width_layer():
         e = rel_l2(logits[i], ref[0, 39 + i])
         print(f"7B-width decode step {i}: logits rel-L2 {e:.3e}")
         assert e <= 3e-2
+
+
+def test_generate_scatter_splice_equals_dense_splice(small, monkeypatch):
+    """UniBind.generate's fast path — text rows spliced first, the AttnPooler's out_proj epilogue scattering its rows straight
+    into inputs_embeds (lhrs_gemm_bf16 row_map epilogue) — builds bit-identical inputs_embeds and emits the same tokens as the
+    dense path (encode_image -> prepare_inputs_for_multimodal), for one and for two images in the prompt."""
+    cfg, model, st = small
+    g = torch.Generator().manual_seed(31)
+    for n_img in (1, 2):
+        ids = torch.randint(3, 1024, (1, 30), generator=g)
+        ids[0, 0] = 1
+        for k in range(n_img):
+            ids[0, 4 + 9 * k] = -200
+        ids = ids.to(DEV)
+        px = torch.randn(n_img, 3, 224, 224, generator=g).bfloat16().to(DEV)
+        with torch.no_grad():
+            feats = model.rgb.encode(px)
+            dense = model.rgb_pooler(feats)
+            _, _, _, ref_embeds, _ = model.text.prepare_inputs_for_multimodal(ids, None, None, None, dense)
+            embeds, row_map = model.text.splice_for_scatter(ids, n_img, model.rgb_pooler.num_query)
+            model.rgb_pooler(feats, scatter_into=embeds.view(-1, embeds.shape[-1]), row_map=row_map)
+            assert torch.equal(embeds, ref_embeds)
+            monkeypatch.setenv("LHRS_SCATTER_SPLICE", "0")
+            a = model.generate(ids, images=px, do_sample=False, max_new_tokens=16, eos_token_id=None)
+            monkeypatch.setenv("LHRS_SCATTER_SPLICE", "1")
+            b = model.generate(ids, images=px, do_sample=False, max_new_tokens=16, eos_token_id=None)
+        assert torch.equal(a, b)
