@@ -676,14 +676,34 @@ def measure_steps(args, workload, dev, rank, world, local, steps, warmup, B=None
     if e2e_leg:
         pre = ClipPreprocessor()
 
+        loss_host = [torch.empty((), dtype=torch.float32).pin_memory() for _ in range(2)]
+        loss_ev = [torch.cuda.Event(), torch.cuda.Event()]
+        seen = []
+
         def e2e_run(n):
+            # a pipelined training loop: every step's loss is copied to pinned host memory (D2H, 4 bytes per step) and is READ
+            # one step late, so the host never drains the GPU queue inside the loop; the last loss is read before the timer stops
             it = iter(InputStager((host_batches[i % 2] for i in range(n)), dev, pre))
-            return lambda i: float(step(next(it)))
+
+            def one(i):
+                loss = step(next(it))
+                loss_host[i % 2].copy_(loss.detach().float(), non_blocking=True)
+                loss_ev[i % 2].record()
+                if i > 0:
+                    loss_ev[(i - 1) % 2].synchronize()
+                    seen.append(float(loss_host[(i - 1) % 2]))
+                if i == n - 1:
+                    loss_ev[i % 2].synchronize()
+                    seen.append(float(loss_host[i % 2]))
+            return one
         timed(e2e_run(1), 1)
+        seen.clear()
         ms_e2e, _ = timed(e2e_run(steps), steps)
+        assert len(seen) == steps and all(v == v for v in seen), "e2e leg: every step's loss must have been read on the host"
         e2e = dict(value=tokens_per_step * steps / (ms_e2e * 1e-3), unit="tokens/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=4,
                    path="pinned host batch (uint8 224x224x3 tiles + ids/labels/mask) -> InputStager (side-stream H2D + lhrs_clip_preprocess) -> "
-                        + ("SftStepper.step" if train else "UniBind.forward") + " -> float(loss)")
+                        + ("SftStepper.step" if train else "UniBind.forward") + " -> loss copied D2H every step, read on the host one step late "
+                        "(pipelined loop; the last one before the timer stops)")
 
     # ---- exchange attribution (N > 1): CUDA events around the exchange + optimizer part of each step
     exchange = None

@@ -287,6 +287,13 @@ typedef struct LhrsLlamaWeights {
      * The mask is a pure function of (lora_seed, layer * 7 + projection, row, column): lhrs_lora_dropout_mask. */
     float lora_dropout;
     uint64_t lora_seed;
+    /* Optional TRANSPOSED copies of the frozen projection weights for the dX GEMMs of lhrs_llama_bwd (all NULL = read the
+     * weights MN-major in place).  180 GB of HBM affords a second, K-major copy (+13 GB for LLaMA-2-7B) and the K-major form of
+     * the tcgen05 GEMM runs the dX contractions 10-20 % faster than the MN-major one:
+     *   qkv_wt[l] = [Wq;Wk;Wv]^T [dim, 3*dim]   o_wt[l] = Wo^T [dim, dim]   gu_wt[l] = [Wgate;Wup]^T [dim, 2*ffn]
+     *   down_wt[l] = Wdown^T [ffn, dim]          lm_head_wt = lm_head^T [dim, vocab] */
+    const void* const* qkv_wt; const void* const* o_wt; const void* const* gu_wt; const void* const* down_wt;
+    const void* lm_head_wt;
 } LhrsLlamaWeights;
 
 size_t lhrs_llama_workspace_bytes(const LhrsLlamaWeights* w, int32_t B, int32_t S);

@@ -126,6 +126,7 @@ class LhrsLlamaWeights(C.Structure):
         ("rope_cos", C.c_void_p), ("rope_sin", C.c_void_p),
         ("lora_r", C.c_int32), ("lora_scale", C.c_float), ("lora_a", _PP), ("lora_b", _PP),
         ("lora_dropout", C.c_float), ("lora_seed", C.c_uint64),
+        ("qkv_wt", _PP), ("o_wt", _PP), ("gu_wt", _PP), ("down_wt", _PP), ("lm_head_wt", C.c_void_p),
     ]
 
 

@@ -98,6 +98,32 @@ __global__ void lora_extract_diag_kernel(const __nv_bfloat16* __restrict__ full,
     if (dst != nullptr) dst[e] = full[(static_cast<long long>(p) * out_dim + row) * (n * r) + p * r + col];
 }
 
+// K-major dX GEMMs (transposed weight copies, LhrsLlamaWeights::*_wt) take the LoRA K-extension dT · [A_0;A_1;..] with the A
+// stack transposed too: At[in, n*r].  The factors change every step, so all of a backward's stacks are transposed up front in
+// one launch per 32 layers (pointers travel as kernel parameters).
+struct LoraATransposeArgs {
+    const __nv_bfloat16* a[32 * 7];
+    __nv_bfloat16* out;        // per layer: At_qkv [D, 3r] | At_o [D, r] | At_gu [D, 2r] | At_down [F, r]
+    int layers, r, D, F;
+};
+__host__ __device__ inline long long lora_at_layer_elems(int r, int D, int F) { return (long long)D * 6 * r + (long long)F * r; }
+__host__ __device__ inline long long lora_at_group_offset(int group, int r, int D) {   // group: 0 qkv, 1 o, 2 gate/up, 3 down
+    return group == 0 ? 0 : (group == 1 ? (long long)D * 3 * r : (group == 2 ? (long long)D * 4 * r : (long long)D * 6 * r));
+}
+__global__ void __launch_bounds__(256) lora_a_transpose_kernel(const LoraATransposeArgs p) {
+    const int mod = blockIdx.y;                       // layer * 7 + projection
+    const int layer = mod / 7, proj = mod - layer * 7;
+    const int group = proj < 3 ? 0 : (proj == 3 ? 1 : (proj < 6 ? 2 : 3));
+    const int first = group == 0 ? 0 : (group == 1 ? 3 : (group == 2 ? 4 : 6));
+    const int n = group == 0 ? 3 : (group == 2 ? 2 : 1);
+    const int in_dim = (proj == 6) ? p.F : p.D;
+    const __nv_bfloat16* a = p.a[mod];
+    __nv_bfloat16* out = p.out + layer * lora_at_layer_elems(p.r, p.D, p.F) + lora_at_group_offset(group, p.r, p.D) + (proj - first) * p.r;
+    const int ldo = n * p.r;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < in_dim; i += gridDim.x * blockDim.x)
+        for (int j = 0; j < p.r; ++j) out[static_cast<long long>(i) * ldo + j] = a[static_cast<long long>(j) * in_dim + i];
+}
+
 // LoRA backward for `nproj` projections that share the input x:  y_p += (s * x A_p^T) B_p^T = T_p B_p^T
 //   dT_p = s * dy_p B_p,   dx += dT_p A_p,   dA_p = dT_p^T x,   dB_p = dy_p^T T_p        (T kept from the forward pass)
 // Grouped path (A factors and their gradients contiguous, dy_p column blocks of one matrix): dT for all projections is ONE
@@ -113,6 +139,7 @@ struct LoraBwd {
     float* scratch = nullptr;           // fp32 split-K accumulator for the skinny side GEMMs
     __nv_bfloat16* drop_x = nullptr;    // [M, in_dim] masked copy of x (LoRA dropout only)
     int drop_t = 0;
+    const __nv_bfloat16* at = nullptr;  // K-major dX GEMM: the transposed A stack [in_dim, nproj*r] of this group
     long long M = 0;
 };
 
@@ -139,7 +166,11 @@ static int lora_bwd_pre(cudaStream_t st, const LhrsLlamaWeights* w, void* const*
     }
     // dx += dT · [A_0;A_1;..] accumulates in the main GEMM's TMEM tile — unless dropout masks each projection's term
     // separately (then lora_bwd_post adds mask_p o (dT_p · A_p) per projection)
-    if (L.drop_t == 0) { g.A2 = L.dt; g.lda2 = ldt; g.B2[0] = w->lora_a[L.idx0]; g.ldb2 = L.in_dim; g.ext_k = n * r; }
+    if (L.drop_t == 0) {
+        g.A2 = L.dt; g.lda2 = ldt; g.ext_k = n * r;
+        if (g.b_mn_major) { g.B2[0] = w->lora_a[L.idx0]; g.ldb2 = L.in_dim; }      // [n*r, in] read MN-major in place
+        else { LHRS_CHECK_ARG(L.at != nullptr, "lora_bwd_pre: K-major dX needs the transposed A stack"); g.B2[0] = L.at; g.ldb2 = ldt; }
+    }
     return LHRS_OK;
 }
 
@@ -257,7 +288,7 @@ typedef __nv_bfloat16 bf16;
 
 // ================================================================================================ LLaMA backward
 namespace {
-struct LlamaBwdBufs { bf16 *dxa, *dxb, *dh, *d_act, *d_gu, *dqkv, *d_o, *h, *t, *dt, *diag, *drop_x; float *delta, *skinny; };
+struct LlamaBwdBufs { bf16 *dxa, *dxb, *dh, *d_act, *d_gu, *dqkv, *d_o, *h, *t, *dt, *diag, *drop_x, *at; float *delta, *skinny; };
 LlamaBwdBufs llama_bwd_plan(Arena& a, const LhrsLlamaWeights* w, long long M) {
     LlamaBwdBufs b;
     const int D = w->dim, F = w->ffn;
@@ -273,6 +304,7 @@ LlamaBwdBufs llama_bwd_plan(Arena& a, const LhrsLlamaWeights* w, long long M) {
     b.diag = lora ? a.take<bf16>(widest * 3 * w->lora_r) : nullptr;
     b.skinny = lora ? a.take<float>(skinny_scratch_elems(w, M)) : nullptr;
     b.drop_x = (lora && w->lora_dropout > 0.f) ? a.take<bf16>(M * (F > D ? F : D)) : nullptr;
+    b.at = (lora && w->qkv_wt != nullptr) ? a.take<bf16>(w->num_layers * lora_at_layer_elems(w->lora_r, D, F)) : nullptr;
     return b;
 }
 }  // namespace
@@ -285,6 +317,10 @@ extern "C" size_t lhrs_llama_bwd_workspace_bytes(const LhrsLlamaWeights* w, int3
 
 extern "C" int lhrs_lm_head_bwd(const LhrsLlamaWeights* w, const void* d_logits, int64_t rows, void* d_hidden, void* stream) {
     LHRS_CHECK_ARG(w && d_logits && d_hidden && rows > 0, "lhrs_lm_head_bwd: null/empty");
+    if (w->lm_head_wt != nullptr) {      // K-major form on the transposed copy [dim, vocab]
+        LhrsGemm g = gemm_desc(rows, w->dim, w->vocab, d_logits, w->vocab, w->lm_head_wt, w->vocab, d_hidden, w->dim);
+        return lhrs_gemm_bf16(&g, stream);
+    }
     return gemm_dx((cudaStream_t)stream, rows, w->dim, w->vocab, d_logits, w->vocab, w->lm_head, w->dim, d_hidden, w->dim);
 }
 
@@ -301,6 +337,24 @@ extern "C" int lhrs_llama_bwd(const LhrsLlamaWeights* w, void* const* lora_a_gra
     Arena sa(const_cast<void*>(stash), (size_t)-1);
     LlamaStash s = llama_stash_plan(sa, w, B, S);
     int rc;
+    const bool kmaj = w->qkv_wt != nullptr && w->o_wt != nullptr && w->gu_wt != nullptr && w->down_wt != nullptr;
+    const bool lora_on = w->lora_r > 0 && w->lora_a != nullptr && w->lora_b != nullptr;
+    const long long at_layer = lora_on ? lora_at_layer_elems(w->lora_r, D, F) : 0;
+    if (kmaj && lora_on && w->lora_dropout <= 0.f) {
+        LHRS_CHECK_ARG(w->num_layers <= 32 * 8, "lhrs_llama_bwd: too many layers");
+        for (int l0 = 0; l0 < w->num_layers; l0 += 32) {
+            LoraATransposeArgs ta;
+            memset(&ta, 0, sizeof(ta));
+            ta.layers = (w->num_layers - l0 < 32) ? w->num_layers - l0 : 32;
+            ta.r = w->lora_r; ta.D = D; ta.F = F; ta.out = b.at + l0 * at_layer;
+            for (int i = 0; i < ta.layers * 7; ++i) ta.a[i] = reinterpret_cast<const bf16*>(w->lora_a[l0 * 7 + i]);
+            lora_a_transpose_kernel<<<dim3((F + 255) / 256, ta.layers * 7), 256, 0, st>>>(ta);
+            LHRS_LAUNCH_CHECK("lora_a_transpose_kernel");
+        }
+    }
+    auto at_of = [&](int layer, int group) -> const bf16* {
+        return (kmaj && lora_on) ? b.at + layer * at_layer + lora_at_group_offset(group, w->lora_r, D) : nullptr;
+    };
     bf16* dx = b.dxa;
     bf16* dx_other = b.dxb;
     if ((rc = lhrs_rmsnorm_bwd(s.x_final, w->norm_w, s.rstd_final, d_hidden, nullptr, dx, M, D, st))) return rc;
@@ -312,6 +366,7 @@ extern "C" int lhrs_llama_bwd(const LhrsLlamaWeights* w, void* const* lora_a_gra
             // d_act = dx · W_down (+ LoRA) with the SwiGLU backward applied in the epilogue: writes d_gu = [d_gate | d_up]
             LhrsGemm g = gemm_desc(M, F, D, dx, D, w->down_w[l], F, b.d_gu, 2 * F);
             g.b_mn_major = 1;
+            if (kmaj) { g = gemm_desc(M, F, D, dx, D, w->down_wt[l], D, b.d_gu, 2 * F); L.at = at_of(l, 3); }   // Wdown^T [F, D]: K-major
             const char* fe = getenv("LHRS_FUSE_SWIGLU_BWD");   // read per call (the parity tests run both forms)
             const int fuse = fe ? atoi(fe) : 0;
             g.pre_gate = t.pre_gate; g.pre_up = t.pre_up;
@@ -330,6 +385,7 @@ extern "C" int lhrs_llama_bwd(const LhrsLlamaWeights* w, void* const* lora_a_gra
             LoraBwd L = lora_ctx(w, l, 4, 2, t.h2, D, D, b.d_gu, 2 * F, F, M, t.lora_t[2], b.dt, b.skinny, b.drop_x);
             LhrsGemm g = gemm_desc(M, D, 2 * F, b.d_gu, 2 * F, w->gate_w[l], D, b.dh, D);
             g.b_mn_major = 1; g.B[1] = w->up_w[l]; g.num_b = 2;
+            if (kmaj) { g = gemm_desc(M, D, 2 * F, b.d_gu, 2 * F, w->gu_wt[l], 2 * F, b.dh, D); L.at = at_of(l, 2); }   // [Wgate;Wup]^T [D, 2F]
             if ((rc = lora_bwd_pre(st, w, lora_a_grads, L, g))) return rc;
             if ((rc = lhrs_gemm_bf16(&g, st))) return rc;
             if ((rc = lora_bwd_post(st, w, lora_a_grads, lora_b_grads, L, b.dh, D, b.diag))) return rc;
@@ -341,6 +397,7 @@ extern "C" int lhrs_llama_bwd(const LhrsLlamaWeights* w, void* const* lora_a_gra
             LoraBwd L = lora_ctx(w, l, 3, 1, t.o, D, D, dx, D, D, M, t.lora_t[1], b.dt, b.skinny, b.drop_x);
             LhrsGemm g = gemm_desc(M, D, D, dx, D, w->o_w[l], D, b.d_o, D);
             g.b_mn_major = 1;
+            if (kmaj) { g = gemm_desc(M, D, D, dx, D, w->o_wt[l], D, b.d_o, D); L.at = at_of(l, 1); }
             if ((rc = lora_bwd_pre(st, w, lora_a_grads, L, g))) return rc;
             if ((rc = lhrs_gemm_bf16(&g, st))) return rc;
             if ((rc = lora_bwd_post(st, w, lora_a_grads, lora_b_grads, L, b.d_o, D, b.diag))) return rc;
@@ -361,6 +418,7 @@ extern "C" int lhrs_llama_bwd(const LhrsLlamaWeights* w, void* const* lora_a_gra
             LoraBwd L = lora_ctx(w, l, 0, 3, t.h1, D, D, b.dqkv, 3 * D, D, M, t.lora_t[0], b.dt, b.skinny, b.drop_x);
             LhrsGemm g = gemm_desc(M, D, 3 * D, b.dqkv, 3 * D, w->q_w[l], D, b.dh, D);
             g.b_mn_major = 1; g.B[1] = w->k_w[l]; g.B[2] = w->v_w[l]; g.num_b = 3;
+            if (kmaj) { g = gemm_desc(M, D, 3 * D, b.dqkv, 3 * D, w->qkv_wt[l], 3 * D, b.dh, D); L.at = at_of(l, 0); }   // [Wq;Wk;Wv]^T [D, 3D]
             if ((rc = lora_bwd_pre(st, w, lora_a_grads, L, g))) return rc;
             if ((rc = lhrs_gemm_bf16(&g, st))) return rc;
             if ((rc = lora_bwd_post(st, w, lora_a_grads, lora_b_grads, L, b.dh, D, b.diag))) return rc;

@@ -331,6 +331,8 @@ class TextModal(BaseModal):
         te = self.text_encoder
         params = list(te.parameters())
         sig = runtime.signature(params)
+        if getattr(self, "_bwd_copies", False):     # in-place writes to a frozen weight (load_state_dict) must refresh its K-major copy
+            sig = sig + tuple(p._version for n, p in te.named_parameters() if "lora_" not in n and p.dim() == 2)
         if self._table is not None and sig == self._table_sig:
             return self._table[0]
         for p in params:
@@ -377,8 +379,31 @@ class TextModal(BaseModal):
         else:
             w.lora_r, w.lora_scale = 0, 0.0
         w.lora_dropout, w.lora_seed = 0.0, 0          # set per training call by autograd.LlamaLossFunction
+        if getattr(self, "_bwd_copies", False):
+            # K-major (transposed) copies of the frozen projection weights for the dX GEMMs of the backward pass: +12.95 GB for
+            # LLaMA-2-7B on a 180 GB part buys the faster form of the tcgen05 GEMM (LhrsLlamaWeights::*_wt, csrc/models_bwd.cu).
+            # Rebuilt with the table whenever a base weight is re-pointed (checkpoint load, cast).
+            def packed_t(l, names, holder):
+                ws = [base_w(getattr(getattr(l, holder), n)).detach() for n in names]
+                return torch.cat(ws, 0).t().contiguous() if len(ws) > 1 else ws[0].t().contiguous()
+            qkv_t = [packed_t(l, ("q_proj", "k_proj", "v_proj"), "self_attn") for l in layers]
+            o_t = [packed_t(l, ("o_proj",), "self_attn") for l in layers]
+            gu_t = [packed_t(l, ("gate_proj", "up_proj"), "mlp") for l in layers]
+            down_t = [packed_t(l, ("down_proj",), "mlp") for l in layers]
+            lm_t = te.lm_head.weight.detach().t().contiguous()
+            arrs = [runtime.PtrArray(x) for x in (qkv_t, o_t, gu_t, down_t)]
+            keep += arrs + [lm_t]
+            w.qkv_wt, w.o_wt, w.gu_wt, w.down_wt = (a.ptr() for a in arrs)
+            w.lm_head_wt = lm_t.data_ptr()
         self._table, self._table_sig = (w, keep), sig
         return w
+
+    def enable_backward_copies(self, on: bool = True) -> None:
+        """Keep K-major copies of the frozen LLaMA projections for the backward dX GEMMs (training with a frozen body only:
+        the copies would go stale if the base weights were updated).  Called by training.SftStepper."""
+        if bool(on) != bool(getattr(self, "_bwd_copies", False)):
+            self._bwd_copies = bool(on)
+            self._table = self._table_sig = None
 
     # ------------------------------------------------------------------ LoRA dropout (peft lora.Linear input dropout)
     def lora_dropout_p(self) -> float:

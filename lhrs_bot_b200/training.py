@@ -315,6 +315,13 @@ class SftStepper:
                     b.requires_grad_(True)
         if prepare:
             model.train()      # the reference's trainer does this once before its loop (IterBasedTrainer.py:87): peft's LoRA dropout is live
+        import os as _os
+        body_frozen = not any(p.requires_grad for n, p in model.text.text_encoder.named_parameters() if "lora_" not in n)
+        if body_frozen and model.text.text_encoder.lm_head.weight.is_cuda and _os.environ.get("LHRS_BWD_COPIES", "0") == "1":
+            # K-major dX GEMMs from transposed copies of the frozen projections (+13 GB of HBM for the 7B body).  Off by default:
+            # the dX GEMMs alone get 2.5 % faster (160.6 -> 156.5 ms of GEMM time per step) but the step is power-capped
+            # (sw_power_cap, SM clock ~1.5 of 1.965 GHz) and comes out the same (246.6 vs 246.6 ms, three interleaved runs each).
+            model.text.enable_backward_copies(True)
         # Flat layout: pooler, then every LoRA A factor in [layer][q,k,v,o,gate,up,down] order, then the B factors.  Keeping
         # A_q/A_k/A_v (and A_gate/A_up) back to back makes [A_q;A_k;A_v] one contiguous [3r, in] matrix, which lets the
         # library batch the LoRA side GEMMs of projections that share an input (lora_a_adjacent in csrc/models_fwd.cu).

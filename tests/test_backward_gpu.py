@@ -371,6 +371,42 @@ def test_unibind_backward_lora_grouped_flat_layout():
     _cmp("grouped pooler out_proj.weight", stepper.opt.grad_views[model.rgb_pooler.out_proj.weight], sd["pooler"]["out_proj.weight"].grad, 5e-2)
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("lora_r", [0, 16, 128])
+def test_backward_with_k_major_weight_copies_equals_in_place(lora_r):
+    """LhrsLlamaWeights::*_wt (transposed copies of the frozen projections, TextModal.enable_backward_copies) only change the
+    operand layout of the dX GEMMs: every gradient must agree with the run that reads the [out, in] weights in place."""
+    lora = dict(enable=lora_r > 0, lora_r=max(lora_r, 1), lora_alpha=32, lora_dropout=0.0, lora_bias="none")
+    cfg = small_config(lora=lora, stage=2 if lora_r else 1)
+    model = build_small_model(cfg, DEV, seed=5)
+    model.prepare_for_training(freeze_vision=True, freeze_text=True, tune_rgb_pooler=True, model_path=None,
+                               tune_im_start=False, compute_dtype=torch.bfloat16)
+    for a, b in model.text.lora_pairs():
+        a.requires_grad_(True)
+        b.requires_grad_(True)
+    batch = synthetic_batch(3, 20, cfg.text.vocab_size, DEV, seed=23, text_only=(1,), ragged_mask=True)
+    grads = []
+    for on in (False, True):
+        model.text.enable_backward_copies(on)
+        w = model.text.weights()
+        assert bool(w.lm_head_wt) == on and bool(w.qkv_wt) == on
+        model.zero_grad(set_to_none=True)
+        model(batch)["total_loss"].backward()
+        grads.append({n: p.grad.float().clone() for n, p in model.named_parameters() if p.grad is not None})
+    assert grads[0].keys() == grads[1].keys() and len(grads[0]) > 4
+    for n in grads[0]:
+        a, b = grads[0][n], grads[1][n]
+        assert torch.isfinite(b).all()
+        err = (a - b).abs().max().item() / max(a.abs().max().item(), 1e-20)
+        assert err <= 2e-2, (n, err)      # same products, same K order; the split of K across the LoRA extension may differ
+    # a weight written in place must refresh its copy
+    with torch.no_grad():
+        model.text.text_encoder.lm_head.weight.mul_(0.5)
+    w2 = model.text.weights()
+    lm_t = [t for t in model.text._table[1] if torch.is_tensor(t) and t.data_ptr() == w2.lm_head_wt][0]
+    assert torch.equal(lm_t, model.text.text_encoder.lm_head.weight.t())
+
+
 # ---------------------------------------------------------------------------------------------- LoRA dropout (peft lora.Linear)
 def test_lora_dropout_mask_kernel_matches_oracle():
     """lhrs_lora_dropout_mask (csrc/dropout.cuh) vs the numpy restatement in oracle/llama.py: bit for bit, for several modules,
