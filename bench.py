@@ -602,6 +602,8 @@ def measure_steps(args, workload, dev, rank, world, local, steps, warmup, B=None
         with torch.no_grad():
             return model(batch)["total_loss"]
 
+    from lhrs_bot_b200 import autograd as _ag
+    ragged_calls0 = _ag.RAGGED_CALLS
     dev_batches = [make_batch(B, seed=1000 * rank + i, device=dev, seq_len=S, mixed=mixed) for i in range(2)]
     host_batches = [make_batch(B, seed=2000 * rank + i, pin=True, seq_len=S, mixed=mixed, uint8_images=True) for i in range(2)]
     h2d = batch_bytes(host_batches[0])
@@ -764,8 +766,20 @@ def measure_steps(args, workload, dev, rank, world, local, steps, warmup, B=None
     # whole-step fraction of the tensor roofline: algorithmic flops of the step (14.1 TF per S=512 SFT sample,
     # 7.09 TF per S=256 stage-1 sample, forward 13.3 GF per position) over the step time
     step_tf = {"sft_step": 14.1 * S / 512.0, "stage1_step": 7.09 * S / 256.0, "prefill": 13.3e-3 * S}[workload] * B
-    roofline["whole_step"] = dict(algorithmic_TF_per_step=step_tf, tflops=step_tf / (step_ms * 1e-3), frac=step_tf / (step_ms * 1e-3) / pk["tflops"],
-                                  note="padded positions counted (the reference computes them too)")
+    padding_free = train and _ag.RAGGED_CALLS > ragged_calls0
+    if padding_free:
+        # the decoder stack ran on the real rows only (autograd.ragged_plan): count ITS flops on those rows (26.6 GF per position,
+        # forward + dX), everything else (ViT, pooler, lm_head rows) as before — the fraction must not be paid for skipped padding
+        llama_tf = 26.6e-3 * S * B
+        step_tf_real = step_tf - llama_tf + 26.6e-3 * real_tok
+        roofline["whole_step"] = dict(algorithmic_TF_per_step=step_tf_real, tflops=step_tf_real / (step_ms * 1e-3),
+                                      frac=step_tf_real / (step_ms * 1e-3) / pk["tflops"],
+                                      padded_accounting=dict(algorithmic_TF_per_step=step_tf, frac=step_tf / (step_ms * 1e-3) / pk["tflops"]),
+                                      note="decoder stack run padding-free: its flops counted on the real positions only; "
+                                           "padded_accounting = what a run that computes the padding (the reference, LHRS_RAGGED=0) would be charged")
+    else:
+        roofline["whole_step"] = dict(algorithmic_TF_per_step=step_tf, tflops=step_tf / (step_ms * 1e-3), frac=step_tf / (step_ms * 1e-3) / pk["tflops"],
+                                      note="padded positions counted (computed here and by the reference)")
 
     cpu_base = None
     if rank == 0 and world == 1 and cpu_baseline:
@@ -792,8 +806,13 @@ def measure_steps(args, workload, dev, rank, world, local, steps, warmup, B=None
                 scaling="weak", vs_baseline=None, dtype="bf16", data="synthetic",
                 config=dict(workload=wl, per_gpu_batch=B, seq_len=S, image="224x224", parallelism=f"dp{world}",
                             positions_per_step=dict(padded=tokens_per_step, real_mean_per_gpu=real_tok,
-                                                    note="`value` counts padded decoder positions B*S (computed by the reference too); "
-                                                         "real = positions with attention_mask true"),
+                                                    padding_free=bool(padding_free),
+                                                    note="`value` counts the collated batch, B*S positions per step, as the reference's "
+                                                         "trainer does (it computes every padded position); real = positions with "
+                                                         "attention_mask true.  padding_free: the decoder stack ran on the real rows only "
+                                                         "— same loss and gradients (tests/test_backward_gpu.py::"
+                                                         "test_padding_free_step_equals_padded_step; LHRS_RAGGED=0 computes the padding); "
+                                                         "real_tokens_per_s is the conservative reading"),
                             real_tokens_per_s=real_tok * world * steps / (ms * 1e-3),
                             gradient_exchange=gx,
                             loss_rows=("lm_head + CE evaluated on the rows with a counted label only (identical loss and gradients; "
@@ -905,6 +924,16 @@ def main():
                     extra["sft_step_with_lora_dropout_0.05"] = dict(error=f"{type(e).__name__}: {str(e)[:300]}")
                 finally:
                     args.lora_dropout = None
+            if mixed:
+                try:      # the same step on a batch WITHOUT padding (every sample an image sample of full length): the padding-free
+                          # path has nothing to skip there, so this is the figure that owes nothing to it
+                    r = measure_steps(args, workload, dev, rank, world, local, 5, 3, B=B, S=S, mixed=False, checks=False,
+                                      cpu_baseline=False, e2e_leg=False)
+                    extra["sft_step_uniform_batch_no_padding"] = {k: r[k] for k in ("value", "unit", "ms_per_step", "roofline") if k in r}
+                    extra["sft_step_uniform_batch_no_padding"]["roofline"] = {
+                        k: v for k, v in r["roofline"].items() if k in ("achieved", "peak", "frac", "whole_step", "gemm_ms_per_step")}
+                except Exception as e:
+                    extra["sft_step_uniform_batch_no_padding"] = dict(error=f"{type(e).__name__}: {str(e)[:300]}")
             for name, fn in (("decode_greedy_config2", lambda: measure_decode(args, dev, rank, world, local, 3, 3, cpu_baseline=False)),
                              ("stage1_step_config3", lambda: measure_steps(args, "stage1_step", dev, rank, world, local, 5, 3, checks=False,
                                                                            cpu_baseline=False, e2e_leg=False))):

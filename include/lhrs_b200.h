@@ -126,6 +126,13 @@ typedef struct LhrsAttention {
     int32_t B, H, Sq, Skv, head_dim; /* head_dim 64 or 128 */
     int32_t causal;                  /* query i attends keys <= i + (Skv - Sq) */
     float scale;
+    /* Ragged ("padding-free") batch, optional: device int32 [B+1] row offsets.  Sequence b then occupies rows
+     * [seq_off[b], seq_off[b+1]) of ONE [total_rows, *] buffer per operand (x_bs is ignored, row s of sequence b is row
+     * seq_off[b] + s), its length replaces Sq = Skv for that batch entry, and Sq / Skv become the LONGEST length: they size the
+     * grid and the [B, H, Sq] lse / delta arrays.  Needs head_dim 128, causal, Sq == Skv >= 128, key_mask == NULL (a right-padded
+     * HF attention_mask is exactly what the lengths say).  NULL = dense [B, S] layout. */
+    const int32_t* seq_off;
+    int64_t total_rows;              /* seq_off[B], on the host (tensor maps are built from it) */
 } LhrsAttention;
 
 int lhrs_attention_fwd(const LhrsAttention* a, void* stream);
@@ -304,6 +311,15 @@ size_t lhrs_llama_stash_bytes(const LhrsLlamaWeights* w, int32_t B, int32_t S);
 int lhrs_llama_fwd(const LhrsLlamaWeights* w, const void* inputs_embeds, int32_t B, int32_t S, const uint8_t* key_mask,
                    void* hidden_out, void* stash, const LhrsKvCache* kv_cache, void* workspace, size_t workspace_bytes,
                    void* stream);
+/* The same stack over a RAGGED batch ("padding-free"): the B sequences sit back to back in `rows` = seq_off[B] rows, without
+ * their right padding — HF's LlamaModel under a right-padded attention_mask computes the padded positions and nobody reads them
+ * (text_modal.py:398-412 passes the mask; the shifted CE ignores label -100, modeling_llama's causal mask keeps padded keys out
+ * of every real query row), so every result on a real position is the same.  seq_off: device int32 [B+1]; positions: device
+ * int32 [rows], each row's index inside its sequence (RoPE); S_max: the longest length (>= 128: tcgen05 attention only).
+ * inputs_embeds / hidden_out are [rows, dim].  Workspace and stash are sized by the dense functions with (B, S_max). */
+int lhrs_llama_fwd_ragged(const LhrsLlamaWeights* w, const void* inputs_embeds, int32_t B, int32_t S_max, int64_t rows,
+                          const int32_t* seq_off, const int32_t* positions, void* hidden_out, void* stash, void* workspace,
+                          size_t workspace_bytes, void* stream);
 /* logits = hidden · lm_head^T (bf16 [rows, vocab]) */
 int lhrs_lm_head(const LhrsLlamaWeights* w, const void* hidden, int64_t rows, void* logits, void* stream);
 
@@ -366,6 +382,10 @@ size_t lhrs_llama_bwd_workspace_bytes(const LhrsLlamaWeights* w, int32_t B, int3
 int lhrs_llama_bwd(const LhrsLlamaWeights* w, void* const* lora_a_grads, void* const* lora_b_grads, const void* d_hidden,
                    int32_t B, int32_t S, const uint8_t* key_mask, const void* stash, void* d_inputs_embeds, void* workspace,
                    size_t workspace_bytes, void* stream);
+/* backward of lhrs_llama_fwd_ragged: d_hidden / d_inputs_embeds are [rows, dim]; workspace of lhrs_llama_bwd_workspace_bytes(B, S_max) */
+int lhrs_llama_bwd_ragged(const LhrsLlamaWeights* w, void* const* lora_a_grads, void* const* lora_b_grads, const void* d_hidden,
+                          int32_t B, int32_t S_max, int64_t rows, const int32_t* seq_off, const void* stash, void* d_inputs_embeds,
+                          void* workspace, size_t workspace_bytes, void* stream);
 int lhrs_lm_head_bwd(const LhrsLlamaWeights* w, const void* d_logits, int64_t rows, void* d_hidden, void* stream);
 
 /* Full backward of the AttnPooler.  `grads` has the layout of the weight table; each pointer is the bf16 DESTINATION of

@@ -45,6 +45,7 @@ class LhrsAttention(C.Structure):
         ("o_bs", C.c_int64), ("o_rs", C.c_int64), ("o_hs", C.c_int64),
         ("B", C.c_int32), ("H", C.c_int32), ("Sq", C.c_int32), ("Skv", C.c_int32), ("head_dim", C.c_int32),
         ("causal", C.c_int32), ("scale", C.c_float),
+        ("seq_off", C.c_void_p), ("total_rows", C.c_int64),
     ]
 
 
@@ -162,6 +163,7 @@ SIGNATURES = {
     "lhrs_llama_workspace_bytes": (C.c_size_t, [C.POINTER(LhrsLlamaWeights), _I32, _I32]),
     "lhrs_llama_stash_bytes": (C.c_size_t, [C.POINTER(LhrsLlamaWeights), _I32, _I32]),
     "lhrs_llama_fwd": (C.c_int, [C.POINTER(LhrsLlamaWeights), _P, _I32, _I32, _P, _P, _P, C.POINTER(LhrsKvCache), _P, C.c_size_t, _P]),
+    "lhrs_llama_fwd_ragged": (C.c_int, [C.POINTER(LhrsLlamaWeights), _P, _I32, _I32, _I64, _P, _P, _P, _P, _P, C.c_size_t, _P]),
     "lhrs_lm_head": (C.c_int, [C.POINTER(LhrsLlamaWeights), _P, _I64, _P, _P]),
     "lhrs_llama_first_token": (C.c_int, [C.POINTER(LhrsLlamaWeights), _P, _I32, C.POINTER(LhrsDecodeBuffers), _I32, _P]),
     "lhrs_llama_decode_step": (C.c_int, [C.POINTER(LhrsLlamaWeights), C.POINTER(LhrsKvCache), C.POINTER(LhrsDecodeBuffers), _I32, _I32, _P]),
@@ -193,6 +195,7 @@ SIGNATURES = {
     "lhrs_lora_rowreduce": (C.c_int, [_P, _I64, _I64, _I32, _P, _I64, _I32, _I32, _I32, _PP, _I64, _F, _P, C.c_size_t, _P]),
     "lhrs_llama_bwd_workspace_bytes": (C.c_size_t, [C.POINTER(LhrsLlamaWeights), _I32, _I32]),
     "lhrs_llama_bwd": (C.c_int, [C.POINTER(LhrsLlamaWeights), _PP, _PP, _P, _I32, _I32, _P, _P, _P, _P, C.c_size_t, _P]),
+    "lhrs_llama_bwd_ragged": (C.c_int, [C.POINTER(LhrsLlamaWeights), _PP, _PP, _P, _I32, _I32, _I64, _P, _P, _P, _P, C.c_size_t, _P]),
     "lhrs_lm_head_bwd": (C.c_int, [C.POINTER(LhrsLlamaWeights), _P, _I64, _P, _P]),
     "lhrs_pooler_bwd_workspace_bytes": (C.c_size_t, [C.POINTER(LhrsPoolerWeights), _I32]),
     "lhrs_pooler_bwd": (C.c_int, [C.POINTER(LhrsPoolerWeights), C.POINTER(LhrsPoolerWeights), _P, _I64, _I32, _P, _P, _P, C.c_size_t, _P]),

@@ -82,6 +82,49 @@ def supervised_rows(new_labels: torch.Tensor):
     return rows, lab
 
 
+RAGGED_CALLS = 0     # training forwards that ran padding-free (read by bench.py for its accounting)
+
+
+class RaggedPlan:
+    """Row bookkeeping of a padding-free ("ragged") training batch: which rows of the right-padded (B, S) layout are real."""
+
+    def __init__(self, B, s_max, rows, seq_off, positions, real_rows, packed_of):
+        self.B, self.s_max, self.rows = B, s_max, rows
+        self.seq_off, self.positions = seq_off, positions        # int32 [B+1], int32 [rows]           (device)
+        self.real_rows, self.packed_of = real_rows, packed_of    # int64 [rows] padded row of each packed row; int64 [B*S] inverse (-1 = padding)
+
+
+def ragged_plan(new_mask: Optional[torch.Tensor], min_saving: float = 0.03) -> Optional[RaggedPlan]:
+    """Decide whether the spliced batch runs padding-free (LHRS_RAGGED=0 turns it off).
+
+    The reference pads every sample to the longest one (DataCollatorForSupervisedDataset, cap_dataset.py:792-810; the splice pads
+    again, text_modal.py:440-505) and HF's LlamaModel then computes all B*S positions.  Under a RIGHT-padded mask the padded
+    positions feed nothing that is read: causal attention keeps them out of every real query row, the shifted CE ignores their
+    label (-100), and their gradient rows are zero.  So the decoder stack only needs the real rows — same loss, same gradients,
+    fewer GEMM rows.  Needs: a mask whose rows are prefixes of ones, longest sequence >= 128 (tcgen05 attention), no empty sample,
+    and at least `min_saving` of the rows being padding.  One small D2H read (the lengths)."""
+    import os
+    if new_mask is None or os.environ.get("LHRS_RAGGED", "1") == "0":
+        return None
+    B, S = new_mask.shape
+    m = new_mask.to(torch.int32)
+    lens = m.sum(1)
+    prefix = (m[:, :-1] >= m[:, 1:]).all().to(torch.int32).reshape(1) if S > 1 else torch.ones(1, dtype=torch.int32, device=m.device)
+    host = torch.cat([lens.to(torch.int32), prefix]).tolist()            # synchronises
+    lens_h, is_prefix = host[:B], bool(host[B])
+    rows, s_max = sum(lens_h), max(lens_h)
+    if not is_prefix or min(lens_h) < 1 or s_max < 128 or rows > (1.0 - min_saving) * B * S:
+        return None
+    dev = new_mask.device
+    real_rows = m.reshape(-1).nonzero().squeeze(1)                       # (row count already known: == rows)
+    positions = (real_rows % S).to(torch.int32)
+    seq_off = torch.zeros(B + 1, dtype=torch.int32, device=dev)
+    seq_off[1:] = torch.cumsum(lens, 0).to(torch.int32)
+    packed_of = torch.full((B * S,), -1, dtype=torch.int64, device=dev)
+    packed_of[real_rows] = torch.arange(rows, device=dev)
+    return RaggedPlan(B, s_max, rows, seq_off, positions, real_rows, packed_of)
+
+
 class LlamaLossFunction(torch.autograd.Function):
     """splice -> LLaMA stack -> lm_head -> shifted CE, and its backward down to the image features / LoRA factors.
 
@@ -101,16 +144,29 @@ class LlamaLossFunction(torch.autograd.Function):
         if p_drop > 0.0:
             ctx.drop = (p_drop, text.next_lora_dropout_seed())
         w.lora_dropout, w.lora_seed = ctx.drop
+        # host-side decisions first (supervised rows, padding-free layout): their small D2H reads then wait for the splice only,
+        # not for the decoder stack
+        sel = supervised_rows(new_labels)
+        # (the dropout masks are keyed by the row index of the padded layout — dropout.cuh — so a dropout step keeps that layout)
+        plan = ragged_plan(new_mask) if (sel is not None and p_drop <= 0.0) else None
+        ctx.plan = plan
         try:
-            hidden = text.llama_forward(embeds, new_mask, stash=stash)
+            if plan is not None:
+                global RAGGED_CALLS
+                RAGGED_CALLS += 1
+                rows_in = embeds.view(B * S, D).index_select(0, plan.real_rows)
+                hidden = text.llama_forward_ragged(rows_in, B, plan.s_max, plan.seq_off, plan.positions, stash=stash)
+            else:
+                hidden = text.llama_forward(embeds, new_mask, stash=stash)
         finally:
             w.lora_dropout, w.lora_seed = 0.0, 0
-        sel = supervised_rows(new_labels)
         ctx.rows = None
         if sel is not None:      # lm_head + CE over the supervised rows only (identical loss and gradients)
             rows, ce_labels = sel
+            if plan is not None:
+                rows = plan.packed_of.index_select(0, rows)     # supervised rows are real positions: never -1
             hc = torch.zeros((rows.numel() + 1, D), device=hidden.device, dtype=hidden.dtype)
-            hc[:-1] = hidden.view(B * S, D).index_select(0, rows)
+            hc[:-1] = hidden.view(-1, D).index_select(0, rows)
             logits = text.lm_head(hc).unsqueeze(0)
             ctx.rows = rows
         else:
@@ -139,7 +195,8 @@ class LlamaLossFunction(torch.autograd.Function):
             nr = ctx.rows.numel() + 1
             dhc = torch.empty((nr, D), device=dev, dtype=torch.bfloat16)
             check(lib.lhrs_lm_head_bwd(C.byref(w), d_logits.data_ptr(), nr, dhc.data_ptr(), runtime.stream()), "lhrs_lm_head_bwd")
-            d_hidden = torch.zeros((B * S, D), device=dev, dtype=torch.bfloat16)
+            plan = ctx.plan
+            d_hidden = torch.zeros((B * S if plan is None else plan.rows, D), device=dev, dtype=torch.bfloat16)
             d_hidden.index_copy_(0, ctx.rows, dhc[:-1])
         else:
             d_hidden = torch.empty((B * S, D), device=dev, dtype=torch.bfloat16)
@@ -164,14 +221,27 @@ class LlamaLossFunction(torch.autograd.Function):
             pa, pb = runtime.PtrArray(a_list), runtime.PtrArray(b_list)
             keep += [pa, pb, a_list, b_list]
             ga, gb = pa.ptr(), pb.ptr()
-        d_embeds = torch.empty((B, S, D), device=dev, dtype=torch.bfloat16)
+        plan = ctx.plan
         w.lora_dropout, w.lora_seed = ctx.drop          # the forward's masks
         try:
-            ws_bytes = lib.lhrs_llama_bwd_workspace_bytes(C.byref(w), B, S)
-            ws = runtime.workspace(ws_bytes, dev, "bwd")
-            check(lib.lhrs_llama_bwd(C.byref(w), ga, gb, d_hidden.data_ptr(), B, S, None if ctx.km is None else ctx.km.data_ptr(),
-                                     ctx.stash.data_ptr(), d_embeds.data_ptr(), ws.data_ptr(), ws.numel(), runtime.stream()),
-                  "lhrs_llama_bwd")
+            if plan is not None:
+                d_rows = torch.empty((plan.rows, D), device=dev, dtype=torch.bfloat16)
+                ws_bytes = lib.lhrs_llama_bwd_workspace_bytes(C.byref(w), B, plan.s_max)
+                ws = runtime.workspace(ws_bytes, dev, "bwd")
+                check(lib.lhrs_llama_bwd_ragged(C.byref(w), ga, gb, d_hidden.data_ptr(), B, plan.s_max, plan.rows, plan.seq_off.data_ptr(),
+                                                ctx.stash.data_ptr(), d_rows.data_ptr(), ws.data_ptr(), ws.numel(), runtime.stream()),
+                      "lhrs_llama_bwd_ragged")
+                d_embeds = None
+                if ctx.need_img:                        # back to the padded row numbering the splice map uses
+                    d_embeds = torch.zeros((B * S, D), device=dev, dtype=torch.bfloat16)
+                    d_embeds.index_copy_(0, plan.real_rows, d_rows)
+            else:
+                d_embeds = torch.empty((B, S, D), device=dev, dtype=torch.bfloat16)
+                ws_bytes = lib.lhrs_llama_bwd_workspace_bytes(C.byref(w), B, S)
+                ws = runtime.workspace(ws_bytes, dev, "bwd")
+                check(lib.lhrs_llama_bwd(C.byref(w), ga, gb, d_hidden.data_ptr(), B, S, None if ctx.km is None else ctx.km.data_ptr(),
+                                         ctx.stash.data_ptr(), d_embeds.data_ptr(), ws.data_ptr(), ws.numel(), runtime.stream()),
+                      "lhrs_llama_bwd")
         finally:
             w.lora_dropout, w.lora_seed = 0.0, 0
         d_img = None

@@ -314,6 +314,10 @@ extern "C" int lhrs_attention_fwd(const LhrsAttention* d, void* stream_) {
     LHRS_CHECK_ARG(d->B > 0 && d->H > 0 && d->Sq > 0 && d->Skv > 0, "lhrs_attention_fwd: empty problem");
     const long long strides[] = {d->q_bs, d->q_rs, d->q_hs, d->k_bs, d->k_rs, d->k_hs, d->v_bs, d->v_rs, d->v_hs, d->o_rs, d->o_hs, d->o_bs};
     for (long long s : strides) LHRS_CHECK_ARG((s % 8) == 0, "lhrs_attention_fwd: strides must be multiples of 8 elements");
+    if (d->seq_off != nullptr)   // ragged batch: tcgen05 kernel only
+        LHRS_CHECK_ARG(d->head_dim == 128 && d->causal && d->Sq == d->Skv && d->Sq >= 128 && d->key_mask == nullptr &&
+                           d->total_rows > 0 && d->total_rows < (1ll << 31) && use_tc_attention(),
+                       "lhrs_attention_fwd: seq_off needs head_dim 128, causal, Sq == Skv >= 128, no key_mask, total_rows (and LHRS_ATTN_TC on)");
     // head_dim 128 with at least one full 128-row query tile runs on the tcgen05 kernel (attention_tc.cu)
     if (d->head_dim == 128 && d->Sq >= 128 && use_tc_attention()) return attention_fwd_tc(d, stream);
     AttnArgsG G;
@@ -344,7 +348,7 @@ extern "C" int lhrs_attention_fwd_grouped(const LhrsAttention* d, int32_t n, voi
     bool same = true;
     for (int i = 0; i < n; ++i) {
         LHRS_CHECK_ARG(d[i].q && d[i].k && d[i].v && d[i].o && d[i].B > 0 && d[i].H > 0 && d[i].Sq > 0 && d[i].Skv > 0, "lhrs_attention_fwd_grouped: null/empty problem %d", i);
-        same = same && d[i].B == d[0].B && d[i].H == d[0].H && d[i].head_dim == 64 && d[i].causal == d[0].causal;
+        same = same && d[i].B == d[0].B && d[i].H == d[0].H && d[i].head_dim == 64 && d[i].causal == d[0].causal && d[i].seq_off == nullptr;
         const long long strides[] = {d[i].q_bs, d[i].q_rs, d[i].q_hs, d[i].k_bs, d[i].k_rs, d[i].k_hs, d[i].v_bs, d[i].v_rs, d[i].v_hs, d[i].o_rs, d[i].o_hs, d[i].o_bs};
         for (long long s : strides) LHRS_CHECK_ARG((s % 8) == 0, "lhrs_attention_fwd_grouped: strides must be multiples of 8 elements");
     }

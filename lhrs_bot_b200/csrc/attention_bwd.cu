@@ -89,9 +89,15 @@ __global__ void __launch_bounds__(256) attn_delta_kernel(const AttnBwdArgsG G) {
     if (static_cast<int>(blockIdx.x) >= p.Sq) return;
     const int s = blockIdx.x, b = static_cast<int>(blockIdx.y) - gi * p.B;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    long long row = s;                                   // ragged batch: row s of sequence b is row seq_off[b] + s (o_bs is 0)
+    if (p.seq_off != nullptr) {
+        const int rb = p.seq_off[b];
+        if (s >= p.seq_off[b + 1] - rb) return;
+        row += rb;
+    }
     for (int h = warp; h < p.H; h += 8) {
-        const __nv_bfloat16* o = p.o + b * p.o_bs + static_cast<long long>(s) * p.o_rs + h * p.o_hs;
-        const __nv_bfloat16* d = p.d_o + b * p.o_bs + static_cast<long long>(s) * p.o_rs + h * p.o_hs;
+        const __nv_bfloat16* o = p.o + b * p.o_bs + row * p.o_rs + h * p.o_hs;
+        const __nv_bfloat16* d = p.d_o + b * p.o_bs + row * p.o_rs + h * p.o_hs;
         float acc = 0.f;
 #pragma unroll
         for (int i = 0; i < HD / 64; ++i) {
@@ -429,9 +435,17 @@ static int launch_bwd(const AttnBwdArgsG& G, cudaStream_t stream) {
     if (G.n == 1 && HD == 128 && a.Sq >= 128 && a.Skv >= 128 && tma_ok && use_tc_attention()) {   // tcgen05 dQ and dK/dV kernels
         const char* pe = getenv("LHRS_ATTN_BWD_PERSIST");   // 0: one CTA per tile (attention_bwd_tc.cu); read per call for A/B runs
         const bool persist = (pe == nullptr || atoi(pe) != 0) && attention_bwd_tcp_ok(a) && (a.kmask == nullptr || a.kbits != nullptr);
+        if (a.seq_off != nullptr && !persist) {
+            set_error("lhrs_attention_bwd: a ragged batch (seq_off) runs on the persistent tcgen05 kernels only");
+            return LHRS_ERR_INVALID;
+        }
         const int rc = persist ? attention_bwd_tcp(a, CAUSAL, stream) : attention_bwd_tc(a, CAUSAL, stream);
         if (prof) prof_end(stream);
         return rc;
+    }
+    if (a.seq_off != nullptr) {
+        set_error("lhrs_attention_bwd: a ragged batch (seq_off) needs the tcgen05 path (head_dim 128, Sq >= 128, 8-element strides)");
+        return LHRS_ERR_INVALID;
     }
     kq<<<dim3((max_sq + 63) / 64, a.H, a.B * G.n), 128, SMEM_DQ, stream>>>(G);
     LHRS_LAUNCH_CHECK("attn_bwd_dq_kernel");
@@ -473,6 +487,13 @@ static int fill_bwd_args(const LhrsAttentionBwd* d, AttnBwdArgs& a) {
     a.B = f->B; a.H = f->H; a.Sq = f->Sq; a.Skv = f->Skv;
     a.scale = f->scale; a.scale_log2 = f->scale * 1.4426950408889634f;
     a.rope_cos = d->rope_cos; a.rope_sin = d->rope_sin;
+    a.seq_off = f->seq_off; a.total_rows = f->total_rows;
+    if (a.seq_off != nullptr) {
+        LHRS_CHECK_ARG(f->head_dim == 128 && f->causal && f->Sq == f->Skv && f->Sq >= 128 && f->key_mask == nullptr && f->total_rows > 0 &&
+                           f->total_rows < (1ll << 31),
+                       "lhrs_attention_bwd: seq_off needs head_dim 128, causal, Sq == Skv >= 128, no key_mask, total_rows");
+        a.q_bs = a.k_bs = a.v_bs = a.o_bs = a.dq_bs = a.dk_bs = a.dv_bs = 0;     // one row space for the whole batch
+    }
     LHRS_CHECK_ARG(a.rope_cos == nullptr || (f->head_dim == 128 && a.rope_sin != nullptr && f->Sq == f->Skv),
                    "lhrs_attention_bwd: fused un-RoPE needs head_dim 128, both tables and Sq == Skv");
     return LHRS_OK;

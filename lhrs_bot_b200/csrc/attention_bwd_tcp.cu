@@ -132,14 +132,19 @@ attn_bwd_dq_tcp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
     const int G = static_cast<int>(gridDim.x);
 
     // item -> geometry; n = number of 64-key steps (0: the tile sees no key)
-    auto item = [&](int w, int& b, int& h, int& q0, int& n) -> bool {
+    // ragged batch (p.seq_off): the sequence's rows start at row rb of the one row space every operand lives in, and there are
+    // lq = lk of them; rows past the end are the next sequence's (finite) values — the length masks keep them out of every sum
+    auto item = [&](int w, int& b, int& h, int& q0, int& n, int& rb, int& lq, int& lk) -> bool {
         int t;
         if (!sched_item(sc, w, b, h, t)) return false;
         q0 = t * 128;
-        const int kv_end = CAUSAL ? min(p.Skv, q0 + 128 + off) : p.Skv;
-        n = kv_end > 0 ? (kv_end + 63) / 64 : 0;
+        rb = 0; lq = p.Sq; lk = p.Skv;
+        if (p.seq_off != nullptr) { rb = p.seq_off[b]; lq = lk = p.seq_off[b + 1] - rb; }
+        const int kv_end = CAUSAL ? min(lk, q0 + 128 + off) : lk;
+        n = (kv_end > 0 && q0 < lq) ? (kv_end + 63) / 64 : 0;
         return true;
     };
+    const bool ragged = p.seq_off != nullptr;
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmDO); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV);
@@ -172,10 +177,10 @@ attn_bwd_dq_tcp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
             int it = 0;
             uint32_t g = 0;
             for (int w = blockIdx.x; w < sc.total; w += G) {
-                int b, h, q0, n;
-                if (!item(w, b, h, q0, n) || n == 0) continue;
+                int b, h, q0, n, rb, lq, lk;
+                if (!item(w, b, h, q0, n, rb, lq, lk) || n == 0) continue;
                 auto load = [&](void* dst, const CUtensorMap* tm, uint64_t* bar, int d0, int r0, int hfirst) {
-                    tma_load_4d(dst, tm, bar, d0, hfirst ? h : r0, hfirst ? r0 : h, b);
+                    tma_load_4d(dst, tm, bar, d0, hfirst ? h : r0 + rb, hfirst ? r0 + rb : h, ragged ? 0 : b);
                 };
                 auto load_kv = [&](int j) {
                     const uint32_t st = g % NKV;
@@ -224,8 +229,8 @@ attn_bwd_dq_tcp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
         int it = 0;
         uint32_t g = 0;
         for (int w = blockIdx.x; w < sc.total; w += G) {
-            int b, h, q0, n;
-            if (!item(w, b, h, q0, n) || n == 0) continue;
+            int b, h, q0, n, rb, lq, lk;
+            if (!item(w, b, h, q0, n, rb, lq, lk) || n == 0) continue;
             mbar_wait(qdo_full, it & 1);
             for (int j = 0; j < n; ++j, ++g) {
                 const uint32_t st = g % NKV, ab = g & 1;
@@ -262,8 +267,8 @@ attn_bwd_dq_tcp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
         int it = 0;
         uint32_t g = 0;
         for (int w = blockIdx.x; w < sc.total; w += G) {
-            int b, h, q0, n;
-            if (!item(w, b, h, q0, n) || n == 0) continue;
+            int b, h, q0, n, rb, lq, lk;
+            if (!item(w, b, h, q0, n, rb, lq, lk) || n == 0) continue;
             const uint32_t buf = it & 1;
             mbar_wait(&dq_empty[buf], ((it >> 1) & 1) ^ 1);       // the epilogue warps have drained this accumulator
             for (int j = 0; j < n; ++j, ++g) {
@@ -308,10 +313,10 @@ attn_bwd_dq_tcp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
         // otherwise sit at the head of every item, three times in a row (measured: 5500 cycles per item)
         auto prefetch_item = [&](int w0) {
             for (int w = w0; w < sc.total; w += G) {
-                int b, h, q0, n;
-                if (!item(w, b, h, q0, n) || n == 0) continue;
+                int b, h, q0, n, rb, lq, lk;
+                if (!item(w, b, h, q0, n, rb, lq, lk) || n == 0) continue;
                 const int qi = q0 + row;
-                if (qi < p.Sq) {
+                if (qi < lq) {
                     const long long si = (static_cast<long long>(b) * p.H + h) * p.Sq + qi;
                     prefetch_l1(p.lse + si);
                     prefetch_l1(p.delta + si);
@@ -322,13 +327,13 @@ attn_bwd_dq_tcp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
         };
         prefetch_item(blockIdx.x);
         for (int w = blockIdx.x; w < sc.total; w += G) {
-            int b, h, q0, n;
-            if (!item(w, b, h, q0, n) || n == 0) continue;
+            int b, h, q0, n, rb, lq, lk;
+            if (!item(w, b, h, q0, n, rb, lq, lk) || n == 0) continue;
             TRACE(20, g);
             const int qi = q0 + row;
             const int row_lim = CAUSAL ? qi + off : 0x7fffffff;
             float lse2 = INFINITY, dl = 0.f;              // +inf: exp2(s*c - inf) = 0 for padded / fully-masked query rows
-            if (qi < p.Sq) {
+            if (qi < lq) {
                 const long long si = (static_cast<long long>(b) * p.H + h) * p.Sq + qi;
                 const float l = p.lse[si];
                 if (l != -INFINITY) lse2 = l * 1.4426950408889634f;
@@ -363,8 +368,8 @@ attn_bwd_dq_tcp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
                         mbar_arrive(&sdp_empty[st]);
                     }
                     uint32_t wm = half ? kw.y : kw.x;
-                    if (kb == nullptr && kc + 32 > p.Skv) {
-                        const int v = p.Skv - kc;
+                    if (kb == nullptr && kc + 32 > lk) {
+                        const int v = lk - kc;
                         wm = v <= 0 ? 0u : ((1u << v) - 1u);
                     }
                     if (CAUSAL) {
@@ -403,11 +408,11 @@ attn_bwd_dq_tcp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
         long long* tr_ = g_attn_trace + 3 * 8192; int tr_n_ = 0; const bool tr_on_ = false;   // (role 3 is MMA issuer B)
 #endif
         for (int w = blockIdx.x; w < sc.total; w += G) {
-            int b, h, q0, n;
-            if (!item(w, b, h, q0, n)) continue;
+            int b, h, q0, n, rb, lq, lk;
+            if (!item(w, b, h, q0, n, rb, lq, lk)) continue;
             const int qi = q0 + row;
-            const bool ok = qi < p.Sq;
-            __nv_bfloat16* dst = p.dq + b * p.dq_bs + h * p.dq_hs + static_cast<long long>(qi) * p.dq_rs;
+            const bool ok = qi < lq;
+            __nv_bfloat16* dst = p.dq + b * p.dq_bs + h * p.dq_hs + static_cast<long long>(rb + qi) * p.dq_rs;
             if (n == 0) {                                  // no key visible from this tile: the gradient is zero
                 store_grad_row(0u, 0, 0.f, nullptr, nullptr, qi, dst, ok, false);
                 store_grad_row(0u, 1, 0.f, nullptr, nullptr, qi, dst, ok, false);
@@ -483,15 +488,19 @@ attn_bwd_dkv_tcp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
     const int G = static_cast<int>(gridDim.x);
 
     // item -> geometry; the item's query steps are i_begin .. i_begin + n - 1 (64 rows each)
-    auto item = [&](int w, int& b, int& h, int& k0, int& i_begin, int& n) -> bool {
+    auto item = [&](int w, int& b, int& h, int& k0, int& i_begin, int& n, int& rb, int& lq, int& lk) -> bool {
         int t;
         if (!sched_item(sc, w, b, h, t)) return false;
         k0 = t * 128;
+        rb = 0; lq = p.Sq; lk = p.Skv;
+        int nq_b = nq;
+        if (p.seq_off != nullptr) { rb = p.seq_off[b]; lq = lk = p.seq_off[b + 1] - rb; nq_b = (lq + 63) / 64; }   // (see the dQ kernel)
         i_begin = 0;
         if (CAUSAL) i_begin = max(0, k0 - off) / 64;      // first query step with a row that can see key k0
-        n = max(0, nq - i_begin);
+        n = k0 < lk ? max(0, nq_b - i_begin) : 0;
         return true;
     };
+    const bool ragged = p.seq_off != nullptr;
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmDO); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV);
@@ -526,10 +535,10 @@ attn_bwd_dkv_tcp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
             int it = 0;
             uint32_t g = 0;
             for (int w = blockIdx.x; w < sc.total; w += G) {
-                int b, h, k0, i_begin, n;
-                if (!item(w, b, h, k0, i_begin, n) || n == 0) continue;
+                int b, h, k0, i_begin, n, rb, lq, lk;
+                if (!item(w, b, h, k0, i_begin, n, rb, lq, lk) || n == 0) continue;
                 auto load = [&](void* dst, const CUtensorMap* tm, uint64_t* bar, int d0, int r0, int hfirst) {
-                    tma_load_4d(dst, tm, bar, d0, hfirst ? h : r0, hfirst ? r0 : h, b);
+                    tma_load_4d(dst, tm, bar, d0, hfirst ? h : r0 + rb, hfirst ? r0 + rb : h, ragged ? 0 : b);
                 };
                 auto load_qdo = [&](int t) {
                     const uint32_t st = g % NST;
@@ -569,8 +578,8 @@ attn_bwd_dkv_tcp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
         int it = 0;
         uint32_t g = 0;
         for (int w = blockIdx.x; w < sc.total; w += G) {
-            int b, h, k0, i_begin, n;
-            if (!item(w, b, h, k0, i_begin, n) || n == 0) continue;
+            int b, h, k0, i_begin, n, rb, lq, lk;
+            if (!item(w, b, h, k0, i_begin, n, rb, lq, lk) || n == 0) continue;
             mbar_wait(kv_full, it & 1);
             for (int t = 0; t < n; ++t, ++g) {
                 const uint32_t st = g % NST, ab = g & 1;
@@ -603,8 +612,8 @@ attn_bwd_dkv_tcp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
         int it = 0;
         uint32_t g = 0;
         for (int w = blockIdx.x; w < sc.total; w += G) {
-            int b, h, k0, i_begin, n;
-            if (!item(w, b, h, k0, i_begin, n) || n == 0) continue;
+            int b, h, k0, i_begin, n, rb, lq, lk;
+            if (!item(w, b, h, k0, i_begin, n, rb, lq, lk) || n == 0) continue;
             mbar_wait(acc_empty, (it & 1) ^ 1);                   // dV / dK of the previous item have been drained
             for (int t = 0; t < n; ++t, ++g) {
                 const uint32_t st = g % NST, pb = g & 1;
@@ -643,24 +652,24 @@ attn_bwd_dkv_tcp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
         int it = 0;
         auto prefetch_item = [&](int w0) {
             for (int w = w0; w < sc.total; w += G) {
-                int b, h, k0, i_begin, n;
-                if (!item(w, b, h, k0, i_begin, n) || n == 0) continue;
+                int b, h, k0, i_begin, n, rb, lq, lk;
+                if (!item(w, b, h, k0, i_begin, n, rb, lq, lk) || n == 0) continue;
                 const int kj = k0 + row;
                 if (p.kmask != nullptr && kj < p.Skv) prefetch_l1(p.kmask + static_cast<long long>(b) * p.Skv + kj);
                 const long long stat_base = (static_cast<long long>(b) * p.H + h) * p.Sq;
                 const int qr = i_begin * 64 + gt;          // the first two steps' statistics (128 consecutive rows)
-                if (qr < p.Sq) { prefetch_l1(p.lse + stat_base + qr); prefetch_l1(p.delta + stat_base + qr); }
+                if (qr < lq) { prefetch_l1(p.lse + stat_base + qr); prefetch_l1(p.delta + stat_base + qr); }
                 return;
             }
         };
         prefetch_item(blockIdx.x);
         for (int w = blockIdx.x; w < sc.total; w += G) {
-            int b, h, k0, i_begin, n;
-            if (!item(w, b, h, k0, i_begin, n)) continue;
+            int b, h, k0, i_begin, n, rb, lq, lk;
+            if (!item(w, b, h, k0, i_begin, n, rb, lq, lk)) continue;
             const int kj = k0 + row;                          // this thread's key
-            const bool ok = kj < p.Skv;
-            __nv_bfloat16* dvp = p.dv + b * p.dv_bs + h * p.dv_hs + static_cast<long long>(kj) * p.dv_rs;
-            __nv_bfloat16* dkp = p.dk + b * p.dk_bs + h * p.dk_hs + static_cast<long long>(kj) * p.dk_rs;
+            const bool ok = kj < lk;
+            __nv_bfloat16* dvp = p.dv + b * p.dv_bs + h * p.dv_hs + static_cast<long long>(rb + kj) * p.dv_rs;
+            __nv_bfloat16* dkp = p.dk + b * p.dk_bs + h * p.dk_hs + static_cast<long long>(rb + kj) * p.dk_rs;
             if (n == 0) {                                     // no query sees this key tile: zero gradients
                 store_grad_row(0u, grp, 0.f, nullptr, nullptr, kj, dvp, ok, false);
                 store_grad_row(0u, grp, 0.f, nullptr, nullptr, kj, dkp, ok, false);
@@ -674,11 +683,11 @@ attn_bwd_dkv_tcp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
                 const int qr = (i_begin + t) * 64 + (gt & 63);
                 if (t >= n) return 0.f;
                 if (gt < 64) {
-                    if (qr >= p.Sq) return INFINITY;
+                    if (qr >= lq) return INFINITY;
                     const float l = p.lse[stat_base + qr];
                     return l == -INFINITY ? INFINITY : l * 1.4426950408889634f;
                 }
-                return qr < p.Sq ? p.delta[stat_base + qr] : 0.f;
+                return qr < lq ? p.delta[stat_base + qr] : 0.f;
             };
             // this group's first step of the item: local index t0 with (g + t0) & 1 == grp
             const int t0 = ((g & 1u) == static_cast<uint32_t>(grp)) ? 0 : 1;
@@ -777,14 +786,16 @@ static int launch_bwd_tcp(const AttnBwdArgs& a, cudaStream_t stream) {
     pa.a = a;
     CUtensorMap q128, do128, k64, v64, q64, do64, k128, v128;
     int rc, f;
-    if ((rc = make_tmap_bshd(&q128, &pa.q_hfirst, a.q, 128, a.Sq, a.H, a.B, a.q_rs, a.q_hs, a.q_bs, 128))) return rc;
-    if ((rc = make_tmap_bshd(&do128, &pa.o_hfirst, a.d_o, 128, a.Sq, a.H, a.B, a.o_rs, a.o_hs, a.o_bs, 128))) return rc;
-    if ((rc = make_tmap_bshd(&k64, &pa.k_hfirst, a.k, 128, a.Skv, a.H, a.B, a.k_rs, a.k_hs, a.k_bs, 64))) return rc;
-    if ((rc = make_tmap_bshd(&v64, &pa.v_hfirst, a.v, 128, a.Skv, a.H, a.B, a.v_rs, a.v_hs, a.v_bs, 64))) return rc;
-    if ((rc = make_tmap_bshd(&q64, &f, a.q, 128, a.Sq, a.H, a.B, a.q_rs, a.q_hs, a.q_bs, 64))) return rc;
-    if ((rc = make_tmap_bshd(&do64, &f, a.d_o, 128, a.Sq, a.H, a.B, a.o_rs, a.o_hs, a.o_bs, 64))) return rc;
-    if ((rc = make_tmap_bshd(&k128, &f, a.k, 128, a.Skv, a.H, a.B, a.k_rs, a.k_hs, a.k_bs, 128))) return rc;
-    if ((rc = make_tmap_bshd(&v128, &f, a.v, 128, a.Skv, a.H, a.B, a.v_rs, a.v_hs, a.v_bs, 128))) return rc;
+    const bool ragged = a.seq_off != nullptr;       // one row space for the whole batch: a single batch entry of total_rows rows
+    const int mB = ragged ? 1 : a.B, mSq = ragged ? (int)a.total_rows : a.Sq, mSkv = ragged ? (int)a.total_rows : a.Skv;
+    if ((rc = make_tmap_bshd(&q128, &pa.q_hfirst, a.q, 128, mSq, a.H, mB, a.q_rs, a.q_hs, a.q_bs, 128))) return rc;
+    if ((rc = make_tmap_bshd(&do128, &pa.o_hfirst, a.d_o, 128, mSq, a.H, mB, a.o_rs, a.o_hs, a.o_bs, 128))) return rc;
+    if ((rc = make_tmap_bshd(&k64, &pa.k_hfirst, a.k, 128, mSkv, a.H, mB, a.k_rs, a.k_hs, a.k_bs, 64))) return rc;
+    if ((rc = make_tmap_bshd(&v64, &pa.v_hfirst, a.v, 128, mSkv, a.H, mB, a.v_rs, a.v_hs, a.v_bs, 64))) return rc;
+    if ((rc = make_tmap_bshd(&q64, &f, a.q, 128, mSq, a.H, mB, a.q_rs, a.q_hs, a.q_bs, 64))) return rc;
+    if ((rc = make_tmap_bshd(&do64, &f, a.d_o, 128, mSq, a.H, mB, a.o_rs, a.o_hs, a.o_bs, 64))) return rc;
+    if ((rc = make_tmap_bshd(&k128, &f, a.k, 128, mSkv, a.H, mB, a.k_rs, a.k_hs, a.k_bs, 128))) return rc;
+    if ((rc = make_tmap_bshd(&v128, &f, a.v, 128, mSkv, a.H, mB, a.v_rs, a.v_hs, a.v_bs, 128))) return rc;
     const int BH = a.B * a.H;
     const int nqt = (a.Sq + 127) / 128, nkt = (a.Skv + 127) / 128;
     {

@@ -17,6 +17,8 @@ struct AttnBwdArgs {
     const uint8_t* kmask;
     uint32_t* kbits;     // kmask packed to bits by the delta pre-pass: [B, kbits_w] words, word t = keys [32t, 32t+32) (tcgen05 path)
     int kbits_w;         // words per batch row (even, >= ceil(Skv / 32))
+    const int* seq_off;  // ragged batch (LhrsAttention::seq_off) or nullptr; then *_bs are 0, Sq == Skv = longest length, kmask == nullptr
+    long long total_rows;
     long long q_bs, q_rs, q_hs, k_bs, k_rs, k_hs, v_bs, v_rs, v_hs;
     long long o_bs, o_rs, o_hs;        // O and dO share a layout
     long long dq_bs, dq_rs, dq_hs, dk_bs, dk_rs, dk_hs, dv_bs, dv_rs, dv_hs;

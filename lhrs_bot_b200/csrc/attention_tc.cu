@@ -26,6 +26,7 @@ struct AttnTcArgs {
     __nv_bfloat16* o;
     float* lse;
     const uint8_t* kmask;
+    const int* seq_off;                 // ragged batch (LhrsAttention::seq_off): per-sequence row offsets, tensor maps over all rows
     long long o_bs, o_rs, o_hs;
     int B, H, Sq, Skv;
     int q_hfirst, k_hfirst, v_hfirst;   // tensor-map dimension order: {d, head, row, batch} instead of {d, row, head, batch}
@@ -72,9 +73,13 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     const int qt = static_cast<int>(gridDim.x) - 1 - static_cast<int>(blockIdx.x);   // longest (latest) query tiles first
     const int h = blockIdx.y, b = blockIdx.z;
     const int q0 = qt * BQ;
-    const int off = p.Skv - p.Sq;
-    const int kv_end = CAUSAL ? min(p.Skv, q0 + BQ + off) : p.Skv;   // keys some row of this tile may attend
-    const int n = kv_end > 0 ? (kv_end + BKV - 1) / BKV : 0;
+    // ragged batch: this sequence's rows start at rb in the shared row space and there are Sq = Skv of them (rows past the end
+    // belong to the next sequence: finite values that the length masks below keep out of every sum, and that are never stored)
+    int Sq = p.Sq, Skv = p.Skv, rb = 0, bc = b;
+    if (p.seq_off != nullptr) { rb = p.seq_off[b]; Sq = Skv = p.seq_off[b + 1] - rb; bc = 0; }
+    const int off = Skv - Sq;
+    const int kv_end = CAUSAL ? min(Skv, q0 + BQ + off) : Skv;   // keys some row of this tile may attend
+    const int n = (kv_end > 0 && q0 < Sq) ? (kv_end + BKV - 1) / BKV : 0;
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmQ);
@@ -108,7 +113,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
             mbar_arrive_expect_tx(q_full, Q_BYTES);
             // the tensor maps list (row, head) in increasing-stride order; pick the coordinate order to match
             auto load = [&](void* dst, const CUtensorMap* tm, uint64_t* bar, int d0, int r0, int hfirst) {
-                tma_load_4d(dst, tm, bar, d0, hfirst ? h : r0, hfirst ? r0 : h, b);
+                tma_load_4d(dst, tm, bar, d0, hfirst ? h : r0 + rb, hfirst ? r0 + rb : h, bc);
             };
             load(smem + OFF_Q, &tmQ, q_full, 0, q0, p.q_hfirst);
             load(smem + OFF_Q + Q_BYTES / 2, &tmQ, q_full, 64, q0, p.q_hfirst);
@@ -198,13 +203,13 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
             // ---- allowed-key bitmask of this step (key mask and sequence end are row-independent; causal is per row)
             uint32_t w0 = 0xffffffffu, w1 = 0xffffffffu;
             if (p.kmask != nullptr) {
-                const uint8_t* km = p.kmask + static_cast<long long>(b) * p.Skv + k0;
-                const uint32_t b0 = (k0 + lane < p.Skv) ? km[lane] : 0u;
-                const uint32_t b1 = (k0 + 32 + lane < p.Skv) ? km[32 + lane] : 0u;
+                const uint8_t* km = p.kmask + static_cast<long long>(b) * Skv + k0;
+                const uint32_t b0 = (k0 + lane < Skv) ? km[lane] : 0u;
+                const uint32_t b1 = (k0 + 32 + lane < Skv) ? km[32 + lane] : 0u;
                 w0 = __ballot_sync(0xffffffffu, b0 != 0u);
                 w1 = __ballot_sync(0xffffffffu, b1 != 0u);
-            } else if (k0 + BKV > p.Skv) {
-                const int v = p.Skv - k0;   // 1..63 valid keys
+            } else if (k0 + BKV > Skv) {
+                const int v = Skv - k0;   // 1..63 valid keys
                 w0 = v >= 32 ? 0xffffffffu : ((1u << v) - 1u);
                 w1 = v > 32 ? ((1u << (v - 32)) - 1u) : 0u;
             }
@@ -284,7 +289,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
             mbar_wait(pv_full, (n - 1) & 1);
             tc_fence_after();
         }
-        __nv_bfloat16* og = p.o + b * p.o_bs + h * p.o_hs + static_cast<long long>(qi) * p.o_rs;
+        __nv_bfloat16* og = p.o + bc * p.o_bs + h * p.o_hs + static_cast<long long>(rb + qi) * p.o_rs;
 #pragma unroll 1
         for (int ch = 0; ch < HD / 32; ++ch) {
             uint32_t o[32];
@@ -295,7 +300,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 #pragma unroll
                 for (int i = 0; i < 32; ++i) o[i] = 0u;
             }
-            if (qi < p.Sq) {
+            if (qi < Sq) {
 #pragma unroll
                 for (int v4 = 0; v4 < 4; ++v4) {
                     uint4 v;
@@ -307,7 +312,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                 }
             }
         }
-        if (p.lse != nullptr && qi < p.Sq)
+        if (p.lse != nullptr && qi < Sq)
             p.lse[(static_cast<long long>(b) * p.H + h) * p.Sq + qi] = (l > 0.f) ? m * p.scale + logf(l) : -INFINITY;
         tc_fence_before();
     }
@@ -393,9 +398,12 @@ int attention_fwd_tc(const LhrsAttention* d, cudaStream_t stream) {
     CUtensorMap tq, tk, tv;
     int rc;
     AttnTcArgs a;
-    if ((rc = make_tmap_bshd(&tq, &a.q_hfirst, d->q, 128, d->Sq, d->H, d->B, d->q_rs, d->q_hs, d->q_bs, atc::BQ))) return rc;
-    if ((rc = make_tmap_bshd(&tk, &a.k_hfirst, d->k, 128, d->Skv, d->H, d->B, d->k_rs, d->k_hs, d->k_bs, atc::BKV))) return rc;
-    if ((rc = make_tmap_bshd(&tv, &a.v_hfirst, d->v, 128, d->Skv, d->H, d->B, d->v_rs, d->v_hs, d->v_bs, atc::BKV))) return rc;
+    const bool ragged = d->seq_off != nullptr;      // one row space for the whole batch: maps with a single batch entry of total_rows rows
+    const int mB = ragged ? 1 : d->B, mSq = ragged ? (int)d->total_rows : d->Sq, mSkv = ragged ? (int)d->total_rows : d->Skv;
+    if ((rc = make_tmap_bshd(&tq, &a.q_hfirst, d->q, 128, mSq, d->H, mB, d->q_rs, d->q_hs, d->q_bs, atc::BQ))) return rc;
+    if ((rc = make_tmap_bshd(&tk, &a.k_hfirst, d->k, 128, mSkv, d->H, mB, d->k_rs, d->k_hs, d->k_bs, atc::BKV))) return rc;
+    if ((rc = make_tmap_bshd(&tv, &a.v_hfirst, d->v, 128, mSkv, d->H, mB, d->v_rs, d->v_hs, d->v_bs, atc::BKV))) return rc;
+    a.seq_off = d->seq_off;
     a.o = reinterpret_cast<__nv_bfloat16*>(d->o);
     a.lse = d->lse;
     a.kmask = d->key_mask;

@@ -324,15 +324,14 @@ extern "C" int lhrs_lm_head_bwd(const LhrsLlamaWeights* w, const void* d_logits,
     return gemm_dx((cudaStream_t)stream, rows, w->dim, w->vocab, d_logits, w->vocab, w->lm_head, w->dim, d_hidden, w->dim);
 }
 
-extern "C" int lhrs_llama_bwd(const LhrsLlamaWeights* w, void* const* lora_a_grads, void* const* lora_b_grads, const void* d_hidden,
-                              int32_t B, int32_t S, const uint8_t* key_mask, const void* stash, void* d_inputs_embeds,
-                              void* workspace, size_t workspace_bytes, void* stream_) {
+static int llama_bwd_impl(const LhrsLlamaWeights* w, void* const* lora_a_grads, void* const* lora_b_grads, const void* d_hidden,
+                          int32_t B, int32_t S, long long M, const uint8_t* key_mask, const int32_t* seq_off, const void* stash,
+                          void* d_inputs_embeds, void* workspace, size_t workspace_bytes, void* stream_) {
     cudaStream_t st = (cudaStream_t)stream_;
     LHRS_CHECK_ARG(w && d_hidden && stash && d_inputs_embeds && B > 0 && S > 0, "lhrs_llama_bwd: null/empty");
-    const long long M = (long long)B * S;
     const int D = w->dim, F = w->ffn;
     Arena a(workspace, workspace_bytes);
-    LlamaBwdBufs b = llama_bwd_plan(a, w, M);
+    LlamaBwdBufs b = llama_bwd_plan(a, w, (long long)B * S);   // (a ragged batch has fewer rows; delta / lse stay [B, heads, S])
     LHRS_CHECK_ARG(a.fits(), "lhrs_llama_bwd: workspace too small (%zu < %zu)", workspace_bytes, a.used());
     Arena sa(const_cast<void*>(stash), (size_t)-1);
     LlamaStash s = llama_stash_plan(sa, w, B, S);
@@ -407,6 +406,7 @@ extern "C" int lhrs_llama_bwd(const LhrsLlamaWeights* w, void* const* lora_a_gra
             memset(&ab, 0, sizeof(ab));
             ab.fwd = attn_desc(t.qkv, t.qkv + D, t.qkv + 2 * D, 3 * D, (long long)S * 3 * D, t.o, D, (long long)S * D, B, w->heads, S, S, 128, 1);
             ab.fwd.lse = t.lse; ab.fwd.key_mask = key_mask;
+            ab.fwd.seq_off = seq_off; ab.fwd.total_rows = seq_off ? M : 0;
             ab.d_o = b.d_o; ab.delta = b.delta;
             ab.dq = b.dqkv; ab.dk = b.dqkv + D; ab.dv = b.dqkv + 2 * D;
             ab.dq_rs = ab.dk_rs = ab.dv_rs = 3 * D; ab.dq_bs = ab.dk_bs = ab.dv_bs = (long long)S * 3 * D;
@@ -428,6 +428,21 @@ extern "C" int lhrs_llama_bwd(const LhrsLlamaWeights* w, void* const* lora_a_gra
         { bf16* tmp = dx; dx = dx_other; dx_other = tmp; }
     }
     return LHRS_OK;
+}
+
+extern "C" int lhrs_llama_bwd(const LhrsLlamaWeights* w, void* const* lora_a_grads, void* const* lora_b_grads, const void* d_hidden,
+                              int32_t B, int32_t S, const uint8_t* key_mask, const void* stash, void* d_inputs_embeds,
+                              void* workspace, size_t workspace_bytes, void* stream_) {
+    return llama_bwd_impl(w, lora_a_grads, lora_b_grads, d_hidden, B, S, (long long)B * S, key_mask, nullptr, stash, d_inputs_embeds,
+                          workspace, workspace_bytes, stream_);
+}
+
+extern "C" int lhrs_llama_bwd_ragged(const LhrsLlamaWeights* w, void* const* lora_a_grads, void* const* lora_b_grads,
+                                     const void* d_hidden, int32_t B, int32_t S_max, int64_t rows, const int32_t* seq_off,
+                                     const void* stash, void* d_inputs_embeds, void* workspace, size_t workspace_bytes, void* stream_) {
+    LHRS_CHECK_ARG(seq_off && rows > 0 && rows <= (long long)B * S_max && S_max >= 128, "lhrs_llama_bwd_ragged: seq_off / rows (<= B * S_max) / S_max >= 128");
+    return llama_bwd_impl(w, lora_a_grads, lora_b_grads, d_hidden, B, S_max, rows, nullptr, seq_off, stash, d_inputs_embeds, workspace,
+                          workspace_bytes, stream_);
 }
 
 // ================================================================================================ AttnPooler backward

@@ -405,17 +405,18 @@ extern "C" size_t lhrs_llama_stash_bytes(const LhrsLlamaWeights* w, int32_t B, i
     return a.used();
 }
 
-extern "C" int lhrs_llama_fwd(const LhrsLlamaWeights* w, const void* inputs_embeds, int32_t B, int32_t S,
-                              const uint8_t* key_mask, void* hidden_out, void* stash, const LhrsKvCache* kv, void* workspace,
-                              size_t workspace_bytes, void* stream_) {
+// Dense batch: M = B * S rows, row b * S + s.  Ragged batch (seq_off != nullptr): M = seq_off[B] rows, the sequences back to back
+// without their right padding (S is then the longest length); `positions` [M] gives each row's index inside its sequence.
+static int llama_fwd_impl(const LhrsLlamaWeights* w, const void* inputs_embeds, int32_t B, int32_t S, long long M,
+                          const uint8_t* key_mask, const int32_t* seq_off, const int32_t* positions, void* hidden_out, void* stash,
+                          const LhrsKvCache* kv, void* workspace, size_t workspace_bytes, void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     LHRS_CHECK_ARG(w && inputs_embeds && hidden_out && B > 0 && S > 0, "lhrs_llama_fwd: null/empty");
     LHRS_CHECK_ARG(w->dim / w->heads == 128 && w->dim % 256 == 0 && w->ffn % 128 == 0, "lhrs_llama_fwd: needs head_dim 128, dim %% 256 == 0, ffn %% 128 == 0");
     LHRS_CHECK_ARG(S <= w->max_pos, "lhrs_llama_fwd: S=%d exceeds max_position_embeddings=%d", S, w->max_pos);
-    const long long M = (long long)B * S;
     const int D = w->dim, F = w->ffn;
     Arena a(workspace, workspace_bytes);
-    LlamaBufs b = llama_plan(a, w, M, stash != nullptr);
+    LlamaBufs b = llama_plan(a, w, (long long)B * S, stash != nullptr);   // (a ragged batch has fewer rows)
     LHRS_CHECK_ARG(a.fits(), "lhrs_llama_fwd: workspace too small (%zu < %zu)", workspace_bytes, a.used());
     LlamaStash st;
     if (stash) {
@@ -440,6 +441,7 @@ extern "C" int lhrs_llama_fwd(const LhrsLlamaWeights* w, const void* inputs_embe
             LhrsGemm g = gemm_desc(M, 3 * D, D, h1, D, w->q_w[l], D, qkv, 3 * D);
             g.B[1] = w->k_w[l]; g.B[2] = w->v_w[l]; g.num_b = 3; g.seg_rows = D;
             g.epilogue = LHRS_EPI_ROPE; g.rope_cos = w->rope_cos; g.rope_sin = w->rope_sin; g.rope_seq_len = S;
+            g.positions = positions;       // ragged batch: the row index no longer gives the position
             if ((rc = lora_attach(g, w, l, 0, 3, h1, D, M, ls ? ls->lora_t[0] : b.lora_t, b.skinny, b.drop_x, stream))) return rc;
             if ((rc = lhrs_gemm_bf16(&g, stream))) return rc;
         }
@@ -451,6 +453,7 @@ extern "C" int lhrs_llama_fwd(const LhrsLlamaWeights* w, const void* inputs_embe
             LhrsAttention at = attn_desc(qkv, qkv + D, qkv + 2 * D, 3 * D, (long long)S * 3 * D, o, D, (long long)S * D, B,
                                          w->heads, S, S, 128, 1);
             at.key_mask = key_mask;
+            at.seq_off = seq_off; at.total_rows = seq_off ? M : 0;
             if (ls) at.lse = ls->lse;
             if ((rc = lhrs_attention_fwd(&at, stream))) return rc;
         }
@@ -479,6 +482,22 @@ extern "C" int lhrs_llama_fwd(const LhrsLlamaWeights* w, const void* inputs_embe
     }
     if ((rc = lhrs_rmsnorm_fwd(x_cur, w->norm_w, hidden_out, stash ? st.rstd_final : nullptr, M, D, w->eps, stream))) return rc;
     return LHRS_OK;
+}
+
+extern "C" int lhrs_llama_fwd(const LhrsLlamaWeights* w, const void* inputs_embeds, int32_t B, int32_t S,
+                              const uint8_t* key_mask, void* hidden_out, void* stash, const LhrsKvCache* kv, void* workspace,
+                              size_t workspace_bytes, void* stream_) {
+    return llama_fwd_impl(w, inputs_embeds, B, S, (long long)B * S, key_mask, nullptr, nullptr, hidden_out, stash, kv, workspace,
+                          workspace_bytes, stream_);
+}
+
+extern "C" int lhrs_llama_fwd_ragged(const LhrsLlamaWeights* w, const void* inputs_embeds, int32_t B, int32_t S_max, int64_t rows,
+                                     const int32_t* seq_off, const int32_t* positions, void* hidden_out, void* stash,
+                                     void* workspace, size_t workspace_bytes, void* stream_) {
+    LHRS_CHECK_ARG(seq_off && positions && rows > 0 && rows <= (long long)B * S_max, "lhrs_llama_fwd_ragged: seq_off / positions / rows (<= B * S_max)");
+    LHRS_CHECK_ARG(S_max >= 128, "lhrs_llama_fwd_ragged: the ragged attention kernels need a longest length >= 128 (got %d)", S_max);
+    return llama_fwd_impl(w, inputs_embeds, B, S_max, rows, nullptr, seq_off, positions, hidden_out, stash, nullptr, workspace,
+                          workspace_bytes, stream_);
 }
 
 extern "C" int lhrs_lm_head(const LhrsLlamaWeights* w, const void* hidden, int64_t rows, void* logits, void* stream_) {

@@ -327,6 +327,60 @@ def attention_bwd(q, k, v, o, lse, d_o, *, causal: bool, scale: Optional[float] 
     return dq, dk, dv
 
 
+def _ragged_desc(f, q, k, v, o, seq_off, max_len):
+    """Fill an LhrsAttention for a ragged batch: q/k/v/o are (rows, H, hd) views over the whole batch's row space."""
+    for t, n in ((q, "q"), (k, "k"), (v, "v"), (o, "o")):
+        _need(t, torch.bfloat16, f"ragged attention {n}")
+        if t.dim() != 3 or t.stride(2) != 1:
+            raise RuntimeError(f"ragged attention {n}: expected (rows, H, hd) with unit stride on hd")
+    _need(seq_off, torch.int32, "ragged attention seq_off")
+    rows, H, hd = q.shape
+    f.q, f.k, f.v, f.o = q.data_ptr(), k.data_ptr(), v.data_ptr(), o.data_ptr()
+    f.q_rs, f.q_hs, f.k_rs, f.k_hs = q.stride(0), q.stride(1), k.stride(0), k.stride(1)
+    f.v_rs, f.v_hs, f.o_rs, f.o_hs = v.stride(0), v.stride(1), o.stride(0), o.stride(1)
+    f.q_bs = f.k_bs = f.v_bs = f.o_bs = 0
+    f.B, f.H, f.Sq, f.Skv, f.head_dim, f.causal = seq_off.numel() - 1, H, int(max_len), int(max_len), hd, 1
+    f.scale = 1.0 / math.sqrt(hd)
+    f.seq_off, f.total_rows = seq_off.data_ptr(), rows
+
+
+def attention_ragged(q, k, v, seq_off: torch.Tensor, max_len: int, *, out=None):
+    """Causal self-attention over a ragged batch (LhrsAttention::seq_off): q/k/v (rows, H, 128) views, sequence b in rows
+    [seq_off[b], seq_off[b+1]).  Returns (out (rows, H, 128), lse (B, H, max_len))."""
+    rows, H, hd = q.shape
+    if out is None:
+        out = torch.empty((rows, H, hd), device=q.device, dtype=torch.bfloat16)
+    B = seq_off.numel() - 1
+    lse = torch.empty((B, H, int(max_len)), device=q.device, dtype=torch.float32)
+    a = LhrsAttention()
+    _ragged_desc(a, q, k, v, out, seq_off, max_len)
+    a.lse = lse.data_ptr()
+    check(_lib.load().lhrs_attention_fwd(C.byref(a), _stream()), "lhrs_attention_fwd")
+    return out, lse
+
+
+def attention_bwd_ragged(q, k, v, o, lse, d_o, seq_off: torch.Tensor, max_len: int, *, rope=None):
+    """Backward of ``attention_ragged``; returns (dq, dk, dv) as contiguous (rows, H, 128)."""
+    from ._lib import LhrsAttentionBwd
+    rows, H, hd = q.shape
+    B = seq_off.numel() - 1
+    dq, dk, dv = (torch.empty((rows, H, hd), device=q.device, dtype=torch.bfloat16) for _ in range(3))
+    delta = torch.empty((int(_lib.load().lhrs_attention_bwd_scratch_floats(B, H, int(max_len), int(max_len))),), device=q.device,
+                        dtype=torch.float32)
+    d_o = d_o.contiguous()
+    if not o.is_contiguous():
+        o = o.contiguous()
+    a = LhrsAttentionBwd()
+    _ragged_desc(a.fwd, q, k, v, o, seq_off, max_len)
+    a.fwd.lse = lse.data_ptr()
+    a.d_o, a.dq, a.dk, a.dv, a.delta = d_o.data_ptr(), dq.data_ptr(), dk.data_ptr(), dv.data_ptr(), delta.data_ptr()
+    a.dq_rs, a.dq_hs, a.dk_rs, a.dk_hs, a.dv_rs, a.dv_hs = dq.stride(0), dq.stride(1), dk.stride(0), dk.stride(1), dv.stride(0), dv.stride(1)
+    if rope is not None:
+        a.rope_cos, a.rope_sin = rope[0].data_ptr(), rope[1].data_ptr()
+    check(_lib.load().lhrs_attention_bwd(C.byref(a), _stream()), "lhrs_attention_bwd")
+    return dq, dk, dv
+
+
 def rmsnorm_bwd(x, w, rstd, dy, dres=None):
     x2, dy2 = x.reshape(-1, x.shape[-1]).contiguous(), dy.reshape(-1, x.shape[-1]).contiguous()
     dx = torch.empty_like(x2)

@@ -531,6 +531,22 @@ class TextModal(BaseModal):
               "lhrs_llama_fwd")
         return hidden
 
+    def llama_forward_ragged(self, embeds_rows: torch.Tensor, B: int, s_max: int, seq_off: torch.Tensor, positions: torch.Tensor,
+                             stash=None) -> torch.Tensor:
+        """The decoder stack over a padding-free batch: ``embeds_rows`` [rows, dim] holds the B sequences back to back
+        (lhrs_llama_fwd_ragged).  Same results on every real position as ``llama_forward`` on the right-padded batch."""
+        lib = _lib.load()
+        w = self.weights()
+        runtime.require_bf16_cuda(embeds_rows, "inputs_embeds")
+        rows = embeds_rows.shape[0]
+        hidden = torch.empty_like(embeds_rows)
+        ws_bytes = lib.lhrs_llama_workspace_bytes(C.byref(w), B, s_max)
+        ws = runtime.workspace(ws_bytes, embeds_rows.device)
+        check(lib.lhrs_llama_fwd_ragged(C.byref(w), embeds_rows.contiguous().data_ptr(), B, s_max, rows, seq_off.data_ptr(),
+                                        positions.data_ptr(), hidden.data_ptr(), None if stash is None else stash.data_ptr(),
+                                        ws.data_ptr(), ws.numel(), runtime.stream()), "lhrs_llama_fwd_ragged")
+        return hidden
+
     def lm_head(self, hidden: torch.Tensor) -> torch.Tensor:
         lib = _lib.load()
         w = self.weights()

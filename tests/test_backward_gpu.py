@@ -3,6 +3,7 @@ on the same weights and inputs.  Gradients are produced in bf16: we require cosi
 <= 3e-2 per tensor (<= 5e-2 for the tiny bias / norm-weight gradients that are sums of many rounded terms)."""
 import math
 
+import numpy as np
 import pytest
 import torch
 
@@ -61,6 +62,43 @@ def test_attention_bwd(B, H, Sq, Skv, hd, causal):
     _cmp("dq", dq, qf.grad)
     _cmp("dk", dk, kf.grad)
     _cmp("dv", dv, vf.grad)
+
+
+@pytest.mark.parametrize("lens,H,rope", [([512, 300, 129, 47, 448, 2, 512], 4, False), ([200, 128, 333], 2, True), ([1024, 17, 640, 64], 3, True),
+                                         ([130] * 40, 8, False)])
+def test_attention_ragged_equals_per_sequence(lens, H, rope):
+    """LhrsAttention::seq_off (padding-free batch: the sequences back to back in one row space).  Forward and backward must give,
+    for every sequence, what the dense kernels give for that sequence alone — bit for bit where the dense problem also runs on the
+    tcgen05 kernels (length >= 128: same tiles, same MMA order; what differs is only that rows past the end of a sequence hold
+    the next sequence's values instead of TMA zero fill, and those are masked)."""
+    from lhrs_bot_b200 import ops
+    hd, rows = 128, sum(lens)
+    qkv = _randn(rows, 3, H, hd, seed=11)
+    q, k, v = qkv[:, 0], qkv[:, 1], qkv[:, 2]                      # strided views into one packed buffer, like the model's
+    d_o = _randn(rows, H, hd, seed=12)
+    off = torch.tensor([0] + list(np.cumsum(lens)), dtype=torch.int32, device=DEV)
+    tabs = None
+    if rope:
+        inv = 1.0 / (10000.0 ** (torch.arange(0, hd, 2).float() / hd))
+        fr = torch.outer(torch.arange(max(lens) + 8).float(), inv)
+        tabs = (fr.cos().to(DEV).contiguous(), fr.sin().to(DEV).contiguous())
+    o, lse = ops.attention_ragged(q, k, v, off, max(lens))
+    dq, dk, dv = ops.attention_bwd_ragged(q, k, v, o, lse, d_o, off, max(lens), rope=tabs)
+    assert torch.isfinite(o.float()).all() and torch.isfinite(dq.float()).all() and torch.isfinite(dk.float()).all()
+    r0 = 0
+    for b, n in enumerate(lens):
+        sl = slice(r0, r0 + n)
+        qb, kb, vb = (t[sl].unsqueeze(0) for t in (q, k, v))
+        ob, lb = ops.attention(qb, kb, vb, causal=True, return_lse=True)
+        gq, gk, gv = ops.attention_bwd(qb, kb, vb, ob, lb, d_o[sl].unsqueeze(0), causal=True, rope=tabs)
+        exact = n >= 128
+        for name, got, ref in (("o", o[sl], ob[0]), ("lse", lse[b, :, :n], lb[0]), ("dq", dq[sl], gq[0]), ("dk", dk[sl], gk[0]),
+                               ("dv", dv[sl], gv[0])):
+            if exact:
+                assert torch.equal(got, ref), (name, b, n, (got.float() - ref.float()).abs().max().item())
+            else:
+                _cmp(f"ragged {name} seq {b} len {n}", got, ref, 2e-2)
+        r0 += n
 
 
 @pytest.mark.parametrize("B,H,Sq,Skv,causal", [(2, 4, 512, 512, True), (3, 5, 640, 640, True), (1, 2, 384, 320, False), (2, 2, 130, 333, True),
@@ -405,6 +443,49 @@ def test_backward_with_k_major_weight_copies_equals_in_place(lora_r):
     w2 = model.text.weights()
     lm_t = [t for t in model.text._table[1] if torch.is_tensor(t) and t.data_ptr() == w2.lm_head_wt][0]
     assert torch.equal(lm_t, model.text.text_encoder.lm_head.weight.t())
+
+
+@pytest.mark.parametrize("lora_r", [0, 16])
+def test_padding_free_step_equals_padded_step(lora_r, monkeypatch):
+    """autograd.ragged_plan / lhrs_llama_{fwd,bwd}_ragged: a right-padded batch run without its padded rows gives the loss and
+    the gradients of the padded run (LHRS_RAGGED=0) — and both match the oracle, which computes every padded position like HF."""
+    from lhrs_bot_b200 import autograd
+    from oracle import unibind
+    lora = dict(enable=lora_r > 0, lora_r=max(lora_r, 1), lora_alpha=32, lora_dropout=0.0, lora_bias="none")
+    cfg = small_config(lora=lora, stage=2 if lora_r else 1)
+    model = build_small_model(cfg, DEV, seed=9)
+    st = to_device(unibind.export_state(model), DEV)
+    model.prepare_for_training(freeze_vision=True, freeze_text=True, tune_rgb_pooler=True, model_path=None,
+                               tune_im_start=False, compute_dtype=torch.bfloat16)
+    for a, b in model.text.lora_pairs():
+        a.requires_grad_(True)
+        b.requires_grad_(True)
+    batch = synthetic_batch(5, 40, cfg.text.vocab_size, DEV, seed=31, text_only=(1, 4), ragged_mask=True)
+    used = []
+    real_plan = autograd.ragged_plan
+    monkeypatch.setattr(autograd, "ragged_plan", lambda m, *a, **k: used.append(real_plan(m, *a, **k)) or used[-1])
+    res = []
+    for flag in ("0", "1"):
+        monkeypatch.setenv("LHRS_RAGGED", flag)
+        model.zero_grad(set_to_none=True)
+        out = model(batch)
+        out["total_loss"].backward()
+        res.append((out["total_loss"].item(), {n: p.grad.float().clone() for n, p in model.named_parameters() if p.grad is not None}))
+    assert used[0] is None and used[1] is not None, "the second run must have taken the padding-free path"
+    plan = used[1]
+    assert plan.rows < 5 * plan.s_max and plan.rows == int(plan.seq_off[-1])
+    (l0, g0), (l1, g1) = res
+    assert abs(l0 - l1) <= 1e-5 * max(1.0, abs(l0)), (l0, l1)
+    assert g0.keys() == g1.keys() and len(g0) > 4
+    for n in g0:
+        err = (g0[n] - g1[n]).abs().max().item() / max(g0[n].abs().max().item(), 1e-20)
+        assert err <= 2e-2, (n, err)          # reductions over rows (dW, LoRA dA / dB) run over fewer rows in a different split
+    ref_loss, sd = _oracle_loss_grads(cfg, st, batch)
+    assert abs(l1 - ref_loss.item()) <= 2e-2
+    _cmp("padding-free pooler query", g1["rgb_pooler.query"], sd["pooler"]["query"].grad, 5e-2)
+    for n, g in g1.items():
+        if "lora_" in n and "layers.0." in n:
+            _cmp(f"padding-free {n}", g, sd["llama"][n.split("text_encoder.")[1].replace(".default.", ".")].grad, 5e-2)
 
 
 # ---------------------------------------------------------------------------------------------- LoRA dropout (peft lora.Linear)
