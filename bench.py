@@ -605,7 +605,7 @@ def measure_steps(args, workload, dev, rank, world, local, steps, warmup, B=None
     from lhrs_bot_b200 import autograd as _ag
     ragged_calls0 = _ag.RAGGED_CALLS
     dev_batches = [make_batch(B, seed=1000 * rank + i, device=dev, seq_len=S, mixed=mixed) for i in range(2)]
-    host_batches = [make_batch(B, seed=2000 * rank + i, pin=True, seq_len=S, mixed=mixed, uint8_images=True) for i in range(2)]
+    host_batches = [make_batch(B, seed=1000 * rank + i, pin=True, seq_len=S, mixed=mixed, uint8_images=True) for i in range(2)]
     h2d = batch_bytes(host_batches[0])
     real_tok = sum(real_positions(b) for b in dev_batches) / len(dev_batches)
 
