@@ -891,8 +891,9 @@ extern "C" int lhrs_gemm_bf16(const LhrsGemm* g, void* stream_) {
     GemmArgs a;
     a.ext_k = ext_k; a.ext_kb = ext_kb;
     {
-        static int env_gm = -1, env_pf = -1000;
-        if (env_gm < 0) { const char* e = getenv("LHRS_GEMM_GROUP_M"); env_gm = e ? atoi(e) : 0; }
+        static int env_pf = -1000;
+        int env_gm = 0;                    // read per call (tools/gemm_raster.py sweeps it)
+        { const char* e = getenv("LHRS_GEMM_GROUP_M"); env_gm = e ? atoi(e) : 0; }
         if (env_pf == -1000) { const char* e = getenv("LHRS_GEMM_PF"); env_pf = e ? atoi(e) : -100; }
         static int env_coal = -1;
         if (env_coal < 0) { const char* e = getenv("LHRS_EPI_COAL"); env_coal = e ? atoi(e) : 1; }
