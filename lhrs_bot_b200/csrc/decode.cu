@@ -8,6 +8,10 @@
 //   gemv<DOWN>    x += Wd · act
 // then gemv<LMHEAD> (final norm fused) + argmax.  Position, context length and the sampled token live in a device-side
 // state block, so the host enqueues steps back to back without a per-token synchronisation.
+// The GEMVs are CTA-cooperative (gemv_coop_kernel: a CTA owns a contiguous range of rows, all 256 threads walk each row, two
+// register sets of loads in flight, 3 CTAs per SM): 322 -> 369 tok/s at 7B over the warp-per-row form (gemv_kernel, kept behind
+// LHRS_GEMV_COOP=0), i.e. 4.98 TB/s of weight streaming = 0.76 of the measured HBM copy rate; what is left is the ~12 us
+// attention launch per layer (latency chain, `LHRS_DECODE_SKIP_ATTN=1` measures it) and the ramp between dependent launches.
 // Every kernel is launched with programmatic dependent launch: before its dependency wait it starts streaming its first weight
 // rows (registers) and prefetches more towards L2, so e.g. the o-projection's weights arrive while the tiny attention runs.
 // (Measured alternative, round 1: ONE persistent cooperative kernel per token with grid barriers between the phases was
@@ -213,6 +217,174 @@ gemv_kernel(const GemvArgs a) {
     pdl_wait();
     if (a.done != nullptr && *a.done != 0) return;   // EOS / stop sequence already hit: the remaining enqueued steps cost nothing
     gemv_main<MODE>(a, reinterpret_cast<__nv_bfloat16*>(smem), sh, gw, nw, blockIdx.x, true, pre);
+}
+
+// ---- CTA-cooperative form (default): a CTA owns a CONTIGUOUS range of output rows and its 256 threads walk every row together
+// (thread t takes 16-byte chunks t, t + 256, ...), the per-warp sums meet in shared memory once at the end.  With one row per
+// warp trip (above) the work is quantised per WARP: 12288 q|k|v rows over 4736 warps is 2.59 rows each, so 41 % of the warps run a
+// third trip while the rest idle (86 % balance; 77 % for gate/up, 87 % for down, whose 22 KB rows also serialise five dependent
+// round trips in one warp).  Here the quantum is a row per CTA: 20.76 rows -> 21 (98.8 %), every row is eight warps wide.
+constexpr int GV_MAX_LOCAL = 192;     // rows of one CTA (x 2 for gate/up pairs) the partial-sum table can hold
+
+template <int MODE>
+__device__ __forceinline__ const __nv_bfloat16* coop_row(const GemvArgs& a, int u0, int j) {
+    if constexpr (MODE == GV_GATEUP) {           // local rows alternate gate_n, up_n
+        const int n = u0 + (j >> 1);
+        return ((j & 1) ? a.w1 : a.w0) + static_cast<long long>(n) * a.K;
+    } else {
+        return gemv_row<MODE>(a, u0 + j);
+    }
+}
+
+// this CTA's unit range: units = output elements (QKV: 3*rows, GATEUP: hidden units, else rows), split as evenly as possible
+template <int MODE>
+__device__ __forceinline__ void coop_range(const GemvArgs& a, int block_id, int nblocks, int& u0, int& cnt) {
+    const int units = (MODE == GV_QKV) ? 3 * a.rows : a.rows;
+    const int base = units / nblocks, rem = units - base * nblocks;
+    u0 = block_id * base + min(block_id, rem);
+    cnt = base + (block_id < rem ? 1 : 0);
+}
+
+template <int MODE, int CPR, int RB>
+__device__ __forceinline__ void coop_load(const GemvArgs& a, int u0, int rows_local, int j0, int nchunks, uint4 (&w)[RB * CPR]) {
+    const int tid = threadIdx.x;
+#pragma unroll
+    for (int r = 0; r < RB; ++r) {
+        const uint4* row = reinterpret_cast<const uint4*>(coop_row<MODE>(a, u0, min(j0 + r, rows_local - 1)));
+#pragma unroll
+        for (int i = 0; i < CPR; ++i) {
+            const int c = tid + 256 * i;
+            w[r * CPR + i] = (j0 + r < rows_local && c < nchunks) ? ldg_stream(row + c) : make_uint4(0, 0, 0, 0);
+        }
+    }
+}
+
+// rows [0, rows_local) of the CTA against the smem-resident input; part[j * 8 + warp] receives each warp's share of row j.
+// Two register sets of RB rows each, refilled alternately: while one set is being consumed the other one's loads are in flight
+// (a single set oscillates between RB * CPR loads in flight and none).  wa / wb hold rows [0, RB) / [RB, 2 RB), loaded before the
+// dependency wait.
+template <int MODE, int CPR, int RB>
+__device__ __forceinline__ void coop_rows(const GemvArgs& a, const uint4* xv, float* part, int u0, int rows_local, int nchunks,
+                                          uint4 (&wa)[RB * CPR], uint4 (&wb)[RB * CPR]) {
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    constexpr bool XREG = CPR <= 2;                  // this thread's slice of the input vector is the same for every row: keep it in
+    uint4 xr[XREG ? CPR : 1];                        // registers when it is short (wide rows re-read shared memory: no spills)
+    if constexpr (XREG) {
+#pragma unroll
+        for (int i = 0; i < CPR; ++i) xr[i] = (tid + 256 * i < nchunks) ? xv[tid + 256 * i] : make_uint4(0, 0, 0, 0);
+    }
+    auto consume = [&](uint4 (&w)[RB * CPR], int j0) {
+        float acc[RB];
+#pragma unroll
+        for (int r = 0; r < RB; ++r) {
+            acc[r] = 0.f;
+#pragma unroll
+            for (int i = 0; i < CPR; ++i) {
+                if constexpr (XREG) acc[r] += dot8(w[r * CPR + i], xr[i]);
+                else if (tid + 256 * i < nchunks) acc[r] += dot8(w[r * CPR + i], xv[tid + 256 * i]);
+            }
+        }
+        if (j0 + 2 * RB < rows_local) coop_load<MODE, CPR, RB>(a, u0, rows_local, j0 + 2 * RB, nchunks, w);   // refill this set
+#pragma unroll
+        for (int r = 0; r < RB; ++r) {
+            const float v = warp_red(acc[r]);
+            if (lane == 0 && j0 + r < rows_local) part[(j0 + r) * 8 + warp] = v;
+        }
+    };
+    for (int j0 = 0; j0 < rows_local; j0 += 2 * RB) {
+        consume(wa, j0);
+        if (j0 + RB < rows_local) consume(wb, j0 + RB);
+    }
+}
+
+template <int MODE, int CPR, int RB>
+__device__ __forceinline__ void gemv_coop(const GemvArgs& a, uint8_t* smem, GemvShared& sh) {
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int nchunks = a.K / 8;
+    __nv_bfloat16* xs = reinterpret_cast<__nv_bfloat16*>(smem);
+    float* part = reinterpret_cast<float*>(smem + static_cast<size_t>(a.K) * 2);
+    int u0, cnt;
+    coop_range<MODE>(a, blockIdx.x, gridDim.x, u0, cnt);
+    const int rows_local = (MODE == GV_GATEUP) ? 2 * cnt : cnt;
+    pdl_launch_dependents();
+    uint4 wa[RB * CPR], wb[RB * CPR];
+    if (rows_local > 0) coop_load<MODE, CPR, RB>(a, u0, rows_local, 0, nchunks, wa);       // weights only: before the dependency wait
+    if (rows_local > RB) coop_load<MODE, CPR, RB>(a, u0, rows_local, RB, nchunks, wb);
+    {   // pull the CTA's next rows towards L2 while the producer of x drains (budgeted; 128-byte lines)
+        const int lines_per_row = a.K / 64;
+        const int lines = min(a.pf_bytes_per_warp * 8 / 128, rows_local * lines_per_row);
+        for (int l = 2 * RB * lines_per_row + tid; l < lines; l += 256) {
+            const int j = l / lines_per_row;
+            prefetch_l2(reinterpret_cast<const char*>(coop_row<MODE>(a, u0, j)) + (l - j * lines_per_row) * 128);
+        }
+    }
+    pdl_wait();
+    if (a.done != nullptr && *a.done != 0) return;
+    if (a.norm_w != nullptr) {                       // HF RMSNorm fused: w * bf16(x * rstd)
+        float ss = 0.f;
+        for (int i = tid; i < a.K; i += 256) { const float v = __bfloat162float(a.x[i]); ss += v * v; }
+        ss = warp_red(ss);
+        if (lane == 0) sh.red[warp] = ss;
+        __syncthreads();
+        float tot = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) tot += sh.red[i];
+        const float rstd = rsqrtf(tot / a.K + a.eps);
+        for (int i = tid; i < a.K; i += 256)
+            xs[i] = __float2bfloat16_rn(__bfloat162float(a.norm_w[i]) * bf16_round(__bfloat162float(a.x[i]) * rstd));
+    } else {
+        for (int i = tid; i < nchunks; i += 256) reinterpret_cast<uint4*>(xs)[i] = reinterpret_cast<const uint4*>(a.x)[i];
+    }
+    __syncthreads();
+    if (rows_local > 0) coop_rows<MODE, CPR, RB>(a, reinterpret_cast<const uint4*>(xs), part, u0, rows_local, nchunks, wa, wb);
+    __syncthreads();
+    // ---- finish: one thread per output element sums the eight warp shares in a fixed order
+    float best = -INFINITY;
+    int best_i = 0x7fffffff;
+    for (int j = tid; j < cnt; j += 256) {
+        const int n = u0 + j;
+        auto total = [&](int row) {
+            const float* q = part + row * 8;
+            return ((q[0] + q[1]) + (q[2] + q[3])) + ((q[4] + q[5]) + (q[6] + q[7]));
+        };
+        if constexpr (MODE == GV_GATEUP) {
+            const float g = bf16_round(total(2 * j)), u = bf16_round(total(2 * j + 1));
+            a.out[n] = __float2bfloat16_rn(bf16_round(g / (1.f + __expf(-g))) * u);
+        } else if constexpr (MODE == GV_QKV) {
+            a.out[n] = __float2bfloat16_rn(total(j));
+        } else if constexpr (MODE == GV_O || MODE == GV_DOWN) {
+            a.out[n] = __float2bfloat16_rn(bf16_round(total(j)) + __bfloat162float(a.out[n]));
+        } else {
+            const float v = bf16_round(total(j));
+            a.logits[n] = v;
+            if (v > best || (v == best && n < best_i)) { best = v; best_i = n; }
+        }
+    }
+    if constexpr (MODE == GV_LMHEAD) {               // block argmax (ties -> lowest index)
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, best_i, o);
+            if (ov > best || (ov == best && oi < best_i)) { best = ov; best_i = oi; }
+        }
+        if (lane == 0) { sh.bval[warp] = best; sh.bidx[warp] = best_i; }
+        __syncthreads();
+        if (tid == 0) {
+            for (int i = 1; i < 8; ++i)
+                if (sh.bval[i] > sh.bval[0] || (sh.bval[i] == sh.bval[0] && sh.bidx[i] < sh.bidx[0])) { sh.bval[0] = sh.bval[i]; sh.bidx[0] = sh.bidx[i]; }
+            a.part_val[blockIdx.x] = sh.bval[0];
+            a.part_idx[blockIdx.x] = sh.bidx[0];
+        }
+    }
+}
+
+// CPR = 16-byte chunks of a row per thread (ceil(K / 8 / 256)), RB = rows per register set (2 * RB * CPR loads in flight per thread)
+template <int MODE, int CPR, int RB>
+__global__ void __launch_bounds__(256, 3)
+gemv_coop_kernel(const GemvArgs a) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    __shared__ GemvShared sh;
+    gemv_coop<MODE, CPR, RB>(a, smem, sh);
 }
 
 // state: [0] token to feed next, [1] ctx_len (positions already in the cache), [2] number of tokens emitted, [3] unused
@@ -520,23 +692,50 @@ static int launch_gemv(const GemvArgs& a_in, cudaStream_t st) {
     const int units = (MODE == GV_QKV) ? 3 * a_in.rows : a_in.rows;   // one weight row (GATEUP: one gate+up row pair) per warp trip
     // CTAs per SM: few enough that the successor grid (programmatic dependent launch) becomes co-resident and prefetches
     static int per_sm = -1, pf_mb = -1;
-    if (per_sm < 0) { const char* e = getenv("LHRS_GEMV_CTAS_PER_SM"); per_sm = e ? atoi(e) : 4; if (per_sm < 1 || per_sm > 8) per_sm = 4; }
-    if (pf_mb < 0) { const char* e = getenv("LHRS_GEMV_PF_MB"); pf_mb = e ? atoi(e) : 24; }
+    if (per_sm < 0) { const char* e = getenv("LHRS_GEMV_CTAS_PER_SM"); per_sm = e ? atoi(e) : 3; if (per_sm < 1 || per_sm > 8) per_sm = 3; }
+    if (pf_mb < 0) { const char* e = getenv("LHRS_GEMV_PF_MB"); pf_mb = e ? atoi(e) : 16; }
     int grid = (units + 7) / 8;
     const int cap = num_sms() * per_sm;
     if (grid > cap) grid = cap;
     GemvArgs a = a_in;
     a.pf_bytes_per_warp = (int)(((long long)pf_mb << 20) / ((long long)grid * 8));
     const size_t smem = (size_t)a.K * 2;
+    LHRS_CHECK_ARG(smem <= 64 * 1024 && a.K % 8 == 0, "gemv: K=%d unsupported", a.K);
+    const bool prof = prof_on();
+    const double bytes = 2.0 * (double)a.K * (MODE == GV_QKV ? 3.0 * a.rows : (MODE == GV_GATEUP ? 2.0 * a.rows : (double)a.rows));
+    // CTA-cooperative rows (default; LHRS_GEMV_COOP=0: one row per warp trip) when a row is 1, 2 or 5-6 chunks per thread wide
+    static int coop = -1;
+    if (coop < 0) { const char* e = getenv("LHRS_GEMV_COOP"); coop = e ? atoi(e) : 1; }
+    const int cpr = (a.K / 8 + 255) / 256;
+    const int cgrid = units < cap ? units : cap;               // GATEUP: `units` counts hidden units (row pairs)
+    const int local = ((units + cgrid - 1) / cgrid) * (MODE == GV_GATEUP ? 2 : 1);
+    if (coop && (cpr == 1 || cpr == 2 || cpr == 5 || cpr == 6) && local <= GV_MAX_LOCAL && a.K % 64 == 0) {
+        const size_t csmem = smem + (size_t)local * 8 * sizeof(float);
+        a.pf_bytes_per_warp = (int)(((long long)pf_mb << 20) / ((long long)cgrid * 8));
+        auto launch = [&](auto kern) -> int {
+            static bool attr_done = false;           // (one flag per instantiation of this generic lambda)
+            if (!attr_done) { LHRS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024)); attr_done = true; }
+            if (prof) prof_begin(PROF_OTHER, 0.0, bytes, st);
+            LHRS_CUDA(launch_pdl(kern, dim3(cgrid), dim3(256), csmem, st, a));
+            if (prof) prof_end(st);
+            LHRS_LAUNCH_CHECK("gemv_coop_kernel");
+            return LHRS_OK;
+        };
+        int rc;
+        static int deep = -1;                        // rows per register set (two sets): LHRS_GEMV_DEEP=1 doubles them
+        if (deep < 0) { const char* e = getenv("LHRS_GEMV_DEEP"); deep = e ? atoi(e) : 0; }
+        if (cpr == 1) rc = launch(gemv_coop_kernel<MODE, 1, 4>);
+        else if (cpr == 2) rc = deep == 1 ? launch(gemv_coop_kernel<MODE, 2, 3>) : launch(gemv_coop_kernel<MODE, 2, 2>);
+        else rc = launch(gemv_coop_kernel<MODE, 6, 1>);
+        return rc ? -1 : cgrid;
+    }
     auto kern = gemv_kernel<MODE>;
     static bool attr = false;
     if (!attr) {
         LHRS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
         attr = true;
     }
-    LHRS_CHECK_ARG(smem <= 64 * 1024 && a.K % 8 == 0, "gemv: K=%d unsupported", a.K);
-    const bool prof = prof_on();
-    if (prof) prof_begin(PROF_OTHER, 0.0, 2.0 * (double)a.K * (MODE == GV_QKV ? 3.0 * a.rows : (MODE == GV_GATEUP ? 2.0 * a.rows : (double)a.rows)), st);
+    if (prof) prof_begin(PROF_OTHER, 0.0, bytes, st);
     LHRS_CUDA(launch_pdl(kern, dim3(grid), dim3(256), smem, st, a));
     if (prof) prof_end(st);
     LHRS_LAUNCH_CHECK("gemv_kernel");
