@@ -25,6 +25,8 @@ typedef __nv_bfloat16 bf16;
 
 constexpr int SK_THREADS = 128;
 constexpr int PN_BM = 32;                 // panel kernel: 32 rows x BK k per stage
+constexpr int PN_KW = 4;                  //   every chunk's k-steps are shared by PN_KW warps per 16-row tile (8 warps per CTA:
+constexpr int PN_THREADS = 2 * PN_KW * 32;  // with 4 the ~1.5 CTAs per SM left the mma / ldmatrix chains latency-bound)
 constexpr int RR_ST = 4;                  // row-reduce kernel: BR rows x BC columns (16 KB) per stage
 
 __device__ __forceinline__ void sk_cp16(uint32_t dst, const void* src, bool valid) {
@@ -82,7 +84,7 @@ __device__ __forceinline__ uint32_t drop_pair_rows(uint32_t v, uint32_t word, ui
 }
 
 template <int NT, bool W_KN, int PN_BK, int PN_ST, bool L2H>
-__global__ void __launch_bounds__(SK_THREADS)
+__global__ void __launch_bounds__(PN_THREADS)
 lora_panel_kernel(const PanelArgs a) {
     constexpr int X_STAGE = PN_BM * PN_BK * 2;
     constexpr int W_STAGE = W_KN ? PN_BK * 16 * 2 : NT * 8 * PN_BK * 2;
@@ -91,7 +93,7 @@ lora_panel_kernel(const PanelArgs a) {
     extern __shared__ __align__(128) uint8_t smem[];
     const uint32_t s0 = smem_u32(smem);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, mat = lane >> 3;
-    const int wr = warp & 1, wk = warp >> 1;
+    const int wr = warp & 1, wk = warp >> 1;                              // row tile (2) x k share (PN_KW) of every chunk
     const int row0 = blockIdx.x * PN_BM;
     const int nchunks = a.K / PN_BK;
 
@@ -99,8 +101,9 @@ lora_panel_kernel(const PanelArgs a) {
         const uint32_t sx = s0 + stage * STAGE, sw = sx + X_STAGE;
         const int k0 = chunk * PN_BK;
 #pragma unroll
-        for (int i = 0; i < (PN_BM * CPR) / SK_THREADS; ++i) {
-            const int idx = tid + i * SK_THREADS, r = idx / CPR, c = idx % CPR;
+        for (int i = 0; i < (PN_BM * CPR + PN_THREADS - 1) / PN_THREADS; ++i) {
+            const int idx = tid + i * PN_THREADS, r = idx / CPR, c = idx % CPR;
+            if ((PN_BM * CPR) % PN_THREADS != 0 && idx >= PN_BM * CPR) break;
             const int gr = row0 + r;
             const bool ok = gr < a.M;
             const bf16* src = a.X + static_cast<long long>(ok ? gr : 0) * a.ldx + k0 + c * 8;
@@ -109,12 +112,12 @@ lora_panel_kernel(const PanelArgs a) {
         if constexpr (W_KN) {
             const int s = k0 / a.kseg, kin = k0 - s * a.kseg;
             const bf16* w = a.W[s] + static_cast<long long>(kin) * 16;
-            for (int idx = tid; idx < PN_BK * 2; idx += SK_THREADS) {       // BK k-rows x 2 chunks
+            for (int idx = tid; idx < PN_BK * 2; idx += PN_THREADS) {       // BK k-rows x 2 chunks
                 const int r = idx >> 1, c = idx & 1;
                 sk_cp16(sw + r * 32 + c * 16, w + r * 16 + c * 8, true);
             }
         } else {
-            for (int idx = tid; idx < NT * 8 * CPR; idx += SK_THREADS) {
+            for (int idx = tid; idx < NT * 8 * CPR; idx += PN_THREADS) {
                 const int r = idx / CPR, c = idx % CPR;
                 sk_cp16(sw + offsw<PN_BK>(r, c), a.W[0] + static_cast<long long>(r) * a.ldw + k0 + c * 8, true);
             }
@@ -137,8 +140,8 @@ lora_panel_kernel(const PanelArgs a) {
         sk_commit();
         const uint32_t sx = s0 + (ch % PN_ST) * STAGE, sw = sx + X_STAGE;
 #pragma unroll
-        for (int kk = 0; kk < PN_BK / 32; ++kk) {
-            const int ks = wk * (PN_BK / 32) + kk;                          // this warp's k-steps of the chunk
+        for (int kk = 0; kk < PN_BK / (16 * PN_KW); ++kk) {
+            const int ks = wk * (PN_BK / (16 * PN_KW)) + kk;                // this warp's k-steps of the chunk
             uint32_t af[4];
             sk_ldsm(sx + offsw<PN_BK>(wr * 16 + (lane & 15), ks * 2 + (lane >> 4)), af[0], af[1], af[2], af[3]);
             if constexpr (W_KN) {
@@ -174,12 +177,12 @@ lora_panel_kernel(const PanelArgs a) {
     }
     sk_wait<0>();
     __syncthreads();
-    // the two k-halves of each 16-row tile meet in shared memory; warps with wk == 0 finish and store
-    float* red = reinterpret_cast<float*>(smem);                            // [2 row tiles][NT][32 lanes][4]
-    if (wk == 1) {
+    // the PN_KW k-shares of each 16-row tile meet in shared memory; warps with wk == 0 finish and store
+    float* red = reinterpret_cast<float*>(smem);                            // [PN_KW - 1][2 row tiles][NT][32 lanes][4]
+    if (wk > 0) {
 #pragma unroll
         for (int i = 0; i < NT; ++i)
-            *reinterpret_cast<float4*>(red + ((wr * NT + i) * 32 + lane) * 4) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+            *reinterpret_cast<float4*>(red + ((((wk - 1) * 2 + wr) * NT + i) * 32 + lane) * 4) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
     }
     __syncthreads();
     if (wk == 0) {
@@ -187,7 +190,12 @@ lora_panel_kernel(const PanelArgs a) {
         const int r_lo = row0 + wr * 16 + g, r_hi = r_lo + 8;
 #pragma unroll
         for (int i = 0; i < NT; ++i) {
-            const float4 o = *reinterpret_cast<const float4*>(red + ((wr * NT + i) * 32 + lane) * 4);
+            float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int w = 0; w < PN_KW - 1; ++w) {                           // fixed order: deterministic
+                const float4 v = *reinterpret_cast<const float4*>(red + (((w * 2 + wr) * NT + i) * 32 + lane) * 4);
+                o.x += v.x; o.y += v.y; o.z += v.z; o.w += v.w;
+            }
             const int col = i * 8 + t4 * 2;
             if (r_lo < a.M)
                 *reinterpret_cast<uint32_t*>(a.out + static_cast<long long>(r_lo) * a.ldo + col) = pack_bf16((acc[i][0] + o.x) * a.alpha, (acc[i][1] + o.y) * a.alpha);
@@ -402,7 +410,7 @@ static int launch_panel_cfg(const PanelArgs& a, cudaStream_t st) {
     if (!attr) { LHRS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM)); attr = true; }
     const bool prof = prof_on();
     if (prof) prof_begin(PROF_SKINNY, 2.0 * a.M * (double)(NT * 8) * (W_KN ? a.kseg : a.K), 2.0 * (double)a.M * a.K, st);
-    kern<<<(a.M + PN_BM - 1) / PN_BM, SK_THREADS, SMEM, st>>>(a);
+    kern<<<(a.M + PN_BM - 1) / PN_BM, PN_THREADS, SMEM, st>>>(a);
     if (prof) prof_end(st);
     LHRS_LAUNCH_CHECK("lora_panel_kernel");
     return LHRS_OK;
@@ -411,8 +419,15 @@ template <int NT, bool W_KN>
 static int launch_panel(const PanelArgs& a, cudaStream_t st) {
     static int bk = -1, l2h = -1;
     if (bk < 0) { bk = env_int("LHRS_SKINNY_BK", 128); l2h = env_int("LHRS_SKINNY_L2HINT", 0); }
-    if (bk == 128 && a.K % 128 == 0 && (!W_KN || a.kseg % 128 == 0))
+    if (bk == 128 && a.K % 128 == 0 && (!W_KN || a.kseg % 128 == 0)) {
+        // deeper ring where two CTAs of it still fit on an SM (stage = 8 KB of X + the W chunk): more bytes in flight per SM
+        static int deep = -1;
+        if (deep < 0) deep = env_int("LHRS_SKINNY_DEEP", 0);
+        constexpr int STAGE = PN_BM * 128 * 2 + (W_KN ? 128 * 16 * 2 : NT * 8 * 128 * 2);
+        constexpr int DEEP_ST = (110 * 1024) / STAGE > 9 ? 9 : (110 * 1024) / STAGE;
+        if (deep && !l2h && DEEP_ST > 5) return launch_panel_cfg<NT, W_KN, 128, DEEP_ST, false>(a, st);
         return l2h ? launch_panel_cfg<NT, W_KN, 128, 5, true>(a, st) : launch_panel_cfg<NT, W_KN, 128, 5, false>(a, st);
+    }
     return l2h ? launch_panel_cfg<NT, W_KN, 64, 8, true>(a, st) : launch_panel_cfg<NT, W_KN, 64, 8, false>(a, st);
 }
 

@@ -32,7 +32,7 @@ def timeit(fn, flush, reps=8):
 
 def main():
     lib = _lib.load()
-    M, r = 8192, 16
+    M, r = int(os.environ.get("M", "8192")), 16
     flush = torch.empty(512 << 20, dtype=torch.uint8, device=DEV)
     rows = []
     st = runtime.stream()
