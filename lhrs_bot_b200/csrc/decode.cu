@@ -19,6 +19,8 @@
 // of every phase lands on a barrier; the dependent-launch chain overlaps exactly those tails.)
 #include <stdlib.h>
 
+#include <cooperative_groups.h>
+
 #include "host_common.h"
 #include "ptx.cuh"
 #include "models_common.h"
@@ -319,10 +321,26 @@ __device__ __forceinline__ void gemv_coop(const GemvArgs& a, uint8_t* smem, Gemv
         }
     }
     pdl_wait();
-    if (a.done != nullptr && *a.done != 0) return;
-    if (a.norm_w != nullptr) {                       // HF RMSNorm fused: w * bf16(x * rstd)
+    // the input vector (cp.async straight into shared memory: no registers next to the two weight sets) and the "sequence finished"
+    // flag are requested together: a flag test in front of the loads would put a second dependent L2 round trip at the head of
+    // every launch of the chain
+    {
+        const uint32_t xs_u = smem_u32(xs);
+        for (int c = tid; c < nchunks; c += 256)
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(xs_u + c * 16), "l"(reinterpret_cast<const uint4*>(a.x) + c) : "memory");
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    }
+    const int finished = (a.done != nullptr) ? __ldcg(a.done) : 0;
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    if (finished != 0) return;
+    if (a.norm_w != nullptr) {                       // HF RMSNorm fused: w * bf16(x * rstd); every thread works on the chunks it copied
         float ss = 0.f;
-        for (int i = tid; i < a.K; i += 256) { const float v = __bfloat162float(a.x[i]); ss += v * v; }
+        for (int c = tid; c < nchunks; c += 256) {
+            const uint4 u = reinterpret_cast<const uint4*>(xs)[c];
+            const uint32_t wds[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) { const float lo = bf16_lo(wds[e]), hi = bf16_hi(wds[e]); ss += lo * lo + hi * hi; }
+        }
         ss = warp_red(ss);
         if (lane == 0) sh.red[warp] = ss;
         __syncthreads();
@@ -330,10 +348,16 @@ __device__ __forceinline__ void gemv_coop(const GemvArgs& a, uint8_t* smem, Gemv
 #pragma unroll
         for (int i = 0; i < 8; ++i) tot += sh.red[i];
         const float rstd = rsqrtf(tot / a.K + a.eps);
-        for (int i = tid; i < a.K; i += 256)
-            xs[i] = __float2bfloat16_rn(__bfloat162float(a.norm_w[i]) * bf16_round(__bfloat162float(a.x[i]) * rstd));
-    } else {
-        for (int i = tid; i < nchunks; i += 256) reinterpret_cast<uint4*>(xs)[i] = reinterpret_cast<const uint4*>(a.x)[i];
+        for (int c = tid; c < nchunks; c += 256) {
+            const uint4 u = reinterpret_cast<const uint4*>(xs)[c];
+            const uint4 wn = reinterpret_cast<const uint4*>(a.norm_w)[c];
+            const uint32_t xd[4] = {u.x, u.y, u.z, u.w}, wd[4] = {wn.x, wn.y, wn.z, wn.w};
+            uint32_t o[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+                o[e] = pack_bf16(bf16_lo(wd[e]) * bf16_round(bf16_lo(xd[e]) * rstd), bf16_hi(wd[e]) * bf16_round(bf16_hi(xd[e]) * rstd));
+            reinterpret_cast<uint4*>(xs)[c] = make_uint4(o[0], o[1], o[2], o[3]);
+        }
     }
     __syncthreads();
     if (rows_local > 0) coop_rows<MODE, CPR, RB>(a, reinterpret_cast<const uint4*>(xs), part, u0, rows_local, nchunks, wa, wb);
@@ -590,6 +614,175 @@ __device__ __forceinline__ void attn_decode_body(float* sc, AttnDecodeShared& sh
         obuf[h * 128 + tid] = __float2bfloat16_rn(o / L);
     }
     if (tid == 0) counter[h] = 0;          // ready for the next layer / token
+}
+
+// ---- cluster form (default): the ATT_SPLITS blocks of a head are one thread-block cluster.  Against the ticket form above:
+//   * K rows (one position per thread, 16 loads) and V rows are requested TOGETHER right after the RoPE barrier — V as 16-byte
+//     chunks with the block's threads laid out (16 position lanes) x (16 dim chunks), so every V row of a <= 128-position slice
+//     is in flight at once instead of 4 rows per warp behind the softmax (three dependent round trips at ctx ~ 300);
+//   * the slices' (max, sum, P·V) meet through distributed shared memory and one cluster barrier instead of a global partial,
+//     __threadfence, an atomic ticket and a read-back.
+struct AttnDecode2Shared {
+    float qs[128];
+    float red[8];
+    float part[16][128];
+    float stat[4];      // m, l of this slice
+    float o[128];       // un-normalised P·V of this slice (read by rank 0 through DSMEM)
+};
+
+__global__ void __launch_bounds__(256)
+attn_decode2_kernel(const __nv_bfloat16* __restrict__ qkv, int dim, KvGeom kv, int layer, int* __restrict__ state,
+                    const float* __restrict__ cosT, const float* __restrict__ sinT, __nv_bfloat16* __restrict__ obuf, int max_ctx) {
+    extern __shared__ float sc[];            // scores [max_ctx] | page ids [max_pages]
+    __shared__ AttnDecode2Shared sh;
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
+    pdl_launch_dependents();
+    const int h = blockIdx.x, split = blockIdx.y;
+    int* spg = reinterpret_cast<int*>(sc + max_ctx);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    // the block table is written once per generation, long before the chain: stage all of it while the q|k|v GEMV drains
+    for (int i = tid; i < kv.max_pages; i += 256) spg[i] = kv.block_table[i];
+    pdl_wait();
+    const int4 stv = __ldcg(reinterpret_cast<const int4*>(state));   // token, position, emitted, finished: one round trip
+    if (stv.w != 0) return;                  // (the same for every block of the cluster: nobody is left at a cluster barrier)
+    const int pos = stv.y;
+    const int n = pos + 1;
+    const int per = (n + ATT_SPLITS - 1) / ATT_SPLITS;
+    const int p0 = min(n, split * per), p1 = min(n, p0 + per);
+    const int cnt = p1 - p0;
+    const int npages = (n + kv.page_size - 1) / kv.page_size;
+    const float scale = rsqrtf(128.f);
+    const __nv_bfloat16* q = qkv + h * 128;
+    const __nv_bfloat16* k = qkv + dim + h * 128;
+    const __nv_bfloat16* v = qkv + 2 * dim + h * 128;
+    (void)npages;
+    const bool owner = pos >= p0 && pos < p1;         // exactly one slice owns the new position
+    const int page_new = kv.block_table[pos / kv.page_size];
+    const int slot_new = pos % kv.page_size;
+    if (tid < 64) {
+        const float c = cosT[static_cast<long long>(pos) * 64 + tid], s = sinT[static_cast<long long>(pos) * 64 + tid];
+        const float q1 = __bfloat162float(q[tid]), q2 = __bfloat162float(q[tid + 64]);
+        // HF apply_rotary_pos_emb in bf16: each product rounded, then the sum rounded
+        sh.qs[tid] = bf16_round(bf16_round(q1 * c) - bf16_round(q2 * s));
+        sh.qs[tid + 64] = bf16_round(bf16_round(q2 * c) + bf16_round(q1 * s));
+        if (owner) {
+            const float k1 = __bfloat162float(k[tid]), k2 = __bfloat162float(k[tid + 64]);
+            __nv_bfloat16* kd = kv_ptr(kv, layer, 0, page_new, h, slot_new);
+            kd[tid] = __float2bfloat16_rn(bf16_round(k1 * c) - bf16_round(k2 * s));
+            kd[tid + 64] = __float2bfloat16_rn(bf16_round(k2 * c) + bf16_round(k1 * s));
+        }
+    } else if (tid < 128 && owner) {
+        __nv_bfloat16* vd = kv_ptr(kv, layer, 1, page_new, h, slot_new);
+        const int d = tid - 64;
+        vd[d] = v[d];
+        vd[d + 64] = v[d + 64];
+    }
+    __syncthreads();
+    // ---- request this thread's K row (first 256 positions of the slice) and its V chunks (first 128 positions) together
+    const int pl = tid >> 4, vc = tid & 15;           // V layout: position lane x 16-byte dim chunk
+    auto k_row = [&](int i) { const int p = p0 + i; return reinterpret_cast<const uint4*>(kv_ptr(kv, layer, 0, spg[p / kv.page_size], h, p % kv.page_size)); };
+    auto v_chunk = [&](int i) { const int p = p0 + i; return reinterpret_cast<const uint4*>(kv_ptr(kv, layer, 1, spg[p / kv.page_size], h, p % kv.page_size)) + vc; };
+    uint4 kw[16], vw[8];
+    if (tid < cnt) {
+        const uint4* kp = k_row(tid);
+#pragma unroll
+        for (int c = 0; c < 16; ++c) kw[c] = kp[c];
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int i = pl + 16 * j;
+        vw[j] = (i < cnt) ? *v_chunk(i) : make_uint4(0, 0, 0, 0);
+    }
+    // ---- scores (fp32, as in the prefill flash kernel)
+    float mx = -INFINITY;
+    for (int i = tid; i < cnt; i += 256) {
+        if (i >= 256) {
+            const uint4* kp = k_row(i);
+#pragma unroll
+            for (int c = 0; c < 16; ++c) kw[c] = kp[c];
+        }
+        float acc = 0.f;
+#pragma unroll
+        for (int c = 0; c < 16; ++c) {
+            const float* qq = sh.qs + c * 8;
+            acc += bf16_lo(kw[c].x) * qq[0] + bf16_hi(kw[c].x) * qq[1] + bf16_lo(kw[c].y) * qq[2] + bf16_hi(kw[c].y) * qq[3] +
+                   bf16_lo(kw[c].z) * qq[4] + bf16_hi(kw[c].z) * qq[5] + bf16_lo(kw[c].w) * qq[6] + bf16_hi(kw[c].w) * qq[7];
+        }
+        acc *= scale;
+        sc[i] = acc;
+        mx = fmaxf(mx, acc);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if (lane == 0) sh.red[warp] = mx;
+    __syncthreads();
+    mx = sh.red[0];
+#pragma unroll
+    for (int i = 1; i < 8; ++i) mx = fmaxf(mx, sh.red[i]);
+    __syncthreads();
+    float sum = 0.f;
+    for (int i = tid; i < cnt; i += 256) {
+        const float e = __expf(sc[i] - mx);
+        sc[i] = e;
+        sum += e;
+    }
+    sum = warp_red(sum);
+    if (lane == 0) sh.red[warp] = sum;
+    __syncthreads();                                  // also publishes every sc[i]
+    float tot = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) tot += sh.red[i];
+    // ---- P·V: thread (pl, vc) accumulates dims [8 vc, 8 vc + 8) over positions pl, pl + 16, ...
+    float a[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) a[e] = 0.f;
+    for (int base = 0; base < cnt; base += 128) {
+        if (base > 0) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int i = base + pl + 16 * j;
+                vw[j] = (i < cnt) ? *v_chunk(i) : make_uint4(0, 0, 0, 0);
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int i = base + pl + 16 * j;
+            const float pr = (i < cnt) ? sc[i] : 0.f;
+            a[0] += pr * bf16_lo(vw[j].x); a[1] += pr * bf16_hi(vw[j].x); a[2] += pr * bf16_lo(vw[j].y); a[3] += pr * bf16_hi(vw[j].y);
+            a[4] += pr * bf16_lo(vw[j].z); a[5] += pr * bf16_hi(vw[j].z); a[6] += pr * bf16_lo(vw[j].w); a[7] += pr * bf16_hi(vw[j].w);
+        }
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) sh.part[pl][vc * 8 + e] = a[e];
+    __syncthreads();
+    if (tid < 128) {
+        float o = 0.f;
+#pragma unroll
+        for (int w = 0; w < 16; ++w) o += sh.part[w][tid];
+        sh.o[tid] = o;
+    }
+    if (tid == 0) { sh.stat[0] = mx; sh.stat[1] = tot; }
+    cluster.sync();
+    if (split == 0 && tid < 128) {                     // rank 0 merges the slices (fixed order)
+        float ms[ATT_SPLITS], M = -INFINITY;
+        const AttnDecode2Shared* peer[ATT_SPLITS];
+#pragma unroll
+        for (int r = 0; r < ATT_SPLITS; ++r) {
+            peer[r] = cluster.map_shared_rank(&sh, r);
+            ms[r] = peer[r]->stat[0];
+            M = fmaxf(M, ms[r]);
+        }
+        float L = 0.f, o = 0.f;
+#pragma unroll
+        for (int r = 0; r < ATT_SPLITS; ++r) {
+            const float wgt = (ms[r] == -INFINITY) ? 0.f : __expf(ms[r] - M);
+            L += wgt * peer[r]->stat[1];
+            o += wgt * peer[r]->o[tid];
+        }
+        obuf[h * 128 + tid] = __float2bfloat16_rn(o / L);
+    }
+    cluster.sync();                                    // the peers' shared memory stays alive until rank 0 has read it
 }
 
 __global__ void __launch_bounds__(256)
@@ -870,8 +1063,22 @@ static int decode_step_impl(const LhrsLlamaWeights* w, const LhrsKvCache* kv, co
         if (launch_gemv<GV_QKV>(a, st) <= 0) return LHRS_ERR_CUDA;
         static int skip_attn = -1;   // experiment knob (changes results): how much of a token is the attention launch?
         if (skip_attn < 0) { const char* e = getenv("LHRS_DECODE_SKIP_ATTN"); skip_attn = e ? atoi(e) : 0; }
-        if (!skip_attn)
-        LHRS_CUDA(launch_pdl(attn_decode_kernel, dim3(w->heads, ATT_SPLITS), dim3(256), (size_t)max_ctx * sizeof(float) + (size_t)kv->max_pages * sizeof(int), st,
+        static int attn2 = -1;       // cluster form of the decode attention (default); LHRS_DECODE_ATTN2=0: ticket form
+        if (attn2 < 0) { const char* e = getenv("LHRS_DECODE_ATTN2"); attn2 = e ? atoi(e) : 1; }
+        const size_t att_smem = (size_t)max_ctx * sizeof(float) + (size_t)kv->max_pages * sizeof(int);
+        if (!skip_attn && attn2) {
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3(w->heads, ATT_SPLITS); cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = att_smem; cfg.stream = st;
+            cudaLaunchAttribute attr[2];
+            attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+            attr[0].val.programmaticStreamSerializationAllowed = 1;
+            attr[1].id = cudaLaunchAttributeClusterDimension;
+            attr[1].val.clusterDim.x = 1; attr[1].val.clusterDim.y = ATT_SPLITS; attr[1].val.clusterDim.z = 1;
+            cfg.attrs = attr; cfg.numAttrs = 2;
+            LHRS_CUDA(cudaLaunchKernelEx(&cfg, attn_decode2_kernel, (const bf16*)b->qkv, (int)D, *kv, (int)l, (int*)b->state,
+                                         (const float*)w->rope_cos, (const float*)w->rope_sin, (bf16*)b->obuf, (int)max_ctx));
+        } else if (!skip_attn)
+        LHRS_CUDA(launch_pdl(attn_decode_kernel, dim3(w->heads, ATT_SPLITS), dim3(256), att_smem, st,
                              (const bf16*)b->qkv, D, *kv, l, (int*)b->state, (const float*)w->rope_cos, (const float*)w->rope_sin, (bf16*)b->obuf,
                              (int)max_ctx, (float*)b->attn_part, (int*)b->attn_count));
         LHRS_LAUNCH_CHECK("attn_decode_kernel");
