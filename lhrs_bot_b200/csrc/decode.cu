@@ -9,9 +9,10 @@
 // then gemv<LMHEAD> (final norm fused) + argmax.  Position, context length and the sampled token live in a device-side
 // state block, so the host enqueues steps back to back without a per-token synchronisation.
 // The GEMVs are CTA-cooperative (gemv_coop_kernel: a CTA owns a contiguous range of rows, all 256 threads walk each row, two
-// register sets of loads in flight, 3 CTAs per SM): 322 -> 369 tok/s at 7B over the warp-per-row form (gemv_kernel, kept behind
-// LHRS_GEMV_COOP=0), i.e. 4.98 TB/s of weight streaming = 0.76 of the measured HBM copy rate; what is left is the ~12 us
-// attention launch per layer (latency chain, `LHRS_DECODE_SKIP_ATTN=1` measures it) and the ramp between dependent launches.
+// register sets of loads in flight, 3 CTAs per SM; the input vector arrives by cp.async together with the "finished" flag) and
+// the attention's four context slices per head are a thread-block cluster (attn_decode2_kernel): 322 -> 392 tok/s at 7B over the
+// round-1 chain (warp-per-row gemv_kernel, ticket-merged attn_decode_kernel; kept behind LHRS_GEMV_COOP=0 / LHRS_DECODE_ATTN2=0),
+// i.e. 5.3 TB/s of weight streaming = 0.80 of the measured HBM copy rate.
 // Every kernel is launched with programmatic dependent launch: before its dependency wait it starts streaming its first weight
 // rows (registers) and prefetches more towards L2, so e.g. the o-projection's weights arrive while the tiny attention runs.
 // (Measured alternative, round 1: ONE persistent cooperative kernel per token with grid barriers between the phases was
@@ -886,7 +887,7 @@ static int launch_gemv(const GemvArgs& a_in, cudaStream_t st) {
     // CTAs per SM: few enough that the successor grid (programmatic dependent launch) becomes co-resident and prefetches
     static int per_sm = -1, pf_mb = -1;
     if (per_sm < 0) { const char* e = getenv("LHRS_GEMV_CTAS_PER_SM"); per_sm = e ? atoi(e) : 3; if (per_sm < 1 || per_sm > 8) per_sm = 3; }
-    if (pf_mb < 0) { const char* e = getenv("LHRS_GEMV_PF_MB"); pf_mb = e ? atoi(e) : 16; }
+    if (pf_mb < 0) { const char* e = getenv("LHRS_GEMV_PF_MB"); pf_mb = e ? atoi(e) : 12; }
     int grid = (units + 7) / 8;
     const int cap = num_sms() * per_sm;
     if (grid > cap) grid = cap;
