@@ -527,7 +527,7 @@ def measure_decode(args, dev, rank, world, local, steps, warmup, cpu_baseline=Tr
     pk = peaks()
     traffic = None
     try:   # measured DRAM bytes per token from the committed ncu launch list
-        with open(os.path.join(ROOT, "profiles", "r1s2_decode_traffic.json")) as f:
+        with open(os.path.join(ROOT, "profiles", "r2_decode_traffic.json")) as f:
             traffic = json.load(f)["per_token_dram_bytes"]
     except Exception:
         pass
@@ -552,7 +552,7 @@ def measure_decode(args, dev, rank, world, local, steps, warmup, cpu_baseline=Tr
                 gpu_launches=int(launches),
                 roofline=dict(bound="hbm", achieved=achieved, peak=pk["hbm"], unit="GB/s", frac=achieved / pk["hbm"], traffic=traffic,
                               algorithmic_bytes_per_token=bytes_tok, per="token (161 launches: 32 x 5 + lm_head)",
-                              kernel="gemv_kernel chain (decode step)", peak_source=pk["which"]),
+                              kernel="gemv_coop_kernel chain (decode step: 4 cooperative GEMVs + cluster attention per layer, programmatic dependent launch)", peak_source=pk["which"]),
                 cpu_baseline=cpu_base)
 
 
