@@ -830,7 +830,7 @@ def measure_steps(args, workload, dev, rank, world, local, steps, warmup, B=None
     return line
 
 
-GEMM_TRAFFIC_FILE = "r1_gemm_traffic.json"
+GEMM_TRAFFIC_FILE = "r2_gemm_traffic.json"
 
 
 def check_exchange(stepper, model, batch, world, rank, dev):
