@@ -187,6 +187,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int num_kb_main = (args.K + BK - 1) / BK;
     const int num_kb = num_kb_main + args.ext_kb;
     const int kb_per = (num_kb + splitk - 1) / splitk;     // k-blocks per split (ext_kb == 0 when splitk > 1)
+    const int ext_span = (KIND == LHRS_EPI_SWIGLU) ? 2 * args.ext_k : args.ext_k;   // non-zero k columns of the K-extension
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmA);
@@ -374,12 +375,17 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     if (issuer) {
                         const uint32_t a_lo = a_lo0 + stage * (Cfg::A_BYTES >> 4);
                         const uint32_t b_lo = b_lo0 + stage * (Cfg::B_BYTES >> 4);
+                        // a LoRA K-extension block only carries ext_span (16 / 32 / 48 at r = 16) non-zero k columns: the rest of the
+                        // 64-wide box is TMA zero fill, so its K=16 steps would add exact zeros
+                        const int nk = (kb >= num_kb_main) ? min(BK / 16, (ext_span - (kb - num_kb_main) * BK + 15) / 16) : BK / 16;
 #pragma unroll
                         for (int k = 0; k < BK / 16; ++k) {
                             // K-major SW128: +32 B per K=16 step inside the 128 B row.  MN-major SW128: 64-wide MN atoms
                             // 8 KB apart (LBO), 8-row K groups 1 KB apart (SBO); +2 KB per K=16.
-                            if constexpr (CG == 2) umma_bf16_2sm_w(tmem_d, a_lo + k * a_kstep, b_lo + k * b_kstep, desc_hi, idesc, k == 0 ? acc : 1u);
-                            else umma_bf16_w(tmem_d, a_lo + k * a_kstep, b_lo + k * b_kstep, desc_hi, idesc, k == 0 ? acc : 1u);
+                            if (k < nk) {
+                                if constexpr (CG == 2) umma_bf16_2sm_w(tmem_d, a_lo + k * a_kstep, b_lo + k * b_kstep, desc_hi, idesc, k == 0 ? acc : 1u);
+                                else umma_bf16_w(tmem_d, a_lo + k * a_kstep, b_lo + k * b_kstep, desc_hi, idesc, k == 0 ? acc : 1u);
+                            }
                         }
                         // slot reusable once these MMAs have read it (pair: released in both CTAs)
                         if constexpr (CG == 2) umma_commit_2sm(&empty_bar[stage]); else umma_commit(&empty_bar[stage]);
