@@ -801,7 +801,12 @@ def measure_steps(args, workload, dev, rank, world, local, steps, warmup, B=None
     wl = (f"stage3_sft_step_b{B}_s{S} (fwd+bwd, LoRA r={args.lora_r} dropout {dropout} + pooler grads, allreduce, AdamW; {shape})" if workload == "sft_step"
           else f"stage1_step_b{B}_s{S} (fwd+bwd, pooler-only grads through the frozen LLaMA, allreduce, Adan; {shape})" if workload == "stage1_step"
           else f"prefill_loss_b{B}_s{S} (UniBind.forward: ViT-L/14 + pooler + splice + LLaMA-7B + CE; {shape})")
-    line = dict(metric=f"tokens/sec (LLaMA-7B, 224px, seq {S}), aggregate", value=value, unit="tokens/s", n_gpus=world,
+    line = dict(metric=f"tokens/sec (LLaMA-7B, 224px, seq {S}), aggregate", value=value,
+                # `value` counts the collated batch (B*S positions per step, the reference computes every one of them); the same
+                # throughput counted on positions that carry a token (attention_mask true) — the conservative reading when the
+                # decoder stack runs padding-free:
+                value_real_positions=real_tok * world * steps / (ms * 1e-3),
+                unit="tokens/s", n_gpus=world,
                 steps=steps, warmup=warmup, ms_per_step=step_ms, higher_is_better=True,
                 scaling="weak", vs_baseline=None, dtype="bf16", data="synthetic",
                 config=dict(workload=wl, per_gpu_batch=B, seq_len=S, image="224x224", parallelism=f"dp{world}",
