@@ -24,10 +24,13 @@ namespace lhrs {
 typedef __nv_bfloat16 bf16;
 
 constexpr int SK_THREADS = 128;
-constexpr int PN_BM = 32;                 // panel kernel: 32 rows x BK k per stage
-constexpr int PN_KW = 4;                  //   every chunk's k-steps are shared by PN_KW warps per 16-row tile (8 warps per CTA:
-constexpr int PN_THREADS = 2 * PN_KW * 32;  // with 4 the ~1.5 CTAs per SM left the mma / ldmatrix chains latency-bound)
+// panel kernel: PN_BM (32 or 16) rows x BK k per stage, 8 warps per CTA = (PN_BM / 16 row tiles) x (4 or 8 k-shares of every chunk).
+// ncu (round 2): 42 % issue-slot utilisation at 18 % warp occupancy, top stalls `wait` and `short_scoreboard` — the kernel is bound by
+// instruction latency, not by HBM, as long as a 32-row panel per CTA leaves only ~1.4 CTAs per SM at M = 6.7-8 k rows; 16-row panels
+// double the resident warps (launch_panel picks them while the grid stays under 4 CTAs per SM).
+constexpr int PN_THREADS = 256;
 constexpr int RR_ST = 4;                  // row-reduce kernel: BR rows x BC columns (16 KB) per stage
+constexpr int RR_THREADS = 256;           //   4 column groups x 2 halves of every chunk's rows (same reason as the panel kernel's 8 warps)
 
 __device__ __forceinline__ void sk_cp16(uint32_t dst, const void* src, bool valid) {
     const int sz = valid ? 16 : 0;
@@ -83,9 +86,11 @@ __device__ __forceinline__ uint32_t drop_pair_rows(uint32_t v, uint32_t word, ui
     return v & __byte_perm(k4, 0u, (col & 1u) ? 0x3311u : 0x2200u);                     // draws c, 2 + c -> low / high half
 }
 
-template <int NT, bool W_KN, int PN_BK, int PN_ST, bool L2H>
+template <int NT, bool W_KN, int PN_BK, int PN_ST, bool L2H, int PN_BM>
 __global__ void __launch_bounds__(PN_THREADS)
 lora_panel_kernel(const PanelArgs a) {
+    constexpr int RT = PN_BM / 16;                                       // 16-row mma tiles of the panel
+    constexpr int PN_KW = (PN_THREADS / 32) / RT;                        // warps sharing the k-steps of every chunk of one row tile
     constexpr int X_STAGE = PN_BM * PN_BK * 2;
     constexpr int W_STAGE = W_KN ? PN_BK * 16 * 2 : NT * 8 * PN_BK * 2;
     constexpr int STAGE = X_STAGE + W_STAGE;
@@ -93,9 +98,12 @@ lora_panel_kernel(const PanelArgs a) {
     extern __shared__ __align__(128) uint8_t smem[];
     const uint32_t s0 = smem_u32(smem);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, mat = lane >> 3;
-    const int wr = warp & 1, wk = warp >> 1;                              // row tile (2) x k share (PN_KW) of every chunk
+    const int wr = warp % RT, wk = warp / RT;                            // row tile x k share of every chunk
     const int row0 = blockIdx.x * PN_BM;
     const int nchunks = a.K / PN_BK;
+    const int cps = W_KN ? a.kseg / PN_BK : nchunks;                    // chunks per K segment
+    int seg_c = 0, seg_left = cps;                                       // segment of the chunk being consumed (no division per chunk)
+    int seg_l = 0, kin_l = 0;                                            // segment / k offset of the next chunk to be requested
 
     auto load = [&](int chunk, int stage) {
         const uint32_t sx = s0 + stage * STAGE, sw = sx + X_STAGE;
@@ -110,8 +118,9 @@ lora_panel_kernel(const PanelArgs a) {
             if (L2H) sk_cp16_l2(sx + offsw<PN_BK>(r, c), src, ok); else sk_cp16(sx + offsw<PN_BK>(r, c), src, ok);
         }
         if constexpr (W_KN) {
-            const int s = k0 / a.kseg, kin = k0 - s * a.kseg;
-            const bf16* w = a.W[s] + static_cast<long long>(kin) * 16;
+            const bf16* w = a.W[seg_l] + static_cast<long long>(kin_l) * 16;   // chunks are requested in order: running segment / offset
+            kin_l += PN_BK;
+            if (kin_l == a.kseg) { kin_l = 0; ++seg_l; }
             for (int idx = tid; idx < PN_BK * 2; idx += PN_THREADS) {       // BK k-rows x 2 chunks
                 const int r = idx >> 1, c = idx & 1;
                 sk_cp16(sw + r * 32 + c * 16, w + r * 16 + c * 8, true);
@@ -139,6 +148,8 @@ lora_panel_kernel(const PanelArgs a) {
         if (ch + PN_ST - 1 < nchunks) load(ch + PN_ST - 1, (ch + PN_ST - 1) % PN_ST);
         sk_commit();
         const uint32_t sx = s0 + (ch % PN_ST) * STAGE, sw = sx + X_STAGE;
+        if (W_KN && seg_left == 0) { ++seg_c; seg_left = cps; }
+        --seg_left;
 #pragma unroll
         for (int kk = 0; kk < PN_BK / (16 * PN_KW); ++kk) {
             const int ks = wk * (PN_BK / (16 * PN_KW)) + kk;                // this warp's k-steps of the chunk
@@ -147,7 +158,7 @@ lora_panel_kernel(const PanelArgs a) {
             if constexpr (W_KN) {
                 uint32_t b0, b1, b2, b3;
                 sk_ldsm_t(sw + (ks * 16 + (mat & 1) * 8 + (lane & 7)) * 32 + (mat >> 1) * 16, b0, b1, b2, b3);
-                const int s = (ch * PN_BK) / a.kseg;                        // block-uniform: which segment's two n-tiles
+                const int s = seg_c;                                        // block-uniform: which segment's two n-tiles
                 if (s == 0) { sk_mma(acc[0], af, b0, b1); sk_mma(acc[1], af, b2, b3); }
                 if constexpr (NT >= 4) { if (s == 1) { sk_mma(acc[2], af, b0, b1); sk_mma(acc[3], af, b2, b3); } }
                 if constexpr (NT >= 6) { if (s == 2) { sk_mma(acc[4], af, b0, b1); sk_mma(acc[5], af, b2, b3); } }
@@ -178,11 +189,11 @@ lora_panel_kernel(const PanelArgs a) {
     sk_wait<0>();
     __syncthreads();
     // the PN_KW k-shares of each 16-row tile meet in shared memory; warps with wk == 0 finish and store
-    float* red = reinterpret_cast<float*>(smem);                            // [PN_KW - 1][2 row tiles][NT][32 lanes][4]
+    float* red = reinterpret_cast<float*>(smem);                            // [PN_KW - 1][RT row tiles][NT][32 lanes][4]
     if (wk > 0) {
 #pragma unroll
         for (int i = 0; i < NT; ++i)
-            *reinterpret_cast<float4*>(red + ((((wk - 1) * 2 + wr) * NT + i) * 32 + lane) * 4) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+            *reinterpret_cast<float4*>(red + ((((wk - 1) * RT + wr) * NT + i) * 32 + lane) * 4) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
     }
     __syncthreads();
     if (wk == 0) {
@@ -193,7 +204,7 @@ lora_panel_kernel(const PanelArgs a) {
             float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
             for (int w = 0; w < PN_KW - 1; ++w) {                           // fixed order: deterministic
-                const float4 v = *reinterpret_cast<const float4*>(red + (((w * 2 + wr) * NT + i) * 32 + lane) * 4);
+                const float4 v = *reinterpret_cast<const float4*>(red + (((w * RT + wr) * NT + i) * 32 + lane) * 4);
                 o.x += v.x; o.y += v.y; o.z += v.z; o.w += v.w;
             }
             const int col = i * 8 + t4 * 2;
@@ -225,7 +236,7 @@ struct ReduceArgs {
 };
 
 template <int NT, int RR_BC, bool L2H>
-__global__ void __launch_bounds__(SK_THREADS)
+__global__ void __launch_bounds__(RR_THREADS)
 lora_rowreduce_kernel(const ReduceArgs a) {
     constexpr int RR_BR = 8192 / RR_BC;               // 64 x 128 or 32 x 256
     constexpr int P_STAGE = RR_BR * RR_BC * 2;        // 16 KB
@@ -235,7 +246,9 @@ lora_rowreduce_kernel(const ReduceArgs a) {
     constexpr int MT = RR_BC / 64;                    // 16-column tiles per warp
     extern __shared__ __align__(128) uint8_t smem[];
     const uint32_t s0 = smem_u32(smem);
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, mat = lane >> 3;
+    const int tid = threadIdx.x, warp_all = tid >> 5, lane = tid & 31, mat = lane >> 3;
+    const int warp = warp_all & 3;                    // column group: 16-column tiles [warp * MT, warp * MT + MT)
+    const int kh = warp_all >> 2;                     // which half of every chunk's k-steps (rows): two warps per column group
     const int c0 = blockIdx.x * RR_BC;
     const int split = blockIdx.y;
     const int m_begin = split * a.rows_per_split;
@@ -247,14 +260,14 @@ lora_rowreduce_kernel(const ReduceArgs a) {
         const uint32_t sp = s0 + stage * STAGE, sq = sp + P_STAGE;
         const int m0 = m_begin + chunk * RR_BR;
 #pragma unroll
-        for (int i = 0; i < (RR_BR * CPR) / SK_THREADS; ++i) {
-            const int idx = tid + i * SK_THREADS, r = idx / CPR, c = idx % CPR;
+        for (int i = 0; i < (RR_BR * CPR) / RR_THREADS; ++i) {
+            const int idx = tid + i * RR_THREADS, r = idx / CPR, c = idx % CPR;
             const int gm = m0 + r;
             const bool ok = gm < m_end && c0 + c * 8 < a.C;
             const bf16* src = a.P + static_cast<long long>(ok ? gm : 0) * a.ldp + (ok ? c0 + c * 8 : 0);
             if (L2H) sk_cp16_l2(sp + offsw<RR_BC>(r, c), src, ok); else sk_cp16(sp + offsw<RR_BC>(r, c), src, ok);
         }
-        for (int idx = tid; idx < RR_BR * NT; idx += SK_THREADS) {
+        for (int idx = tid; idx < RR_BR * NT; idx += RR_THREADS) {
             const int r = idx / NT, c = idx - r * NT;
             const int gm = m0 + r;
             const bool ok = gm < m_end;
@@ -280,7 +293,8 @@ lora_rowreduce_kernel(const ReduceArgs a) {
         sk_commit();
         const uint32_t sp = s0 + (ch % RR_ST) * STAGE, sq = sp + P_STAGE;
 #pragma unroll
-        for (int ks = 0; ks < RR_BR / 16; ++ks) {
+        for (int kk = 0; kk < RR_BR / 32; ++kk) {
+            const int ks = kh * (RR_BR / 32) + kk;
             uint32_t bq[NT / 2][4];
 #pragma unroll
             for (int np = 0; np < NT / 2; ++np)
@@ -318,14 +332,35 @@ lora_rowreduce_kernel(const ReduceArgs a) {
     }
     sk_wait<0>();
     const int g = lane >> 2, t4 = lane & 3;
+    {   // the two k-halves of every column group meet in shared memory (fixed order); warps 0-3 carry the sums from here on
+        __syncthreads();                                   // every warp is done with the pipeline buffers
+        float* mrg = reinterpret_cast<float*>(smem);       // [4 groups][MT][NT][32 lanes][4] fp32 (<= 24.6 KB)
+        if (kh == 1) {
+#pragma unroll
+            for (int t = 0; t < MT; ++t)
+#pragma unroll
+                for (int i = 0; i < NT; ++i)
+                    *reinterpret_cast<float4*>(mrg + (((warp * MT + t) * NT + i) * 32 + lane) * 4) = make_float4(acc[t][i][0], acc[t][i][1], acc[t][i][2], acc[t][i][3]);
+        }
+        __syncthreads();
+        if (kh == 0) {
+#pragma unroll
+            for (int t = 0; t < MT; ++t)
+#pragma unroll
+                for (int i = 0; i < NT; ++i) {
+                    const float4 o = *reinterpret_cast<const float4*>(mrg + (((warp * MT + t) * NT + i) * 32 + lane) * 4);
+                    acc[t][i][0] += o.x; acc[t][i][1] += o.y; acc[t][i][2] += o.z; acc[t][i][3] += o.w;
+                }
+        }
+    }
     if (a.cluster) {
         namespace cg = cooperative_groups;
         cg::cluster_group cluster = cg::this_cluster();
         constexpr int NQ = NT * 8;
-        __syncthreads();                                   // every warp is done with the pipeline buffers
+        __syncthreads();                                   // the merge area is read: it may be overwritten
         float* red = reinterpret_cast<float*>(smem);       // [RR_BC][NQ] fp32 (<= 48 KB, inside the first stages)
 #pragma unroll
-        for (int t = 0; t < MT; ++t) {
+        for (int t = 0; t < MT && kh == 0; ++t) {
             const int cl = warp * (MT * 16) + t * 16 + g;
 #pragma unroll
             for (int i = 0; i < NT; ++i) {
@@ -342,7 +377,7 @@ lora_rowreduce_kernel(const ReduceArgs a) {
             const float* tiles[8];
 #pragma unroll
             for (unsigned r = 0; r < 8; ++r) tiles[r] = r < nranks ? cluster.map_shared_rank(red, r) : red;
-            for (int idx = me * SK_THREADS + tid; idx < RR_BC * NQ; idx += nranks * SK_THREADS) {
+            for (int idx = me * RR_THREADS + tid; idx < RR_BC * NQ; idx += nranks * RR_THREADS) {
                 // transpose: consecutive threads walk the columns of one output row; else consecutive elements of [c][j]
                 const int cl = a.transpose ? idx % RR_BC : idx / NQ;
                 const int j = a.transpose ? idx / RR_BC : idx % NQ;
@@ -362,7 +397,7 @@ lora_rowreduce_kernel(const ReduceArgs a) {
     }
     float* dst = a.partial + static_cast<long long>(split) * a.C * (NT * 8);
 #pragma unroll
-    for (int t = 0; t < MT; ++t) {
+    for (int t = 0; t < MT && kh == 0; ++t) {
         const int c_lo = c0 + warp * (MT * 16) + t * 16 + g, c_hi = c_lo + 8;
 #pragma unroll
         for (int i = 0; i < NT; ++i) {
@@ -401,34 +436,34 @@ static int env_int(const char* name, int dflt) {
     return e ? atoi(e) : dflt;
 }
 
-template <int NT, bool W_KN, int BK, int ST, bool L2H>
+template <int NT, bool W_KN, int BK, int ST, bool L2H, int BM>
 static int launch_panel_cfg(const PanelArgs& a, cudaStream_t st) {
-    constexpr int STAGE = PN_BM * BK * 2 + (W_KN ? BK * 16 * 2 : NT * 8 * BK * 2);
-    constexpr int SMEM = STAGE * ST;
-    auto kern = lora_panel_kernel<NT, W_KN, BK, ST, L2H>;
+    constexpr int STAGE = BM * BK * 2 + (W_KN ? BK * 16 * 2 : NT * 8 * BK * 2);
+    constexpr int RED = (8 / (BM / 16) - 1) * (BM / 16) * NT * 32 * 4 * 4;   // k-share meeting area (aliases the ring after the loop)
+    constexpr int SMEM = STAGE * ST > RED ? STAGE * ST : RED;
+    auto kern = lora_panel_kernel<NT, W_KN, BK, ST, L2H, BM>;
     static bool attr = false;
     if (!attr) { LHRS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM)); attr = true; }
     const bool prof = prof_on();
     if (prof) prof_begin(PROF_SKINNY, 2.0 * a.M * (double)(NT * 8) * (W_KN ? a.kseg : a.K), 2.0 * (double)a.M * a.K, st);
-    kern<<<(a.M + PN_BM - 1) / PN_BM, PN_THREADS, SMEM, st>>>(a);
+    kern<<<(a.M + BM - 1) / BM, PN_THREADS, SMEM, st>>>(a);
     if (prof) prof_end(st);
     LHRS_LAUNCH_CHECK("lora_panel_kernel");
     return LHRS_OK;
 }
 template <int NT, bool W_KN>
 static int launch_panel(const PanelArgs& a, cudaStream_t st) {
-    static int bk = -1, l2h = -1;
-    if (bk < 0) { bk = env_int("LHRS_SKINNY_BK", 128); l2h = env_int("LHRS_SKINNY_L2HINT", 0); }
+    static int bk = -1, l2h = -1, bm = -1;
+    if (bk < 0) { bk = env_int("LHRS_SKINNY_BK", 128); l2h = env_int("LHRS_SKINNY_L2HINT", 0); bm = env_int("LHRS_SKINNY_BM", 0); }
+    // 16-row panels while 32-row ones would leave fewer than two CTAs per SM (LHRS_SKINNY_BM=16 / 32 forces one)
+    // (measured at M = 6740: dT qkv 66.6 -> 58.5 us, dT gate/up 100.4 -> 87.0, dT o / down 25.6 -> 23.6, T down 43.1 -> 40.0; the
+    //  48-column forward form re-stages a 12 KB factor chunk per 4 KB of activation with 16 rows and loses: 27.6 -> 31.7 us)
+    const bool small = bm == 16 || (bm != 32 && (a.M + 31) / 32 < 2 * num_sms() && (W_KN || NT <= 4));
     if (bk == 128 && a.K % 128 == 0 && (!W_KN || a.kseg % 128 == 0)) {
-        // deeper ring where two CTAs of it still fit on an SM (stage = 8 KB of X + the W chunk): more bytes in flight per SM
-        static int deep = -1;
-        if (deep < 0) deep = env_int("LHRS_SKINNY_DEEP", 0);
-        constexpr int STAGE = PN_BM * 128 * 2 + (W_KN ? 128 * 16 * 2 : NT * 8 * 128 * 2);
-        constexpr int DEEP_ST = (110 * 1024) / STAGE > 9 ? 9 : (110 * 1024) / STAGE;
-        if (deep && !l2h && DEEP_ST > 5) return launch_panel_cfg<NT, W_KN, 128, DEEP_ST, false>(a, st);
-        return l2h ? launch_panel_cfg<NT, W_KN, 128, 5, true>(a, st) : launch_panel_cfg<NT, W_KN, 128, 5, false>(a, st);
+        if (l2h) return launch_panel_cfg<NT, W_KN, 128, 5, true, 32>(a, st);
+        return small ? launch_panel_cfg<NT, W_KN, 128, 6, false, 16>(a, st) : launch_panel_cfg<NT, W_KN, 128, 5, false, 32>(a, st);
     }
-    return l2h ? launch_panel_cfg<NT, W_KN, 64, 8, true>(a, st) : launch_panel_cfg<NT, W_KN, 64, 8, false>(a, st);
+    return l2h ? launch_panel_cfg<NT, W_KN, 64, 8, true, 32>(a, st) : launch_panel_cfg<NT, W_KN, 64, 8, false, 32>(a, st);
 }
 
 template <int NT, int BC, bool L2H>
@@ -441,14 +476,14 @@ static int launch_rowreduce_cfg(const ReduceArgs& a, int nsplit, cudaStream_t st
     if (prof) prof_begin(PROF_SKINNY, 2.0 * a.M * (double)a.C * (NT * 8), 2.0 * (double)a.M * a.C, st);
     if (a.cluster) {
         cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3((a.C + BC - 1) / BC, nsplit); cfg.blockDim = dim3(SK_THREADS); cfg.dynamicSmemBytes = SMEM; cfg.stream = st;
+        cfg.gridDim = dim3((a.C + BC - 1) / BC, nsplit); cfg.blockDim = dim3(RR_THREADS); cfg.dynamicSmemBytes = SMEM; cfg.stream = st;
         cudaLaunchAttribute attr[1];
         attr[0].id = cudaLaunchAttributeClusterDimension;
         attr[0].val.clusterDim.x = 1; attr[0].val.clusterDim.y = nsplit; attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr; cfg.numAttrs = 1;
         LHRS_CUDA(cudaLaunchKernelEx(&cfg, kern, a));
     } else {
-        kern<<<dim3((a.C + BC - 1) / BC, nsplit), SK_THREADS, SMEM, st>>>(a);
+        kern<<<dim3((a.C + BC - 1) / BC, nsplit), RR_THREADS, SMEM, st>>>(a);
     }
     if (prof) prof_end(st);
     LHRS_LAUNCH_CHECK("lora_rowreduce_kernel");
