@@ -443,3 +443,37 @@ def test_zero2_checkpoint_directory_roundtrip(tmp_path):
     zc.load_state_dict_from_zero_checkpoint(m3, str(d2))
     assert m3.text.text_encoder.has_lora() and m3._zero_load_report["unexpected"] == []
     assert torch.equal(m3.text.lora_pairs()[9][1], m2.text.lora_pairs()[9][1])
+
+
+def test_ragged_plan_bookkeeping(monkeypatch):
+    """autograd.ragged_plan (host logic of the padding-free decoder stack): taken only for right-padded masks with
+    enough padding and a longest sequence >= 128; offsets / positions / row maps are consistent with the mask."""
+    import torch
+    from lhrs_bot_b200 import autograd
+    lens = [300, 128, 17, 256]
+    B, S = len(lens), 300
+    mask = torch.zeros(B, S, dtype=torch.bool)
+    for b, n in enumerate(lens):
+        mask[b, :n] = True
+    plan = autograd.ragged_plan(mask)
+    assert plan is not None and plan.rows == sum(lens) and plan.s_max == 300 and plan.B == B
+    assert plan.seq_off.tolist() == [0, 300, 428, 445, 701]
+    # every packed row points at a real position of the padded layout, in order, and back
+    rr = plan.real_rows.tolist()
+    assert rr == [b * S + s for b, n in enumerate(lens) for s in range(n)]
+    assert plan.positions.tolist() == [s for n in lens for s in range(n)]
+    po = plan.packed_of
+    assert (po[plan.real_rows] == torch.arange(plan.rows)).all() and int((po >= 0).sum()) == plan.rows
+    assert (po.view(B, S)[~mask] == -1).all()
+    # not taken: no mask, left padding / holes, too little padding, short sequences, an empty sample, switched off
+    assert autograd.ragged_plan(None) is None
+    holes = mask.clone(); holes[0, 5] = False
+    assert autograd.ragged_plan(holes) is None
+    assert autograd.ragged_plan(mask.flip(1)) is None
+    nearly_full = torch.ones(4, 300, dtype=torch.bool); nearly_full[1, 295:] = False
+    assert autograd.ragged_plan(nearly_full) is None
+    assert autograd.ragged_plan(mask[:, :100]) is None            # longest sequence 100 < 128
+    empty = mask.clone(); empty[2] = False
+    assert autograd.ragged_plan(empty) is None
+    monkeypatch.setenv("LHRS_RAGGED", "0")
+    assert autograd.ragged_plan(mask) is None
