@@ -2,6 +2,8 @@
 // hot path (HF LlamaAttention as driven by lhrs/models/text_modal.py:398-412 and, through it, modeling_llama's eager
 // softmax(QK^T/sqrt(d) + mask)V).  Same contract as attn_fwd_kernel in attention.cu (which keeps head_dim 64 and short
 // query blocks): strided Q/K/V views, causal with the (Skv - Sq) offset, optional [B, Skv] key mask, fp32 lse.
+// Ragged batches (LhrsAttention::seq_off): the tensor maps span the whole batch's row space as one entry, a tile of sequence b
+// starts at row seq_off[b] + q0, and the sequence length takes the place of Sq = Skv in every mask and store predicate.
 //
 // One CTA = one 128-row query tile of one (batch, head); two CTAs are resident per SM so one tile's softmax overlaps
 // the other's MMAs.  Per 64-key step:   S = Q K^T   (128x64x128, accumulator in TMEM, double buffered)

@@ -2,10 +2,13 @@
 // With r = 16 these products have 16..48 output columns against 4096..22016 input columns: they are HBM-bound (one pass over an
 // activation of 64..360 MB per call), not tensor-bound, so they do not belong on 128-row tcgen05 tiles (which left them at ~1/3 of
 // HBM speed and 13 % of the SFT step).  Two kernels, both built from warp-level mma.sync.m16n8k16 tiles fed by a multi-stage cp.async
-// ring, sized so that every SM keeps >= 48 KB of loads in flight (measured round 1, M = 8192: 2.4-4.4 TB/s, 21.7 ms per SFT step for
-// all 512 side products against 32 ms on the tcgen05 tiles; 128-wide k chunks beat 64-wide ones by 10 %, the L2::256B prefetch hint
-// and 256-column row-reduce blocks change nothing — tools/lora_bench.py, gpurun_out/s2d_lora_variants.txt):
-//   lora_panel_kernel      out[M, n] = alpha * X[M, K] · W          one CTA per 32-row panel, X streamed once, W from L2
+// ring (tools/lora_bench.py; round 1, M = 8192: 2.4-4.4 TB/s, 21.7 ms per SFT step for all 512 side products against 32 ms on the
+// tcgen05 tiles; 128-wide k chunks beat 64-wide ones by 10 %, the L2::256B prefetch hint and 256-column row-reduce blocks change
+// nothing).  Round 2 (ncu --set full): with ~1.4 CTAs of 4 warps per SM the panels were bound by instruction latency (42 % issue
+// slots busy at 18 % occupancy, stalls `wait` / `short_scoreboard`), not by HBM: 8 warps per CTA, 16-row panels where they pay and
+// no integer divisions per chunk brought dT qkv from 66.6 to 47.1 us and dT gate/up from 100.4 to 71.7 us at M = 6740 (3.5 / 4.1
+// TB/s); a deeper ring (LHRS_SKINNY_DEEP) does not help.
+//   lora_panel_kernel      out[M, n] = alpha * X[M, K] · W          one CTA per 16- or 32-row panel, X streamed once, W from L2
 //        W_KN = false:  W = [n, K] K-major (forward  T  = s · x · [A_0;A_1;..]^T)
 //        W_KN = true :  W_s = [kseg, 16] per K segment, block diagonal (backward dT_s = s · dy_s · B_s, B_s = lora_B [out, r])
 //   lora_rowreduce_kernel  G[C, n] = P[M, C]^T · Q[M, n]            one CTA per 128-column block x row split, P streamed once;
