@@ -766,12 +766,14 @@ def measure_steps(args, workload, dev, rank, world, local, steps, warmup, B=None
     # whole-step fraction of the tensor roofline: algorithmic flops of the step (14.1 TF per S=512 SFT sample,
     # 7.09 TF per S=256 stage-1 sample, forward 13.3 GF per position) over the step time
     step_tf = {"sft_step": 14.1 * S / 512.0, "stage1_step": 7.09 * S / 256.0, "prefill": 13.3e-3 * S}[workload] * B
-    padding_free = train and _ag.RAGGED_CALLS > ragged_calls0
+    padding_free = _ag.RAGGED_CALLS > ragged_calls0
     if padding_free:
-        # the decoder stack ran on the real rows only (autograd.ragged_plan): count ITS flops on those rows (26.6 GF per position,
-        # forward + dX), everything else (ViT, pooler, lm_head rows) as before — the fraction must not be paid for skipped padding
-        llama_tf = 26.6e-3 * S * B
-        step_tf_real = step_tf - llama_tf + 26.6e-3 * real_tok
+        # the decoder stack ran on the real rows only (autograd.ragged_plan): count ITS flops on those rows (26.6 GF per position
+        # for forward + dX, 13.3 for forward only), everything else (ViT, pooler, lm_head rows) as before — the fraction must not
+        # be paid for skipped padding
+        per_pos = 26.6e-3 if train else 13.3e-3      # TF per decoder position: forward + dX, or forward only
+        llama_tf = per_pos * S * B
+        step_tf_real = step_tf - llama_tf + per_pos * real_tok
         roofline["whole_step"] = dict(algorithmic_TF_per_step=step_tf_real, tflops=step_tf_real / (step_ms * 1e-3),
                                       frac=step_tf_real / (step_ms * 1e-3) / pk["tflops"],
                                       padded_accounting=dict(algorithmic_TF_per_step=step_tf, frac=step_tf / (step_ms * 1e-3) / pk["tflops"]),

@@ -494,11 +494,22 @@ class TextModal(BaseModal):
         if embeds is None:   # text-only call without image features
             embeds = self.embed(input_ids)
             new_labels = labels
-        hidden = self.llama_forward(embeds, mask)
-        from .autograd import supervised_rows
+        from .autograd import ragged_plan, supervised_rows
         sel = supervised_rows(new_labels)
+        # scoring a right-padded batch: the decoder stack runs on the real rows only (same loss; autograd.ragged_plan)
+        plan = ragged_plan(mask) if sel is not None else None
+        if plan is not None:
+            from . import autograd as _ag
+            _ag.RAGGED_CALLS += 1
+            B, S, D = embeds.shape
+            hidden = self.llama_forward_ragged(embeds.view(B * S, D).index_select(0, plan.real_rows), B, plan.s_max, plan.seq_off,
+                                               plan.positions)
+        else:
+            hidden = self.llama_forward(embeds, mask)
         if sel is not None:      # lm_head + CE over the supervised rows only (identical loss)
             rows, ce_labels = sel
+            if plan is not None:
+                rows = plan.packed_of.index_select(0, rows)
             hc = torch.zeros((rows.numel() + 1, hidden.shape[-1]), device=hidden.device, dtype=hidden.dtype)
             hc[:-1] = hidden.reshape(-1, hidden.shape[-1]).index_select(0, rows)
             logits = self.lm_head(hc).unsqueeze(0)

@@ -482,6 +482,15 @@ def test_padding_free_step_equals_padded_step(lora_r, monkeypatch):
         assert err <= 2e-2, (n, err)          # reductions over rows (dW, LoRA dA / dB) run over fewer rows in a different split
     ref_loss, sd = _oracle_loss_grads(cfg, st, batch)
     assert abs(l1 - ref_loss.item()) <= 2e-2
+    # the scoring (no-grad) path takes the same plan and gives the same loss as its padded form
+    with torch.no_grad():
+        n_used = len(used)
+        s1 = model(batch)["total_loss"].item()
+        assert used[n_used] is not None
+        monkeypatch.setenv("LHRS_RAGGED", "0")
+        s0 = model(batch)["total_loss"].item()
+        monkeypatch.setenv("LHRS_RAGGED", "1")
+    assert abs(s0 - s1) <= 1e-5 * max(1.0, abs(s0)) and abs(s1 - l1) <= 1e-5 * max(1.0, abs(l1)), (s0, s1, l1)
     _cmp("padding-free pooler query", g1["rgb_pooler.query"], sd["pooler"]["query"].grad, 5e-2)
     for n, g in g1.items():
         if "lora_" in n and "layers.0." in n:
