@@ -73,23 +73,30 @@ def make_batch(B, seed, device=None, pin=False, t_text=None, seq_len=None, mixed
     """One collated batch shaped like DataCollatorForSupervisedDataset's output (lhrs/Dataset/cap_dataset.py:792-810).
 
     mixed=False: every sample is [BOS, <image>, text...] of the same length, no padding (stage-1 captions; round-1 bench).
-    mixed=True : BASELINE config 4 as written — "mixed image/text instructions": every 4th sample is text-only (it still carries
-    a dummy image and consumes an image slot, text_modal.py:321-339), lengths are ragged and right-padded with pad id 0
-    (attention_mask = ids != pad), so the splice takes the reference's padding branch (text_modal.py:440-505): image samples
-    come out at seq_len positions, text-only samples at seq_len - 143 and are padded up.  Sample 0 always has full length."""
+    mixed=True : BASELINE config 4 as SURVEY 8d writes it — "mixed image/text instructions": 75 % image samples with
+    T ~ U[150, 369] text ids (S = T + 143 after the splice), 25 % text-only samples (every 4th: no <image>, T ~ U[64, 369]; they
+    still carry a dummy image and consume an image slot, text_modal.py:321-339), right-padded by the collator to the batch's
+    longest id row with pad id 0 (attention_mask = ids != pad), so the splice takes the reference's padding branch
+    (text_modal.py:440-505).  (SURVEY lets text-only samples run to 512 ids; under the reference's collator + splice the padded id
+    row of every image sample is embedded too and grows by 143, so a batch that is to come out at S = 512 has id rows of at most
+    369.)  Sample 0 is an image sample of full length, which pins the spliced batch at exactly seq_len positions.  The last 40 %
+    of every sample's text positions are supervised.  (For other seq_len the ranges keep their lower ends.)"""
     g = torch.Generator().manual_seed(seed)
     if seq_len is not None:
         t_text = seq_len - (NUM_QUERY - 1)
-    T = T_TEXT if t_text is None else t_text
-    ids = torch.randint(3, 32000, (B, T), generator=g)
+    T = T_TEXT if t_text is None else t_text          # text ids of a full-length image sample
+    W = T                                              # width of input_ids (the collator pads to the longest row)
+    ids = torch.randint(3, 32000, (B, W), generator=g)
     ids[:, 0] = 1                                   # BOS
     labels = ids.clone()
-    mask = torch.ones(B, T, dtype=torch.bool)
+    mask = torch.ones(B, W, dtype=torch.bool)
     for b in range(B):
         text_only = mixed and (b % 4 == 3)
         n = T
-        if mixed and b > 0:
-            n = T - int(torch.randint(0, T // 3 if text_only else T // 4, (1,), generator=g))
+        if mixed and text_only:
+            n = int(torch.randint(min(64, W), W + 1, (1,), generator=g))
+        elif mixed and b > 0:
+            n = int(torch.randint(min(150, T), T + 1, (1,), generator=g))
         if not text_only:
             ids[b, 1] = -200                        # plain template: [BOS, <image>, text...]
         n_prompt = int(n * 0.6)                     # last 40 % of the real text positions supervised (SURVEY 8d config 4)
