@@ -83,6 +83,89 @@ rmsnorm_bwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __r
     }
 }
 
+// ------------------------------------------------------------------ LayerNorm backward, one WARP per row (dim = 256 * WC <= 1024)
+// The block-per-row form below pays four block barriers per row and, at dim 1024, keeps half of its 256 threads idle: 85 us per
+// launch on the pooler's 14592 x 1024 key/value rows.  Here every warp walks its own rows (lane l owns 16-byte chunks l, l + 32,
+// ...), the two row sums are warp shuffles, and the eight warps' dgamma / dbeta columns meet in shared memory once at the end.
+// Same partial layout as the block form: part[2][grid][dim], summed by colsum_final_kernel.
+template <int WC>
+__global__ void __launch_bounds__(BT)
+layernorm_bwd_warp_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, const __nv_bfloat16* __restrict__ w,
+                          const float* __restrict__ mean, const float* __restrict__ rstd, const __nv_bfloat16* __restrict__ dy,
+                          const __nv_bfloat16* __restrict__ dres, __nv_bfloat16* __restrict__ dx, float* __restrict__ part,
+                          long long rows, int dim) {
+    __shared__ float buf[8][256 * WC];                     // <= 32 KB
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float dg[WC][8], db[WC][8], wv[WC][8];
+#pragma unroll
+    for (int i = 0; i < WC; ++i) {
+        up8(__ldg(reinterpret_cast<const uint4*>(w) + lane + 32 * i), wv[i]);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { dg[i][j] = 0.f; db[i][j] = 0.f; }
+    }
+    const float inv_dim = 1.f / dim;
+    for (long long row = static_cast<long long>(blockIdx.x) * 8 + warp; row < rows; row += static_cast<long long>(gridDim.x) * 8) {
+        const uint4* xr = reinterpret_cast<const uint4*>(x + row * ldx);
+        const uint4* dr = reinterpret_cast<const uint4*>(dy + row * dim);
+        const uint4* rr = dres ? reinterpret_cast<const uint4*>(dres + row * dim) : nullptr;
+        uint4 xraw[WC], draw[WC], rraw[WC];
+#pragma unroll
+        for (int i = 0; i < WC; ++i) {                     // every load of the row is in flight before the first use
+            xraw[i] = xr[lane + 32 * i];
+            draw[i] = dr[lane + 32 * i];
+            rraw[i] = (rr != nullptr && dx != nullptr) ? rr[lane + 32 * i] : make_uint4(0, 0, 0, 0);
+        }
+        const float mu = mean[row], rs = rstd[row];
+        float u[WC][8], xh[WC][8];
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int i = 0; i < WC; ++i) {
+            float xv[8], dv[8];
+            up8(xraw[i], xv); up8(draw[i], dv);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                xh[i][j] = (xv[j] - mu) * rs;
+                u[i][j] = dv[j] * wv[i][j];
+                s1 += u[i][j];
+                s2 += u[i][j] * xh[i][j];
+                dg[i][j] += dv[j] * xh[i][j];
+                db[i][j] += dv[j];
+            }
+        }
+        s1 = wsum(s1) * inv_dim;
+        s2 = wsum(s2) * inv_dim;
+        if (dx != nullptr) {
+            uint4* o = reinterpret_cast<uint4*>(dx + row * dim);
+#pragma unroll
+            for (int i = 0; i < WC; ++i) {
+                float r[8], out[8];
+                up8(rraw[i], r);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) out[j] = r[j] + rs * (u[i][j] - s1 - xh[i][j] * s2);
+                o[lane + 32 * i] = pk8(out);
+            }
+        }
+    }
+    // the eight warps' column partials -> one row of part[] per block (dgamma, then dbeta through the same buffer)
+    float* pg = part + static_cast<long long>(blockIdx.x) * dim;
+    float* pb = part + (static_cast<long long>(gridDim.x) + blockIdx.x) * dim;
+#pragma unroll
+    for (int pass = 0; pass < 2; ++pass) {
+#pragma unroll
+        for (int i = 0; i < WC; ++i)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) buf[warp][(lane + 32 * i) * 8 + j] = pass == 0 ? dg[i][j] : db[i][j];
+        __syncthreads();
+        for (int c = threadIdx.x; c < dim; c += BT) {
+            float t = 0.f;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) t += buf[q][c];
+            (pass == 0 ? pg : pb)[c] = t;
+        }
+        __syncthreads();
+    }
+}
+
 // ------------------------------------------------------------------ LayerNorm backward
 // Each block walks rows blockIdx.x, +gridDim.x, ...; per-thread column partials of dgamma/dbeta go to part[2][grid][dim].
 __global__ void __launch_bounds__(BT)
@@ -168,12 +251,32 @@ colsum_partial_kernel(const __nv_bfloat16* __restrict__ a, long long ld, long lo
     for (int j = 0; j < 8; ++j) p[j] = acc[j];
 }
 // out[c] (bf16) = sum_p part[p][c]  (+ out[c] if accumulate)
-__global__ void colsum_final_kernel(const float* __restrict__ part, int nparts, int n, __nv_bfloat16* __restrict__ out, int accumulate) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= n) return;
-    float s = accumulate ? __bfloat162float(out[c]) : 0.f;
-    for (int p = 0; p < nparts; ++p) s += part[static_cast<long long>(p) * n + c];
-    out[c] = __float2bfloat16_rn(s);
+// 256 threads = 32 columns x 8 row lanes, four independent partial chains per thread (a single thread walking all ~296 partial
+// rows was 16 us of dependent L2 round trips per launch, 67 launches per step); fixed summation order: deterministic.
+// Launch with COLSUM_FINAL_GRID(n) blocks of 256 threads.
+#define COLSUM_FINAL_GRID(n) (((n) + 31) / 32)
+__global__ void __launch_bounds__(256)
+colsum_final_kernel(const float* __restrict__ part, int nparts, int n, __nv_bfloat16* __restrict__ out, int accumulate) {
+    __shared__ float red[8][33];
+    const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
+    const int c = blockIdx.x * 32 + cx;
+    float s[4] = {0.f, 0.f, 0.f, 0.f};
+    if (c < n) {
+        int p = ry;
+        for (; p + 24 < nparts; p += 32) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) s[q] += part[static_cast<long long>(p + 8 * q) * n + c];
+        }
+        for (int q = 0; p < nparts; p += 8, ++q) s[q & 3] += part[static_cast<long long>(p) * n + c];
+    }
+    red[ry][cx] = (s[0] + s[1]) + (s[2] + s[3]);
+    __syncthreads();
+    if (ry == 0 && c < n) {
+        float t = accumulate ? __bfloat162float(out[c]) : 0.f;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) t += red[q][cx];
+        out[c] = __float2bfloat16_rn(t);
+    }
 }
 
 // ------------------------------------------------------------------ SwiGLU backward: act = silu(g) * u
@@ -315,16 +418,31 @@ extern "C" int lhrs_layernorm_bwd(const void* x, int64_t ldx, const void* w, con
                                   const void* dres, void* dx, void* dw, void* db, int32_t accumulate, float* scratch,
                                   int64_t rows, int32_t dim, void* stream) {
     LHRS_CHECK_ARG(x && w && mean && rstd && dy && scratch && rows > 0 && dim % 8 == 0 && dim <= 8 * BT * MAXC, "lhrs_layernorm_bwd: bad args");
-    const unsigned nb = (unsigned)(rows < 296 ? rows : 296);
-    layernorm_bwd_kernel<<<nb, BT, 0, (cudaStream_t)stream>>>((const bf16*)x, ldx, (const bf16*)w, mean, rstd, (const bf16*)dy,
-                                                             (const bf16*)dres, (bf16*)dx, scratch, rows, dim);
+    unsigned nb = (unsigned)(rows < 296 ? rows : 296);
+    const bool warp_form = (dim == 256 || dim == 512 || dim == 768 || dim == 1024) && ldx % 8 == 0 &&
+                           ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(w)) & 15) == 0;
+    if (warp_form) {
+        const long long need = (rows + 7) / 8;               // blocks of eight row-warps
+        nb = (unsigned)(need < 296 ? need : 296);
+        auto launch = [&](auto kern) {
+            kern<<<nb, BT, 0, (cudaStream_t)stream>>>((const bf16*)x, ldx, (const bf16*)w, mean, rstd, (const bf16*)dy, (const bf16*)dres,
+                                                      (bf16*)dx, scratch, rows, dim);
+        };
+        if (dim == 256) launch(layernorm_bwd_warp_kernel<1>);
+        else if (dim == 512) launch(layernorm_bwd_warp_kernel<2>);
+        else if (dim == 768) launch(layernorm_bwd_warp_kernel<3>);
+        else launch(layernorm_bwd_warp_kernel<4>);
+    } else {
+        layernorm_bwd_kernel<<<nb, BT, 0, (cudaStream_t)stream>>>((const bf16*)x, ldx, (const bf16*)w, mean, rstd, (const bf16*)dy,
+                                                                 (const bf16*)dres, (bf16*)dx, scratch, rows, dim);
+    }
     LHRS_LAUNCH_CHECK("layernorm_bwd_kernel");
     if (dw) {
-        colsum_final_kernel<<<(dim + 255) / 256, 256, 0, (cudaStream_t)stream>>>(scratch, nb, dim, (bf16*)dw, accumulate);
+        colsum_final_kernel<<<COLSUM_FINAL_GRID(dim), 256, 0, (cudaStream_t)stream>>>(scratch, nb, dim, (bf16*)dw, accumulate);
         LHRS_LAUNCH_CHECK("colsum_final_kernel");
     }
     if (db) {
-        colsum_final_kernel<<<(dim + 255) / 256, 256, 0, (cudaStream_t)stream>>>(scratch + (size_t)nb * dim, nb, dim, (bf16*)db, accumulate);
+        colsum_final_kernel<<<COLSUM_FINAL_GRID(dim), 256, 0, (cudaStream_t)stream>>>(scratch + (size_t)nb * dim, nb, dim, (bf16*)db, accumulate);
         LHRS_LAUNCH_CHECK("colsum_final_kernel");
     }
     return LHRS_OK;
@@ -338,7 +456,7 @@ extern "C" int lhrs_colsum(const void* a, int64_t ld, int64_t rows, int32_t n, v
     const unsigned ny = (unsigned)(rows < 64 ? rows : 64);
     colsum_partial_kernel<<<dim3((n / 8 + BT - 1) / BT, ny), BT, 0, (cudaStream_t)stream>>>((const bf16*)a, ld, rows, n, scratch);
     LHRS_LAUNCH_CHECK("colsum_partial_kernel");
-    colsum_final_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(scratch, ny, n, (bf16*)out, accumulate);
+    colsum_final_kernel<<<COLSUM_FINAL_GRID(n), 256, 0, (cudaStream_t)stream>>>(scratch, ny, n, (bf16*)out, accumulate);
     LHRS_LAUNCH_CHECK("colsum_final_kernel");
     return LHRS_OK;
 }

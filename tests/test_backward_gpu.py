@@ -195,6 +195,20 @@ def test_norm_and_elementwise_bwd():
     _cmp("layernorm dw", dw, wf.grad, 5e-2)
     _cmp("layernorm db", db, bf.grad, 5e-2)
     _cmp("colsum", ops.colsum(dy), dy.float().sum(0), 5e-2)
+    # LayerNorm backward at the pooler's row counts: warp-per-row form (dim 256 .. 1024) and block-per-row form (other dims),
+    # with the residual-stream gradient added
+    for rows, dim in ((14592, 1024), (2304, 768), (777, 256), (1000, 640)):
+        xx, dd, rr = _randn(rows, dim, seed=15), _randn(rows, dim, seed=16), _randn(rows, dim, seed=17)
+        ww = (1 + 0.1 * torch.randn(dim)).bfloat16().to(DEV)
+        bb = (0.1 * torch.randn(dim)).bfloat16().to(DEV)
+        _, mean, rs = ops.layernorm(xx, ww, bb, 1e-5, return_stats=True)
+        dx, dw, db = ops.layernorm_bwd(xx, ww, mean, rs, dd, rr)
+        xf = xx.float().requires_grad_(True)
+        wf, bf = ww.float().requires_grad_(True), bb.float().requires_grad_(True)
+        torch.nn.functional.layer_norm(xf, (dim,), wf, bf, 1e-5).backward(dd.float())
+        _cmp(f"layernorm dx+res {rows}x{dim}", dx, xf.grad + rr.float())
+        _cmp(f"layernorm dw {rows}x{dim}", dw, wf.grad, 5e-2)
+        _cmp(f"layernorm db {rows}x{dim}", db, bf.grad, 5e-2)
     # SwiGLU
     g, u, da = _randn(64, 512, seed=8), _randn(64, 512, seed=9), _randn(64, 512, seed=10)
     dgu = ops.swiglu_bwd(da, g, u)
