@@ -451,8 +451,8 @@ constexpr int OFF_Q = OFF_V + T128;          // NST stages
 constexpr int OFF_DO = OFF_Q + NST * T64;    // NST stages
 constexpr int OFF_PT = OFF_DO + NST * T64;   // 2 buffers (one per compute group)
 constexpr int OFF_DST = OFF_PT + 2 * PS;     // 2 buffers
-constexpr int OFF_STAT = OFF_DST + 2 * PS;   // [2 groups][lse2 64 | delta 64] fp32
-constexpr int OFF_BAR = OFF_STAT + 2 * 128 * 4;
+constexpr int OFF_STAT = OFF_DST + 2 * PS;   // [2 groups][2 buffers][lse2 64 | delta 64] fp32
+constexpr int OFF_BAR = OFF_STAT + 2 * 2 * 128 * 4;
 constexpr int SMEM_BYTES = OFF_BAR + 512;
 constexpr int TM_S = 0, TM_DP = 128, TM_DV = 256, TM_DK = 384;
 constexpr int THREADS = 384;
@@ -647,8 +647,8 @@ attn_bwd_dkv_tcp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
         const int row = quarter * 32 + lane;
         const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
         const float c = p.scale_log2;
-        float* gstat = stat + grp * 128;
-        uint32_t g = 0;
+        float* gstat2 = stat + grp * 256;                 // two buffers per group: one group barrier per step instead of two
+        uint32_t g = 0, ks = 0;                           // ks: this group's step counter (selects the statistics buffer)
         int it = 0;
         auto prefetch_item = [&](int w0) {
             for (int w = w0; w < sc.total; w += G) {
@@ -697,7 +697,10 @@ attn_bwd_dkv_tcp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
                 if ((g & 1u) != static_cast<uint32_t>(grp)) continue;
                 const uint32_t st = grp;
                 const int i0 = (i_begin + t) * 64;
-                bar_sync_group(grp);                          // the group has finished reading the previous step's statistics
+                // the buffer written here was last read two of this group's steps ago, and every thread has passed the previous
+                // step's barrier since: no barrier is needed in front of the write
+                float* gstat = gstat2 + (ks & 1u) * 128;
+                ++ks;
                 gstat[gt] = nxt;
                 nxt = fetch_stat(t + 2);                      // in flight under this step's work
                 bar_sync_group(grp);
